@@ -1,0 +1,220 @@
+/*
+ * islplace.h — C ABI of the B200-native MIG-slot placement engine (libislplace.so).
+ *
+ * This is the drop-in boundary for ONE path of project-codeflare/instaslice: the
+ * controller's allocator.  Every entry point below names the reference interface
+ * it replaces (paths relative to the reference tree, commit b34e86d):
+ *
+ *   internal/controller/instaslice_controller.go
+ *     :240-262  InstasliceReconciler.findDeviceForASlice      -> isl_place_batch
+ *     :303-384  getStartIndexFromPreparedState                -> isl_place_batch / isl_eval_starts
+ *     :283-300  extractGpuProfile                             -> isl_profile.{size,gi,ci,cieng} (echoed by the host shim)
+ *     :48-50, :436-453  AllocationPolicy / FirstFitPolicy     -> isl_config.policy (the Go hook itself stays in Go and
+ *                                                                packs AllocationDetails from isl_result)
+ *   api/v1alpha1/instaslice_types.go
+ *     :23-34    Mig / Placement                               -> isl_profile
+ *     :37-50    AllocationDetails {start,size,gpuUUID,...}    -> isl_result {gpu,start,size,status}
+ *     :53-62    PreparedDetails, :65-72 InstasliceSpec        -> isl_load_inventory (occupancy bytes built by the host shim
+ *                                                                exactly as :306-328 does)
+ *
+ * Plain C, fixed-width integers, caller-owned buffers, no exceptions across the
+ * boundary, no torch types.  The Go side binds it with cgo; the
+ * tests and bench bind it with ctypes.
+ *
+ * Data model
+ *   - G GPUs in canonical order (node index ascending, GPU index ascending inside
+ *     a node; the host supplies the order, SURVEY.md section 8c "Q6").
+ *   - occupancy: one byte per GPU, bit i set = memory slice i busy  (the
+ *     reference's [8]uint32 gpuAllocatedIndex, :306).
+ *   - profile table: up to ISL_MAX_PROFILES rows {size, ordered legal starts},
+ *     one row per Migplacement entry (first entry with a given name wins for the
+ *     start search, :332-340).
+ *   - a request names a profile row; the engine answers (gpu, start) or "none"
+ *     with the reference's sentinel start 9 (:248, :343).
+ *
+ * Batch semantics (canonical; DESIGN.md "Semantics"): within one batch every FREE
+ * is applied first, then ALLOC requests are resolved strictly in array order,
+ * each one seeing every earlier commit — identical to calling the reference's
+ * allocator once per pod in that order on the same inventory.
+ */
+#ifndef ISLPLACE_H
+#define ISLPLACE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISL_ABI_VERSION      1u
+#define ISL_MAX_PROFILES     16u          /* NVML_GPU_INSTANCE_PROFILE_COUNT is 0x11 incl. gaps; the reference tables have <= 10 rows */
+#define ISL_MAX_STARTS       8u
+#define ISL_SLOTS            8u           /* :306  var gpuAllocatedIndex [8]uint32 */
+#define ISL_START_NONE       9u           /* :248, :343  notValidIndex */
+#define ISL_GPU_NONE         0xFFFFFFFFu
+#define ISL_MAX_GPUS         (1u << 24)   /* candidate records pack (gpu << 8 | occ) */
+#define ISL_PROFILE_UNKNOWN  0xFFu        /* request for a profile name that is in no Migplacement row */
+
+/* return codes */
+#define ISL_OK        0
+#define ISL_EINVAL   -1     /* malformed argument / table (the reference would panic: SURVEY Q7) */
+#define ISL_ENOMEM   -2
+#define ISL_ECUDA    -3     /* see isl_last_cuda_error */
+#define ISL_ESTATE   -4     /* call order: profiles and inventory must be loaded before placing */
+#define ISL_ERANGE   -5     /* batch or inventory larger than the engine was created for */
+
+/* isl_config.policy */
+#define ISL_POLICY_FIRST_FIT 0u   /* the only policy the reference implements (:66-67, :436) */
+#define ISL_POLICY_BEST_FIT  1u   /* extension, no reference counterpart; parity unpinned */
+
+/* isl_config.quirks — bit set = reproduce the reference bug exactly */
+#define ISL_QUIRK_STRICT_BOUND 1u /* Q1: `value+size < 8` (:351,:360,:370) instead of <= 8 */
+#define ISL_QUIRK_POW2_ONLY    2u /* Q2: only sizes 1,2,4,8 are ever placed (:346-378) */
+#define ISL_QUIRKS_REF_EXACT   (ISL_QUIRK_STRICT_BOUND | ISL_QUIRK_POW2_ONLY)
+#define ISL_QUIRKS_FIXED       0u
+
+/* isl_request.op */
+#define ISL_OP_ALLOC 0u
+#define ISL_OP_FREE  1u
+#define ISL_OP_NOOP  2u
+
+/* isl_result.status */
+#define ISL_ST_PLACED      0u
+#define ISL_ST_NO_CAPACITY 1u   /* the reference's error "failed to find allocatable gpu" (:261) on every node */
+#define ISL_ST_BAD_PROFILE 2u   /* profile index >= loaded rows (the reference also ends at :261) */
+#define ISL_ST_FREED       3u
+#define ISL_ST_BAD_SPAN    4u   /* FREE outside the inventory or start+size > 8 (the reference would panic, Q7) */
+#define ISL_ST_NOOP        5u
+
+typedef struct isl_engine isl_engine;
+
+typedef struct isl_config {
+    uint32_t abi_version;   /* ISL_ABI_VERSION */
+    uint32_t policy;        /* ISL_POLICY_* */
+    uint32_t quirks;        /* ISL_QUIRK_* mask; ISL_QUIRKS_REF_EXACT for bit-exact parity */
+    int32_t  device;        /* CUDA device ordinal; -1 = current device */
+    uint32_t max_gpus;      /* capacity, <= ISL_MAX_GPUS */
+    uint32_t max_batch;     /* capacity of one isl_place_batch call (requests) */
+    uint32_t flags;         /* ISL_FLAG_* */
+    uint32_t reserved;
+} isl_config;
+
+#define ISL_FLAG_TIMING 1u  /* record per-kernel CUDA-event timings (isl_get_stats) */
+
+/* One Migplacement row (api/v1alpha1/instaslice_types.go:23-29).  `size` is
+ * Placements[0].Size (:334); `starts` is [p.Start for p in Placements] in CRD
+ * order (:335-337), duplicates removed by the shim (a repeated start can never
+ * change the first hit). */
+typedef struct isl_profile {
+    uint8_t  size;
+    uint8_t  n_starts;
+    uint8_t  starts[ISL_MAX_STARTS];
+    uint8_t  pad[2];
+    int32_t  gi_profile_id;     /* Giprofileid     */
+    int32_t  ci_profile_id;     /* CIProfileID     */
+    int32_t  ci_eng_profile_id; /* CIEngProfileID  */
+} isl_profile;                  /* 24 bytes */
+
+/* 8 bytes.  ALLOC: `profile` = row index (or ISL_PROFILE_UNKNOWN), `handle` is
+ * opaque to the engine (the shim's pod index).  FREE: `handle` = canonical GPU
+ * index, `start`/`size` = the span being released (an Allocations entry removed
+ * by the daemonset, instaslice_daemonset.go:261-263). */
+typedef struct isl_request {
+    uint32_t handle;
+    uint8_t  profile;
+    uint8_t  op;
+    uint8_t  start;
+    uint8_t  size;
+} isl_request;
+
+/* 8 bytes; the fields of AllocationDetails the allocator decides
+ * (instaslice_types.go:39-42).  gpu == ISL_GPU_NONE and start == 9 when nothing fits. */
+typedef struct isl_result {
+    uint32_t gpu;
+    uint8_t  start;
+    uint8_t  size;
+    uint16_t status;
+} isl_result;
+
+typedef struct isl_span {
+    uint32_t gpu;
+    uint8_t  start;
+    uint8_t  size;
+    uint16_t pad;
+} isl_span;
+
+typedef struct isl_stats {
+    uint64_t batches;
+    uint64_t requests;
+    uint64_t placed;
+    uint64_t no_capacity;
+    uint64_t freed;
+    uint64_t kernel_launches;      /* kernels launched by this engine since creation */
+    uint64_t chain_steps;          /* accepted placements walked by the commit chain */
+    uint64_t chain_gpus_visited;   /* candidate GPUs the chain looked at */
+    /* accumulated CUDA-event milliseconds (only with ISL_FLAG_TIMING) */
+    double   ms_free;
+    double   ms_partition;
+    double   ms_sweep;
+    double   ms_commit;
+    double   ms_total;             /* first kernel start -> last kernel end, per batch, summed */
+} isl_stats;
+
+/* ---- lifetime ---------------------------------------------------------- */
+int  isl_create(const isl_config* cfg, isl_engine** out);
+int  isl_destroy(isl_engine* e);
+/* Run all engine work on an existing CUDA stream (cudaStream_t passed as void*),
+ * e.g. torch's current stream so that torch.cuda.Event brackets it. NULL = engine-owned stream. */
+int  isl_set_stream(isl_engine* e, void* cuda_stream);
+
+/* ---- tables and inventory --------------------------------------------- */
+/* Replaces reading instaslice.Spec.Migplacement (:332-340, :288-298). Builds the
+ * per-(profile, occupancy byte) first-start table on the device. */
+int  isl_load_profiles(isl_engine* e, uint32_t n, const isl_profile* rows);
+/* Replaces the occupancy rebuild (:306-328) for every GPU of every node.
+ * node_off has n_nodes+1 entries (node i owns GPUs [node_off[i], node_off[i+1]));
+ * occ has node_off[n_nodes] bytes.  This is also "resume": the CR is the checkpoint. */
+int  isl_load_inventory(isl_engine* e, uint32_t n_nodes, const uint32_t* node_off, const uint8_t* occ);
+int  isl_read_occupancy(isl_engine* e, uint8_t* out /* G bytes */);
+uint32_t isl_num_gpus(const isl_engine* e);
+/* node that owns canonical GPU index `gpu` (binary search over node_off), or ISL_GPU_NONE */
+uint32_t isl_gpu_to_node(const isl_engine* e, uint32_t gpu);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* Replaces the node loop (:190-227) x findDeviceForASlice (:240-262) x
+ * getStartIndexFromPreparedState (:303-384) for n pods at once. `in` and `out`
+ * are host buffers of n entries; copies are part of the call. */
+int  isl_place_batch(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out);
+/* Same, requests and results already resident in device memory (CUdeviceptr as void*). */
+int  isl_place_batch_device(isl_engine* e, uint32_t n, const void* d_in, void* d_out);
+/* Releases spans (Allocations entries deleted by the daemonset). */
+int  isl_free_batch(isl_engine* e, uint32_t n, const isl_span* spans);
+/* getStartIndexFromPreparedState's search (:343-383) for n arbitrary occupancy
+ * bytes and one profile row, evaluated by the device table: out[i] in {0..7, 9}. */
+int  isl_eval_starts(isl_engine* e, uint32_t profile, uint32_t n, const uint8_t* occ, uint8_t* out);
+
+/* ---- partitioned inventory (BASELINE config 4; DESIGN.md "Multi-GPU") ---- */
+/* Restrict this engine to the canonical GPU range [lo, hi) of the loaded
+ * inventory.  The batch is resolved by chaining ranks in range order: rank d
+ * starts from the per-profile queue heads rank d-1 ended with. */
+int  isl_set_partition(isl_engine* e, uint32_t lo, uint32_t hi);
+/* d_heads_in / d_heads_out: ISL_MAX_PROFILES uint32 each in device memory
+ * (NULL d_heads_in = first rank).  Results of requests this rank did not place
+ * keep status NO_CAPACITY / gpu NONE so that an elementwise MIN over ranks of the
+ * 8-byte records (as little-endian uint64) yields the global answer. */
+int  isl_place_batch_partitioned(isl_engine* e, uint32_t n, const void* d_in, void* d_out,
+                                 const void* d_heads_in, void* d_heads_out);
+/* Device address of the occupancy bytes owned by this engine (for the NCCL all-gather). */
+void* isl_device_occupancy(isl_engine* e);
+
+/* ---- diagnostics ------------------------------------------------------- */
+int         isl_get_stats(isl_engine* e, isl_stats* out);
+int         isl_reset_stats(isl_engine* e);
+const char* isl_strerror(int code);
+const char* isl_last_cuda_error(const isl_engine* e);
+uint32_t    isl_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISLPLACE_H */

@@ -1,0 +1,233 @@
+"""ctypes binding of ``libislplace.so`` (the C ABI declared in ``include/islplace.h``).
+
+This is the same boundary the Go controller binds with cgo; nothing here computes a
+placement.  If the library has not been built (``python -c "import __graft_entry__ as g; g.build()"``)
+loading fails loudly — there is no CPU path in the product.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libislplace.so")
+
+# ---- constants (mirror include/islplace.h) -------------------------------------------------
+ABI_VERSION = 1
+MAX_PROFILES = 16
+MAX_STARTS = 8
+START_NONE = 9
+GPU_NONE = 0xFFFFFFFF
+PROFILE_UNKNOWN = 0xFF
+OK, EINVAL, ENOMEM, ECUDA, ESTATE, ERANGE = 0, -1, -2, -3, -4, -5
+POLICY_FIRST_FIT, POLICY_BEST_FIT = 0, 1
+QUIRK_STRICT_BOUND, QUIRK_POW2_ONLY = 1, 2
+QUIRKS_REF_EXACT, QUIRKS_FIXED = 3, 0
+OP_ALLOC, OP_FREE, OP_NOOP = 0, 1, 2
+ST_PLACED, ST_NO_CAPACITY, ST_BAD_PROFILE, ST_FREED, ST_BAD_SPAN, ST_NOOP = 0, 1, 2, 3, 4, 5
+FLAG_TIMING = 1
+
+# ---- record layouts -------------------------------------------------------------------------
+REQUEST_DTYPE = np.dtype([("handle", "<u4"), ("profile", "u1"), ("op", "u1"), ("start", "u1"), ("size", "u1")])
+RESULT_DTYPE = np.dtype([("gpu", "<u4"), ("start", "u1"), ("size", "u1"), ("status", "<u2")])
+SPAN_DTYPE = np.dtype([("gpu", "<u4"), ("start", "u1"), ("size", "u1"), ("pad", "<u2")])
+PROFILE_DTYPE = np.dtype([("size", "u1"), ("n_starts", "u1"), ("starts", "u1", (8,)), ("pad", "u1", (2,)),
+                          ("gi", "<i4"), ("ci", "<i4"), ("cieng", "<i4")])
+assert REQUEST_DTYPE.itemsize == 8 and RESULT_DTYPE.itemsize == 8 and SPAN_DTYPE.itemsize == 8
+assert PROFILE_DTYPE.itemsize == 24
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("policy", C.c_uint32), ("quirks", C.c_uint32), ("device", C.c_int32),
+                ("max_gpus", C.c_uint32), ("max_batch", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("batches", C.c_uint64), ("requests", C.c_uint64), ("placed", C.c_uint64), ("no_capacity", C.c_uint64),
+                ("freed", C.c_uint64), ("kernel_launches", C.c_uint64), ("chain_steps", C.c_uint64),
+                ("chain_gpus_visited", C.c_uint64), ("ms_free", C.c_double), ("ms_partition", C.c_double),
+                ("ms_sweep", C.c_double), ("ms_commit", C.c_double), ("ms_total", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/islplace.h declares; tests check that the library exports all of them
+EXPORTED_SYMBOLS = [
+    "isl_create", "isl_destroy", "isl_set_stream", "isl_load_profiles", "isl_load_inventory", "isl_read_occupancy",
+    "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_free_batch",
+    "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_device_occupancy", "isl_get_stats",
+    "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
+]
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the engine.  Raises (never falls back) when the CUDA library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not built: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    p = C.c_void_p
+    sig = {
+        "isl_create": (C.c_int, [C.POINTER(Config), C.POINTER(p)]),
+        "isl_destroy": (C.c_int, [p]),
+        "isl_set_stream": (C.c_int, [p, p]),
+        "isl_load_profiles": (C.c_int, [p, C.c_uint32, p]),
+        "isl_load_inventory": (C.c_int, [p, C.c_uint32, p, p]),
+        "isl_read_occupancy": (C.c_int, [p, p]),
+        "isl_num_gpus": (C.c_uint32, [p]),
+        "isl_gpu_to_node": (C.c_uint32, [p, C.c_uint32]),
+        "isl_place_batch": (C.c_int, [p, C.c_uint32, p, p]),
+        "isl_place_batch_device": (C.c_int, [p, C.c_uint32, p, p]),
+        "isl_free_batch": (C.c_int, [p, C.c_uint32, p]),
+        "isl_eval_starts": (C.c_int, [p, C.c_uint32, C.c_uint32, p, p]),
+        "isl_set_partition": (C.c_int, [p, C.c_uint32, C.c_uint32]),
+        "isl_place_batch_partitioned": (C.c_int, [p, C.c_uint32, p, p, p, p]),
+        "isl_device_occupancy": (p, [p]),
+        "isl_get_stats": (C.c_int, [p, C.POINTER(Stats)]),
+        "isl_reset_stats": (C.c_int, [p]),
+        "isl_strerror": (C.c_char_p, [C.c_int]),
+        "isl_last_cuda_error": (C.c_char_p, [p]),
+        "isl_abi_version": (C.c_uint32, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, what, detail=""):
+        super().__init__(f"{what}: {load_library().isl_strerror(code).decode()} ({code}) {detail}".strip())
+        self.code = code
+
+
+def make_profiles(table) -> np.ndarray:
+    """``tables.A100_40GB``-style rows -> isl_profile records (duplicate starts dropped, order kept)."""
+    rows = np.zeros(len(table), dtype=PROFILE_DTYPE)
+    for i, (_name, size, starts, gi) in enumerate(table):
+        uniq = []
+        for s in starts:
+            if s not in uniq:
+                uniq.append(s)
+        rows[i]["size"] = size
+        rows[i]["n_starts"] = len(uniq)
+        rows[i]["starts"][: len(uniq)] = uniq
+        rows[i]["gi"], rows[i]["ci"], rows[i]["cieng"] = gi, gi, 0
+    return rows
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One placement engine on one B200 (thin, 1:1 over the C ABI)."""
+
+    def __init__(self, max_gpus: int, max_batch: int, policy: int = POLICY_FIRST_FIT, quirks: int = QUIRKS_REF_EXACT,
+                 device: int = -1, timing: bool = False):
+        self._lib = load_library()
+        cfg = Config(ABI_VERSION, policy, quirks, device, max_gpus, max_batch, FLAG_TIMING if timing else 0, 0)
+        h = C.c_void_p()
+        rc = self._lib.isl_create(C.byref(cfg), C.byref(h))
+        if rc != OK:
+            raise EngineError(rc, "isl_create")
+        self._h = h
+        self.max_batch = max_batch
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.isl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != OK:
+            detail = self._lib.isl_last_cuda_error(self._h).decode() if rc == ECUDA else ""
+            raise EngineError(rc, what, detail)
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.isl_set_stream(self._h, C.c_void_p(cuda_stream)), "isl_set_stream")
+
+    # -- tables / inventory
+    def load_profiles(self, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, dtype=PROFILE_DTYPE)
+        self._check(self._lib.isl_load_profiles(self._h, len(rows), _ptr(rows)), "isl_load_profiles")
+
+    def load_inventory(self, node_off, occ):
+        node_off = np.ascontiguousarray(node_off, dtype=np.uint32)
+        occ = np.ascontiguousarray(occ, dtype=np.uint8)
+        assert len(occ) == int(node_off[-1])
+        self._check(self._lib.isl_load_inventory(self._h, len(node_off) - 1, _ptr(node_off), _ptr(occ)), "isl_load_inventory")
+
+    def read_occupancy(self) -> np.ndarray:
+        out = np.empty(self.num_gpus, dtype=np.uint8)
+        self._check(self._lib.isl_read_occupancy(self._h, _ptr(out)), "isl_read_occupancy")
+        return out
+
+    @property
+    def num_gpus(self) -> int:
+        return int(self._lib.isl_num_gpus(self._h))
+
+    def gpu_to_node(self, gpu: int) -> int:
+        return int(self._lib.isl_gpu_to_node(self._h, gpu))
+
+    # -- hot path
+    def place_batch(self, requests: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """Host buffers in, host buffers out (the call the Go shim makes)."""
+        requests = np.ascontiguousarray(requests, dtype=REQUEST_DTYPE)
+        if out is None:
+            out = np.empty(len(requests), dtype=RESULT_DTYPE)
+        self._check(self._lib.isl_place_batch(self._h, len(requests), _ptr(requests), _ptr(out)), "isl_place_batch")
+        return out
+
+    def place_batch_ptr(self, n: int, in_ptr: int, out_ptr: int):
+        """Host buffers by raw address (pinned torch tensors in the bench)."""
+        self._check(self._lib.isl_place_batch(self._h, n, C.c_void_p(in_ptr), C.c_void_p(out_ptr)), "isl_place_batch")
+
+    def place_batch_device(self, n: int, d_in: int, d_out: int):
+        self._check(self._lib.isl_place_batch_device(self._h, n, C.c_void_p(d_in), C.c_void_p(d_out)), "isl_place_batch_device")
+
+    def free_batch(self, spans: np.ndarray):
+        spans = np.ascontiguousarray(spans, dtype=SPAN_DTYPE)
+        self._check(self._lib.isl_free_batch(self._h, len(spans), _ptr(spans)), "isl_free_batch")
+
+    def eval_starts(self, profile: int, occ: np.ndarray) -> np.ndarray:
+        occ = np.ascontiguousarray(occ, dtype=np.uint8)
+        out = np.empty(len(occ), dtype=np.uint8)
+        self._check(self._lib.isl_eval_starts(self._h, profile, len(occ), _ptr(occ), _ptr(out)), "isl_eval_starts")
+        return out
+
+    # -- partitioned inventory
+    def set_partition(self, lo: int, hi: int):
+        self._check(self._lib.isl_set_partition(self._h, lo, hi), "isl_set_partition")
+
+    def place_batch_partitioned(self, n: int, d_in: int, d_out: int, d_heads_in: int | None, d_heads_out: int):
+        self._check(self._lib.isl_place_batch_partitioned(self._h, n, C.c_void_p(d_in), C.c_void_p(d_out),
+                                                          C.c_void_p(d_heads_in or 0), C.c_void_p(d_heads_out)),
+                    "isl_place_batch_partitioned")
+
+    def device_occupancy(self) -> int:
+        return int(self._lib.isl_device_occupancy(self._h) or 0)
+
+    # -- diagnostics
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._lib.isl_get_stats(self._h, C.byref(s)), "isl_get_stats")
+        return s.as_dict()
+
+    def reset_stats(self):
+        self._check(self._lib.isl_reset_stats(self._h), "isl_reset_stats")
