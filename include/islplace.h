@@ -166,6 +166,8 @@ int  isl_destroy(isl_engine* e);
 /* Run all engine work on an existing CUDA stream (cudaStream_t passed as void*),
  * e.g. torch's current stream so that torch.cuda.Event brackets it. NULL = engine-owned stream. */
 int  isl_set_stream(isl_engine* e, void* cuda_stream);
+/* Wait for everything isl_place_batch_device / _partitioned enqueued (those two only enqueue). */
+int  isl_synchronize(isl_engine* e);
 
 /* ---- tables and inventory --------------------------------------------- */
 /* Replaces reading instaslice.Spec.Migplacement (:332-340, :288-298). Builds the

@@ -1,0 +1,437 @@
+// isl_kernels.cuh — sm_100a kernels of the MIG-slot placement engine.
+//
+// Replaces, for a whole batch of pending pods at once, the reference's per-pod scan
+//   Reconcile node loop            internal/controller/instaslice_controller.go:190
+//   findDeviceForASlice GPU loop   :240-262
+//   getStartIndexFromPreparedState :303-384
+// Pure integer / bitmask work: no tensor cores, nothing to reshape into a GEMM.
+//
+// Pipeline per batch (DESIGN.md "Kernels"):
+//   k_prepare            frees (atomicAnd on packed occupancy words), default results, per-tile
+//                        per-profile histogram of the ALLOC requests
+//   per chunk of <= 65536 requests:
+//     k_partition        stable P-way partition of the chunk's ALLOC requests into per-profile queues
+//     k_sweep_count/_scatter   vectorised sweep over the occupancy bytes: feasibility bitmask via a
+//                        256-entry shared-memory table, ordered compaction of the candidate GPUs
+//     k_chain<K>         exact first-fit commit: GPU-major stream filtering with one lane per
+//                        (profile, start) candidate and a warp min-reduction per accepted placement
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/islplace.h"
+
+namespace isl {
+
+constexpr uint32_t kChunk = 65536;         // requests per commit chunk: in-chunk request index fits 16 bits
+constexpr uint32_t kTile = 1024;           // requests per partition tile (256 threads x 4 rounds)
+constexpr uint32_t kTileThreads = 256;
+constexpr uint32_t kTilesPerChunk = kChunk / kTile;
+constexpr uint32_t kQPad = 32;             // per-profile queue segments start on 32-entry boundaries
+constexpr uint32_t kQCap = kChunk + kQPad * ISL_MAX_PROFILES;
+constexpr uint32_t kSweepThreads = 256;
+constexpr uint32_t kSweepPerThread = 16;   // one 16-byte vector load = 16 GPUs
+constexpr uint32_t kSweepBlock = kSweepThreads * kSweepPerThread;   // 4096 GPUs per CTA
+constexpr uint32_t kSkip = 0xFFu;          // partition key of a request that is not a valid ALLOC
+constexpr uint32_t kInf = 0xFFFFFFFFu;
+constexpr uint32_t kMaxCand = ISL_MAX_PROFILES * ISL_MAX_STARTS;   // 128 (profile,start) candidates
+constexpr uint32_t kChainThreads = 256;
+
+struct DevProfiles {            // kernel parameter (by value)
+    uint32_t n;
+    uint32_t quirks;
+    isl_profile rows[ISL_MAX_PROFILES];
+};
+
+// One (profile, start) candidate of the chain: bits  [3:0] profile | [6:4] order in the row |
+// [10:7] start | [14:11] size | [23:16] slot mask | [31] valid
+struct CandTab {                // kernel parameter (by value): slot k of lane l is desc[k][l]
+    uint32_t desc[4][32];
+};
+
+struct Ctrl {                   // device-resident control block, rewritten per chunk
+    uint32_t qoff[ISL_MAX_PROFILES + 1];   // queue segment offsets (entries) inside the chunk's queue buffer
+    uint32_t qcnt[ISL_MAX_PROFILES];       // requests of profile p in this chunk
+    uint32_t active;                       // profiles with requests in this chunk AND >= 1 valid candidate
+    uint32_t n_cand;                       // candidate GPUs found by the sweep
+    uint32_t heads_out[ISL_MAX_PROFILES];  // queue heads after the chain (token for the next rank)
+    uint32_t pad;
+    unsigned long long placed, freed, bad, steps, visited, allocs;
+};
+
+// The one rule both the device table and the chain candidates come from: slot mask of placing a
+// `size`-slice profile at start v, or 0 when getStartIndexFromPreparedState can never return v
+//   size 1            -> only busy[v] is tested (:346-349)
+//   size 2/4/8        -> needs v+size < 8 (strict, Q1) and all slots free (:350-378)
+//   any other size    -> never placed under Q2; with the quirk off, any size 2..8 with v+size <= 8
+__host__ __device__ inline uint32_t candidate_mask(uint32_t size, uint32_t v, uint32_t quirks) {
+    if (v >= ISL_SLOTS || size == 0 || size > ISL_SLOTS) return 0;
+    if (size == 1) return 1u << v;
+    const bool pow2_only = quirks & ISL_QUIRK_POW2_ONLY;
+    if (pow2_only && !(size == 2 || size == 4 || size == 8)) return 0;
+    const bool strict = quirks & ISL_QUIRK_STRICT_BOUND;
+    if (strict ? !(v + size < ISL_SLOTS) : !(v + size <= ISL_SLOTS)) return 0;
+    return (((1u << size) - 1u) << v) & 0xFFu;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device table: lut[p][occ] = first legal start of profile p on a GPU with occupancy byte occ
+// (or 9), feas[occ] = bitmask of profiles that have a legal start.  256 threads, one per byte.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_lut(DevProfiles prof, uint8_t* __restrict__ lut, uint16_t* __restrict__ feas) {
+    const uint32_t occ = threadIdx.x;
+    uint32_t fmask = 0;
+    for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) {
+        uint32_t found = ISL_START_NONE;
+        if (p < prof.n) {
+            const isl_profile& row = prof.rows[p];
+            for (uint32_t k = 0; k < row.n_starts; ++k) {                        // CRD order (:344)
+                const uint32_t m = candidate_mask(row.size, row.starts[k], prof.quirks);
+                if (m != 0 && (occ & m) == 0) { found = row.starts[k]; break; }
+            }
+        }
+        lut[p * 256 + occ] = (uint8_t)found;
+        if (found != ISL_START_NONE) fmask |= 1u << p;
+    }
+    feas[occ] = (uint16_t)fmask;
+}
+
+__global__ void k_eval_starts(const uint8_t* __restrict__ lut, uint32_t profile, uint32_t n,
+                              const uint8_t* __restrict__ occ, uint8_t* __restrict__ out) {
+    __shared__ uint8_t s_lut[256];
+    if (threadIdx.x < 256) s_lut[threadIdx.x] = lut[profile * 256 + threadIdx.x];
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = s_lut[occ[i]];
+}
+
+__global__ void k_free_spans(uint32_t n, const isl_span* __restrict__ spans, uint32_t* __restrict__ occ32,
+                             uint32_t G, uint32_t lo, uint32_t hi, Ctrl* ctrl) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const isl_span s = spans[i];
+    if (s.gpu >= G || s.size == 0 || (uint32_t)s.start + s.size > ISL_SLOTS) { atomicAdd(&ctrl->bad, 1ull); return; }
+    if (s.gpu < lo || s.gpu >= hi) return;
+    const uint32_t m = (((1u << s.size) - 1u) << s.start) << ((s.gpu & 3u) * 8u);
+    atomicAnd(&occ32[s.gpu >> 2], ~m);
+    atomicAdd(&ctrl->freed, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_prepare: one pass over the request stream (8 B coalesced loads, 8 B coalesced stores).
+//   FREE  -> clear the span in the packed occupancy word, result FREED / BAD_SPAN
+//   ALLOC -> default result (gpu NONE, start 9, NO_CAPACITY); the chain overwrites what it places
+//   per-tile histogram of ALLOC requests by profile (warp match + one shared atomic per group)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint2 pack_result(uint32_t gpu, uint32_t start, uint32_t size, uint32_t status) {
+    return make_uint2(gpu, start | (size << 8) | (status << 16));
+}
+
+__global__ void __launch_bounds__(kTileThreads) k_prepare(uint32_t n, const uint2* __restrict__ in, uint2* __restrict__ out,
+                                                           uint32_t* __restrict__ occ32, uint32_t G, uint32_t lo, uint32_t hi,
+                                                           DevProfiles prof, uint32_t* __restrict__ tile_counts, Ctrl* ctrl) {
+    __shared__ uint32_t s_cnt[ISL_MAX_PROFILES];
+    __shared__ uint32_t s_freed;
+    if (threadIdx.x < ISL_MAX_PROFILES) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_freed = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (uint32_t r = 0; r < kTile / kTileThreads; ++r) {
+        const uint32_t i = blockIdx.x * kTile + r * kTileThreads + threadIdx.x;
+        uint32_t key = kSkip;
+        if (i < n) {
+            const uint2 rq = in[i];
+            const uint32_t handle = rq.x, profile = rq.y & 0xFFu, op = (rq.y >> 8) & 0xFFu;
+            const uint32_t start = (rq.y >> 16) & 0xFFu, size = rq.y >> 24;
+            if (op == ISL_OP_ALLOC) {
+                if (profile < prof.n) { key = profile; out[i] = pack_result(ISL_GPU_NONE, ISL_START_NONE, prof.rows[profile].size, ISL_ST_NO_CAPACITY); }
+                else out[i] = pack_result(ISL_GPU_NONE, ISL_START_NONE, 0, ISL_ST_BAD_PROFILE);
+            } else if (op == ISL_OP_FREE) {
+                if (handle >= G || size == 0 || start + size > ISL_SLOTS) out[i] = pack_result(handle, start, size, ISL_ST_BAD_SPAN);
+                else {
+                    if (handle >= lo && handle < hi) {
+                        const uint32_t m = (((1u << size) - 1u) << start) << ((handle & 3u) * 8u);
+                        atomicAnd(&occ32[handle >> 2], ~m);
+                        atomicAdd(&s_freed, 1u);
+                    }
+                    out[i] = pack_result(handle, start, size, ISL_ST_FREED);
+                }
+            } else out[i] = pack_result(ISL_GPU_NONE, ISL_START_NONE, 0, ISL_ST_NOOP);
+        }
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (key != kSkip && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_cnt[key], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < ISL_MAX_PROFILES) tile_counts[blockIdx.x * ISL_MAX_PROFILES + threadIdx.x] = s_cnt[threadIdx.x];
+    if (threadIdx.x == 0) {
+        if (s_freed) atomicAdd(&ctrl->freed, (unsigned long long)s_freed);
+        uint32_t allocs = 0;
+        for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) allocs += s_cnt[p];
+        if (allocs) atomicAdd(&ctrl->allocs, (unsigned long long)allocs);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_partition: stable P-way partition of one chunk's ALLOC requests.  Queue p receives the
+// in-chunk indices (16 bit) of the requests for profile p, in request order.
+// grid = tiles of the chunk; every CTA re-derives the chunk-wide offsets from tile_counts
+// (<= 64 tiles x 16 counters), so no inter-CTA communication is needed.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTileThreads) k_partition(uint32_t n_chunk, const uint2* __restrict__ in_chunk, uint32_t n_profiles,
+                                                             const uint32_t* __restrict__ tile_counts_chunk, uint32_t n_tiles,
+                                                             uint32_t cand_profiles, uint16_t* __restrict__ q, Ctrl* ctrl) {
+    __shared__ uint32_t s_part[16][ISL_MAX_PROFILES][2];   // [j][p][0]=total, [1]=prefix before this tile
+    __shared__ uint32_t s_base[ISL_MAX_PROFILES];
+    __shared__ uint32_t s_seg[32][ISL_MAX_PROFILES];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    {   // chunk-wide per-profile totals and the prefix of the tiles before this one
+        const uint32_t p = tid & 15u, j = tid >> 4;
+        uint32_t tot = 0, pre = 0;
+        for (uint32_t t = j; t < n_tiles; t += 16) {
+            const uint32_t c = tile_counts_chunk[t * ISL_MAX_PROFILES + p];
+            tot += c;
+            if (t < blockIdx.x) pre += c;
+        }
+        s_part[j][p][0] = tot; s_part[j][p][1] = pre;
+    }
+    for (uint32_t k = tid; k < 32 * ISL_MAX_PROFILES; k += kTileThreads) (&s_seg[0][0])[k] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t off = 0, active = 0;
+        for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) {
+            uint32_t tot = 0, pre = 0;
+            for (uint32_t j = 0; j < 16; ++j) { tot += s_part[j][p][0]; pre += s_part[j][p][1]; }
+            s_base[p] = off + pre;
+            if (blockIdx.x == 0) {
+                ctrl->qoff[p] = off; ctrl->qcnt[p] = tot;
+                if (tot && ((cand_profiles >> p) & 1u)) active |= 1u << p;
+            }
+            off += (tot + kQPad - 1) & ~(kQPad - 1);
+        }
+        if (blockIdx.x == 0) { ctrl->qoff[ISL_MAX_PROFILES] = off; ctrl->active = active; ctrl->n_cand = 0; }
+    }
+    uint32_t key[4], rank[4];
+#pragma unroll
+    for (uint32_t r = 0; r < 4; ++r) {
+        const uint32_t i = blockIdx.x * kTile + r * kTileThreads + tid;
+        key[r] = kSkip;
+        if (i < n_chunk) {
+            const uint32_t w = in_chunk[i].y;
+            const uint32_t profile = w & 0xFFu, op = (w >> 8) & 0xFFu;
+            if (op == ISL_OP_ALLOC && profile < n_profiles) key[r] = profile;
+        }
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key[r]);
+        rank[r] = __popc(peers & ((1u << lane) - 1u));
+        if (key[r] != kSkip && lane == (uint32_t)(__ffs(peers) - 1)) s_seg[r * 8 + warp][key[r]] = __popc(peers);
+    }
+    __syncthreads();
+    if (tid < ISL_MAX_PROFILES) {           // exclusive scan over the 32 (round, warp) segments, in request order
+        uint32_t run = 0;
+        for (uint32_t s = 0; s < 32; ++s) { const uint32_t c = s_seg[s][tid]; s_seg[s][tid] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < 4; ++r) {
+        if (key[r] == kSkip) continue;
+        const uint32_t i = blockIdx.x * kTile + r * kTileThreads + tid;
+        q[s_base[key[r]] + s_seg[r * 8 + warp][key[r]] + rank[r]] = (uint16_t)i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sweep: every thread loads 16 occupancy bytes with one 128-bit read-only load, looks each byte
+// up in the 256-entry feasibility table staged in shared memory, and keeps the GPUs on which at
+// least one profile that is pending in this chunk has a legal start.  Two passes (count, then
+// ordered scatter) keep the candidate list in canonical GPU order without inter-CTA spinning.
+// Candidate record = (gpu << 8) | occupancy byte.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t sweep_mask16(const uint4 v, const uint16_t* s_feas, uint32_t active, uint32_t g0, uint32_t lo, uint32_t hi) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t mask = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) {
+        const uint32_t o = (w[j >> 2] >> ((j & 3u) * 8u)) & 0xFFu;
+        const uint32_t g = g0 + j;
+        if ((s_feas[o] & active) && g >= lo && g < hi) mask |= 1u << j;
+    }
+    return mask;
+}
+
+__global__ void __launch_bounds__(kSweepThreads) k_sweep_count(const uint4* __restrict__ occ16, const uint16_t* __restrict__ feas,
+                                                                uint32_t first_block, uint32_t lo, uint32_t hi,
+                                                                const Ctrl* __restrict__ ctrl, uint32_t* __restrict__ counts) {
+    __shared__ uint16_t s_feas[256];
+    __shared__ uint32_t s_warp[kSweepThreads / 32];
+    s_feas[threadIdx.x] = feas[threadIdx.x];
+    __syncthreads();
+    const uint32_t active = ctrl->active;
+    const uint32_t g0 = (first_block + blockIdx.x) * kSweepBlock + threadIdx.x * kSweepPerThread;
+    uint32_t c = 0;
+    if (active && g0 < hi && g0 + kSweepPerThread > lo) c = __popc(sweep_mask16(ld_nc_v4(&occ16[g0 >> 4]), s_feas, active, g0, lo, hi));
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    if ((threadIdx.x & 31u) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (uint32_t w = 0; w < kSweepThreads / 32; ++w) t += s_warp[w];
+        counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __restrict__ occ16, const uint16_t* __restrict__ feas,
+                                                                  uint32_t first_block, uint32_t lo, uint32_t hi, Ctrl* ctrl,
+                                                                  const uint32_t* __restrict__ counts, uint32_t* __restrict__ cand) {
+    __shared__ uint16_t s_feas[256];
+    __shared__ uint32_t s_warp[kSweepThreads / 32];
+    __shared__ uint32_t s_red[kSweepThreads / 32];
+    __shared__ uint32_t s_base;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    s_feas[tid] = feas[tid];
+    // base = number of candidates in the CTAs before this one (and the grand total for the last CTA)
+    uint32_t pre = 0;
+    for (uint32_t b = tid; b < blockIdx.x; b += kSweepThreads) pre += counts[b];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) pre += __shfl_xor_sync(0xFFFFFFFFu, pre, d);
+    if (lane == 0) s_red[warp] = pre;
+    __syncthreads();
+    if (tid == 0) { uint32_t t = 0; for (uint32_t w = 0; w < kSweepThreads / 32; ++w) t += s_red[w]; s_base = t; }
+    const uint32_t active = ctrl->active;
+    const uint32_t g0 = (first_block + blockIdx.x) * kSweepBlock + tid * kSweepPerThread;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    uint32_t mask = 0;
+    if (active && g0 < hi && g0 + kSweepPerThread > lo) { v = ld_nc_v4(&occ16[g0 >> 4]); mask = sweep_mask16(v, s_feas, active, g0, lo, hi); }
+    const uint32_t c = __popc(mask);
+    uint32_t incl = c;                                  // inclusive warp scan of the per-thread counts
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t off = s_base + incl - c;
+    for (uint32_t w = 0; w < warp; ++w) off += s_warp[w];
+    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = mask;
+    while (m) {
+        const uint32_t j = __ffs(m) - 1; m &= m - 1;
+        const uint32_t o = (wv[j >> 2] >> ((j & 3u) * 8u)) & 0xFFu;
+        cand[off++] = ((g0 + j) << 8) | o;
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == kSweepThreads - 1) ctrl->n_cand = off;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_chain<K>: the exact commit.
+//
+// First-fit in canonical GPU order is GPU-major stream filtering: GPU g accepts, in request
+// order, a prefix of each profile's remaining queue (occupancy only grows inside an alloc phase, so
+// a profile that stopped fitting on g never fits again).  The state between GPUs is one queue head
+// per profile.  One warp walks the candidate GPUs; lane l owns up to K (profile, start) candidates
+// with their slot masks in registers.  Per accepted placement:
+//     key = (next request index of the candidate's profile) << 15 | profile << 11 | order << 8 | mask
+//     for candidates whose mask is free on the current occupancy, else INF
+//     m   = warp-min(key)                -> earliest pending request that fits, first legal start
+//     occupancy |= m & 0xFF; the lanes of that profile advance their queue head
+// The queues (16-bit in-chunk indices) are staged once in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* ctrl, const uint16_t* __restrict__ q_global,
+                                                             const uint32_t* __restrict__ cand, uint8_t* __restrict__ occ,
+                                                             uint2* __restrict__ out_chunk, const uint32_t* __restrict__ heads_in,
+                                                             uint32_t* __restrict__ heads_out) {
+    extern __shared__ __align__(16) uint16_t s_q[];
+    const uint32_t q_total = ctrl->qoff[ISL_MAX_PROFILES];
+    {   // stage every queue of the chunk: <= 129 KB, 16-byte vector copies
+        const uint4* src = reinterpret_cast<const uint4*>(q_global);
+        uint4* dst = reinterpret_cast<uint4*>(s_q);
+        for (uint32_t i = threadIdx.x; i < (q_total + 7) / 8; i += kChainThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t n_cand = ctrl->n_cand;
+
+    uint32_t cdesc[K], keylow[K], cmask[K], cprof[K], head[K], end[K], qb[K], tcur[K], tnext[K];
+    uint32_t rem = 0;                       // requests still pending over all profiles that have a candidate (warp-uniform)
+    {
+        uint32_t seen = 0;
+        for (uint32_t k = 0; k < 4; ++k)
+            for (uint32_t l = 0; l < 32; ++l) {
+                const uint32_t d = tab.desc[k][l];
+                if (!(d >> 31)) continue;
+                const uint32_t p = d & 15u;
+                if ((seen >> p) & 1u) continue;
+                seen |= 1u << p;
+                const uint32_t h = heads_in ? heads_in[p] : 0u, e = ctrl->qcnt[p];
+                rem += e > h ? e - h : 0u;
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t d = tab.desc[k][lane];
+        const bool valid = d >> 31;
+        cdesc[k] = d;
+        cprof[k] = d & 15u;
+        cmask[k] = valid ? (d >> 16) & 0xFFu : 0xFFu;
+        keylow[k] = (cprof[k] << 11) | (((d >> 4) & 7u) << 8) | cmask[k];
+        qb[k] = ctrl->qoff[cprof[k]];
+        end[k] = valid ? ctrl->qcnt[cprof[k]] : 0u;
+        head[k] = heads_in ? heads_in[cprof[k]] : 0u;
+        tcur[k] = head[k] < end[k] ? s_q[qb[k] + head[k]] : kInf;
+        tnext[k] = head[k] + 1 < end[k] ? s_q[qb[k] + head[k] + 1] : kInf;
+    }
+    uint32_t steps = 0, visited = 0;
+    for (uint32_t base = 0; base < n_cand && rem; base += 32) {
+        const uint32_t mine = base + lane < n_cand ? cand[base + lane] : kInf;
+        const uint32_t cnt = min(32u, n_cand - base);
+        for (uint32_t j = 0; j < cnt && rem; ++j) {
+            const uint32_t c = __shfl_sync(0xFFFFFFFFu, mine, j);
+            const uint32_t g = c >> 8;
+            uint32_t o = c & 0xFFu;
+            const uint32_t o0 = o;
+            ++visited;
+            while (true) {
+                uint32_t key = kInf;
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (tcur[k] != kInf && (o & cmask[k]) == 0) key = min(key, (tcur[k] << 15) | keylow[k]);
+                const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, key);
+                if (m == kInf) break;
+                o |= m & 0xFFu;
+                const uint32_t pw = (m >> 11) & 15u;
+                if (key == m) {             // exactly one lane: the winning (profile, start) candidate
+                    uint32_t d = 0;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) if (((tcur[k] << 15) | keylow[k]) == m) d = cdesc[k];
+                    out_chunk[m >> 15] = pack_result(g, (d >> 7) & 15u, (d >> 11) & 15u, ISL_ST_PLACED);
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (cprof[k] == pw && end[k]) {
+                        ++head[k];
+                        tcur[k] = tnext[k];
+                        tnext[k] = head[k] + 1 < end[k] ? s_q[qb[k] + head[k] + 1] : kInf;
+                    }
+                ++steps; --rem;
+                if (!rem) break;
+            }
+            if (o != o0 && lane == 0) occ[g] = (uint8_t)o;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        if ((cdesc[k] >> 31) && ((cdesc[k] >> 4) & 7u) == 0 && heads_out) heads_out[cprof[k]] = head[k];   // first candidate of the row reports
+    if (lane == 0) {
+        atomicAdd(&ctrl->placed, (unsigned long long)steps);
+        atomicAdd(&ctrl->steps, (unsigned long long)steps);
+        atomicAdd(&ctrl->visited, (unsigned long long)visited);
+    }
+}
+
+}  // namespace isl

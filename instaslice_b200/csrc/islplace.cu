@@ -1,0 +1,433 @@
+// islplace.cu — C ABI (include/islplace.h) and host-side orchestration of the placement engine.
+//
+// The entry points replace, for the allocator path only, what the Go controller does in
+// internal/controller/instaslice_controller.go:188-262,303-384 (see the header for the per-symbol map).
+// No Go pointer is retained after a call returns; every buffer the engine keeps is its own.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "isl_kernels.cuh"
+
+using namespace isl;
+
+struct isl_engine {
+    isl_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::mutex mu;
+    char cuda_err[256] = {0};
+
+    DevProfiles prof{};
+    bool have_profiles = false, have_inventory = false;
+    CandTab tab{};
+    uint32_t n_cand_slots = 0;       // K of k_chain<K>
+    uint32_t cand_profiles = 0;      // profiles with >= 1 valid (profile, start) candidate
+
+    uint32_t G = 0, lo = 0, hi = 0;
+    std::vector<uint32_t> node_off;
+
+    // device buffers
+    uint8_t* d_occ = nullptr;        // one byte per GPU, padded to whole sweep blocks with 0xFF
+    size_t occ_bytes = 0;
+    uint8_t* d_lut = nullptr;        // [16][256]
+    uint16_t* d_feas = nullptr;      // [256]
+    uint2* d_req = nullptr;          // staging for the host-buffer entry point
+    uint2* d_res = nullptr;
+    uint16_t* d_q = nullptr;         // per-chunk queues
+    uint32_t* d_tile_counts = nullptr;
+    uint32_t* d_cand = nullptr;
+    uint32_t* d_sweep_counts = nullptr;
+    Ctrl* d_ctrl = nullptr;
+    uint8_t* d_scratch = nullptr;    // eval_starts / free_batch staging
+    size_t scratch_bytes = 0;
+
+    // stats
+    isl_stats st{};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+#define ISL_CUDA(e, call)                                                                    \
+    do {                                                                                     \
+        cudaError_t _err = (call);                                                           \
+        if (_err != cudaSuccess) {                                                           \
+            snprintf((e)->cuda_err, sizeof((e)->cuda_err), "%s: %s", #call, cudaGetErrorString(_err)); \
+            return ISL_ECUDA;                                                                \
+        }                                                                                    \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+int check_launch(isl_engine* e, const char* what) {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { snprintf(e->cuda_err, sizeof(e->cuda_err), "%s: %s", what, cudaGetErrorString(err)); return ISL_ECUDA; }
+    ++e->st.kernel_launches;
+    return ISL_OK;
+}
+
+int ensure_scratch(isl_engine* e, size_t bytes) {
+    if (bytes <= e->scratch_bytes) return ISL_OK;
+    if (e->d_scratch) cudaFree(e->d_scratch);
+    e->d_scratch = nullptr; e->scratch_bytes = 0;
+    ISL_CUDA(e, cudaMalloc(&e->d_scratch, bytes));
+    e->scratch_bytes = bytes;
+    return ISL_OK;
+}
+
+template <int K>
+int launch_chain(isl_engine* e, uint2* d_out_chunk, const uint32_t* d_heads_in, uint32_t* d_heads_out) {
+    const size_t smem = (size_t)kQCap * sizeof(uint16_t);
+    static bool attr_set[8] = {false};
+    if (!attr_set[e->device & 7]) {
+        ISL_CUDA(e, cudaFuncSetAttribute(k_chain<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[e->device & 7] = true;
+    }
+    k_chain<K><<<1, kChainThreads, smem, e->stream>>>(e->tab, e->d_ctrl, e->d_q, e->d_cand, e->d_occ, d_out_chunk, d_heads_in, d_heads_out);
+    return check_launch(e, "k_chain");
+}
+
+// Resolve n requests that already sit in device memory.  Enqueues only; the caller synchronises.
+int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const uint32_t* d_heads_in, uint32_t* d_heads_out) {
+    if (n == 0) return ISL_OK;
+    const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
+    const uint32_t tiles = ceil_div(n, kTile);
+    if (timing) cudaEventRecord(e->ev[0], e->stream);
+    k_prepare<<<tiles, kTileThreads, 0, e->stream>>>(n, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi,
+                                                     e->prof, e->d_tile_counts, e->d_ctrl);
+    if (int rc = check_launch(e, "k_prepare")) return rc;
+    if (timing) cudaEventRecord(e->ev[1], e->stream);
+    const uint32_t first_block = e->lo / kSweepBlock;
+    const uint32_t sweep_blocks = e->hi > e->lo ? ceil_div(e->hi, kSweepBlock) - first_block : 0;
+    float ms_part = 0, ms_sweep = 0, ms_commit = 0;
+    for (uint32_t c0 = 0; c0 < n; c0 += kChunk) {
+        const uint32_t n_chunk = std::min(kChunk, n - c0);
+        const uint32_t first_tile = c0 / kTile, n_tiles = ceil_div(n_chunk, kTile);
+        if (timing) cudaEventRecord(e->ev[2], e->stream);
+        k_partition<<<n_tiles, kTileThreads, 0, e->stream>>>(n_chunk, d_in + c0, e->prof.n, e->d_tile_counts + (size_t)first_tile * ISL_MAX_PROFILES,
+                                                             n_tiles, e->cand_profiles, e->d_q, e->d_ctrl);
+        if (int rc = check_launch(e, "k_partition")) return rc;
+        if (timing) cudaEventRecord(e->ev[3], e->stream);
+        if (sweep_blocks) {
+            k_sweep_count<<<sweep_blocks, kSweepThreads, 0, e->stream>>>(reinterpret_cast<const uint4*>(e->d_occ), e->d_feas, first_block, e->lo, e->hi,
+                                                                         e->d_ctrl, e->d_sweep_counts);
+            if (int rc = check_launch(e, "k_sweep_count")) return rc;
+            k_sweep_scatter<<<sweep_blocks, kSweepThreads, 0, e->stream>>>(reinterpret_cast<const uint4*>(e->d_occ), e->d_feas, first_block, e->lo, e->hi,
+                                                                           e->d_ctrl, e->d_sweep_counts, e->d_cand);
+            if (int rc = check_launch(e, "k_sweep_scatter")) return rc;
+        }
+        if (timing) cudaEventRecord(e->ev[4], e->stream);
+        // the heads token of a chunk: first chunk of a partitioned call chains from the previous rank
+        const uint32_t* h_in = d_heads_in ? d_heads_in + (size_t)(c0 / kChunk) * ISL_MAX_PROFILES : nullptr;
+        uint32_t* h_out = d_heads_out ? d_heads_out + (size_t)(c0 / kChunk) * ISL_MAX_PROFILES : nullptr;
+        if (h_out) {
+            if (h_in) ISL_CUDA(e, cudaMemcpyAsync(h_out, h_in, ISL_MAX_PROFILES * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+            else ISL_CUDA(e, cudaMemsetAsync(h_out, 0, ISL_MAX_PROFILES * sizeof(uint32_t), e->stream));
+        }
+        int rc;
+        switch (e->n_cand_slots) {
+            case 1: rc = launch_chain<1>(e, d_out + c0, h_in, h_out); break;
+            case 2: rc = launch_chain<2>(e, d_out + c0, h_in, h_out); break;
+            default: rc = launch_chain<4>(e, d_out + c0, h_in, h_out); break;
+        }
+        if (rc) return rc;
+        if (timing) {
+            cudaEventRecord(e->ev[5], e->stream);
+            cudaEventSynchronize(e->ev[5]);
+            float t;
+            cudaEventElapsedTime(&t, e->ev[2], e->ev[3]); ms_part += t;
+            cudaEventElapsedTime(&t, e->ev[3], e->ev[4]); ms_sweep += t;
+            cudaEventElapsedTime(&t, e->ev[4], e->ev[5]); ms_commit += t;
+        }
+    }
+    if (timing) {
+        float t;
+        cudaEventElapsedTime(&t, e->ev[0], e->ev[1]); e->st.ms_free += t;     // prepare = frees + defaults + histogram
+        e->st.ms_partition += ms_part; e->st.ms_sweep += ms_sweep; e->st.ms_commit += ms_commit;
+        cudaEventElapsedTime(&t, e->ev[0], e->ev[5]); e->st.ms_total += t;
+    }
+    ++e->st.batches;
+    e->st.requests += n;
+    return ISL_OK;
+}
+
+int validate_ready(isl_engine* e, uint32_t n) {
+    if (!e->have_profiles || !e->have_inventory) return ISL_ESTATE;
+    if (n > e->cfg.max_batch) return ISL_ERANGE;
+    if (e->cfg.policy != ISL_POLICY_FIRST_FIT) return ISL_EINVAL;
+    return ISL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t isl_abi_version(void) { return ISL_ABI_VERSION; }
+
+const char* isl_strerror(int code) {
+    switch (code) {
+        case ISL_OK: return "ok";
+        case ISL_EINVAL: return "invalid argument or malformed table";
+        case ISL_ENOMEM: return "out of memory";
+        case ISL_ECUDA: return "CUDA error (see isl_last_cuda_error)";
+        case ISL_ESTATE: return "profiles and inventory must be loaded first";
+        case ISL_ERANGE: return "batch or inventory exceeds the engine's capacity";
+        default: return "unknown error";
+    }
+}
+
+const char* isl_last_cuda_error(const isl_engine* e) { return e ? e->cuda_err : "null engine"; }
+
+int isl_create(const isl_config* cfg, isl_engine** out) {
+    if (!cfg || !out) return ISL_EINVAL;
+    *out = nullptr;
+    if (cfg->abi_version != ISL_ABI_VERSION) return ISL_EINVAL;
+    if (cfg->max_gpus == 0 || cfg->max_gpus > ISL_MAX_GPUS || cfg->max_batch == 0) return ISL_EINVAL;
+    if (cfg->policy != ISL_POLICY_FIRST_FIT) return ISL_EINVAL;      // best-fit: see DESIGN.md "What comes next"
+    if (cfg->quirks & ~ISL_QUIRKS_REF_EXACT) return ISL_EINVAL;
+    isl_engine* e = new (std::nothrow) isl_engine;
+    if (!e) return ISL_ENOMEM;
+    e->cfg = *cfg;
+    int dev = cfg->device;
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) { delete e; return ISL_ECUDA; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || dev >= ndev) { delete e; return ISL_ECUDA; }
+    e->device = dev;
+    DeviceGuard guard(dev);
+    auto fail = [&](int rc) { isl_destroy(e); return rc; };
+#define ISL_TRY(call) do { if ((call) != cudaSuccess) { return fail(ISL_ECUDA); } } while (0)
+    ISL_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+    e->occ_bytes = ((size_t)cfg->max_gpus + kSweepBlock - 1) / kSweepBlock * kSweepBlock;
+    const uint32_t max_tiles = ceil_div(cfg->max_batch, kTile);
+    ISL_TRY(cudaMalloc(&e->d_occ, e->occ_bytes));
+    ISL_TRY(cudaMalloc(&e->d_lut, ISL_MAX_PROFILES * 256));
+    ISL_TRY(cudaMalloc(&e->d_feas, 256 * sizeof(uint16_t)));
+    ISL_TRY(cudaMalloc(&e->d_req, (size_t)cfg->max_batch * sizeof(uint2)));
+    ISL_TRY(cudaMalloc(&e->d_res, (size_t)cfg->max_batch * sizeof(uint2)));
+    ISL_TRY(cudaMalloc(&e->d_q, (size_t)kQCap * sizeof(uint16_t)));
+    ISL_TRY(cudaMalloc(&e->d_tile_counts, (size_t)max_tiles * ISL_MAX_PROFILES * sizeof(uint32_t)));
+    ISL_TRY(cudaMalloc(&e->d_cand, e->occ_bytes * sizeof(uint32_t)));
+    ISL_TRY(cudaMalloc(&e->d_sweep_counts, (e->occ_bytes / kSweepBlock) * sizeof(uint32_t)));
+    ISL_TRY(cudaMalloc(&e->d_ctrl, sizeof(Ctrl)));
+    ISL_TRY(cudaMemset(e->d_ctrl, 0, sizeof(Ctrl)));
+    ISL_TRY(cudaMemset(e->d_occ, 0xFF, e->occ_bytes));
+    for (auto& ev : e->ev) ISL_TRY(cudaEventCreate(&ev));
+#undef ISL_TRY
+    *out = e;
+    return ISL_OK;
+}
+
+int isl_destroy(isl_engine* e) {
+    if (!e) return ISL_EINVAL;
+    {
+        DeviceGuard guard(e->device);
+        if (e->stream) cudaStreamSynchronize(e->stream);
+        cudaFree(e->d_occ); cudaFree(e->d_lut); cudaFree(e->d_feas); cudaFree(e->d_req); cudaFree(e->d_res);
+        cudaFree(e->d_q); cudaFree(e->d_tile_counts); cudaFree(e->d_cand); cudaFree(e->d_sweep_counts);
+        cudaFree(e->d_ctrl); cudaFree(e->d_scratch);
+        for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+        if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    }
+    delete e;
+    return ISL_OK;
+}
+
+int isl_set_stream(isl_engine* e, void* cuda_stream) {
+    if (!e) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    if (e->stream) ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (e->own_stream && e->stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
+    if (cuda_stream) e->stream = static_cast<cudaStream_t>(cuda_stream);
+    else { ISL_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
+    return ISL_OK;
+}
+
+int isl_synchronize(isl_engine* e) {
+    if (!e) return ISL_EINVAL;
+    DeviceGuard guard(e->device);
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ISL_OK;
+}
+
+int isl_load_profiles(isl_engine* e, uint32_t n, const isl_profile* rows) {
+    if (!e || !rows || n == 0 || n > ISL_MAX_PROFILES) return ISL_EINVAL;
+    // Validate what would make the reference panic: empty Placements (:334), start >= 8 (:345).
+    for (uint32_t p = 0; p < n; ++p) {
+        if (rows[p].n_starts == 0 || rows[p].n_starts > ISL_MAX_STARTS) return ISL_EINVAL;
+        for (uint32_t k = 0; k < rows[p].n_starts; ++k) {
+            if (rows[p].starts[k] >= ISL_SLOTS) return ISL_EINVAL;
+            for (uint32_t j = 0; j < k; ++j) if (rows[p].starts[j] == rows[p].starts[k]) return ISL_EINVAL;   // shim de-duplicates
+        }
+    }
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    e->prof.n = n; e->prof.quirks = e->cfg.quirks;
+    memset(e->prof.rows, 0, sizeof(e->prof.rows));
+    memcpy(e->prof.rows, rows, n * sizeof(isl_profile));
+    // chain candidates: every (profile, start) the search can ever return, in row order
+    memset(&e->tab, 0, sizeof(e->tab));
+    uint32_t c = 0; e->cand_profiles = 0;
+    for (uint32_t p = 0; p < n; ++p) {
+        uint32_t ord = 0;
+        for (uint32_t k = 0; k < rows[p].n_starts; ++k) {
+            const uint32_t m = candidate_mask(rows[p].size, rows[p].starts[k], e->cfg.quirks);
+            if (!m) continue;
+            e->tab.desc[c / 32][c % 32] = p | (ord << 4) | ((uint32_t)rows[p].starts[k] << 7) | ((uint32_t)rows[p].size << 11) | (m << 16) | (1u << 31);
+            ++c; ++ord;
+            e->cand_profiles |= 1u << p;
+        }
+    }
+    e->n_cand_slots = c <= 32 ? 1 : (c <= 64 ? 2 : 4);
+    k_build_lut<<<1, 256, 0, e->stream>>>(e->prof, e->d_lut, e->d_feas);
+    if (int rc = check_launch(e, "k_build_lut")) return rc;
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->have_profiles = true;
+    return ISL_OK;
+}
+
+int isl_load_inventory(isl_engine* e, uint32_t n_nodes, const uint32_t* node_off, const uint8_t* occ) {
+    if (!e || !node_off || n_nodes == 0) return ISL_EINVAL;
+    if (node_off[0] != 0) return ISL_EINVAL;
+    for (uint32_t i = 0; i < n_nodes; ++i) if (node_off[i + 1] < node_off[i]) return ISL_EINVAL;
+    const uint32_t G = node_off[n_nodes];
+    if (G == 0 || !occ) return ISL_EINVAL;
+    if (G > e->cfg.max_gpus) return ISL_ERANGE;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    e->node_off.assign(node_off, node_off + n_nodes + 1);
+    e->G = G; e->lo = 0; e->hi = G;
+    ISL_CUDA(e, cudaMemsetAsync(e->d_occ, 0xFF, e->occ_bytes, e->stream));
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_occ, occ, G, cudaMemcpyHostToDevice, e->stream));
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->have_inventory = true;
+    return ISL_OK;
+}
+
+int isl_read_occupancy(isl_engine* e, uint8_t* out) {
+    if (!e || !out) return ISL_EINVAL;
+    if (!e->have_inventory) return ISL_ESTATE;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    ISL_CUDA(e, cudaMemcpyAsync(out, e->d_occ, e->G, cudaMemcpyDeviceToHost, e->stream));
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ISL_OK;
+}
+
+uint32_t isl_num_gpus(const isl_engine* e) { return e ? e->G : 0; }
+
+uint32_t isl_gpu_to_node(const isl_engine* e, uint32_t gpu) {
+    if (!e || gpu >= e->G) return ISL_GPU_NONE;
+    auto it = std::upper_bound(e->node_off.begin(), e->node_off.end(), gpu);
+    return (uint32_t)(it - e->node_off.begin()) - 1;
+}
+
+int isl_place_batch(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out) {
+    if (!e || (n && (!in || !out))) return ISL_EINVAL;
+    if (int rc = validate_ready(e, n)) return rc;
+    if (n == 0) return ISL_OK;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_req, in, (size_t)n * sizeof(isl_request), cudaMemcpyHostToDevice, e->stream));
+    if (int rc = run_batch(e, n, e->d_req, e->d_res, nullptr, nullptr)) return rc;
+    ISL_CUDA(e, cudaMemcpyAsync(out, e->d_res, (size_t)n * sizeof(isl_result), cudaMemcpyDeviceToHost, e->stream));
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ISL_OK;
+}
+
+int isl_place_batch_device(isl_engine* e, uint32_t n, const void* d_in, void* d_out) {
+    if (!e || (n && (!d_in || !d_out))) return ISL_EINVAL;
+    if (int rc = validate_ready(e, n)) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    return run_batch(e, n, static_cast<const uint2*>(d_in), static_cast<uint2*>(d_out), nullptr, nullptr);
+}
+
+int isl_place_batch_partitioned(isl_engine* e, uint32_t n, const void* d_in, void* d_out, const void* d_heads_in, void* d_heads_out) {
+    if (!e || (n && (!d_in || !d_out)) || !d_heads_out) return ISL_EINVAL;
+    if (int rc = validate_ready(e, n)) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    return run_batch(e, n, static_cast<const uint2*>(d_in), static_cast<uint2*>(d_out), static_cast<const uint32_t*>(d_heads_in),
+                     static_cast<uint32_t*>(d_heads_out));
+}
+
+int isl_set_partition(isl_engine* e, uint32_t lo, uint32_t hi) {
+    if (!e) return ISL_EINVAL;
+    if (!e->have_inventory) return ISL_ESTATE;
+    if (lo > hi || hi > e->G) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->lo = lo; e->hi = hi;
+    return ISL_OK;
+}
+
+void* isl_device_occupancy(isl_engine* e) { return e ? e->d_occ : nullptr; }
+
+int isl_free_batch(isl_engine* e, uint32_t n, const isl_span* spans) {
+    if (!e || (n && !spans)) return ISL_EINVAL;
+    if (!e->have_inventory) return ISL_ESTATE;
+    if (n == 0) return ISL_OK;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    if (int rc = ensure_scratch(e, (size_t)n * sizeof(isl_span))) return rc;
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_scratch, spans, (size_t)n * sizeof(isl_span), cudaMemcpyHostToDevice, e->stream));
+    k_free_spans<<<ceil_div(n, 256), 256, 0, e->stream>>>(n, reinterpret_cast<const isl_span*>(e->d_scratch), reinterpret_cast<uint32_t*>(e->d_occ),
+                                                          e->G, e->lo, e->hi, e->d_ctrl);
+    if (int rc = check_launch(e, "k_free_spans")) return rc;
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ISL_OK;
+}
+
+int isl_eval_starts(isl_engine* e, uint32_t profile, uint32_t n, const uint8_t* occ, uint8_t* out) {
+    if (!e || (n && (!occ || !out))) return ISL_EINVAL;
+    if (!e->have_profiles) return ISL_ESTATE;
+    if (profile >= e->prof.n) return ISL_EINVAL;
+    if (n == 0) return ISL_OK;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    if (int rc = ensure_scratch(e, (size_t)n * 2)) return rc;
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_scratch, occ, n, cudaMemcpyHostToDevice, e->stream));
+    k_eval_starts<<<std::min(ceil_div(n, 256), 1184u), 256, 0, e->stream>>>(e->d_lut, profile, n, e->d_scratch, e->d_scratch + n);
+    if (int rc = check_launch(e, "k_eval_starts")) return rc;
+    ISL_CUDA(e, cudaMemcpyAsync(out, e->d_scratch + n, n, cudaMemcpyDeviceToHost, e->stream));
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ISL_OK;
+}
+
+int isl_get_stats(isl_engine* e, isl_stats* out) {
+    if (!e || !out) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    Ctrl c;
+    ISL_CUDA(e, cudaMemcpyAsync(&c, e->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, e->stream));
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->st.placed = c.placed; e->st.freed = c.freed; e->st.no_capacity = c.allocs - c.placed; e->st.chain_steps = c.steps; e->st.chain_gpus_visited = c.visited;
+    *out = e->st;
+    return ISL_OK;
+}
+
+int isl_reset_stats(isl_engine* e) {
+    if (!e) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    const uint64_t launches = e->st.kernel_launches;
+    e->st = isl_stats{};
+    e->st.kernel_launches = launches;      // launches are counted since creation
+    ISL_CUDA(e, cudaMemsetAsync(&e->d_ctrl->placed, 0, 6 * sizeof(unsigned long long), e->stream));
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ISL_OK;
+}
+
+}  // extern "C"

@@ -56,7 +56,7 @@ class Stats(C.Structure):
 
 # every symbol include/islplace.h declares; tests check that the library exports all of them
 EXPORTED_SYMBOLS = [
-    "isl_create", "isl_destroy", "isl_set_stream", "isl_load_profiles", "isl_load_inventory", "isl_read_occupancy",
+    "isl_create", "isl_destroy", "isl_set_stream", "isl_synchronize", "isl_load_profiles", "isl_load_inventory", "isl_read_occupancy",
     "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_free_batch",
     "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_device_occupancy", "isl_get_stats",
     "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
@@ -78,6 +78,7 @@ def load_library(path: str = LIB_PATH):
         "isl_create": (C.c_int, [C.POINTER(Config), C.POINTER(p)]),
         "isl_destroy": (C.c_int, [p]),
         "isl_set_stream": (C.c_int, [p, p]),
+        "isl_synchronize": (C.c_int, [p]),
         "isl_load_profiles": (C.c_int, [p, C.c_uint32, p]),
         "isl_load_inventory": (C.c_int, [p, C.c_uint32, p, p]),
         "isl_read_occupancy": (C.c_int, [p, p]),
@@ -161,6 +162,9 @@ class Engine:
 
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.isl_set_stream(self._h, C.c_void_p(cuda_stream)), "isl_set_stream")
+
+    def synchronize(self):
+        self._check(self._lib.isl_synchronize(self._h), "isl_synchronize")
 
     # -- tables / inventory
     def load_profiles(self, rows: np.ndarray):

@@ -1,0 +1,49 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/islplace.h declares."""
+import ctypes
+import os
+import re
+
+from instaslice_b200 import engine as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "islplace.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(isl_[a-z_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(E.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(E.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+
+
+def test_record_layouts_match_header():
+    assert E.REQUEST_DTYPE.itemsize == 8 and E.RESULT_DTYPE.itemsize == 8 and E.SPAN_DTYPE.itemsize == 8
+    assert E.PROFILE_DTYPE.itemsize == 24
+    assert ctypes.sizeof(E.Config) == 32
+    lib = E.load_library()
+    assert lib.isl_abi_version() == E.ABI_VERSION
+    assert lib.isl_strerror(E.EINVAL).decode().startswith("invalid")
+
+
+def test_argument_validation_without_gpu():
+    """Pure argument checks return before any CUDA call."""
+    lib = E.load_library()
+    h = ctypes.c_void_p()
+    bad = E.Config(99, 0, 3, -1, 16, 16, 0, 0)          # wrong ABI version
+    assert lib.isl_create(ctypes.byref(bad), ctypes.byref(h)) == E.EINVAL
+    bad = E.Config(E.ABI_VERSION, 0, 3, -1, 0, 16, 0, 0)  # zero capacity
+    assert lib.isl_create(ctypes.byref(bad), ctypes.byref(h)) == E.EINVAL
+    bad = E.Config(E.ABI_VERSION, 0, 3, -1, (1 << 24) + 1, 16, 0, 0)
+    assert lib.isl_create(ctypes.byref(bad), ctypes.byref(h)) == E.EINVAL
+    bad = E.Config(E.ABI_VERSION, 0, 0xF0, -1, 16, 16, 0, 0)   # unknown quirk bits
+    assert lib.isl_create(ctypes.byref(bad), ctypes.byref(h)) == E.EINVAL
+    assert lib.isl_destroy(None) == E.EINVAL
+    assert lib.isl_num_gpus(None) == 0
