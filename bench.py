@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — MIG placements/s on BASELINE config 4 (1M ops x 65 536 GPUs, 50/50 alloc/free churn).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over the whole recorded workload: the inventory is reset to the
+pre-filled state (64 KiB device copy, inside the timed region) and the 16 recorded batches (15 x 65 536 +
+1 x 16 960 operations) are resolved in order.  The recording itself (which allocation each FREE names depends
+on earlier placements) is made once, untimed, by running the generator through the engine.
+
+value   whole-job placements/s with requests and results resident in HBM (isl_place_batch_device)
+e2e     the same through isl_place_batch with pinned HOST buffers: H2D of every batch and D2H of every result
+        array are inside the timed region
+N > 1   the inventory is partitioned over the ranks (contiguous GPU ranges); every rank holds the request
+        batches; the per-profile queue-head token travels rank -> rank per batch (NCCL send/recv), results are
+        combined with an all-reduce(MIN) over the 8-byte records and the occupancy shards are all-gathered.
+        Strong scaling (the job is fixed).
+
+The CPU oracle is used only for the cpu_baseline leg (timed baseline + parity check of the same sample) and
+for --impl reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "placements_per_sec"
+UNIT = "placements/s"
+WORKLOAD = "C4: 8192 nodes x 8 GPUs (65536), H100-80GB table, prefill 50%, 1e6 ops, 50/50 alloc/free, batches of 65536, seed 42"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per k_chain launch from the committed ncu capture, if one has been summarised."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "chain_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------------------
+def record_workload(E, W, torch):
+    """Generate config 4 through the engine (untimed).  Returns (churn object, prefilled occupancy, churn batches, results)."""
+    ch = W.Churn()
+    eng = E.Engine(max_gpus=ch.G, max_batch=65536)
+    eng.load_profiles(ch.rows)
+    eng.load_inventory(ch.node_off, np.zeros(ch.G, dtype=np.uint8))
+    results, occ_after_prefill = [], [None]
+
+    def placer(req):
+        if len(results) == ch.n_prefill_batches and occ_after_prefill[0] is None and ch._busy_slices >= ch.fill * 7 * ch.G:
+            occ_after_prefill[0] = eng.read_occupancy()
+        res = eng.place_batch(req)
+        results.append(res)
+        return res
+
+    ch.generate(placer)
+    eng.close()
+    nb = ch.n_prefill_batches
+    return ch, occ_after_prefill[0], ch.batches[nb:], results[nb:]
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    from instaslice_b200 import engine as E
+    from instaslice_b200 import workloads as W
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+
+    ch, occ0, batches, want = record_workload(E, W, torch)
+    n_ops = sum(len(b) for b in batches)
+    G = ch.G
+
+    # engine on torch's current stream so that torch.cuda.Event brackets its kernels
+    stream = torch.cuda.current_stream()
+    eng = E.Engine(max_gpus=G, max_batch=65536)
+    eng.set_stream(stream.cuda_stream)
+    eng.load_profiles(ch.rows)
+    eng.load_inventory(ch.node_off, occ0)
+    d_occ0 = torch.from_numpy(occ0).cuda()
+    occ_view = _device_view(torch, eng.device_occupancy(), G)
+    d_in = [torch.from_numpy(b.view(np.int64).copy()).cuda() for b in batches]
+    d_out = [torch.empty_like(t) for t in d_in]
+    h_in = [torch.from_numpy(b.view(np.int64).copy()).pin_memory() for b in batches]
+    h_out = [torch.empty_like(t).pin_memory() for t in h_in]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    if world > 1:
+        lo, hi = rank * G // world, (rank + 1) * G // world
+        eng.set_partition(lo, hi)
+        heads = [torch.zeros((-(-len(b) // 65536)) * 16, dtype=torch.int32, device="cuda") for b in batches]
+        heads_in = [torch.zeros_like(h) for h in heads]
+        gathered = torch.empty(G, dtype=torch.uint8, device="cuda")
+
+    def step_device():
+        occ_view.copy_(d_occ0)
+        if world == 1:
+            for b, t_in, t_out in zip(batches, d_in, d_out):
+                eng.place_batch_device(len(b), t_in.data_ptr(), t_out.data_ptr())
+            return
+        for i, (b, t_in, t_out) in enumerate(zip(batches, d_in, d_out)):
+            if rank > 0:
+                dist.recv(heads_in[i], src=rank - 1)
+            eng.place_batch_partitioned(len(b), t_in.data_ptr(), t_out.data_ptr(), heads_in[i].data_ptr() if rank > 0 else None, heads[i].data_ptr())
+            if rank < world - 1:
+                dist.send(heads[i], dst=rank + 1)
+        for t_out in d_out:                                    # global answer = elementwise MIN over the ranks' records
+            dist.all_reduce(t_out, op=dist.ReduceOp.MIN)
+        dist.all_gather_into_tensor(gathered, occ_view[lo:hi].contiguous())
+        occ_view.copy_(gathered)
+
+    def step_e2e():
+        occ_view.copy_(d_occ0)
+        for b, t_in, t_out in zip(batches, h_in, h_out):
+            eng.place_batch_ptr(len(b), t_in.data_ptr(), t_out.data_ptr())
+
+    def timed(step_fn, steps, warmup, flush_l2=True):
+        for _ in range(warmup):
+            step_fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = 0.0
+        for _ in range(steps):
+            if flush_l2:
+                flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn()
+            e1.record()
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.stats()["kernel_launches"]
+    ms_dev = timed(step_device, args.steps, args.warmup)
+    launches = eng.stats()["kernel_launches"] - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # parity gate on the last timed step: byte-identical to the recorded (single-GPU) results
+    got = [t.cpu().numpy().view(E.RESULT_DTYPE) for t in d_out]
+    parity = all(np.array_equal(a, b) for a, b in zip(got, want))
+
+    e2e = None
+    if world == 1:
+        ms_e2e = timed(step_e2e, args.steps, args.warmup)
+        parity = parity and all(np.array_equal(t.numpy().view(E.RESULT_DTYPE), b) for t, b in zip(h_out, want))
+        e2e = {"value": n_ops * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n_ops, "d2h_bytes_per_step": 8 * n_ops,
+               "ms_per_step": ms_e2e / args.steps}
+
+    roofline = cpu = None
+    if rank == 0 and world == 1:
+        # dominant kernel (k_chain), timed live with CUDA events on the engine's own stream in timing mode
+        teng = E.Engine(max_gpus=G, max_batch=65536, timing=True)
+        teng.load_profiles(ch.rows)
+        for rep in range(2):
+            teng.load_inventory(ch.node_off, occ0)
+            teng.reset_stats()
+            l0 = teng.stats()["kernel_launches"]
+            for b, t_in, t_out in zip(batches, d_in, d_out):
+                teng.place_batch_device(len(b), t_in.data_ptr(), t_out.data_ptr())
+            teng.synchronize()
+        st = teng.stats()
+        n_chain = len(batches)
+        ms_chain = st["ms_commit"] / n_chain
+        alg_bytes = 16 * 65536 + 2 * G                       # B_alg(R, G) = 16 R + 2 G for one commit chunk
+        peak, how = measured_peak()
+        achieved = alg_bytes / (ms_chain / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_chain", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic(), "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes,
+                    "avg_launch_ms": ms_chain, "launches": n_chain,
+                    "note": "latency-bound sequential commit; the inventory (64 KiB) is on-chip by construction",
+                    "phase_ms_per_step": {"prepare": st["ms_free"], "partition": st["ms_partition"], "sweep": st["ms_sweep"],
+                                          "commit": st["ms_commit"], "total": st["ms_total"]}}
+        teng.close()
+        cpu = cpu_baseline(ch, occ0, batches, want)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": n_ops * args.steps / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "ops_per_step": n_ops, "batches_per_step": len(batches), "gpus_in_inventory": G,
+                           "policy": "first-fit", "quirks": "REF_EXACT",
+                           "parallelism": "single" if world == 1 else "inventory partitioned over %d ranks, token chain + all-gather" % world,
+                           "l2": "flushed between timed steps (256 MiB write)", "timing": "cuda events per step, max over ranks"},
+                "parity": "bit-exact vs recorded single-GPU results" if parity else "MISMATCH",
+                "gpu_launches": int(launches), "clocks": clocks}
+        if e2e:
+            line["e2e"] = e2e
+        if roofline:
+            line["roofline"] = roofline
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0 if parity else 1
+
+
+def _device_view(torch, ptr: int, n: int):
+    """uint8 torch view of engine-owned device memory (no copy)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+    return torch.as_tensor(h, device="cuda")
+
+
+# ---- CPU legs (the only places that touch oracle/) ------------------------------------------------------------
+def _prefilled_faithful(oracle, ch, batches_prefill_results):
+    f = oracle.Faithful(ch.node_off, ch.rows)
+    pod = 0
+    for req, res in batches_prefill_results:
+        placed = (req["op"] == 0) & (res["status"] == 0)
+        for g, s, z in zip(res["gpu"][placed].tolist(), res["start"][placed].tolist(), res["size"][placed].tolist()):
+            f.add_allocation(g, s, z, pod)
+            pod += 1
+    return f
+
+
+def cpu_baseline(ch, occ0, batches, want, sample_ops=1500):
+    """ref_faithful (the reference as written, 1 reconcile worker) on the first `sample_ops` operations of churn
+    batch 0 against the pre-filled inventory; ref_fast on the whole job.  Also the parity check of that sample."""
+    import oracle
+    from instaslice_b200 import engine as E
+    f = oracle.Faithful(ch.node_off, ch.rows)
+    f.load_occupancy_as_dangling(occ0)       # the pre-fill as realised slices
+    req = batches[0][:sample_ops].copy()
+    req = req[req["op"] == E.OP_ALLOC]        # frees of the sample would name pod-keyed entries; the sample times allocations
+    t0 = time.perf_counter()
+    res = f.place(req)
+    dt = time.perf_counter() - t0
+    fast = oracle.Fast(ch.node_off, ch.rows)
+    fast.load(occ0)
+    t1 = time.perf_counter()
+    ok = True
+    for b, w in zip(batches, want):
+        ok = ok and np.array_equal(fast.place(b), w)
+    dt_fast = time.perf_counter() - t1
+    fast2 = oracle.Fast(ch.node_off, ch.rows)
+    fast2.load(occ0)
+    ok_sample = np.array_equal(fast2.place(req), res)
+    return {"value": len(req) / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "ref_faithful.cpp on the %d ALLOC requests among the first %d ops of churn batch 0, pre-filled 65536-GPU inventory, %.1f s" % (len(req), sample_ops, dt),
+            "ref_fast_value": sum(len(b) for b in batches) / dt_fast, "ref_fast_note": "bitmask restatement, whole job, 1 core (strong CPU baseline)",
+            "parity_full_job_vs_ref_fast": bool(ok), "parity_sample_faithful_vs_fast": bool(ok_sample)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (ref_faithful.cpp, the port — the Go binary cannot be built here)."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    import oracle
+    from instaslice_b200 import engine as E
+    from instaslice_b200 import workloads as W
+    oracle.build()
+    # the recorded workload needs a placer; the reference arm may execute oracle/, so ref_fast records it
+    ch = W.Churn()
+    fast = oracle.Fast(ch.node_off, ch.rows)
+    fast.load(np.zeros(ch.G, dtype=np.uint8))
+    state = {"occ0": None}
+
+    def placer(req):
+        if state["occ0"] is None and ch._busy_slices >= ch.fill * 7 * ch.G:
+            state["occ0"] = fast.occupancy()
+        return fast.place(req)
+
+    ch.generate(placer)
+    batches = ch.batches[ch.n_prefill_batches:]
+    sample_ops = args.sample
+    req = batches[0][:sample_ops].copy()
+    req = req[req["op"] == E.OP_ALLOC]
+    times = []
+    for i in range(args.warmup + args.steps):
+        f = oracle.Faithful(ch.node_off, ch.rows)
+        f.load_occupancy_as_dangling(state["occ0"])
+        t0 = time.perf_counter()
+        f.place(req)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = len(req) * args.steps / total
+    sample = "ref_faithful.cpp, %d ALLOC requests among the first %d ops of churn batch 0 per step, pre-filled 65536-GPU inventory" % (len(req), sample_ops)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                      "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                                       "note": "single reconcile worker like the reference (controller-runtime default); the Go binary cannot be built in this image"},
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--sample", type=int, default=1500, help="ops per step of the CPU reference arm")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
+    sys.exit(run_reference(args) if args.impl == "reference" else run_own(args))
+
+
+if __name__ == "__main__":
+    main()
