@@ -116,19 +116,17 @@ def record_workload(E, W, torch):
     eng = E.Engine(max_gpus=ch.G, max_batch=65536)
     eng.load_profiles(ch.rows)
     eng.load_inventory(ch.node_off, np.zeros(ch.G, dtype=np.uint8))
-    results, occ_after_prefill = [], [None]
+    results, snap = [], {}
 
     def placer(req):
-        if len(results) == ch.n_prefill_batches and occ_after_prefill[0] is None and ch._busy_slices >= ch.fill * 7 * ch.G:
-            occ_after_prefill[0] = eng.read_occupancy()
         res = eng.place_batch(req)
         results.append(res)
         return res
 
-    ch.generate(placer)
+    ch.generate(placer, after_prefill=lambda: snap.update(occ=eng.read_occupancy()))
     eng.close()
     nb = ch.n_prefill_batches
-    return ch, occ_after_prefill[0], ch.batches[nb:], results[nb:]
+    return ch, snap["occ"], ch.batches[nb:], results[nb:]
 
 
 def run_own(args):
@@ -353,13 +351,7 @@ def run_reference(args):
     fast = oracle.Fast(ch.node_off, ch.rows)
     fast.load(np.zeros(ch.G, dtype=np.uint8))
     state = {"occ0": None}
-
-    def placer(req):
-        if state["occ0"] is None and ch._busy_slices >= ch.fill * 7 * ch.G:
-            state["occ0"] = fast.occupancy()
-        return fast.place(req)
-
-    ch.generate(placer)
+    ch.generate(fast.place, after_prefill=lambda: state.update(occ0=fast.occupancy()))
     batches = ch.batches[ch.n_prefill_batches:]
     sample_ops = args.sample
     req = batches[0][:sample_ops].copy()

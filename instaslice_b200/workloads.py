@@ -121,8 +121,9 @@ class Churn:
         self._live += k
         self._busy_slices += int(res["size"][placed].astype(np.int64).sum())
 
-    def generate(self, placer):
-        """Run pre-fill and churn through ``placer``; returns the list of recorded batches."""
+    def generate(self, placer, after_prefill=None):
+        """Run pre-fill and churn through ``placer``; returns the list of recorded batches.
+        ``after_prefill()`` is called once between the two phases (e.g. to snapshot the occupancy)."""
         target = self.fill * 7 * self.G
         prefill_batch = min(self.batch, max(64, self.G // 8))     # small steps so the target is not overshot by much
         while self._busy_slices < target:
@@ -133,6 +134,8 @@ class Churn:
             self.n_prefill_batches += 1
             if self.n_prefill_batches > 256:
                 raise RuntimeError("pre-fill did not reach the target occupancy")
+        if after_prefill is not None:
+            after_prefill()
         done = 0
         while done < self.n_ops:
             n = min(self.batch, self.n_ops - done)
