@@ -153,7 +153,8 @@ def run_own(args):
     G = ch.G
 
     # engine on torch's current stream so that torch.cuda.Event brackets its kernels
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: the legacy default stream has handle 0
+    torch.cuda.set_stream(stream)
     eng = E.Engine(max_gpus=G, max_batch=65536)
     eng.set_stream(stream.cuda_stream)
     eng.load_profiles(ch.rows)

@@ -152,6 +152,7 @@ typedef struct isl_stats {
     uint64_t kernel_launches;      /* kernels launched by this engine since creation */
     uint64_t chain_steps;          /* accepted placements walked by the commit chain */
     uint64_t chain_gpus_visited;   /* candidate GPUs the chain looked at */
+    uint64_t chain_jumps;          /* ballot skips over candidates that no pending profile fits */
     /* accumulated CUDA-event milliseconds (only with ISL_FLAG_TIMING) */
     double   ms_free;
     double   ms_partition;

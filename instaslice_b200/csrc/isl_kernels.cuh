@@ -56,8 +56,8 @@ struct Ctrl {                   // device-resident control block, rewritten per 
     uint32_t active;                       // profiles with requests in this chunk AND >= 1 valid candidate
     uint32_t n_cand;                       // candidate GPUs found by the sweep
     uint32_t heads_out[ISL_MAX_PROFILES];  // queue heads after the chain (token for the next rank)
-    uint32_t pad;
-    unsigned long long placed, freed, bad, steps, visited, allocs;
+    uint32_t n_log;                        // decisions logged by the chain of this chunk
+    unsigned long long placed, freed, bad, steps, visited, allocs, jumps;
 };
 
 // The one rule both the device table and the chain candidates come from: slot mask of placing a
@@ -327,37 +327,52 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_chain<K>: the exact commit.
+// k_chain<K>: the exact commit decision chain.
 //
 // First-fit in canonical GPU order is GPU-major stream filtering: GPU g accepts, in request
 // order, a prefix of each profile's remaining queue (occupancy only grows inside an alloc phase, so
 // a profile that stopped fitting on g never fits again).  The state between GPUs is one queue head
-// per profile.  One warp walks the candidate GPUs; lane l owns up to K (profile, start) candidates
-// with their slot masks in registers.  Per accepted placement:
-//     key = (next request index of the candidate's profile) << 15 | profile << 11 | order << 8 | mask
-//     for candidates whose mask is free on the current occupancy, else INF
-//     m   = warp-min(key)                -> earliest pending request that fits, first legal start
-//     occupancy |= m & 0xFF; the lanes of that profile advance their queue head
-// The queues (16-bit in-chunk indices) are staged once in shared memory.
+// per profile.  The chain is a latency-bound sequential recurrence, so ONE warp walks the candidate
+// GPUs and does nothing but decide; lane l owns up to K (profile, start) candidates with their slot
+// masks in registers.  One warp min-reduction per accepted placement answers "which pending
+// request is next and where does it start", looking at the current candidate GPU and the one after
+// it at once:
+//     key = sel << 31 | t << 15 | profile << 11 | order << 8 | mask
+//       sel  0 = the candidate's mask is free on the current GPU, 1 = only on the next GPU
+//       t    in-chunk index of the next pending request of the candidate's profile
+//     m = warp-min(key):  lowest GPU first, then earliest request, then first legal start in row order
+//     occupancy |= m & 0xFF; the lanes of the winning profile pop their queue head.
+// Every decision is appended to a log (8 B: m, candidate index); k_commit turns the log into result
+// records and occupancy updates with full parallelism afterwards.
+// m == INF means neither GPU can take anything: a ballot over the feasibility table jumps straight to
+// the next candidate GPU on which a profile that still has pending requests fits.
+// The queues (16-bit in-chunk indices) are staged once in shared memory; the candidate list streams
+// through a 256-entry shared ring refilled one 32-entry block ahead from a register-held load.
 // ---------------------------------------------------------------------------------------------
+constexpr uint32_t kRing = 256;
+
 template <int K>
 __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* ctrl, const uint16_t* __restrict__ q_global,
-                                                             const uint32_t* __restrict__ cand, uint8_t* __restrict__ occ,
-                                                             uint2* __restrict__ out_chunk, const uint32_t* __restrict__ heads_in,
+                                                             const uint32_t* __restrict__ cand, const uint16_t* __restrict__ feas,
+                                                             uint2* __restrict__ log, const uint32_t* __restrict__ heads_in,
                                                              uint32_t* __restrict__ heads_out) {
     extern __shared__ __align__(16) uint16_t s_q[];
+    __shared__ uint32_t s_ring[kRing];
+    __shared__ uint16_t s_feas[256];
     const uint32_t q_total = ctrl->qoff[ISL_MAX_PROFILES];
     {   // stage every queue of the chunk: <= 129 KB, 16-byte vector copies
         const uint4* src = reinterpret_cast<const uint4*>(q_global);
         uint4* dst = reinterpret_cast<uint4*>(s_q);
         for (uint32_t i = threadIdx.x; i < (q_total + 7) / 8; i += kChainThreads) dst[i] = src[i];
+        s_feas[threadIdx.x] = feas[threadIdx.x];
     }
     __syncthreads();
     if (threadIdx.x >= 32) return;
     const uint32_t lane = threadIdx.x;
     const uint32_t n_cand = ctrl->n_cand;
 
-    uint32_t cdesc[K], keylow[K], cmask[K], cprof[K], head[K], end[K], qb[K], tcur[K], tnext[K];
+    uint32_t cmask[K], keylow[K], pbit[K], head[K], left[K], qa[K], tcur[K], tnext[K];
+    bool reports[K];
     uint32_t rem = 0;                       // requests still pending over all profiles that have a candidate (warp-uniform)
     {
         uint32_t seen = 0;
@@ -372,66 +387,122 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
                 rem += e > h ? e - h : 0u;
             }
     }
+    const uint32_t rem0 = rem;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t d = tab.desc[k][lane];
         const bool valid = d >> 31;
-        cdesc[k] = d;
-        cprof[k] = d & 15u;
+        const uint32_t p = d & 15u;
         cmask[k] = valid ? (d >> 16) & 0xFFu : 0xFFu;
-        keylow[k] = (cprof[k] << 11) | (((d >> 4) & 7u) << 8) | cmask[k];
-        qb[k] = ctrl->qoff[cprof[k]];
-        end[k] = valid ? ctrl->qcnt[cprof[k]] : 0u;
-        head[k] = heads_in ? heads_in[cprof[k]] : 0u;
-        tcur[k] = head[k] < end[k] ? s_q[qb[k] + head[k]] : kInf;
-        tnext[k] = head[k] + 1 < end[k] ? s_q[qb[k] + head[k] + 1] : kInf;
+        keylow[k] = (p << 11) | (((d >> 4) & 7u) << 8) | cmask[k];
+        pbit[k] = valid ? 1u << p : 0u;
+        reports[k] = valid && ((d >> 4) & 7u) == 0;       // first candidate of the row reports the head
+        const uint32_t qb = ctrl->qoff[p], end = valid ? ctrl->qcnt[p] : 0u;
+        head[k] = heads_in ? heads_in[p] : 0u;
+        left[k] = end > head[k] ? end - head[k] : 0u;      // requests of this profile not yet popped
+        qa[k] = qb + head[k];                              // shared-memory index of the current head entry
+        tcur[k] = left[k] > 0 ? ((uint32_t)s_q[qa[k]] << 15) | keylow[k] : kInf;
+        tnext[k] = left[k] > 1 ? ((uint32_t)s_q[qa[k] + 1] << 15) | keylow[k] : kInf;
     }
-    uint32_t steps = 0, visited = 0;
-    for (uint32_t base = 0; base < n_cand && rem; base += 32) {
-        const uint32_t mine = base + lane < n_cand ? cand[base + lane] : kInf;
-        const uint32_t cnt = min(32u, n_cand - base);
-        for (uint32_t j = 0; j < cnt && rem; ++j) {
-            const uint32_t c = __shfl_sync(0xFFFFFFFFu, mine, j);
-            const uint32_t g = c >> 8;
-            uint32_t o = c & 0xFFu;
-            const uint32_t o0 = o;
-            ++visited;
-            while (true) {
-                uint32_t key = kInf;
+    auto ldc = [&](uint32_t idx) -> uint32_t { return idx < n_cand ? cand[idx] : kInf; };   // past the end: occupancy 0xFF, nothing fits
+    uint32_t fill = 0, pending;
+    auto reload = [&](uint32_t at) {       // synchronous (re)fill of 5 blocks starting at the block that holds `at`
+        fill = at & ~31u;
+        for (int b = 0; b < 5; ++b) { s_ring[(fill + lane) & (kRing - 1)] = ldc(fill + lane); fill += 32; }
+        pending = ldc(fill + lane);
+        __syncwarp();
+    };
+    reload(0);
+    uint32_t i0 = 0;
+    uint32_t o0 = s_ring[0] & 0xFFu, o1 = s_ring[1] & 0xFFu, o2 = s_ring[2] & 0xFFu;
+    uint32_t jumps = 0;
+    uint2* lp = log;
+    while (rem) {
+        uint32_t key = kInf;
 #pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (tcur[k] != kInf && (o & cmask[k]) == 0) key = min(key, (tcur[k] << 15) | keylow[k]);
-                const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, key);
-                if (m == kInf) break;
-                o |= m & 0xFFu;
-                const uint32_t pw = (m >> 11) & 15u;
-                if (key == m) {             // exactly one lane: the winning (profile, start) candidate
-                    uint32_t d = 0;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) if (((tcur[k] << 15) | keylow[k]) == m) d = cdesc[k];
-                    out_chunk[m >> 15] = pack_result(g, (d >> 7) & 15u, (d >> 11) & 15u, ISL_ST_PLACED);
-                }
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (cprof[k] == pw && end[k]) {
-                        ++head[k];
-                        tcur[k] = tnext[k];
-                        tnext[k] = head[k] + 1 < end[k] ? s_q[qb[k] + head[k] + 1] : kInf;
-                    }
-                ++steps; --rem;
-                if (!rem) break;
-            }
-            if (o != o0 && lane == 0) occ[g] = (uint8_t)o;
+        for (int k = 0; k < K; ++k) {
+            const uint32_t kk = (o0 & cmask[k]) == 0 ? tcur[k] : ((o1 & cmask[k]) == 0 ? tcur[k] | 0x80000000u : kInf);
+            key = min(key, kk);
         }
+        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, key);
+        if (m == kInf) {
+            // Neither GPU takes anything.  Ballot over the next candidates for one on which a profile that still has
+            // pending requests fits (the list was built for every profile pending at chunk start).
+            uint32_t alive = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) alive |= tcur[k] != kInf ? pbit[k] : 0u;
+            alive = __reduce_or_sync(0xFFFFFFFFu, alive);
+            uint32_t j = i0 + 2;
+            bool found = false;
+            while (j < n_cand) {
+                const uint32_t c = ldc(j + lane);
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, (s_feas[c & 0xFFu] & alive) != 0 && c != kInf);
+                if (b) { j += __ffs(b) - 1; found = true; break; }
+                j += 32;
+            }
+            ++jumps;
+            if (!found) break;
+            i0 = j;
+            if (i0 + 64 > fill) reload(i0);
+            o0 = s_ring[i0 & (kRing - 1)] & 0xFFu; o1 = s_ring[(i0 + 1) & (kRing - 1)] & 0xFFu; o2 = s_ring[(i0 + 2) & (kRing - 1)] & 0xFFu;
+            continue;
+        }
+        const uint32_t sel = m >> 31;
+        *lp++ = make_uint2(m, i0 + sel);                  // decision log: (key, candidate index it landed on)
+        if (sel) {      // warp-uniform: the current GPU is finished, the next one becomes current
+            o0 = o1 | (m & 0xFFu); o1 = o2;
+            ++i0;
+            o2 = s_ring[(i0 + 2) & (kRing - 1)] & 0xFFu;
+            if ((i0 & 31u) == 0 && fill < i0 + 224) {
+                s_ring[(fill + lane) & (kRing - 1)] = pending;
+                fill += 32;
+                pending = ldc(fill + lane);
+                __syncwarp();
+            }
+        } else {
+            o0 |= m & 0xFFu;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {       // lanes of the winning profile (same t, same profile field) pop their queue
+            // branch-free: the shared-memory read is unconditional (index 0 when there is nothing to read)
+            const bool adv = ((m ^ tcur[k]) & 0x7FFFF800u) == 0 && tcur[k] != kInf;
+            left[k] -= adv ? 1u : 0u;
+            qa[k] += adv ? 1u : 0u;
+            const bool more = left[k] > 1;
+            const uint32_t v = s_q[more ? qa[k] + 1 : 0u];
+            const uint32_t tn = more ? (v << 15) | keylow[k] : kInf;
+            tcur[k] = adv ? tnext[k] : tcur[k];
+            tnext[k] = adv ? tn : tnext[k];
+        }
+        --rem;
     }
+    const uint32_t steps = rem0 - rem;
 #pragma unroll
     for (int k = 0; k < K; ++k)
-        if ((cdesc[k] >> 31) && ((cdesc[k] >> 4) & 7u) == 0 && heads_out) heads_out[cprof[k]] = head[k];   // first candidate of the row reports
+        if (reports[k] && heads_out) heads_out[(keylow[k] >> 11) & 15u] = ctrl->qcnt[(keylow[k] >> 11) & 15u] - left[k];
     if (lane == 0) {
+        ctrl->n_log = steps;
         atomicAdd(&ctrl->placed, (unsigned long long)steps);
         atomicAdd(&ctrl->steps, (unsigned long long)steps);
-        atomicAdd(&ctrl->visited, (unsigned long long)visited);
+        atomicAdd(&ctrl->visited, (unsigned long long)i0);
+        atomicAdd(&ctrl->jumps, (unsigned long long)jumps);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_commit: one thread per logged decision.  Writes the result record of the request (the fields of
+// AllocationDetails the allocator decides) and ORs the slot mask into the packed occupancy word.
+// Distinct decisions on one GPU have disjoint masks (the chain only accepts free masks): no double
+// booking; the atomics only serialise neighbours that share a 32-bit word.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_commit(const Ctrl* __restrict__ ctrl, const uint2* __restrict__ log, const uint32_t* __restrict__ cand,
+                                                 uint32_t* __restrict__ occ32, uint2* __restrict__ out_chunk) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ctrl->n_log) return;
+    const uint2 e = log[j];
+    const uint32_t g = cand[e.y] >> 8, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
+    out_chunk[t] = pack_result(g, __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
+    atomicOr(&occ32[g >> 2], mask << ((g & 3u) * 8u));
 }
 
 }  // namespace isl

@@ -41,6 +41,7 @@ struct isl_engine {
     uint16_t* d_q = nullptr;         // per-chunk queues
     uint32_t* d_tile_counts = nullptr;
     uint32_t* d_cand = nullptr;
+    uint2* d_log = nullptr;          // decision log of one chunk (chain -> commit)
     uint32_t* d_sweep_counts = nullptr;
     Ctrl* d_ctrl = nullptr;
     uint8_t* d_scratch = nullptr;    // eval_starts / free_batch staging
@@ -94,8 +95,10 @@ int launch_chain(isl_engine* e, uint2* d_out_chunk, const uint32_t* d_heads_in, 
         ISL_CUDA(e, cudaFuncSetAttribute(k_chain<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[e->device & 7] = true;
     }
-    k_chain<K><<<1, kChainThreads, smem, e->stream>>>(e->tab, e->d_ctrl, e->d_q, e->d_cand, e->d_occ, d_out_chunk, d_heads_in, d_heads_out);
-    return check_launch(e, "k_chain");
+    k_chain<K><<<1, kChainThreads, smem, e->stream>>>(e->tab, e->d_ctrl, e->d_q, e->d_cand, e->d_feas, e->d_log, d_heads_in, d_heads_out);
+    if (int rc = check_launch(e, "k_chain")) return rc;
+    k_commit<<<kChunk / 256, 256, 0, e->stream>>>(e->d_ctrl, e->d_log, e->d_cand, reinterpret_cast<uint32_t*>(e->d_occ), d_out_chunk);
+    return check_launch(e, "k_commit");
 }
 
 // Resolve n requests that already sit in device memory.  Enqueues only; the caller synchronises.
@@ -219,6 +222,7 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
     ISL_TRY(cudaMalloc(&e->d_q, (size_t)kQCap * sizeof(uint16_t)));
     ISL_TRY(cudaMalloc(&e->d_tile_counts, (size_t)max_tiles * ISL_MAX_PROFILES * sizeof(uint32_t)));
     ISL_TRY(cudaMalloc(&e->d_cand, e->occ_bytes * sizeof(uint32_t)));
+    ISL_TRY(cudaMalloc(&e->d_log, (size_t)kChunk * sizeof(uint2)));
     ISL_TRY(cudaMalloc(&e->d_sweep_counts, (e->occ_bytes / kSweepBlock) * sizeof(uint32_t)));
     ISL_TRY(cudaMalloc(&e->d_ctrl, sizeof(Ctrl)));
     ISL_TRY(cudaMemset(e->d_ctrl, 0, sizeof(Ctrl)));
@@ -235,7 +239,7 @@ int isl_destroy(isl_engine* e) {
         DeviceGuard guard(e->device);
         if (e->stream) cudaStreamSynchronize(e->stream);
         cudaFree(e->d_occ); cudaFree(e->d_lut); cudaFree(e->d_feas); cudaFree(e->d_req); cudaFree(e->d_res);
-        cudaFree(e->d_q); cudaFree(e->d_tile_counts); cudaFree(e->d_cand); cudaFree(e->d_sweep_counts);
+        cudaFree(e->d_q); cudaFree(e->d_tile_counts); cudaFree(e->d_cand); cudaFree(e->d_log); cudaFree(e->d_sweep_counts);
         cudaFree(e->d_ctrl); cudaFree(e->d_scratch);
         for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
         if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -413,7 +417,7 @@ int isl_get_stats(isl_engine* e, isl_stats* out) {
     Ctrl c;
     ISL_CUDA(e, cudaMemcpyAsync(&c, e->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
-    e->st.placed = c.placed; e->st.freed = c.freed; e->st.no_capacity = c.allocs - c.placed; e->st.chain_steps = c.steps; e->st.chain_gpus_visited = c.visited;
+    e->st.placed = c.placed; e->st.freed = c.freed; e->st.no_capacity = c.allocs - c.placed; e->st.chain_steps = c.steps; e->st.chain_gpus_visited = c.visited; e->st.chain_jumps = c.jumps;
     *out = e->st;
     return ISL_OK;
 }
@@ -425,7 +429,7 @@ int isl_reset_stats(isl_engine* e) {
     const uint64_t launches = e->st.kernel_launches;
     e->st = isl_stats{};
     e->st.kernel_launches = launches;      // launches are counted since creation
-    ISL_CUDA(e, cudaMemsetAsync(&e->d_ctrl->placed, 0, 6 * sizeof(unsigned long long), e->stream));
+    ISL_CUDA(e, cudaMemsetAsync(&e->d_ctrl->placed, 0, 7 * sizeof(unsigned long long), e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     return ISL_OK;
 }

@@ -47,7 +47,7 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("batches", C.c_uint64), ("requests", C.c_uint64), ("placed", C.c_uint64), ("no_capacity", C.c_uint64),
                 ("freed", C.c_uint64), ("kernel_launches", C.c_uint64), ("chain_steps", C.c_uint64),
-                ("chain_gpus_visited", C.c_uint64), ("ms_free", C.c_double), ("ms_partition", C.c_double),
+                ("chain_gpus_visited", C.c_uint64), ("chain_jumps", C.c_uint64), ("ms_free", C.c_double), ("ms_partition", C.c_double),
                 ("ms_sweep", C.c_double), ("ms_commit", C.c_double), ("ms_total", C.c_double)]
 
     def as_dict(self):
