@@ -100,6 +100,8 @@ typedef struct isl_config {
 } isl_config;
 
 #define ISL_FLAG_TIMING 1u  /* record per-kernel CUDA-event timings (isl_get_stats) */
+#define ISL_FLAG_NO_PIPELINE    2u  /* always resolve chunk after chunk with the single-chain path */
+#define ISL_FLAG_FORCE_PIPELINE 4u  /* use the segment pipeline even for a single chunk (tests) */
 
 /* One Migplacement row (api/v1alpha1/instaslice_types.go:23-29).  `size` is
  * Placements[0].Size (:334); `starts` is [p.Start for p in Placements] in CRD
@@ -188,6 +190,11 @@ uint32_t isl_gpu_to_node(const isl_engine* e, uint32_t gpu);
  * getStartIndexFromPreparedState (:303-384) for n pods at once. `in` and `out`
  * are host buffers of n entries; copies are part of the call. */
 int  isl_place_batch(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out);
+/* A STREAM of batches in one call: batch i has sizes[i] requests, `in`/`out` hold the batches back to back.
+ * Semantics are exactly those of calling isl_place_batch once per batch in order; the engine pipelines the
+ * batches over inventory segments (DESIGN.md "Segment pipeline").  Sum of sizes <= isl_config.max_batch. */
+int  isl_place_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const isl_request* in, isl_result* out);
+int  isl_place_stream_device(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const void* d_in, void* d_out);
 /* Same, requests and results already resident in device memory (CUdeviceptr as void*). */
 int  isl_place_batch_device(isl_engine* e, uint32_t n, const void* d_in, void* d_out);
 /* Releases spans (Allocations entries deleted by the daemonset). */

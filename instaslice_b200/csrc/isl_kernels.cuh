@@ -129,7 +129,10 @@ __device__ __forceinline__ uint2 pack_result(uint32_t gpu, uint32_t start, uint3
 
 __global__ void __launch_bounds__(kTileThreads) k_prepare(uint32_t n, const uint2* __restrict__ in, uint2* __restrict__ out,
                                                            uint32_t* __restrict__ occ32, uint32_t G, uint32_t lo, uint32_t hi,
-                                                           DevProfiles prof, uint32_t* __restrict__ tile_counts, Ctrl* ctrl) {
+                                                           DevProfiles prof, uint32_t* __restrict__ tile_counts, Ctrl* ctrl,
+                                                           uint2* __restrict__ free_list, uint32_t* __restrict__ free_cnt) {
+    // free_list != nullptr (stream mode): FREEs are not applied here but appended as (gpu, slot mask) for the
+    // segment pipeline, which applies them in batch order inside the segment that owns the GPU.
     __shared__ uint32_t s_cnt[ISL_MAX_PROFILES];
     __shared__ uint32_t s_freed;
     if (threadIdx.x < ISL_MAX_PROFILES) s_cnt[threadIdx.x] = 0;
@@ -151,8 +154,9 @@ __global__ void __launch_bounds__(kTileThreads) k_prepare(uint32_t n, const uint
                 if (handle >= G || size == 0 || start + size > ISL_SLOTS) out[i] = pack_result(handle, start, size, ISL_ST_BAD_SPAN);
                 else {
                     if (handle >= lo && handle < hi) {
-                        const uint32_t m = (((1u << size) - 1u) << start) << ((handle & 3u) * 8u);
-                        atomicAnd(&occ32[handle >> 2], ~m);
+                        const uint32_t span = ((1u << size) - 1u) << start;
+                        if (free_list) free_list[atomicAdd(free_cnt, 1u)] = make_uint2(handle, span);
+                        else atomicAnd(&occ32[handle >> 2], ~(span << ((handle & 3u) * 8u)));
                         atomicAdd(&s_freed, 1u);
                     }
                     out[i] = pack_result(handle, start, size, ISL_ST_FREED);
@@ -503,6 +507,240 @@ __global__ void __launch_bounds__(256) k_commit(const Ctrl* __restrict__ ctrl, c
     const uint32_t g = cand[e.y] >> 8, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
     out_chunk[t] = pack_result(g, __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
     atomicOr(&occ32[g >> 2], mask << ((g & 3u) * 8u));
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_pipeline<K>: the segment pipeline for STREAMS of batches (BASELINE config 4's shape).
+//
+// The commit chain of one chunk is sequential, but chunks of a stream pipeline exactly over
+// inventory segments: segment s may work on chunk c+1 while segment s+1 is still on chunk c, because
+//   * inside a segment everything happens in stream order: allocs of chunk c, then the frees of the
+//     next batch, then its allocs (occupancy of the segment lives in this CTA's shared memory), and
+//   * the only state that crosses a segment boundary is the per-profile queue-head token (16 counters).
+// One persistent CTA per segment (cooperative launch, all co-resident).  Per chunk a CTA
+//   1. applies the batch's frees that fall into its range                      (all threads)
+//   2. sweeps its occupancy bytes into an ordered candidate list               (all threads, before the token arrives)
+//   3. waits for the token of segment s-1 (global flag, acquire), stages the queue windows it may pop
+//   4. runs the decision chain of k_chain on its candidates                    (warp 0)
+//   5. publishes the token for segment s+1 (release) and only then
+//   6. commits the logged decisions: result records + occupancy bits           (all threads)
+// Results are bit-identical to resolving the batches one after the other.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kSegMax = 512;                   // GPUs per segment (2 per thread in the local sweep)
+constexpr uint32_t kPipeThreads = 256;
+constexpr uint32_t kWin = 8 * kSegMax + 8;          // queue window per profile: a GPU accepts at most 8 placements
+constexpr uint32_t kTokStride = 32;                 // uint32 per token: heads[16], flag at [16]
+constexpr uint32_t kPipeSmem = kSegMax + 4 * (kSegMax + 8) + 8 * (8 * kSegMax) + 2 * ISL_MAX_PROFILES * kWin;
+
+struct ChunkDesc { uint32_t req_off, n, batch, first_of_batch; };
+
+struct PipeArgs {
+    uint32_t n_chunks, n_seg, seg, lo, hi, epoch;
+    const ChunkDesc* chunks;
+    const Ctrl* cctl;               // per chunk: qoff / qcnt / active (written by k_partition)
+    const uint16_t* q_all;          // per chunk queues, stride kQCap
+    const uint2* free_list;         // (gpu, slot mask) per FREE, batch b's entries start at free_off[b]
+    const uint32_t* free_off;
+    const uint32_t* free_cnt;
+    uint32_t* tokens;               // [chunk][segment][kTokStride]
+    uint8_t* occ;
+    uint2* out;
+    const uint16_t* feas;
+    Ctrl* stats;
+    const uint32_t* heads_in;       // [chunk][16] token entering the first segment (nullptr = zeros)
+    uint32_t* heads_out;            // [chunk][16] token leaving the last segment (may be nullptr)
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int K>
+__global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t* s_occ32 = reinterpret_cast<uint32_t*>(smem);                                   // kSegMax occupancy bytes
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + kSegMax);                          // kSegMax + 8 records (local gpu << 8 | occ)
+    uint2* s_log = reinterpret_cast<uint2*>(smem + kSegMax + 4 * (kSegMax + 8));             // 8 * kSegMax decisions
+    uint16_t* s_win = reinterpret_cast<uint16_t*>(smem + kSegMax + 4 * (kSegMax + 8) + 8 * (8 * kSegMax));
+    __shared__ uint16_t s_feas[256];
+    __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_qsrc[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
+    __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_warp[kPipeThreads / 32], s_ncand, s_nlog;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
+    const uint32_t lo_s = min(a.hi, a.lo + seg * a.seg), hi_s = min(a.hi, lo_s + a.seg), n_g = hi_s - lo_s;
+
+    for (uint32_t i = tid; i < kSegMax / 4; i += kPipeThreads) s_occ32[i] = 0xFFFFFFFFu;
+    s_feas[tid] = a.feas[tid];
+    if (tid < ISL_MAX_PROFILES) {
+        uint32_t n = 0;
+        for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) { const uint32_t d = tab.desc[k][l]; n += (d >> 31) && (d & 15u) == tid; }
+        s_maxacc[tid] = n;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n_g; i += kPipeThreads) reinterpret_cast<uint8_t*>(s_occ32)[i] = a.occ[lo_s + i];
+    __syncthreads();
+
+    // chain-warp constants
+    uint32_t cmask[K], keylow[K], cprof[K];
+    bool valid[K], reports[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t d = tab.desc[k][lane];
+        valid[k] = d >> 31;
+        cprof[k] = d & 15u;
+        cmask[k] = valid[k] ? (d >> 16) & 0xFFu : 0xFFu;
+        keylow[k] = (cprof[k] << 11) | (((d >> 4) & 7u) << 8) | cmask[k];
+        reports[k] = valid[k] && ((d >> 4) & 7u) == 0;
+    }
+    unsigned long long st_steps = 0, st_jumps = 0, st_visited = 0;
+
+    for (uint32_t c = 0; c < a.n_chunks; ++c) {
+        const ChunkDesc cd = a.chunks[c];
+        const Ctrl* cc = a.cctl + c;
+        if (cd.first_of_batch) {            // 1. frees of this batch inside my range
+            const uint32_t n_free = a.free_cnt[cd.batch];
+            const uint2* fl = a.free_list + a.free_off[cd.batch];
+            for (uint32_t i = tid; i < n_free; i += kPipeThreads) {
+                const uint2 f = fl[i];
+                if (f.x >= lo_s && f.x < hi_s) { const uint32_t l = f.x - lo_s; atomicAnd(&s_occ32[l >> 2], ~(f.y << ((l & 3u) * 8u))); }
+            }
+            __syncthreads();
+        }
+        const uint32_t active = cc->active;
+        {   // 2. local sweep: thread t owns local GPUs 2t and 2t+1; ordered compaction
+            const uint32_t w = reinterpret_cast<uint16_t*>(s_occ32)[tid];
+            const uint32_t oa = w & 0xFFu, ob = w >> 8;
+            const bool fa = 2 * tid < n_g && (s_feas[oa] & active), fb = 2 * tid + 1 < n_g && (s_feas[ob] & active);
+            const uint32_t cnt = (fa ? 1u : 0u) + (fb ? 1u : 0u);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            uint32_t off = incl - cnt;
+            for (uint32_t x = 0; x < warp; ++x) off += s_warp[x];
+            if (fa) s_cand[off++] = ((2 * tid) << 8) | oa;
+            if (fb) s_cand[off++] = ((2 * tid + 1) << 8) | ob;
+            if (tid == kPipeThreads - 1) { s_ncand = off; for (uint32_t x = 0; x < 8; ++x) s_cand[off + x] = kInf; }   // sentinels: nothing fits
+        }
+        // 3. token of the previous segment
+        if (tid == 0 && seg > 0) {
+            const uint32_t* flag = a.tokens + ((size_t)c * a.n_seg + seg - 1) * kTokStride + ISL_MAX_PROFILES;
+            while (ld_acquire_gpu(flag) != a.epoch) { }
+        }
+        __syncthreads();
+        if (tid < ISL_MAX_PROFILES) {
+            uint32_t h;
+            if (seg > 0) h = __ldcg(a.tokens + ((size_t)c * a.n_seg + seg - 1) * kTokStride + tid);
+            else h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
+            const uint32_t qc = cc->qcnt[tid], left = qc > h ? qc - h : 0u;
+            uint32_t wn = min(left, s_ncand * s_maxacc[tid] + 2u);
+            wn = ((active >> tid) & 1u) ? min(wn, kWin) : 0u;
+            s_heads[tid] = h; s_wn[tid] = wn; s_pop[tid] = 0;
+            s_qsrc[tid] = c * kQCap + cc->qoff[tid] + h;
+        }
+        __syncthreads();
+        for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) {          // stage the queue windows this segment may pop
+            const uint32_t wn = s_wn[p];
+            const uint16_t* src = a.q_all + s_qsrc[p];
+            for (uint32_t i = tid; i < wn; i += kPipeThreads) s_win[p * kWin + i] = src[i];
+        }
+        __syncthreads();
+        if (warp == 0) {                    // 4. the decision chain (see k_chain)
+            const uint32_t n_cand = s_ncand;
+            uint32_t pos[K], wn[K], tcur[K], tnext[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                wn[k] = valid[k] ? s_wn[cprof[k]] : 0u;
+                pos[k] = 0;
+                const uint16_t* wq = s_win + cprof[k] * kWin;
+                tcur[k] = wn[k] > 0 ? ((uint32_t)wq[0] << 15) | keylow[k] : kInf;
+                tnext[k] = wn[k] > 1 ? ((uint32_t)wq[1] << 15) | keylow[k] : kInf;
+            }
+            uint32_t i0 = 0, nlog = 0;
+            uint32_t o0 = s_cand[0] & 0xFFu, o1 = s_cand[1] & 0xFFu, o2 = s_cand[2] & 0xFFu;
+            while (true) {
+                uint32_t key = kInf;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t kk = (o0 & cmask[k]) == 0 ? tcur[k] : ((o1 & cmask[k]) == 0 ? tcur[k] | 0x80000000u : kInf);
+                    key = min(key, kk);
+                }
+                const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, key);
+                if (m == kInf) {            // neither GPU takes anything: ballot to the next candidate a pending profile fits on
+                    uint32_t alive = 0;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) alive |= tcur[k] != kInf ? 1u << cprof[k] : 0u;
+                    alive = __reduce_or_sync(0xFFFFFFFFu, alive);
+                    uint32_t j = i0 + 2;
+                    bool found = false;
+                    while (alive && j < n_cand) {
+                        const uint32_t cr = j + lane < n_cand ? s_cand[j + lane] : kInf;
+                        const uint32_t b = __ballot_sync(0xFFFFFFFFu, cr != kInf && (s_feas[cr & 0xFFu] & alive) != 0);
+                        if (b) { j += __ffs(b) - 1; found = true; break; }
+                        j += 32;
+                    }
+                    ++st_jumps;
+                    if (!found) break;
+                    i0 = j;
+                    o0 = s_cand[i0] & 0xFFu; o1 = s_cand[i0 + 1] & 0xFFu; o2 = s_cand[i0 + 2] & 0xFFu;
+                    continue;
+                }
+                const uint32_t sel = m >> 31;
+                if (lane == 0) s_log[nlog] = make_uint2(m, i0 + sel);
+                ++nlog;
+                o0 = (sel ? o1 : o0) | (m & 0xFFu);
+                o1 = sel ? o2 : o1;
+                i0 += sel;
+                o2 = s_cand[i0 + 2] & 0xFFu;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {       // lanes of the winning profile pop their queue window
+                    const bool adv = ((m ^ tcur[k]) & 0x7FFFF800u) == 0 && tcur[k] != kInf;
+                    pos[k] += adv ? 1u : 0u;
+                    const bool more = pos[k] + 1 < wn[k];
+                    const uint32_t v = s_win[cprof[k] * kWin + (more ? pos[k] + 1 : 0u)];
+                    const uint32_t tn = more ? (v << 15) | keylow[k] : kInf;
+                    tcur[k] = adv ? tnext[k] : tcur[k];
+                    tnext[k] = adv ? tn : tnext[k];
+                }
+            }
+            st_steps += nlog; st_visited += i0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) if (reports[k]) s_pop[cprof[k]] = pos[k];
+            __syncwarp();
+            // 5. token for the next segment: heads first, then the flag (release)
+            uint32_t* tok = a.tokens + ((size_t)c * a.n_seg + seg) * kTokStride;
+            if (lane < ISL_MAX_PROFILES) {
+                const uint32_t h = s_heads[lane] + s_pop[lane];
+                tok[lane] = h;
+                if (seg == a.n_seg - 1 && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + lane] = h;
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence(); st_release_gpu(tok + ISL_MAX_PROFILES, a.epoch); s_nlog = nlog; }
+        }
+        __syncthreads();
+        {   // 6. commit
+            const uint32_t nlog = s_nlog;
+            for (uint32_t j = tid; j < nlog; j += kPipeThreads) {
+                const uint2 e = s_log[j];
+                const uint32_t l = s_cand[e.y] >> 8, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
+                a.out[cd.req_off + t] = pack_result(lo_s + l, __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
+                atomicOr(&s_occ32[l >> 2], mask << ((l & 3u) * 8u));
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = tid; i < n_g; i += kPipeThreads) a.occ[lo_s + i] = reinterpret_cast<uint8_t*>(s_occ32)[i];
+    if (tid == 0 && st_steps + st_jumps) {
+        atomicAdd(&a.stats->placed, st_steps);
+        atomicAdd(&a.stats->steps, st_steps);
+        atomicAdd(&a.stats->visited, st_visited);
+        atomicAdd(&a.stats->jumps, st_jumps);
+    }
 }
 
 }  // namespace isl

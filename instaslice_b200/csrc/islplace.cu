@@ -45,6 +45,13 @@ struct isl_engine {
     uint32_t* d_sweep_counts = nullptr;
     Ctrl* d_ctrl = nullptr;
     uint8_t* d_scratch = nullptr;    // eval_starts / free_batch staging
+    // stream / segment-pipeline state (grown on demand)
+    ChunkDesc* d_chunks = nullptr; Ctrl* d_cctl = nullptr; uint16_t* d_qall = nullptr; uint32_t* d_tokens = nullptr;
+    uint2* d_free_list = nullptr; uint32_t* d_free_off = nullptr; uint32_t* d_free_cnt = nullptr;
+    uint32_t cap_chunks = 0, cap_cctl = 0, cap_qall = 0, cap_batches = 0, cap_free_cnt = 0, cap_tokens = 0, cap_free = 0;
+    std::vector<ChunkDesc> h_chunks; std::vector<uint32_t> h_free_off;
+    uint32_t epoch = 0;
+    int max_coresident = 0;          // CTAs of k_pipeline that can be resident at once (0 = not queried)
     size_t scratch_bytes = 0;
 
     // stats
@@ -108,7 +115,7 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
     const uint32_t tiles = ceil_div(n, kTile);
     if (timing) cudaEventRecord(e->ev[0], e->stream);
     k_prepare<<<tiles, kTileThreads, 0, e->stream>>>(n, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi,
-                                                     e->prof, e->d_tile_counts, e->d_ctrl);
+                                                     e->prof, e->d_tile_counts, e->d_ctrl, nullptr, nullptr);
     if (int rc = check_launch(e, "k_prepare")) return rc;
     if (timing) cudaEventRecord(e->ev[1], e->stream);
     const uint32_t first_block = e->lo / kSweepBlock;
@@ -165,6 +172,141 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
     return ISL_OK;
 }
 
+
+template <int K>
+int launch_pipeline(isl_engine* e, PipeArgs& args) {
+    static bool attr_set[8] = {false};
+    if (!attr_set[e->device & 7]) {
+        ISL_CUDA(e, cudaFuncSetAttribute(k_pipeline<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+        attr_set[e->device & 7] = true;
+    }
+    void* params[] = {&e->tab, &args};
+    ISL_CUDA(e, cudaLaunchCooperativeKernel((void*)k_pipeline<K>, dim3(args.n_seg), dim3(kPipeThreads), params, kPipeSmem, e->stream));
+    ++e->st.kernel_launches;
+    return ISL_OK;
+}
+
+int query_coresident(isl_engine* e) {
+    if (e->max_coresident) return ISL_OK;
+    int per_sm = 0, sms = 0, coop = 0;
+    ISL_CUDA(e, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
+    ISL_CUDA(e, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+    ISL_CUDA(e, cudaFuncSetAttribute(k_pipeline<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+    ISL_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline<1>, kPipeThreads, kPipeSmem));
+    e->max_coresident = coop ? std::max(1, per_sm * sms) : -1;
+    return ISL_OK;
+}
+
+template <typename T>
+int grow(isl_engine* e, T** buf, uint32_t* cap, size_t need, size_t elems_per_unit) {
+    if (need <= *cap) return ISL_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *cap = 0;
+    const size_t units = need + need / 4 + 1;
+    ISL_CUDA(e, cudaMalloc(buf, units * elems_per_unit * sizeof(T)));
+    *cap = (uint32_t)units;
+    return ISL_OK;
+}
+
+// Resolve a stream of batches (semantics: one batch after the other).  Enqueues only.
+int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const uint2* d_in, uint2* d_out,
+               const uint32_t* d_heads_in, uint32_t* d_heads_out) {
+    uint64_t total = 0;
+    uint32_t n_chunks = 0;
+    for (uint32_t b = 0; b < n_batches; ++b) { total += sizes[b]; n_chunks += ceil_div(sizes[b], kChunk); }
+    if (total == 0) return ISL_OK;
+    if (total > e->cfg.max_batch) return ISL_ERANGE;
+    const uint32_t range = e->hi - e->lo;
+    bool pipeline = !(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE));
+    uint32_t seg = 0, n_seg = 0;
+    if (pipeline) {
+        if (int rc = query_coresident(e)) return rc;
+        seg = std::min(kSegMax, std::max(64u, (ceil_div(range, 128u) + 63u) / 64u * 64u));
+        n_seg = ceil_div(range, seg);
+        if (e->max_coresident <= 0 || n_seg > (uint32_t)e->max_coresident) pipeline = false;
+    }
+    if (!pipeline) {       // one batch after the other through the single-chain path
+        uint64_t off = 0;
+        uint32_t hoff = 0;
+        for (uint32_t b = 0; b < n_batches; ++b) {
+            if (int rc = run_batch(e, sizes[b], d_in + off, d_out + off, d_heads_in ? d_heads_in + hoff : nullptr, d_heads_out ? d_heads_out + hoff : nullptr)) return rc;
+            off += sizes[b]; hoff += ceil_div(sizes[b], kChunk) * ISL_MAX_PROFILES;
+        }
+        return ISL_OK;
+    }
+    const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
+    // chunk table: batches are cut into chunks of <= kChunk requests; FREEs belong to the first chunk of their batch
+    e->h_chunks.clear(); e->h_free_off.clear();
+    uint32_t off = 0;
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        e->h_free_off.push_back(off);
+        for (uint32_t c0 = 0; c0 < sizes[b]; c0 += kChunk)
+            e->h_chunks.push_back(ChunkDesc{off + c0, std::min(kChunk, sizes[b] - c0), b, c0 == 0 ? 1u : 0u});
+        off += sizes[b];
+    }
+    n_chunks = (uint32_t)e->h_chunks.size();
+    if (int rc = grow(e, &e->d_chunks, &e->cap_chunks, n_chunks, 1)) return rc;
+    if (int rc = grow(e, &e->d_cctl, &e->cap_cctl, n_chunks, 1)) return rc;
+    if (int rc = grow(e, &e->d_qall, &e->cap_qall, n_chunks, kQCap)) return rc;
+    if (int rc = grow(e, &e->d_free_off, &e->cap_batches, n_batches, 1)) return rc;
+    if (int rc = grow(e, &e->d_free_cnt, &e->cap_free_cnt, n_batches, 1)) return rc;
+    if (int rc = grow(e, &e->d_free_list, &e->cap_free, (size_t)total, 1)) return rc;
+    {   // token flags carry the call epoch: a (re)allocated buffer must not hold stale flags of an earlier owner
+        const uint32_t before = e->cap_tokens;
+        if (int rc = grow(e, &e->d_tokens, &e->cap_tokens, (size_t)n_chunks * n_seg, kTokStride)) return rc;
+        if (e->cap_tokens != before) ISL_CUDA(e, cudaMemsetAsync(e->d_tokens, 0, (size_t)e->cap_tokens * kTokStride * sizeof(uint32_t), e->stream));
+    }
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_chunks, e->h_chunks.data(), n_chunks * sizeof(ChunkDesc), cudaMemcpyHostToDevice, e->stream));
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_free_off, e->h_free_off.data(), n_batches * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    ISL_CUDA(e, cudaMemsetAsync(e->d_free_cnt, 0, n_batches * sizeof(uint32_t), e->stream));
+    if (timing) cudaEventRecord(e->ev[0], e->stream);
+    uint32_t tile_off = 0;
+    std::vector<uint32_t> batch_tile(n_batches);
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        batch_tile[b] = tile_off;
+        if (sizes[b] == 0) continue;
+        const uint32_t tiles = ceil_div(sizes[b], kTile);
+        k_prepare<<<tiles, kTileThreads, 0, e->stream>>>(sizes[b], d_in + e->h_free_off[b], d_out + e->h_free_off[b], reinterpret_cast<uint32_t*>(e->d_occ),
+                                                         e->G, e->lo, e->hi, e->prof, e->d_tile_counts + (size_t)tile_off * ISL_MAX_PROFILES, e->d_ctrl,
+                                                         e->d_free_list + e->h_free_off[b], e->d_free_cnt + b);
+        if (int rc = check_launch(e, "k_prepare")) return rc;
+        tile_off += tiles;
+    }
+    if (timing) cudaEventRecord(e->ev[1], e->stream);
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const ChunkDesc& cd = e->h_chunks[c];
+        const uint32_t first_tile = batch_tile[cd.batch] + (cd.req_off - e->h_free_off[cd.batch]) / kTile, n_tiles = ceil_div(cd.n, kTile);
+        k_partition<<<n_tiles, kTileThreads, 0, e->stream>>>(cd.n, d_in + cd.req_off, e->prof.n, e->d_tile_counts + (size_t)first_tile * ISL_MAX_PROFILES, n_tiles,
+                                                             e->cand_profiles, e->d_qall + (size_t)c * kQCap, e->d_cctl + c);
+        if (int rc = check_launch(e, "k_partition")) return rc;
+    }
+    if (timing) cudaEventRecord(e->ev[2], e->stream);
+    PipeArgs args{};
+    args.n_chunks = n_chunks; args.n_seg = n_seg; args.seg = seg; args.lo = e->lo; args.hi = e->hi; args.epoch = ++e->epoch;
+    args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_list = e->d_free_list; args.free_off = e->d_free_off;
+    args.free_cnt = e->d_free_cnt; args.tokens = e->d_tokens; args.occ = e->d_occ; args.out = d_out; args.feas = e->d_feas; args.stats = e->d_ctrl;
+    args.heads_in = d_heads_in; args.heads_out = d_heads_out;
+    int rc;
+    switch (e->n_cand_slots) {
+        case 1: rc = launch_pipeline<1>(e, args); break;
+        case 2: rc = launch_pipeline<2>(e, args); break;
+        default: rc = launch_pipeline<4>(e, args); break;
+    }
+    if (rc) return rc;
+    if (timing) {
+        cudaEventRecord(e->ev[3], e->stream);
+        cudaEventSynchronize(e->ev[3]);
+        float t;
+        cudaEventElapsedTime(&t, e->ev[0], e->ev[1]); e->st.ms_free += t;
+        cudaEventElapsedTime(&t, e->ev[1], e->ev[2]); e->st.ms_partition += t;
+        cudaEventElapsedTime(&t, e->ev[2], e->ev[3]); e->st.ms_commit += t;
+        cudaEventElapsedTime(&t, e->ev[0], e->ev[3]); e->st.ms_total += t;
+    }
+    e->st.batches += n_batches;
+    e->st.requests += total;
+    return ISL_OK;
+}
+
 int validate_ready(isl_engine* e, uint32_t n) {
     if (!e->have_profiles || !e->have_inventory) return ISL_ESTATE;
     if (n > e->cfg.max_batch) return ISL_ERANGE;
@@ -213,7 +355,7 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
     ISL_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->own_stream = true;
     e->occ_bytes = ((size_t)cfg->max_gpus + kSweepBlock - 1) / kSweepBlock * kSweepBlock;
-    const uint32_t max_tiles = ceil_div(cfg->max_batch, kTile);
+    const uint32_t max_tiles = ceil_div(cfg->max_batch, kTile) + 4096;   // + one partial tile per batch of a stream
     ISL_TRY(cudaMalloc(&e->d_occ, e->occ_bytes));
     ISL_TRY(cudaMalloc(&e->d_lut, ISL_MAX_PROFILES * 256));
     ISL_TRY(cudaMalloc(&e->d_feas, 256 * sizeof(uint16_t)));
@@ -241,6 +383,8 @@ int isl_destroy(isl_engine* e) {
         cudaFree(e->d_occ); cudaFree(e->d_lut); cudaFree(e->d_feas); cudaFree(e->d_req); cudaFree(e->d_res);
         cudaFree(e->d_q); cudaFree(e->d_tile_counts); cudaFree(e->d_cand); cudaFree(e->d_log); cudaFree(e->d_sweep_counts);
         cudaFree(e->d_ctrl); cudaFree(e->d_scratch);
+        cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens);
+        cudaFree(e->d_free_list); cudaFree(e->d_free_off); cudaFree(e->d_free_cnt);
         for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
         if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     }
@@ -345,10 +489,38 @@ int isl_place_batch(isl_engine* e, uint32_t n, const isl_request* in, isl_result
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
     ISL_CUDA(e, cudaMemcpyAsync(e->d_req, in, (size_t)n * sizeof(isl_request), cudaMemcpyHostToDevice, e->stream));
-    if (int rc = run_batch(e, n, e->d_req, e->d_res, nullptr, nullptr)) return rc;
+    if (int rc = run_stream(e, 1, &n, e->d_req, e->d_res, nullptr, nullptr)) return rc;
     ISL_CUDA(e, cudaMemcpyAsync(out, e->d_res, (size_t)n * sizeof(isl_result), cudaMemcpyDeviceToHost, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     return ISL_OK;
+}
+
+int isl_place_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const isl_request* in, isl_result* out) {
+    if (!e || !sizes || n_batches == 0 || n_batches > 4096) return ISL_EINVAL;
+    uint64_t total = 0;
+    for (uint32_t b = 0; b < n_batches; ++b) total += sizes[b];
+    if (total && (!in || !out)) return ISL_EINVAL;
+    if (total > e->cfg.max_batch) return ISL_ERANGE;
+    if (int rc = validate_ready(e, (uint32_t)total)) return rc;
+    if (total == 0) return ISL_OK;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_req, in, (size_t)total * sizeof(isl_request), cudaMemcpyHostToDevice, e->stream));
+    if (int rc = run_stream(e, n_batches, sizes, e->d_req, e->d_res, nullptr, nullptr)) return rc;
+    ISL_CUDA(e, cudaMemcpyAsync(out, e->d_res, (size_t)total * sizeof(isl_result), cudaMemcpyDeviceToHost, e->stream));
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ISL_OK;
+}
+
+int isl_place_stream_device(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const void* d_in, void* d_out) {
+    if (!e || !sizes || n_batches == 0 || n_batches > 4096 || !d_in || !d_out) return ISL_EINVAL;
+    uint64_t total = 0;
+    for (uint32_t b = 0; b < n_batches; ++b) total += sizes[b];
+    if (total > e->cfg.max_batch) return ISL_ERANGE;
+    if (int rc = validate_ready(e, (uint32_t)total)) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    return run_stream(e, n_batches, sizes, static_cast<const uint2*>(d_in), static_cast<uint2*>(d_out), nullptr, nullptr);
 }
 
 int isl_place_batch_device(isl_engine* e, uint32_t n, const void* d_in, void* d_out) {
@@ -356,7 +528,7 @@ int isl_place_batch_device(isl_engine* e, uint32_t n, const void* d_in, void* d_
     if (int rc = validate_ready(e, n)) return rc;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
-    return run_batch(e, n, static_cast<const uint2*>(d_in), static_cast<uint2*>(d_out), nullptr, nullptr);
+    return run_stream(e, 1, &n, static_cast<const uint2*>(d_in), static_cast<uint2*>(d_out), nullptr, nullptr);
 }
 
 int isl_place_batch_partitioned(isl_engine* e, uint32_t n, const void* d_in, void* d_out, const void* d_heads_in, void* d_heads_out) {
@@ -364,8 +536,8 @@ int isl_place_batch_partitioned(isl_engine* e, uint32_t n, const void* d_in, voi
     if (int rc = validate_ready(e, n)) return rc;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
-    return run_batch(e, n, static_cast<const uint2*>(d_in), static_cast<uint2*>(d_out), static_cast<const uint32_t*>(d_heads_in),
-                     static_cast<uint32_t*>(d_heads_out));
+    return run_stream(e, 1, &n, static_cast<const uint2*>(d_in), static_cast<uint2*>(d_out), static_cast<const uint32_t*>(d_heads_in),
+                      static_cast<uint32_t*>(d_heads_out));
 }
 
 int isl_set_partition(isl_engine* e, uint32_t lo, uint32_t hi) {

@@ -27,7 +27,7 @@ QUIRK_STRICT_BOUND, QUIRK_POW2_ONLY = 1, 2
 QUIRKS_REF_EXACT, QUIRKS_FIXED = 3, 0
 OP_ALLOC, OP_FREE, OP_NOOP = 0, 1, 2
 ST_PLACED, ST_NO_CAPACITY, ST_BAD_PROFILE, ST_FREED, ST_BAD_SPAN, ST_NOOP = 0, 1, 2, 3, 4, 5
-FLAG_TIMING = 1
+FLAG_TIMING, FLAG_NO_PIPELINE, FLAG_FORCE_PIPELINE = 1, 2, 4
 
 # ---- record layouts -------------------------------------------------------------------------
 REQUEST_DTYPE = np.dtype([("handle", "<u4"), ("profile", "u1"), ("op", "u1"), ("start", "u1"), ("size", "u1")])
@@ -57,7 +57,7 @@ class Stats(C.Structure):
 # every symbol include/islplace.h declares; tests check that the library exports all of them
 EXPORTED_SYMBOLS = [
     "isl_create", "isl_destroy", "isl_set_stream", "isl_synchronize", "isl_load_profiles", "isl_load_inventory", "isl_read_occupancy",
-    "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_free_batch",
+    "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_place_stream", "isl_place_stream_device", "isl_free_batch",
     "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_device_occupancy", "isl_get_stats",
     "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
 ]
@@ -86,6 +86,8 @@ def load_library(path: str = LIB_PATH):
         "isl_gpu_to_node": (C.c_uint32, [p, C.c_uint32]),
         "isl_place_batch": (C.c_int, [p, C.c_uint32, p, p]),
         "isl_place_batch_device": (C.c_int, [p, C.c_uint32, p, p]),
+        "isl_place_stream": (C.c_int, [p, C.c_uint32, p, p, p]),
+        "isl_place_stream_device": (C.c_int, [p, C.c_uint32, p, p, p]),
         "isl_free_batch": (C.c_int, [p, C.c_uint32, p]),
         "isl_eval_starts": (C.c_int, [p, C.c_uint32, C.c_uint32, p, p]),
         "isl_set_partition": (C.c_int, [p, C.c_uint32, C.c_uint32]),
@@ -133,9 +135,9 @@ class Engine:
     """One placement engine on one B200 (thin, 1:1 over the C ABI)."""
 
     def __init__(self, max_gpus: int, max_batch: int, policy: int = POLICY_FIRST_FIT, quirks: int = QUIRKS_REF_EXACT,
-                 device: int = -1, timing: bool = False):
+                 device: int = -1, timing: bool = False, flags: int = 0):
         self._lib = load_library()
-        cfg = Config(ABI_VERSION, policy, quirks, device, max_gpus, max_batch, FLAG_TIMING if timing else 0, 0)
+        cfg = Config(ABI_VERSION, policy, quirks, device, max_gpus, max_batch, (FLAG_TIMING if timing else 0) | flags, 0)
         h = C.c_void_p()
         rc = self._lib.isl_create(C.byref(cfg), C.byref(h))
         if rc != OK:
@@ -197,6 +199,19 @@ class Engine:
             out = np.empty(len(requests), dtype=RESULT_DTYPE)
         self._check(self._lib.isl_place_batch(self._h, len(requests), _ptr(requests), _ptr(out)), "isl_place_batch")
         return out
+
+    def place_stream(self, batches: list) -> list:
+        """A stream of batches in one call (host buffers); same results as place_batch per batch, pipelined on the device."""
+        sizes = np.array([len(b) for b in batches], dtype=np.uint32)
+        req = np.ascontiguousarray(np.concatenate(batches) if len(batches) else np.zeros(0, dtype=REQUEST_DTYPE), dtype=REQUEST_DTYPE)
+        out = np.empty(len(req), dtype=RESULT_DTYPE)
+        self._check(self._lib.isl_place_stream(self._h, len(sizes), _ptr(sizes), _ptr(req), _ptr(out)), "isl_place_stream")
+        return np.split(out, np.cumsum(sizes)[:-1]) if len(sizes) else []
+
+    def place_stream_ptr(self, sizes: np.ndarray, in_ptr: int, out_ptr: int, device: bool):
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
+        fn = self._lib.isl_place_stream_device if device else self._lib.isl_place_stream
+        self._check(fn(self._h, len(sizes), _ptr(sizes), C.c_void_p(in_ptr), C.c_void_p(out_ptr)), "isl_place_stream")
 
     def place_batch_ptr(self, n: int, in_ptr: int, out_ptr: int):
         """Host buffers by raw address (pinned torch tensors in the bench)."""

@@ -23,22 +23,32 @@ def load(name):
         return json.load(f)
 
 
-def make_engine(node_off, occ, rows, quirks=E.QUIRKS_REF_EXACT, max_batch=1 << 20):
-    eng = E.Engine(max_gpus=max(4096, len(occ)), max_batch=max_batch, quirks=quirks)
+def make_engine(node_off, occ, rows, quirks=E.QUIRKS_REF_EXACT, max_batch=1 << 20, flags=0):
+    eng = E.Engine(max_gpus=max(4096, len(occ)), max_batch=max_batch, quirks=quirks, flags=flags)
     eng.load_profiles(rows)
     eng.load_inventory(node_off, occ)
     return eng
 
 
 def check_against_fast(node_off, occ, rows, batches, quirks=E.QUIRKS_REF_EXACT):
-    eng = make_engine(node_off, occ, rows, quirks)
+    """Every batch through both device paths (single chain, forced segment pipeline) and as ONE stream call."""
     ref = oracle.Fast(node_off, rows, quirks)
     ref.load(occ)
-    for i, req in enumerate(batches):
-        got, want = eng.place_batch(req), ref.place(req)
-        bad = np.flatnonzero(got != want)
-        assert len(bad) == 0, (i, bad[:5], got[bad[:5]], want[bad[:5]], req[bad[:5]])
-        assert np.array_equal(eng.read_occupancy(), ref.occupancy()), i
+    want = [ref.place(req) for req in batches]
+    final = ref.occupancy()
+    for flags in (E.FLAG_NO_PIPELINE, E.FLAG_FORCE_PIPELINE):
+        eng = make_engine(node_off, occ, rows, quirks, flags=flags)
+        for i, req in enumerate(batches):
+            got = eng.place_batch(req)
+            bad = np.flatnonzero(got != want[i])
+            assert len(bad) == 0, (flags, i, bad[:5], got[bad[:5]], want[i][bad[:5]], req[bad[:5]])
+        assert np.array_equal(eng.read_occupancy(), final), flags
+    eng = make_engine(node_off, occ, rows, quirks)
+    got = eng.place_stream(batches)
+    for i, (g, w) in enumerate(zip(got, want)):
+        bad = np.flatnonzero(g != w)
+        assert len(bad) == 0, ("stream", i, bad[:5], g[bad[:5]], w[bad[:5]])
+    assert np.array_equal(eng.read_occupancy(), final)
     return eng
 
 
@@ -161,9 +171,10 @@ def test_regress_crd_batched_equals_pod_by_pod():
 
 
 # ---- randomised parity, edge cases ------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [E.FLAG_NO_PIPELINE, E.FLAG_FORCE_PIPELINE])
 @pytest.mark.parametrize("quirks", [3, 0])
 @pytest.mark.parametrize("tname", ["a100-40gb", "h100-80gb"])
-def test_random_occupancy_and_frees(tname, quirks):
+def test_random_occupancy_and_frees(tname, quirks, flags):
     table = tables.TABLES[tname]
     rows = E.make_profiles(table)
     rng = W.SplitMix64(31 + quirks)
@@ -172,7 +183,7 @@ def test_random_occupancy_and_frees(tname, quirks):
         node_off = np.concatenate([[0], np.cumsum(1 + (rng.next(n_nodes) % np.uint64(9)).astype(np.int64))]).astype(np.uint32)
         G = int(node_off[-1])
         occ = ((rng.next(G) & rng.next(G)) & np.uint64(0xFF)).astype(np.uint8)
-        eng = make_engine(node_off, occ, rows, quirks)
+        eng = make_engine(node_off, occ, rows, quirks, flags=flags)
         ref = oracle.Fast(node_off, rows, quirks)
         ref.load(occ)
         live = []
@@ -314,6 +325,14 @@ def test_config4_churn_full_size():
     eng2 = make_engine(ch.node_off, np.zeros(ch.G, dtype=np.uint8), ch.rows)
     for req, res in zip(batches, results):
         assert np.array_equal(eng2.place_batch(req), res)
+    # the whole recorded run as ONE stream call through the segment pipeline: identical, byte for byte
+    eng3 = make_engine(ch.node_off, np.zeros(ch.G, dtype=np.uint8), ch.rows, max_batch=2 << 20)
+    got = eng3.place_stream(batches)
+    for i, (g, res) in enumerate(zip(got, results)):
+        assert np.array_equal(g, res), i
+    assert np.array_equal(eng3.read_occupancy(), occ)
+    st = eng3.stats()
+    assert st["placed"] == sum(int(((r["status"] == E.ST_PLACED) & (q["op"] == E.OP_ALLOC)).sum()) for q, r in zip(batches, results))
 
 
 def test_device_resident_entry_point_matches_host_entry_point():
