@@ -174,31 +174,32 @@ def run_own(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
     if world > 1:
-        lo, hi = rank * G // world, (rank + 1) * G // world
+        from instaslice_b200 import dist as D
+        lo, hi = D.partition_bounds(G, world, rank)
         eng.set_partition(lo, hi)
-        heads = [torch.zeros((-(-len(b) // 65536)) * 16, dtype=torch.int32, device="cuda") for b in batches]
-        heads_in = [torch.zeros_like(h) for h in heads]
-        gathered = torch.empty(G, dtype=torch.uint8, device="cuda")
+        D.connect_ring(eng, rank, world)          # next rank's token inbox mapped through CUDA IPC (peer store over NVLink)
+        stream_ids = iter(range(1, 1 << 30))
 
     def step_device():
         occ_view.copy_(d_occ0)
         if world == 1:      # ONE call for the stream of batches: the engine pipelines them over inventory segments
             eng.place_stream_ptr(sizes, d_in_all.data_ptr(), d_out_all.data_ptr(), device=True)
             return
-        for i, (b, t_in, t_out) in enumerate(zip(batches, d_in, d_out)):
-            if rank > 0:
-                dist.recv(heads_in[i], src=rank - 1)
-            eng.place_batch_partitioned(len(b), t_in.data_ptr(), t_out.data_ptr(), heads_in[i].data_ptr() if rank > 0 else None, heads[i].data_ptr())
-            if rank < world - 1:
-                dist.send(heads[i], dst=rank + 1)
-        for t_out in d_out:                                    # global answer = elementwise MIN over the ranks' records
-            dist.all_reduce(t_out, op=dist.ReduceOp.MIN)
-        dist.all_gather_into_tensor(gathered, occ_view[lo:hi].contiguous())
-        occ_view.copy_(gathered)
+        # every rank runs the segment pipeline over its own GPU range; tokens cross ranks inside the running kernels
+        eng.place_stream_partitioned(sizes, d_in_all.data_ptr(), d_out_all.data_ptr(), next(stream_ids))
+        D.merge_results(d_out_all)                                        # NCCL all-reduce(MIN) of the 8-byte records
+        occ_view.copy_(D.gather_occupancy(occ_view[lo:hi], G, world, rank))   # NCCL all-gather of the occupancy shards
 
-    def step_e2e():         # pinned host buffers in, pinned host buffers out: H2D + kernels + D2H inside the call
+    def step_e2e():         # pinned host buffers in, pinned host buffers out: H2D + kernels + D2H inside the timed region
         occ_view.copy_(d_occ0)
-        eng.place_stream_ptr(sizes, h_in_all.data_ptr(), h_out_all.data_ptr(), device=False)
+        if world == 1:
+            eng.place_stream_ptr(sizes, h_in_all.data_ptr(), h_out_all.data_ptr(), device=False)
+            return
+        d_in_all.copy_(h_in_all, non_blocking=True)                       # every rank stages the request stream
+        eng.place_stream_partitioned(sizes, d_in_all.data_ptr(), d_out_all.data_ptr(), next(stream_ids))
+        D.merge_results(d_out_all)
+        occ_view.copy_(D.gather_occupancy(occ_view[lo:hi], G, world, rank))
+        h_out_all.copy_(d_out_all, non_blocking=True)                     # merged results back to the host
 
     def timed(step_fn, steps, warmup, flush_l2=True):
         for _ in range(warmup):
@@ -237,6 +238,11 @@ def run_own(args):
     parity = all(np.array_equal(a, b) for a, b in zip(got, want))
 
     e2e = None
+    if world > 1:
+        ms_e2e = timed(step_e2e, args.steps, args.warmup)
+        parity = parity and all(np.array_equal(t.numpy().view(E.RESULT_DTYPE), b) for t, b in zip(h_out, want))
+        e2e = {"value": n_ops * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n_ops * world, "d2h_bytes_per_step": 8 * n_ops * world,
+               "ms_per_step": ms_e2e / args.steps, "api": "isl_place_stream_partitioned per rank + NCCL merge; every rank copies the stream in and the merged results out"}
     if world == 1:
         ms_e2e = timed(step_e2e, args.steps, args.warmup)
         parity = parity and all(np.array_equal(t.numpy().view(E.RESULT_DTYPE), b) for t, b in zip(h_out, want))
@@ -290,7 +296,7 @@ def run_own(args):
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "ops_per_step": n_ops, "batches_per_step": len(batches), "gpus_in_inventory": G,
                            "policy": "first-fit", "quirks": "REF_EXACT",
-                           "parallelism": "single" if world == 1 else "inventory partitioned over %d ranks, token chain + all-gather" % world,
+                           "parallelism": "segment pipeline, 1 GPU" if world == 1 else "inventory partitioned over %d ranks: peer-memory token ring + NCCL all-reduce(MIN) of results + NCCL all-gather of occupancy" % world,
                            "l2": "flushed between timed steps (256 MiB write)", "timing": "cuda events per step, max over ranks"},
                 "parity": "bit-exact vs recorded single-GPU results" if parity else "MISMATCH",
                 "gpu_launches": int(launches), "clocks": clocks}

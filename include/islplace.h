@@ -214,6 +214,19 @@ int  isl_set_partition(isl_engine* e, uint32_t lo, uint32_t hi);
  * 8-byte records (as little-endian uint64) yields the global answer. */
 int  isl_place_batch_partitioned(isl_engine* e, uint32_t n, const void* d_in, void* d_out,
                                  const void* d_heads_in, void* d_heads_out);
+/* Stream variant for a partitioned inventory, one engine (process, GPU) per rank, ranks ordered by GPU range.
+ * The queue-head token of every chunk crosses from the last segment of rank d to the first segment of rank d+1
+ * through rank d+1's inbox, mapped into rank d with CUDA IPC (a peer store over NVLink inside the running kernel):
+ *   1. every rank:  isl_ipc_inbox_handle(e, h)             -> 64-byte handle, exchanged by the caller (e.g. all_gather)
+ *   2. every rank:  isl_ipc_connect(e, next rank's handle or NULL for the last rank, has_prev)
+ *   3. every rank:  isl_place_stream_partitioned(..., stream_id) with the same batches and the same non-zero,
+ *      never repeated stream_id; only enqueues.  Results: element-wise MIN over ranks as for the batch variant. */
+int  isl_ipc_inbox_handle(isl_engine* e, void* handle64);
+int  isl_ipc_connect(isl_engine* e, const void* next_handle64, int has_prev);
+/* Same wiring for two engines of ONE process (same device or peer-enabled devices): no IPC handle needed. */
+int  isl_connect_local(isl_engine* e, isl_engine* next, int has_prev);
+int  isl_place_stream_partitioned(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const void* d_in, void* d_out,
+                                  uint32_t stream_id);
 /* Device address of the occupancy bytes owned by this engine (for the NCCL all-gather). */
 void* isl_device_occupancy(isl_engine* e);
 

@@ -549,6 +549,10 @@ struct PipeArgs {
     Ctrl* stats;
     const uint32_t* heads_in;       // [chunk][16] token entering the first segment (nullptr = zeros)
     uint32_t* heads_out;            // [chunk][16] token leaving the last segment (may be nullptr)
+    // partitioned inventory: the token crosses GPUs through peer-mapped memory (NVLink), system-scope release/acquire
+    const uint32_t* inbox;          // local [chunk][kTokStride], written by the previous rank's last segment (nullptr = first rank)
+    uint32_t* outbox;               // the next rank's inbox, peer-mapped (nullptr = last rank)
+    uint32_t xepoch;                // stream id shared by all ranks
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -558,6 +562,19 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 template <int K>
@@ -628,14 +645,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             if (tid == kPipeThreads - 1) { s_ncand = off; for (uint32_t x = 0; x < 8; ++x) s_cand[off + x] = kInf; }   // sentinels: nothing fits
         }
         // 3. token of the previous segment
-        if (tid == 0 && seg > 0) {
-            const uint32_t* flag = a.tokens + ((size_t)c * a.n_seg + seg - 1) * kTokStride + ISL_MAX_PROFILES;
-            while (ld_acquire_gpu(flag) != a.epoch) { }
+        if (tid == 0) {
+            if (seg > 0) {
+                const uint32_t* flag = a.tokens + ((size_t)c * a.n_seg + seg - 1) * kTokStride + ISL_MAX_PROFILES;
+                while (ld_acquire_gpu(flag) != a.epoch) { }
+            } else if (a.inbox) {       // first segment of a rank that has a predecessor: the token comes over NVLink
+                const uint32_t* flag = a.inbox + (size_t)c * kTokStride + ISL_MAX_PROFILES;
+                while (ld_acquire_sys(flag) != a.xepoch) { }
+            }
         }
         __syncthreads();
         if (tid < ISL_MAX_PROFILES) {
             uint32_t h;
             if (seg > 0) h = __ldcg(a.tokens + ((size_t)c * a.n_seg + seg - 1) * kTokStride + tid);
+            else if (a.inbox) h = ld_relaxed_sys(a.inbox + (size_t)c * kTokStride + tid);
             else h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
             const uint32_t qc = cc->qcnt[tid], left = qc > h ? qc - h : 0u;
             uint32_t wn = min(left, s_ncand * s_maxacc[tid] + 2u);
@@ -714,13 +737,21 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             __syncwarp();
             // 5. token for the next segment: heads first, then the flag (release)
             uint32_t* tok = a.tokens + ((size_t)c * a.n_seg + seg) * kTokStride;
+            const bool last = seg == a.n_seg - 1;
+            uint32_t* peer = last && a.outbox ? a.outbox + (size_t)c * kTokStride : nullptr;
             if (lane < ISL_MAX_PROFILES) {
                 const uint32_t h = s_heads[lane] + s_pop[lane];
                 tok[lane] = h;
-                if (seg == a.n_seg - 1 && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + lane] = h;
+                if (last && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + lane] = h;
+                if (peer) peer[lane] = h;
             }
             __syncwarp();
-            if (lane == 0) { __threadfence(); st_release_gpu(tok + ISL_MAX_PROFILES, a.epoch); s_nlog = nlog; }
+            if (lane == 0) {
+                __threadfence();
+                st_release_gpu(tok + ISL_MAX_PROFILES, a.epoch);
+                if (peer) { __threadfence_system(); st_release_sys(peer + ISL_MAX_PROFILES, a.xepoch); }
+                s_nlog = nlog;
+            }
         }
         __syncthreads();
         {   // 6. commit

@@ -14,6 +14,8 @@
 
 using namespace isl;
 
+static constexpr uint32_t kMaxStreamChunks = 4096;
+
 struct isl_engine {
     isl_config cfg{};
     int device = 0;
@@ -51,6 +53,9 @@ struct isl_engine {
     uint32_t cap_chunks = 0, cap_cctl = 0, cap_qall = 0, cap_batches = 0, cap_free_cnt = 0, cap_tokens = 0, cap_free = 0;
     std::vector<ChunkDesc> h_chunks; std::vector<uint32_t> h_free_off;
     uint32_t epoch = 0;
+    uint32_t* d_inbox = nullptr;      // [kMaxStreamChunks][kTokStride] tokens written by the previous rank (peer store)
+    uint32_t* d_outbox = nullptr;     // next rank's inbox, opened through CUDA IPC
+    bool has_prev = false, outbox_local = false;
     int max_coresident = 0;          // CTAs of k_pipeline that can be resident at once (0 = not queried)
     size_t scratch_bytes = 0;
 
@@ -210,20 +215,22 @@ int grow(isl_engine* e, T** buf, uint32_t* cap, size_t need, size_t elems_per_un
 
 // Resolve a stream of batches (semantics: one batch after the other).  Enqueues only.
 int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const uint2* d_in, uint2* d_out,
-               const uint32_t* d_heads_in, uint32_t* d_heads_out) {
+               const uint32_t* d_heads_in, uint32_t* d_heads_out, uint32_t xepoch = 0) {
     uint64_t total = 0;
     uint32_t n_chunks = 0;
     for (uint32_t b = 0; b < n_batches; ++b) { total += sizes[b]; n_chunks += ceil_div(sizes[b], kChunk); }
     if (total == 0) return ISL_OK;
     if (total > e->cfg.max_batch) return ISL_ERANGE;
     const uint32_t range = e->hi - e->lo;
-    bool pipeline = !(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE));
+    const bool ring = xepoch != 0;      // partitioned inventory: tokens cross ranks through peer memory, pipeline mandatory
+    if (ring && n_chunks > kMaxStreamChunks) return ISL_ERANGE;
+    bool pipeline = ring || (!(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE)));
     uint32_t seg = 0, n_seg = 0;
     if (pipeline) {
         if (int rc = query_coresident(e)) return rc;
         seg = std::min(kSegMax, std::max(64u, (ceil_div(range, 128u) + 63u) / 64u * 64u));
-        n_seg = ceil_div(range, seg);
-        if (e->max_coresident <= 0 || n_seg > (uint32_t)e->max_coresident) pipeline = false;
+        n_seg = std::max(1u, ceil_div(range, seg));
+        if (e->max_coresident <= 0 || n_seg > (uint32_t)e->max_coresident) { if (ring) return ISL_ERANGE; pipeline = false; }
     }
     if (!pipeline) {       // one batch after the other through the single-chain path
         uint64_t off = 0;
@@ -286,6 +293,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_list = e->d_free_list; args.free_off = e->d_free_off;
     args.free_cnt = e->d_free_cnt; args.tokens = e->d_tokens; args.occ = e->d_occ; args.out = d_out; args.feas = e->d_feas; args.stats = e->d_ctrl;
     args.heads_in = d_heads_in; args.heads_out = d_heads_out;
+    args.inbox = ring && e->has_prev ? e->d_inbox : nullptr; args.outbox = ring ? e->d_outbox : nullptr; args.xepoch = xepoch;
     int rc;
     switch (e->n_cand_slots) {
         case 1: rc = launch_pipeline<1>(e, args); break;
@@ -385,6 +393,8 @@ int isl_destroy(isl_engine* e) {
         cudaFree(e->d_ctrl); cudaFree(e->d_scratch);
         cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens);
         cudaFree(e->d_free_list); cudaFree(e->d_free_off); cudaFree(e->d_free_cnt);
+        if (e->d_outbox && !e->outbox_local) cudaIpcCloseMemHandle(e->d_outbox);
+        cudaFree(e->d_inbox);
         for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
         if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     }
@@ -521,6 +531,64 @@ int isl_place_stream_device(isl_engine* e, uint32_t n_batches, const uint32_t* s
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
     return run_stream(e, n_batches, sizes, static_cast<const uint2*>(d_in), static_cast<uint2*>(d_out), nullptr, nullptr);
+}
+
+int isl_ipc_inbox_handle(isl_engine* e, void* handle64) {
+    if (!e || !handle64) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    if (!e->d_inbox) {
+        ISL_CUDA(e, cudaMalloc(&e->d_inbox, (size_t)kMaxStreamChunks * kTokStride * sizeof(uint32_t)));
+        ISL_CUDA(e, cudaMemset(e->d_inbox, 0, (size_t)kMaxStreamChunks * kTokStride * sizeof(uint32_t)));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    ISL_CUDA(e, cudaIpcGetMemHandle(&h, e->d_inbox));
+    memcpy(handle64, &h, sizeof h);
+    return ISL_OK;
+}
+
+int isl_ipc_connect(isl_engine* e, const void* next_handle64, int has_prev) {
+    if (!e) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    if (e->d_outbox && !e->outbox_local) cudaIpcCloseMemHandle(e->d_outbox);
+    e->d_outbox = nullptr; e->outbox_local = false;
+    if (next_handle64) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, next_handle64, sizeof h);
+        void* p = nullptr;
+        ISL_CUDA(e, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        e->d_outbox = static_cast<uint32_t*>(p);
+    }
+    e->has_prev = has_prev != 0;
+    if (e->has_prev && !e->d_inbox) return ISL_ESTATE;
+    return ISL_OK;
+}
+
+int isl_connect_local(isl_engine* e, isl_engine* next, int has_prev) {
+    if (!e) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (e->d_outbox && !e->outbox_local) cudaIpcCloseMemHandle(e->d_outbox);
+    e->d_outbox = nullptr; e->outbox_local = true;
+    if (next) {
+        if (!next->d_inbox) return ISL_ESTATE;
+        e->d_outbox = next->d_inbox;
+    }
+    e->has_prev = has_prev != 0;
+    if (e->has_prev && !e->d_inbox) return ISL_ESTATE;
+    return ISL_OK;
+}
+
+int isl_place_stream_partitioned(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const void* d_in, void* d_out, uint32_t stream_id) {
+    if (!e || !sizes || n_batches == 0 || n_batches > 4096 || !d_in || !d_out || stream_id == 0) return ISL_EINVAL;
+    uint64_t total = 0;
+    for (uint32_t b = 0; b < n_batches; ++b) total += sizes[b];
+    if (total > e->cfg.max_batch) return ISL_ERANGE;
+    if (int rc = validate_ready(e, (uint32_t)total)) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    return run_stream(e, n_batches, sizes, static_cast<const uint2*>(d_in), static_cast<uint2*>(d_out), nullptr, nullptr, stream_id);
 }
 
 int isl_place_batch_device(isl_engine* e, uint32_t n, const void* d_in, void* d_out) {

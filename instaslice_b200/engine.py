@@ -58,7 +58,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "isl_create", "isl_destroy", "isl_set_stream", "isl_synchronize", "isl_load_profiles", "isl_load_inventory", "isl_read_occupancy",
     "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_place_stream", "isl_place_stream_device", "isl_free_batch",
-    "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_device_occupancy", "isl_get_stats",
+    "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_ipc_inbox_handle", "isl_ipc_connect", "isl_connect_local", "isl_place_stream_partitioned", "isl_device_occupancy", "isl_get_stats",
     "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
 ]
 
@@ -92,6 +92,10 @@ def load_library(path: str = LIB_PATH):
         "isl_eval_starts": (C.c_int, [p, C.c_uint32, C.c_uint32, p, p]),
         "isl_set_partition": (C.c_int, [p, C.c_uint32, C.c_uint32]),
         "isl_place_batch_partitioned": (C.c_int, [p, C.c_uint32, p, p, p, p]),
+        "isl_ipc_inbox_handle": (C.c_int, [p, p]),
+        "isl_ipc_connect": (C.c_int, [p, p, C.c_int]),
+        "isl_connect_local": (C.c_int, [p, p, C.c_int]),
+        "isl_place_stream_partitioned": (C.c_int, [p, C.c_uint32, p, p, p, C.c_uint32]),
         "isl_device_occupancy": (p, [p]),
         "isl_get_stats": (C.c_int, [p, C.POINTER(Stats)]),
         "isl_reset_stats": (C.c_int, [p]),
@@ -238,6 +242,22 @@ class Engine:
         self._check(self._lib.isl_place_batch_partitioned(self._h, n, C.c_void_p(d_in), C.c_void_p(d_out),
                                                           C.c_void_p(d_heads_in or 0), C.c_void_p(d_heads_out)),
                     "isl_place_batch_partitioned")
+
+    def ipc_inbox_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.isl_ipc_inbox_handle(self._h, buf), "isl_ipc_inbox_handle")
+        return buf.raw
+
+    def ipc_connect(self, next_handle: bytes | None, has_prev: bool):
+        self._check(self._lib.isl_ipc_connect(self._h, next_handle, 1 if has_prev else 0), "isl_ipc_connect")
+
+    def connect_local(self, nxt: "Engine | None", has_prev: bool):
+        self._check(self._lib.isl_connect_local(self._h, nxt._h if nxt is not None else None, 1 if has_prev else 0), "isl_connect_local")
+
+    def place_stream_partitioned(self, sizes: np.ndarray, d_in: int, d_out: int, stream_id: int):
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
+        self._check(self._lib.isl_place_stream_partitioned(self._h, len(sizes), _ptr(sizes), C.c_void_p(d_in), C.c_void_p(d_out), stream_id),
+                    "isl_place_stream_partitioned")
 
     def device_occupancy(self) -> int:
         return int(self._lib.isl_device_occupancy(self._h) or 0)

@@ -350,3 +350,58 @@ def test_device_resident_entry_point_matches_host_entry_point():
     assert np.array_equal(got, want)
     st = eng.stats()
     assert st["placed"] == int((want["status"] == E.ST_PLACED).sum()) * 2 and st["kernel_launches"] > 0
+
+
+# ---- partitioned inventory: token ring between engines (the N > 1 device path) on ONE GPU ---------------------------
+@pytest.mark.parametrize("n_ranks", [2, 3])
+def test_partitioned_ring_on_one_gpu(n_ranks):
+    """Several engines in one process, each owning a GPU range, wired with isl_connect_local: the queue-head token of
+    every chunk crosses from the last segment of one engine's running kernel to the first segment of the next one's
+    (the same mechanism the multi-GPU run uses through CUDA IPC).  Merged results == global sequential first-fit."""
+    import torch
+    from instaslice_b200 import dist as D
+    rows = E.make_profiles(tables.H100_80GB)
+    rng = W.SplitMix64(4242 + n_ranks)
+    G = 4096
+    node_off = W.node_offsets(G // 8, 8)
+    occ0 = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+    ref = oracle.Fast(node_off, rows)
+    ref.load(occ0)
+    batches, want, live = [], [], []
+    for b in range(6):
+        n = 3000 + 500 * b
+        req = W.alloc_requests(W.mix_profiles(rng, n))
+        for i in range(min(len(live), n // 3)):
+            g, s, z = live.pop(int(rng.next1() % len(live)))
+            req[int(rng.next1() % n)] = (g, 0, E.OP_FREE, s, z)
+        res = ref.place(req)
+        for r in res[(req["op"] == E.OP_ALLOC) & (res["status"] == E.ST_PLACED)]:
+            live.append((int(r["gpu"]), int(r["start"]), int(r["size"])))
+        batches.append(req)
+        want.append(res)
+    sizes = np.array([len(b) for b in batches], dtype=np.uint32)
+    d_in = torch.from_numpy(np.concatenate(batches).view(np.int64).copy()).cuda()
+    bounds = D.all_bounds(G, n_ranks, align=64)
+    engines, outs = [], []
+    for r, (lo, hi) in enumerate(bounds):
+        eng = make_engine(node_off, occ0, rows)
+        eng.set_partition(lo, hi)
+        eng.ipc_inbox_handle()                       # allocates the inbox
+        engines.append(eng)
+        outs.append(torch.empty_like(d_in))
+    for r, eng in enumerate(engines):
+        eng.connect_local(engines[r + 1] if r + 1 < n_ranks else None, has_prev=r > 0)
+    torch.cuda.synchronize()
+    for stream_id in (1, 2):                          # twice: the second run re-uses inbox slots with a new stream id
+        for eng in engines:
+            eng.load_inventory(node_off, occ0)
+        for eng, (lo, hi) in zip(engines, bounds):
+            eng.set_partition(lo, hi)
+        for eng, out in zip(engines, outs):
+            eng.place_stream_partitioned(sizes, d_in.data_ptr(), out.data_ptr(), stream_id)
+        for eng in engines:
+            eng.synchronize()
+        merged = np.minimum.reduce([o.cpu().numpy() for o in outs]).view(E.RESULT_DTYPE)
+        assert np.array_equal(merged, np.concatenate(want))
+        occ = np.concatenate([eng.read_occupancy()[lo:hi] for eng, (lo, hi) in zip(engines, bounds)])
+        assert np.array_equal(occ, ref.occupancy())
