@@ -101,6 +101,7 @@ typedef struct isl_config {
 
 #define ISL_FLAG_TIMING 1u  /* record per-kernel CUDA-event timings (isl_get_stats) */
 #define ISL_FLAG_NO_PIPELINE    2u  /* always resolve chunk after chunk with the single-chain path */
+#define ISL_FLAG_TRACE          8u  /* record per (chunk, segment) timestamps of the segment pipeline (isl_read_trace) */
 #define ISL_FLAG_FORCE_PIPELINE 4u  /* use the segment pipeline even for a single chunk (tests) */
 
 /* One Migplacement row (api/v1alpha1/instaslice_types.go:23-29).  `size` is
@@ -232,6 +233,9 @@ void* isl_device_occupancy(isl_engine* e);
 
 /* ---- diagnostics ------------------------------------------------------- */
 int         isl_get_stats(isl_engine* e, isl_stats* out);
+/* ISL_FLAG_TRACE: uint64 globaltimer ns [chunk][segment][4] = local sweep done, token arrived, chain done, commit done
+ * of the last stream call; out may be NULL to query the dimensions. */
+int         isl_read_trace(isl_engine* e, uint64_t* out, uint32_t max_words, uint32_t* n_chunks, uint32_t* n_seg);
 int         isl_reset_stats(isl_engine* e);
 const char* isl_strerror(int code);
 const char* isl_last_cuda_error(const isl_engine* e);

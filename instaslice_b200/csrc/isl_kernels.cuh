@@ -127,12 +127,27 @@ __device__ __forceinline__ uint2 pack_result(uint32_t gpu, uint32_t start, uint3
     return make_uint2(gpu, start | (size << 8) | (status << 16));
 }
 
+// One tile of 1024 requests of a stream: which batch / pipeline chunk it belongs to (host-built table, one launch
+// of k_prepare and one of k_partition cover every batch and chunk of a stream call).
+struct TileDesc {
+    uint32_t batch_off, batch_n, batch, batch_first_tile;      // batch: request offset in the stream, size, index, first global tile
+    uint32_t chunk, chunk_first_tile, chunk_tiles, chunk_off;  // chunk: index, first global tile, tiles, request offset in the stream
+    uint32_t chunk_n, pad0, pad1, pad2;
+};
+
 __global__ void __launch_bounds__(kTileThreads) k_prepare(uint32_t n, const uint2* __restrict__ in, uint2* __restrict__ out,
                                                            uint32_t* __restrict__ occ32, uint32_t G, uint32_t lo, uint32_t hi,
                                                            DevProfiles prof, uint32_t* __restrict__ tile_counts, Ctrl* ctrl,
-                                                           uint2* __restrict__ free_list, uint32_t* __restrict__ free_cnt) {
-    // free_list != nullptr (stream mode): FREEs are not applied here but appended as (gpu, slot mask) for the
-    // segment pipeline, which applies them in batch order inside the segment that owns the GPU.
+                                                           const TileDesc* __restrict__ descs, uint32_t* __restrict__ free_acc, uint32_t free_stride) {
+    // descs != nullptr (stream mode): the tile's batch comes from the table, and FREEs are not applied here but ORed
+    // into the batch's free-mask array (one byte per GPU); the segment pipeline clears them in batch order inside the
+    // segment that owns the GPU.
+    uint32_t tile = blockIdx.x;
+    if (descs) {
+        const TileDesc d = descs[blockIdx.x];
+        n = d.batch_n; in += d.batch_off; out += d.batch_off; tile = blockIdx.x - d.batch_first_tile;
+        free_acc += (size_t)d.batch * free_stride;
+    }
     __shared__ uint32_t s_cnt[ISL_MAX_PROFILES];
     __shared__ uint32_t s_freed;
     if (threadIdx.x < ISL_MAX_PROFILES) s_cnt[threadIdx.x] = 0;
@@ -141,7 +156,7 @@ __global__ void __launch_bounds__(kTileThreads) k_prepare(uint32_t n, const uint
     const uint32_t lane = threadIdx.x & 31u;
 #pragma unroll
     for (uint32_t r = 0; r < kTile / kTileThreads; ++r) {
-        const uint32_t i = blockIdx.x * kTile + r * kTileThreads + threadIdx.x;
+        const uint32_t i = tile * kTile + r * kTileThreads + threadIdx.x;
         uint32_t key = kSkip;
         if (i < n) {
             const uint2 rq = in[i];
@@ -154,9 +169,9 @@ __global__ void __launch_bounds__(kTileThreads) k_prepare(uint32_t n, const uint
                 if (handle >= G || size == 0 || start + size > ISL_SLOTS) out[i] = pack_result(handle, start, size, ISL_ST_BAD_SPAN);
                 else {
                     if (handle >= lo && handle < hi) {
-                        const uint32_t span = ((1u << size) - 1u) << start;
-                        if (free_list) free_list[atomicAdd(free_cnt, 1u)] = make_uint2(handle, span);
-                        else atomicAnd(&occ32[handle >> 2], ~(span << ((handle & 3u) * 8u)));
+                        const uint32_t span = (((1u << size) - 1u) << start) << ((handle & 3u) * 8u);
+                        if (descs) atomicOr(&free_acc[handle >> 2], span);
+                        else atomicAnd(&occ32[handle >> 2], ~span);
                         atomicAdd(&s_freed, 1u);
                     }
                     out[i] = pack_result(handle, start, size, ISL_ST_FREED);
@@ -184,7 +199,16 @@ __global__ void __launch_bounds__(kTileThreads) k_prepare(uint32_t n, const uint
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTileThreads) k_partition(uint32_t n_chunk, const uint2* __restrict__ in_chunk, uint32_t n_profiles,
                                                              const uint32_t* __restrict__ tile_counts_chunk, uint32_t n_tiles,
-                                                             uint32_t cand_profiles, uint16_t* __restrict__ q, Ctrl* ctrl) {
+                                                             uint32_t cand_profiles, uint16_t* __restrict__ q, Ctrl* ctrl,
+                                                             const TileDesc* __restrict__ descs, uint32_t q_stride) {
+    // descs != nullptr (stream mode): in_chunk / tile_counts_chunk / q / ctrl are the bases of the whole stream and
+    // the tile's chunk comes from the table.
+    uint32_t tile = blockIdx.x;
+    if (descs) {
+        const TileDesc d = descs[blockIdx.x];
+        n_chunk = d.chunk_n; in_chunk += d.chunk_off; tile_counts_chunk += (size_t)d.chunk_first_tile * ISL_MAX_PROFILES;
+        n_tiles = d.chunk_tiles; tile = blockIdx.x - d.chunk_first_tile; q += (size_t)d.chunk * q_stride; ctrl += d.chunk;
+    }
     __shared__ uint32_t s_part[16][ISL_MAX_PROFILES][2];   // [j][p][0]=total, [1]=prefix before this tile
     __shared__ uint32_t s_base[ISL_MAX_PROFILES];
     __shared__ uint32_t s_seg[32][ISL_MAX_PROFILES];
@@ -195,7 +219,7 @@ __global__ void __launch_bounds__(kTileThreads) k_partition(uint32_t n_chunk, co
         for (uint32_t t = j; t < n_tiles; t += 16) {
             const uint32_t c = tile_counts_chunk[t * ISL_MAX_PROFILES + p];
             tot += c;
-            if (t < blockIdx.x) pre += c;
+            if (t < tile) pre += c;
         }
         s_part[j][p][0] = tot; s_part[j][p][1] = pre;
     }
@@ -207,18 +231,18 @@ __global__ void __launch_bounds__(kTileThreads) k_partition(uint32_t n_chunk, co
             uint32_t tot = 0, pre = 0;
             for (uint32_t j = 0; j < 16; ++j) { tot += s_part[j][p][0]; pre += s_part[j][p][1]; }
             s_base[p] = off + pre;
-            if (blockIdx.x == 0) {
+            if (tile == 0) {
                 ctrl->qoff[p] = off; ctrl->qcnt[p] = tot;
                 if (tot && ((cand_profiles >> p) & 1u)) active |= 1u << p;
             }
             off += (tot + kQPad - 1) & ~(kQPad - 1);
         }
-        if (blockIdx.x == 0) { ctrl->qoff[ISL_MAX_PROFILES] = off; ctrl->active = active; ctrl->n_cand = 0; }
+        if (tile == 0) { ctrl->qoff[ISL_MAX_PROFILES] = off; ctrl->active = active; ctrl->n_cand = 0; }
     }
     uint32_t key[4], rank[4];
 #pragma unroll
     for (uint32_t r = 0; r < 4; ++r) {
-        const uint32_t i = blockIdx.x * kTile + r * kTileThreads + tid;
+        const uint32_t i = tile * kTile + r * kTileThreads + tid;
         key[r] = kSkip;
         if (i < n_chunk) {
             const uint32_t w = in_chunk[i].y;
@@ -238,7 +262,7 @@ __global__ void __launch_bounds__(kTileThreads) k_partition(uint32_t n_chunk, co
 #pragma unroll
     for (uint32_t r = 0; r < 4; ++r) {
         if (key[r] == kSkip) continue;
-        const uint32_t i = blockIdx.x * kTile + r * kTileThreads + tid;
+        const uint32_t i = tile * kTile + r * kTileThreads + tid;
         q[s_base[key[r]] + s_seg[r * 8 + warp][key[r]] + rank[r]] = (uint16_t)i;
     }
 }
@@ -528,9 +552,21 @@ __global__ void __launch_bounds__(256) k_commit(const Ctrl* __restrict__ ctrl, c
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kSegMax = 512;                   // GPUs per segment (2 per thread in the local sweep)
 constexpr uint32_t kPipeThreads = 256;
-constexpr uint32_t kWin = 8 * kSegMax + 8;          // queue window per profile: a GPU accepts at most 8 placements
+constexpr uint32_t kWinTotal = 16384;               // 32-bit queue-window keys a segment can stage for all profiles together
+constexpr uint32_t kLogCap = 8 * kSegMax;           // a GPU accepts at most 8 placements
 constexpr uint32_t kTokStride = 32;                 // uint32 per token: heads[16], flag at [16]
-constexpr uint32_t kPipeSmem = kSegMax + 4 * (kSegMax + 8) + 8 * (8 * kSegMax) + 2 * ISL_MAX_PROFILES * kWin;
+// shared memory: occupancy bytes | candidate records (+8 sentinels) | decision log | queue-window keys
+constexpr uint32_t kPipeOffCand = kSegMax;
+constexpr uint32_t kPipeOffLog = kPipeOffCand + 4 * (kSegMax + 8);
+constexpr uint32_t kPipeOffWin = kPipeOffLog + 8 * kLogCap;
+constexpr uint32_t kPipeSmem = kPipeOffWin + 4 * (kWinTotal + 4 * ISL_MAX_PROFILES);
+
+// largest segment whose worst-case queue windows (every candidate GPU accepting every legal start of every
+// profile) fit: n_cand * total_candidates + 2 sentinels per profile <= kWinTotal
+__host__ __device__ inline uint32_t max_segment_for(uint32_t total_candidates) {
+    const uint32_t s = (kWinTotal - 2 * ISL_MAX_PROFILES) / (total_candidates ? total_candidates : 1u);
+    return s >= kSegMax ? kSegMax : s / 64u * 64u;
+}
 
 struct ChunkDesc { uint32_t req_off, n, batch, first_of_batch; };
 
@@ -538,10 +574,9 @@ struct PipeArgs {
     uint32_t n_chunks, n_seg, seg, lo, hi, epoch;
     const ChunkDesc* chunks;
     const Ctrl* cctl;               // per chunk: qoff / qcnt / active (written by k_partition)
-    const uint16_t* q_all;          // per chunk queues, stride kQCap
-    const uint2* free_list;         // (gpu, slot mask) per FREE, batch b's entries start at free_off[b]
-    const uint32_t* free_off;
-    const uint32_t* free_cnt;
+    const uint16_t* q_all;          // per chunk queues, stride q_stride entries
+    const uint8_t* free_acc;        // per batch one byte per GPU: OR of the slot masks its FREEs release (stride free_stride bytes)
+    uint32_t q_stride, free_stride;
     uint32_t* tokens;               // [chunk][segment][kTokStride]
     uint8_t* occ;
     uint2* out;
@@ -553,8 +588,14 @@ struct PipeArgs {
     const uint32_t* inbox;          // local [chunk][kTokStride], written by the previous rank's last segment (nullptr = first rank)
     uint32_t* outbox;               // the next rank's inbox, peer-mapped (nullptr = last rank)
     uint32_t xepoch;                // stream id shared by all ranks
+    unsigned long long* trace;      // optional [chunk][segment][4] globaltimer ns: sweep done, token in, chain done, commit done
 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -577,18 +618,30 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
     return v;
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
+__device__ __forceinline__ void sts_v2_if(bool pred, uint32_t sa, uint32_t x, uint32_t y) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.v2.u32 [%1], {%2, %3}; }" ::"r"((uint32_t)pred), "r"(sa), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32_if(bool pred, uint32_t sa, uint32_t keep) {   // predicated load: keeps `keep` when !pred
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p ld.shared.u32 %0, [%2]; }" : "+r"(keep) : "r"((uint32_t)pred), "r"(sa));
+    return keep;
+}
+
 template <int K>
 __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint32_t* s_occ32 = reinterpret_cast<uint32_t*>(smem);                                   // kSegMax occupancy bytes
-    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + kSegMax);                          // kSegMax + 8 records (local gpu << 8 | occ)
-    uint2* s_log = reinterpret_cast<uint2*>(smem + kSegMax + 4 * (kSegMax + 8));             // 8 * kSegMax decisions
-    uint16_t* s_win = reinterpret_cast<uint16_t*>(smem + kSegMax + 4 * (kSegMax + 8) + 8 * (8 * kSegMax));
+    uint32_t* s_occ32 = reinterpret_cast<uint32_t*>(smem);                       // kSegMax occupancy bytes
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + kPipeOffCand);         // records (local gpu << 8 | occ) + sentinels
+    uint2* s_log = reinterpret_cast<uint2*>(smem + kPipeOffLog);                 // (key, candidate index) per decision
+    uint32_t* s_wkey = reinterpret_cast<uint32_t*>(smem + kPipeOffWin);          // per-profile windows of ready-made keys t<<15 | p<<11
     __shared__ uint16_t s_feas[256];
-    __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_qsrc[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
+    __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_wbase[ISL_MAX_PROFILES], s_qsrc[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
     __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_warp[kPipeThreads / 32], s_ncand, s_nlog;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     const uint32_t lo_s = min(a.hi, a.lo + seg * a.seg), hi_s = min(a.hi, lo_s + a.seg), n_g = hi_s - lo_s;
+    const uint32_t sa_cand = (uint32_t)__cvta_generic_to_shared(s_cand), sa_log = (uint32_t)__cvta_generic_to_shared(s_log);
+    const uint32_t sa_wkey = (uint32_t)__cvta_generic_to_shared(s_wkey);
 
     for (uint32_t i = tid; i < kSegMax / 4; i += kPipeThreads) s_occ32[i] = 0xFFFFFFFFu;
     s_feas[tid] = a.feas[tid];
@@ -601,8 +654,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     for (uint32_t i = tid; i < n_g; i += kPipeThreads) reinterpret_cast<uint8_t*>(s_occ32)[i] = a.occ[lo_s + i];
     __syncthreads();
 
-    // chain-warp constants
-    uint32_t cmask[K], keylow[K], cprof[K];
+    // chain-warp constants: one (profile, start) candidate per slot
+    uint32_t cmask[K], klow[K], cprof[K];
     bool valid[K], reports[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -610,7 +663,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         valid[k] = d >> 31;
         cprof[k] = d & 15u;
         cmask[k] = valid[k] ? (d >> 16) & 0xFFu : 0xFFu;
-        keylow[k] = (cprof[k] << 11) | (((d >> 4) & 7u) << 8) | cmask[k];
+        klow[k] = (((d >> 4) & 7u) << 8) | cmask[k];            // order-in-row and slot mask; t and profile come from the window key
         reports[k] = valid[k] && ((d >> 4) & 7u) == 0;
     }
     unsigned long long st_steps = 0, st_jumps = 0, st_visited = 0;
@@ -618,12 +671,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     for (uint32_t c = 0; c < a.n_chunks; ++c) {
         const ChunkDesc cd = a.chunks[c];
         const Ctrl* cc = a.cctl + c;
-        if (cd.first_of_batch) {            // 1. frees of this batch inside my range
-            const uint32_t n_free = a.free_cnt[cd.batch];
-            const uint2* fl = a.free_list + a.free_off[cd.batch];
-            for (uint32_t i = tid; i < n_free; i += kPipeThreads) {
-                const uint2 f = fl[i];
-                if (f.x >= lo_s && f.x < hi_s) { const uint32_t l = f.x - lo_s; atomicAnd(&s_occ32[l >> 2], ~(f.y << ((l & 3u) * 8u))); }
+        if (cd.first_of_batch) {            // 1. frees of this batch inside my range: one byte per GPU
+            const uint8_t* fa = a.free_acc + (size_t)cd.batch * a.free_stride + lo_s;
+            for (uint32_t i = tid; i < n_g; i += kPipeThreads) {
+                const uint32_t f = fa[i];
+                if (f) atomicAnd(&s_occ32[i >> 2], ~(f << ((i & 3u) * 8u)));
             }
             __syncthreads();
         }
@@ -645,7 +697,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             if (tid == kPipeThreads - 1) { s_ncand = off; for (uint32_t x = 0; x < 8; ++x) s_cand[off + x] = kInf; }   // sentinels: nothing fits
         }
         // 3. token of the previous segment
+        unsigned long long* tr = a.trace ? a.trace + ((size_t)c * a.n_seg + seg) * 4 : nullptr;
         if (tid == 0) {
+            if (tr) tr[0] = globaltimer_ns();
             if (seg > 0) {
                 const uint32_t* flag = a.tokens + ((size_t)c * a.n_seg + seg - 1) * kTokStride + ISL_MAX_PROFILES;
                 while (ld_acquire_gpu(flag) != a.epoch) { }
@@ -653,39 +707,48 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 const uint32_t* flag = a.inbox + (size_t)c * kTokStride + ISL_MAX_PROFILES;
                 while (ld_acquire_sys(flag) != a.xepoch) { }
             }
+            if (tr) tr[1] = globaltimer_ns();
         }
         __syncthreads();
-        if (tid < ISL_MAX_PROFILES) {
-            uint32_t h;
-            if (seg > 0) h = __ldcg(a.tokens + ((size_t)c * a.n_seg + seg - 1) * kTokStride + tid);
-            else if (a.inbox) h = ld_relaxed_sys(a.inbox + (size_t)c * kTokStride + tid);
-            else h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
-            const uint32_t qc = cc->qcnt[tid], left = qc > h ? qc - h : 0u;
-            uint32_t wn = min(left, s_ncand * s_maxacc[tid] + 2u);
-            wn = ((active >> tid) & 1u) ? min(wn, kWin) : 0u;
-            s_heads[tid] = h; s_wn[tid] = wn; s_pop[tid] = 0;
-            s_qsrc[tid] = c * kQCap + cc->qoff[tid] + h;
+        if (tid < 32) {     // heads, window sizes and the compact window layout (exclusive scan over the 16 profiles)
+            uint32_t h = 0, wn = 0;
+            if (tid < ISL_MAX_PROFILES) {
+                if (seg > 0) h = __ldcg(a.tokens + ((size_t)c * a.n_seg + seg - 1) * kTokStride + tid);
+                else if (a.inbox) h = ld_relaxed_sys(a.inbox + (size_t)c * kTokStride + tid);
+                else h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
+                const uint32_t qc = cc->qcnt[tid], left = qc > h ? qc - h : 0u;
+                wn = ((active >> tid) & 1u) ? min(left, s_ncand * s_maxacc[tid]) : 0u;     // no more pops than that are possible here
+                s_heads[tid] = h; s_wn[tid] = wn; s_pop[tid] = 0;
+                s_qsrc[tid] = c * a.q_stride + cc->qoff[tid] + h;
+            }
+            uint32_t incl = wn + 2;                             // two INF sentinels close every window
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+            if (tid < ISL_MAX_PROFILES) s_wbase[tid] = incl - (wn + 2);
         }
         __syncthreads();
-        for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) {          // stage the queue windows this segment may pop
-            const uint32_t wn = s_wn[p];
+        for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) {          // stage the windows as ready-made keys: t << 15 | profile << 11
+            const uint32_t wn = s_wn[p], base = s_wbase[p];
             const uint16_t* src = a.q_all + s_qsrc[p];
-            for (uint32_t i = tid; i < wn; i += kPipeThreads) s_win[p * kWin + i] = src[i];
+            for (uint32_t i = tid; i < wn; i += kPipeThreads) s_wkey[base + i] = ((uint32_t)src[i] << 15) | (p << 11);
+            if (tid < 2) s_wkey[base + wn + tid] = kInf;
         }
         __syncthreads();
-        if (warp == 0) {                    // 4. the decision chain (see k_chain)
+        if (warp == 0) {                    // 4. the decision chain (see k_chain), tuned for the shortest loop-carried path
             const uint32_t n_cand = s_ncand;
-            uint32_t pos[K], wn[K], tcur[K], tnext[K];
+            uint32_t tcur[K], tnext[K], tnn[K], wa[K], wa0[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                wn[k] = valid[k] ? s_wn[cprof[k]] : 0u;
-                pos[k] = 0;
-                const uint16_t* wq = s_win + cprof[k] * kWin;
-                tcur[k] = wn[k] > 0 ? ((uint32_t)wq[0] << 15) | keylow[k] : kInf;
-                tnext[k] = wn[k] > 1 ? ((uint32_t)wq[1] << 15) | keylow[k] : kInf;
+                wa0[k] = sa_wkey + 4 * s_wbase[cprof[k]];
+                const bool has = valid[k];
+                tcur[k] = has ? lds_u32(wa0[k]) | klow[k] : kInf;               // INF | anything = INF
+                tnext[k] = has ? lds_u32(wa0[k] + 4) | klow[k] : kInf;
+                const bool two = has && s_wn[cprof[k]] >= 1;                    // a third entry exists only behind >= 1 real one
+                tnn[k] = two ? lds_u32(wa0[k] + 8) : kInf;
+                wa[k] = wa0[k] + 12;                                            // next entry to load on a pop
             }
-            uint32_t i0 = 0, nlog = 0;
-            uint32_t o0 = s_cand[0] & 0xFFu, o1 = s_cand[1] & 0xFFu, o2 = s_cand[2] & 0xFFu;
+            uint32_t i0 = 0, la = sa_log, ca = sa_cand + 8;                     // ca: address of candidate record i0 + 2
+            uint32_t o0 = lds_u8(sa_cand), o1 = lds_u8(sa_cand + 4), o2 = lds_u8(sa_cand + 8);
             while (true) {
                 uint32_t key = kInf;
 #pragma unroll
@@ -694,7 +757,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     key = min(key, kk);
                 }
                 const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, key);
-                if (m == kInf) {            // neither GPU takes anything: ballot to the next candidate a pending profile fits on
+                if (__builtin_expect(m == kInf, 0)) {   // neither GPU takes anything: ballot to the next candidate a pending profile fits on
                     uint32_t alive = 0;
 #pragma unroll
                     for (int k = 0; k < K; ++k) alive |= tcur[k] != kInf ? 1u << cprof[k] : 0u;
@@ -709,31 +772,32 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     }
                     ++st_jumps;
                     if (!found) break;
-                    i0 = j;
-                    o0 = s_cand[i0] & 0xFFu; o1 = s_cand[i0 + 1] & 0xFFu; o2 = s_cand[i0 + 2] & 0xFFu;
+                    i0 = j; ca = sa_cand + 4 * (i0 + 2);
+                    o0 = lds_u8(ca - 8); o1 = lds_u8(ca - 4); o2 = lds_u8(ca);
                     continue;
                 }
                 const uint32_t sel = m >> 31;
-                if (lane == 0) s_log[nlog] = make_uint2(m, i0 + sel);
-                ++nlog;
+                i0 += sel;
+                sts_v2_if(lane == 0, la, m, i0);                    // decision log: (key, candidate index it landed on)
+                la += 8;
                 o0 = (sel ? o1 : o0) | (m & 0xFFu);
                 o1 = sel ? o2 : o1;
-                i0 += sel;
-                o2 = s_cand[i0 + 2] & 0xFFu;
+                ca += sel * 4;
+                o2 = lds_u8(ca);
+                const uint32_t mm = m & 0x7FFFF800u;                // t and profile of the winner, without sel
 #pragma unroll
-                for (int k = 0; k < K; ++k) {       // lanes of the winning profile pop their queue window
-                    const bool adv = ((m ^ tcur[k]) & 0x7FFFF800u) == 0 && tcur[k] != kInf;
-                    pos[k] += adv ? 1u : 0u;
-                    const bool more = pos[k] + 1 < wn[k];
-                    const uint32_t v = s_win[cprof[k] * kWin + (more ? pos[k] + 1 : 0u)];
-                    const uint32_t tn = more ? (v << 15) | keylow[k] : kInf;
+                for (int k = 0; k < K; ++k) {       // lanes of the winning profile pop their window (INF never matches: bit 31)
+                    const bool adv = ((mm ^ tcur[k]) & 0xFFFFF800u) == 0;
                     tcur[k] = adv ? tnext[k] : tcur[k];
-                    tnext[k] = adv ? tn : tnext[k];
+                    tnext[k] = adv ? (tnn[k] | klow[k]) : tnext[k];
+                    tnn[k] = lds_u32_if(adv, wa[k], tnn[k]);        // consumed at the earliest one pop later
+                    wa[k] += adv ? 4u : 0u;
                 }
             }
+            const uint32_t nlog = (la - sa_log) >> 3;
             st_steps += nlog; st_visited += i0;
 #pragma unroll
-            for (int k = 0; k < K; ++k) if (reports[k]) s_pop[cprof[k]] = pos[k];
+            for (int k = 0; k < K; ++k) if (reports[k]) s_pop[cprof[k]] = (wa[k] - wa0[k] - 12) >> 2;
             __syncwarp();
             // 5. token for the next segment: heads first, then the flag (release)
             uint32_t* tok = a.tokens + ((size_t)c * a.n_seg + seg) * kTokStride;
@@ -751,6 +815,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 st_release_gpu(tok + ISL_MAX_PROFILES, a.epoch);
                 if (peer) { __threadfence_system(); st_release_sys(peer + ISL_MAX_PROFILES, a.xepoch); }
                 s_nlog = nlog;
+                if (tr) tr[2] = globaltimer_ns();
             }
         }
         __syncthreads();
@@ -764,6 +829,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             }
         }
         __syncthreads();
+        if (tr && tid == 0) tr[3] = globaltimer_ns();
     }
     for (uint32_t i = tid; i < n_g; i += kPipeThreads) a.occ[lo_s + i] = reinterpret_cast<uint8_t*>(s_occ32)[i];
     if (tid == 0 && st_steps + st_jumps) {

@@ -5,6 +5,7 @@
 // No Go pointer is retained after a call returns; every buffer the engine keeps is its own.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -49,13 +50,15 @@ struct isl_engine {
     uint8_t* d_scratch = nullptr;    // eval_starts / free_batch staging
     // stream / segment-pipeline state (grown on demand)
     ChunkDesc* d_chunks = nullptr; Ctrl* d_cctl = nullptr; uint16_t* d_qall = nullptr; uint32_t* d_tokens = nullptr;
-    uint2* d_free_list = nullptr; uint32_t* d_free_off = nullptr; uint32_t* d_free_cnt = nullptr;
-    uint32_t cap_chunks = 0, cap_cctl = 0, cap_qall = 0, cap_batches = 0, cap_free_cnt = 0, cap_tokens = 0, cap_free = 0;
-    std::vector<ChunkDesc> h_chunks; std::vector<uint32_t> h_free_off;
+    uint32_t* d_free_acc = nullptr; TileDesc* d_tiles = nullptr; std::vector<TileDesc> h_tiles;
+    uint32_t cap_chunks = 0, cap_cctl = 0, cap_qall = 0, cap_tokens = 0, cap_free = 0, cap_tiles = 0;
+    uint32_t pipe_chunk = 0;         // requests per pipeline chunk (multiple of kTile, <= kChunk)
+    std::vector<ChunkDesc> h_chunks;
     uint32_t epoch = 0;
     uint32_t* d_inbox = nullptr;      // [kMaxStreamChunks][kTokStride] tokens written by the previous rank (peer store)
     uint32_t* d_outbox = nullptr;     // next rank's inbox, opened through CUDA IPC
     bool has_prev = false, outbox_local = false;
+    unsigned long long* d_trace = nullptr; uint32_t cap_trace = 0, trace_chunks = 0, trace_seg = 0;
     int max_coresident = 0;          // CTAs of k_pipeline that can be resident at once (0 = not queried)
     size_t scratch_bytes = 0;
 
@@ -120,7 +123,7 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
     const uint32_t tiles = ceil_div(n, kTile);
     if (timing) cudaEventRecord(e->ev[0], e->stream);
     k_prepare<<<tiles, kTileThreads, 0, e->stream>>>(n, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi,
-                                                     e->prof, e->d_tile_counts, e->d_ctrl, nullptr, nullptr);
+                                                     e->prof, e->d_tile_counts, e->d_ctrl, nullptr, nullptr, 0);
     if (int rc = check_launch(e, "k_prepare")) return rc;
     if (timing) cudaEventRecord(e->ev[1], e->stream);
     const uint32_t first_block = e->lo / kSweepBlock;
@@ -131,7 +134,7 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
         const uint32_t first_tile = c0 / kTile, n_tiles = ceil_div(n_chunk, kTile);
         if (timing) cudaEventRecord(e->ev[2], e->stream);
         k_partition<<<n_tiles, kTileThreads, 0, e->stream>>>(n_chunk, d_in + c0, e->prof.n, e->d_tile_counts + (size_t)first_tile * ISL_MAX_PROFILES,
-                                                             n_tiles, e->cand_profiles, e->d_q, e->d_ctrl);
+                                                             n_tiles, e->cand_profiles, e->d_q, e->d_ctrl, nullptr, 0);
         if (int rc = check_launch(e, "k_partition")) return rc;
         if (timing) cudaEventRecord(e->ev[3], e->stream);
         if (sweep_blocks) {
@@ -218,17 +221,22 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
                const uint32_t* d_heads_in, uint32_t* d_heads_out, uint32_t xepoch = 0) {
     uint64_t total = 0;
     uint32_t n_chunks = 0;
-    for (uint32_t b = 0; b < n_batches; ++b) { total += sizes[b]; n_chunks += ceil_div(sizes[b], kChunk); }
+    for (uint32_t b = 0; b < n_batches; ++b) { total += sizes[b]; n_chunks += ceil_div(sizes[b], e->pipe_chunk); }
     if (total == 0) return ISL_OK;
     if (total > e->cfg.max_batch) return ISL_ERANGE;
     const uint32_t range = e->hi - e->lo;
     const bool ring = xepoch != 0;      // partitioned inventory: tokens cross ranks through peer memory, pipeline mandatory
     if (ring && n_chunks > kMaxStreamChunks) return ISL_ERANGE;
-    bool pipeline = ring || (!(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE)));
+    const bool legacy_token = d_heads_in || d_heads_out;   // isl_place_batch_partitioned: host-carried token, kChunk layout
+    bool pipeline = ring || (!legacy_token && !(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE)));
     uint32_t seg = 0, n_seg = 0;
     if (pipeline) {
         if (int rc = query_coresident(e)) return rc;
-        seg = std::min(kSegMax, std::max(64u, (ceil_div(range, 128u) + 63u) / 64u * 64u));
+        uint32_t total_cand = 0;
+        for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) total_cand += e->tab.desc[k][l] >> 31;
+        const uint32_t seg_cap = max_segment_for(total_cand);      // queue windows of a segment must fit in shared memory
+        seg = std::min(seg_cap, std::max(64u, (ceil_div(range, 128u) + 63u) / 64u * 64u));
+        if (seg_cap < 64) { if (ring) return ISL_ERANGE; pipeline = false; seg = 64; }
         n_seg = std::max(1u, ceil_div(range, seg));
         if (e->max_coresident <= 0 || n_seg > (uint32_t)e->max_coresident) { if (ring) return ISL_ERANGE; pipeline = false; }
     }
@@ -242,57 +250,62 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         return ISL_OK;
     }
     const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
-    // chunk table: batches are cut into chunks of <= kChunk requests; FREEs belong to the first chunk of their batch
-    e->h_chunks.clear(); e->h_free_off.clear();
+    // Tables: every batch is cut into pipeline chunks of pipe_chunk requests (the FREEs of a batch belong to its first
+    // chunk) and into tiles of kTile requests for the two pre-pass launches.
+    const uint32_t pc = e->pipe_chunk;
+    e->h_chunks.clear(); e->h_tiles.clear();
     uint32_t off = 0;
     for (uint32_t b = 0; b < n_batches; ++b) {
-        e->h_free_off.push_back(off);
-        for (uint32_t c0 = 0; c0 < sizes[b]; c0 += kChunk)
-            e->h_chunks.push_back(ChunkDesc{off + c0, std::min(kChunk, sizes[b] - c0), b, c0 == 0 ? 1u : 0u});
+        const uint32_t batch_first_tile = (uint32_t)e->h_tiles.size();
+        for (uint32_t c0 = 0; c0 < sizes[b]; c0 += pc) {
+            const uint32_t cn = std::min(pc, sizes[b] - c0), chunk = (uint32_t)e->h_chunks.size();
+            const uint32_t chunk_first_tile = (uint32_t)e->h_tiles.size(), chunk_tiles = ceil_div(cn, kTile);
+            e->h_chunks.push_back(ChunkDesc{off + c0, cn, b, c0 == 0 ? 1u : 0u});
+            for (uint32_t t = 0; t < chunk_tiles; ++t)
+                e->h_tiles.push_back(TileDesc{off, sizes[b], b, batch_first_tile, chunk, chunk_first_tile, chunk_tiles, off + c0, cn, 0, 0, 0});
+        }
         off += sizes[b];
     }
     n_chunks = (uint32_t)e->h_chunks.size();
+    const uint32_t n_tiles_total = (uint32_t)e->h_tiles.size();
+    if (ring && n_chunks > kMaxStreamChunks) return ISL_ERANGE;
+    const uint32_t q_stride = pc + kQPad * ISL_MAX_PROFILES;
+    const uint32_t free_stride = (uint32_t)e->occ_bytes;           // bytes per batch
+    if ((uint64_t)n_batches * free_stride > (256ull << 20)) return ISL_ERANGE;
     if (int rc = grow(e, &e->d_chunks, &e->cap_chunks, n_chunks, 1)) return rc;
     if (int rc = grow(e, &e->d_cctl, &e->cap_cctl, n_chunks, 1)) return rc;
-    if (int rc = grow(e, &e->d_qall, &e->cap_qall, n_chunks, kQCap)) return rc;
-    if (int rc = grow(e, &e->d_free_off, &e->cap_batches, n_batches, 1)) return rc;
-    if (int rc = grow(e, &e->d_free_cnt, &e->cap_free_cnt, n_batches, 1)) return rc;
-    if (int rc = grow(e, &e->d_free_list, &e->cap_free, (size_t)total, 1)) return rc;
+    if (int rc = grow(e, &e->d_qall, &e->cap_qall, (size_t)n_chunks * q_stride, 1)) return rc;
+    if (int rc = grow(e, &e->d_tiles, &e->cap_tiles, n_tiles_total, 1)) return rc;
+    if (int rc = grow(e, &e->d_free_acc, &e->cap_free, (size_t)n_batches * (free_stride / 4), 1)) return rc;
     {   // token flags carry the call epoch: a (re)allocated buffer must not hold stale flags of an earlier owner
         const uint32_t before = e->cap_tokens;
         if (int rc = grow(e, &e->d_tokens, &e->cap_tokens, (size_t)n_chunks * n_seg, kTokStride)) return rc;
         if (e->cap_tokens != before) ISL_CUDA(e, cudaMemsetAsync(e->d_tokens, 0, (size_t)e->cap_tokens * kTokStride * sizeof(uint32_t), e->stream));
     }
+    if (n_tiles_total > ceil_div(e->cfg.max_batch, kTile) + 4096) return ISL_ERANGE;
     ISL_CUDA(e, cudaMemcpyAsync(e->d_chunks, e->h_chunks.data(), n_chunks * sizeof(ChunkDesc), cudaMemcpyHostToDevice, e->stream));
-    ISL_CUDA(e, cudaMemcpyAsync(e->d_free_off, e->h_free_off.data(), n_batches * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
-    ISL_CUDA(e, cudaMemsetAsync(e->d_free_cnt, 0, n_batches * sizeof(uint32_t), e->stream));
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_tiles, e->h_tiles.data(), n_tiles_total * sizeof(TileDesc), cudaMemcpyHostToDevice, e->stream));
+    ISL_CUDA(e, cudaMemsetAsync(e->d_free_acc, 0, (size_t)n_batches * free_stride, e->stream));
     if (timing) cudaEventRecord(e->ev[0], e->stream);
-    uint32_t tile_off = 0;
-    std::vector<uint32_t> batch_tile(n_batches);
-    for (uint32_t b = 0; b < n_batches; ++b) {
-        batch_tile[b] = tile_off;
-        if (sizes[b] == 0) continue;
-        const uint32_t tiles = ceil_div(sizes[b], kTile);
-        k_prepare<<<tiles, kTileThreads, 0, e->stream>>>(sizes[b], d_in + e->h_free_off[b], d_out + e->h_free_off[b], reinterpret_cast<uint32_t*>(e->d_occ),
-                                                         e->G, e->lo, e->hi, e->prof, e->d_tile_counts + (size_t)tile_off * ISL_MAX_PROFILES, e->d_ctrl,
-                                                         e->d_free_list + e->h_free_off[b], e->d_free_cnt + b);
-        if (int rc = check_launch(e, "k_prepare")) return rc;
-        tile_off += tiles;
-    }
+    k_prepare<<<n_tiles_total, kTileThreads, 0, e->stream>>>(0, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi, e->prof,
+                                                             e->d_tile_counts, e->d_ctrl, e->d_tiles, e->d_free_acc, free_stride / 4);
+    if (int rc = check_launch(e, "k_prepare")) return rc;
     if (timing) cudaEventRecord(e->ev[1], e->stream);
-    for (uint32_t c = 0; c < n_chunks; ++c) {
-        const ChunkDesc& cd = e->h_chunks[c];
-        const uint32_t first_tile = batch_tile[cd.batch] + (cd.req_off - e->h_free_off[cd.batch]) / kTile, n_tiles = ceil_div(cd.n, kTile);
-        k_partition<<<n_tiles, kTileThreads, 0, e->stream>>>(cd.n, d_in + cd.req_off, e->prof.n, e->d_tile_counts + (size_t)first_tile * ISL_MAX_PROFILES, n_tiles,
-                                                             e->cand_profiles, e->d_qall + (size_t)c * kQCap, e->d_cctl + c);
-        if (int rc = check_launch(e, "k_partition")) return rc;
-    }
+    k_partition<<<n_tiles_total, kTileThreads, 0, e->stream>>>(0, d_in, e->prof.n, e->d_tile_counts, 0, e->cand_profiles, e->d_qall, e->d_cctl,
+                                                               e->d_tiles, q_stride);
+    if (int rc = check_launch(e, "k_partition")) return rc;
     if (timing) cudaEventRecord(e->ev[2], e->stream);
     PipeArgs args{};
     args.n_chunks = n_chunks; args.n_seg = n_seg; args.seg = seg; args.lo = e->lo; args.hi = e->hi; args.epoch = ++e->epoch;
-    args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_list = e->d_free_list; args.free_off = e->d_free_off;
-    args.free_cnt = e->d_free_cnt; args.tokens = e->d_tokens; args.occ = e->d_occ; args.out = d_out; args.feas = e->d_feas; args.stats = e->d_ctrl;
+    args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
+    args.q_stride = q_stride; args.free_stride = free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.out = d_out; args.feas = e->d_feas; args.stats = e->d_ctrl;
     args.heads_in = d_heads_in; args.heads_out = d_heads_out;
+    if (e->cfg.flags & ISL_FLAG_TRACE) {
+        if (int rc = grow(e, &e->d_trace, &e->cap_trace, (size_t)n_chunks * n_seg, 4)) return rc;
+        ISL_CUDA(e, cudaMemsetAsync(e->d_trace, 0, (size_t)n_chunks * n_seg * 4 * sizeof(unsigned long long), e->stream));
+        e->trace_chunks = n_chunks; e->trace_seg = n_seg;
+    }
+    args.trace = (e->cfg.flags & ISL_FLAG_TRACE) ? e->d_trace : nullptr;
     args.inbox = ring && e->has_prev ? e->d_inbox : nullptr; args.outbox = ring ? e->d_outbox : nullptr; args.xepoch = xepoch;
     int rc;
     switch (e->n_cand_slots) {
@@ -352,6 +365,12 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
     isl_engine* e = new (std::nothrow) isl_engine;
     if (!e) return ISL_ENOMEM;
     e->cfg = *cfg;
+    {   // pipeline chunk size: ISL_PIPE_CHUNK (requests, rounded to tiles) overrides the default
+        uint32_t pc = kChunk;
+        if (const char* v = getenv("ISL_PIPE_CHUNK")) pc = (uint32_t)strtoul(v, nullptr, 10);
+        pc = std::max(kTile, std::min(kChunk, pc / kTile * kTile));
+        e->pipe_chunk = pc;
+    }
     int dev = cfg->device;
     if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) { delete e; return ISL_ECUDA; }
     int ndev = 0;
@@ -392,9 +411,9 @@ int isl_destroy(isl_engine* e) {
         cudaFree(e->d_q); cudaFree(e->d_tile_counts); cudaFree(e->d_cand); cudaFree(e->d_log); cudaFree(e->d_sweep_counts);
         cudaFree(e->d_ctrl); cudaFree(e->d_scratch);
         cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens);
-        cudaFree(e->d_free_list); cudaFree(e->d_free_off); cudaFree(e->d_free_cnt);
+        cudaFree(e->d_free_acc); cudaFree(e->d_tiles);
         if (e->d_outbox && !e->outbox_local) cudaIpcCloseMemHandle(e->d_outbox);
-        cudaFree(e->d_inbox);
+        cudaFree(e->d_inbox); cudaFree(e->d_trace);
         for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
         if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     }
@@ -646,6 +665,19 @@ int isl_eval_starts(isl_engine* e, uint32_t profile, uint32_t n, const uint8_t* 
     k_eval_starts<<<std::min(ceil_div(n, 256), 1184u), 256, 0, e->stream>>>(e->d_lut, profile, n, e->d_scratch, e->d_scratch + n);
     if (int rc = check_launch(e, "k_eval_starts")) return rc;
     ISL_CUDA(e, cudaMemcpyAsync(out, e->d_scratch + n, n, cudaMemcpyDeviceToHost, e->stream));
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ISL_OK;
+}
+
+int isl_read_trace(isl_engine* e, uint64_t* out, uint32_t max_words, uint32_t* n_chunks, uint32_t* n_seg) {
+    if (!e || !n_chunks || !n_seg) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    *n_chunks = e->trace_chunks; *n_seg = e->trace_seg;
+    const size_t words = (size_t)e->trace_chunks * e->trace_seg * 4;
+    if (!out || words == 0) return ISL_OK;
+    if (words > max_words) return ISL_ERANGE;
+    ISL_CUDA(e, cudaMemcpyAsync(out, e->d_trace, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     return ISL_OK;
 }

@@ -27,7 +27,7 @@ QUIRK_STRICT_BOUND, QUIRK_POW2_ONLY = 1, 2
 QUIRKS_REF_EXACT, QUIRKS_FIXED = 3, 0
 OP_ALLOC, OP_FREE, OP_NOOP = 0, 1, 2
 ST_PLACED, ST_NO_CAPACITY, ST_BAD_PROFILE, ST_FREED, ST_BAD_SPAN, ST_NOOP = 0, 1, 2, 3, 4, 5
-FLAG_TIMING, FLAG_NO_PIPELINE, FLAG_FORCE_PIPELINE = 1, 2, 4
+FLAG_TIMING, FLAG_NO_PIPELINE, FLAG_FORCE_PIPELINE, FLAG_TRACE = 1, 2, 4, 8
 
 # ---- record layouts -------------------------------------------------------------------------
 REQUEST_DTYPE = np.dtype([("handle", "<u4"), ("profile", "u1"), ("op", "u1"), ("start", "u1"), ("size", "u1")])
@@ -58,7 +58,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "isl_create", "isl_destroy", "isl_set_stream", "isl_synchronize", "isl_load_profiles", "isl_load_inventory", "isl_read_occupancy",
     "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_place_stream", "isl_place_stream_device", "isl_free_batch",
-    "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_ipc_inbox_handle", "isl_ipc_connect", "isl_connect_local", "isl_place_stream_partitioned", "isl_device_occupancy", "isl_get_stats",
+    "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_ipc_inbox_handle", "isl_ipc_connect", "isl_connect_local", "isl_place_stream_partitioned", "isl_device_occupancy", "isl_get_stats", "isl_read_trace",
     "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
 ]
 
@@ -98,6 +98,7 @@ def load_library(path: str = LIB_PATH):
         "isl_place_stream_partitioned": (C.c_int, [p, C.c_uint32, p, p, p, C.c_uint32]),
         "isl_device_occupancy": (p, [p]),
         "isl_get_stats": (C.c_int, [p, C.POINTER(Stats)]),
+        "isl_read_trace": (C.c_int, [p, p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "isl_reset_stats": (C.c_int, [p]),
         "isl_strerror": (C.c_char_p, [C.c_int]),
         "isl_last_cuda_error": (C.c_char_p, [p]),
@@ -263,6 +264,15 @@ class Engine:
         return int(self._lib.isl_device_occupancy(self._h) or 0)
 
     # -- diagnostics
+    def read_trace(self) -> np.ndarray:
+        """[chunk][segment][4] globaltimer ns of the last stream call (FLAG_TRACE)."""
+        nc, ns = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.isl_read_trace(self._h, None, 0, C.byref(nc), C.byref(ns)), "isl_read_trace")
+        out = np.zeros((nc.value, ns.value, 4), dtype=np.uint64)
+        if out.size:
+            self._check(self._lib.isl_read_trace(self._h, _ptr(out), out.size, C.byref(nc), C.byref(ns)), "isl_read_trace")
+        return out
+
     def stats(self) -> dict:
         s = Stats()
         self._check(self._lib.isl_get_stats(self._h, C.byref(s)), "isl_get_stats")
