@@ -577,7 +577,7 @@ struct PipeArgs {
     const uint16_t* q_all;          // per chunk queues, stride q_stride entries
     const uint8_t* free_acc;        // per batch one byte per GPU: OR of the slot masks its FREEs release (stride free_stride bytes)
     uint32_t q_stride, free_stride;
-    uint32_t* tokens;               // [chunk][segment][kTokStride]
+    uint32_t* tokens;               // [chunk][segment + 1][kTokStride]; slot n_seg = 'everything placeable is placed' broadcast
     uint8_t* occ;
     uint2* out;
     const uint16_t* feas;
@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     uint32_t* s_wkey = reinterpret_cast<uint32_t*>(smem + kPipeOffWin);          // per-profile windows of ready-made keys t<<15 | p<<11
     __shared__ uint16_t s_feas[256];
     __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_wbase[ISL_MAX_PROFILES], s_qsrc[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
-    __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_warp[kPipeThreads / 32], s_ncand, s_nlog;
+    __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_warp[kPipeThreads / 32], s_ncand, s_nlog, s_src, s_idle;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     const uint32_t lo_s = min(a.hi, a.lo + seg * a.seg), hi_s = min(a.hi, lo_s + a.seg), n_g = hi_s - lo_s;
     const uint32_t sa_cand = (uint32_t)__cvta_generic_to_shared(s_cand), sa_log = (uint32_t)__cvta_generic_to_shared(s_log);
@@ -698,35 +698,77 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         }
         // 3. token of the previous segment
         unsigned long long* tr = a.trace ? a.trace + ((size_t)c * a.n_seg + seg) * 4 : nullptr;
+        const size_t tok_chunk = (size_t)c * (a.n_seg + 1);
         if (tid == 0) {
             if (tr) tr[0] = globaltimer_ns();
+            uint32_t src = 0;                                       // 0: heads_in / zeros, 1: previous segment, 2: peer inbox, 3: done broadcast
             if (seg > 0) {
-                const uint32_t* flag = a.tokens + ((size_t)c * a.n_seg + seg - 1) * kTokStride + ISL_MAX_PROFILES;
-                while (ld_acquire_gpu(flag) != a.epoch) { }
+                const uint32_t* flag = a.tokens + (tok_chunk + seg - 1) * kTokStride + ISL_MAX_PROFILES;
+                const uint32_t* done = a.tokens + (tok_chunk + a.n_seg) * kTokStride + ISL_MAX_PROFILES;
+                while (true) {
+                    if (ld_acquire_gpu(flag) == a.epoch) { src = 1; break; }
+                    if (ld_acquire_gpu(done) == a.epoch) { src = 3; break; }
+                }
             } else if (a.inbox) {       // first segment of a rank that has a predecessor: the token comes over NVLink
                 const uint32_t* flag = a.inbox + (size_t)c * kTokStride + ISL_MAX_PROFILES;
                 while (ld_acquire_sys(flag) != a.xepoch) { }
+                src = 2;
             }
+            s_src = src;
             if (tr) tr[1] = globaltimer_ns();
         }
         __syncthreads();
         if (tid < 32) {     // heads, window sizes and the compact window layout (exclusive scan over the 16 profiles)
-            uint32_t h = 0, wn = 0;
+            uint32_t h = 0, wn = 0, left = 0;
+            const uint32_t src = s_src;
             if (tid < ISL_MAX_PROFILES) {
-                if (seg > 0) h = __ldcg(a.tokens + ((size_t)c * a.n_seg + seg - 1) * kTokStride + tid);
-                else if (a.inbox) h = ld_relaxed_sys(a.inbox + (size_t)c * kTokStride + tid);
+                if (src == 1) h = __ldcg(a.tokens + (tok_chunk + seg - 1) * kTokStride + tid);
+                else if (src == 3) h = __ldcg(a.tokens + (tok_chunk + a.n_seg) * kTokStride + tid);
+                else if (src == 2) h = ld_relaxed_sys(a.inbox + (size_t)c * kTokStride + tid);
                 else h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
-                const uint32_t qc = cc->qcnt[tid], left = qc > h ? qc - h : 0u;
-                wn = ((active >> tid) & 1u) ? min(left, s_ncand * s_maxacc[tid]) : 0u;     // no more pops than that are possible here
+                const uint32_t qc = cc->qcnt[tid];
+                left = ((active >> tid) & 1u) && qc > h ? qc - h : 0u;
+                wn = min(left, s_ncand * s_maxacc[tid]);            // no more pops than that are possible here
                 s_heads[tid] = h; s_wn[tid] = wn; s_pop[tid] = 0;
                 s_qsrc[tid] = c * a.q_stride + cc->qoff[tid] + h;
             }
+            // nothing placeable is pending any more: tell every later segment at once instead of relaying hop by hop
+            const bool idle = __ballot_sync(0xFFFFFFFFu, left != 0) == 0;
+            if (idle && src != 3) {
+                uint32_t* done = a.tokens + (tok_chunk + a.n_seg) * kTokStride;
+                if (tid < ISL_MAX_PROFILES) done[tid] = h;
+                __syncwarp();
+                if (tid == 0) { __threadfence(); st_release_gpu(done + ISL_MAX_PROFILES, a.epoch); }
+            }
+            if (tid == 0) s_idle = idle ? 1u : 0u;
             uint32_t incl = wn + 2;                             // two INF sentinels close every window
 #pragma unroll
             for (int d = 1; d < 16; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
             if (tid < ISL_MAX_PROFILES) s_wbase[tid] = incl - (wn + 2);
         }
         __syncthreads();
+        if (s_idle) {       // pass-through: the token (unchanged heads) still reaches the next rank / the caller from the last segment
+            if (warp == 0) {
+                const bool last = seg == a.n_seg - 1;
+                uint32_t* tok = a.tokens + (tok_chunk + seg) * kTokStride;
+                uint32_t* peer = last && a.outbox ? a.outbox + (size_t)c * kTokStride : nullptr;
+                if (lane < ISL_MAX_PROFILES) {
+                    const uint32_t h = s_heads[lane];
+                    tok[lane] = h;
+                    if (last && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + lane] = h;
+                    if (peer) peer[lane] = h;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    st_release_gpu(tok + ISL_MAX_PROFILES, a.epoch);
+                    if (peer) { __threadfence_system(); st_release_sys(peer + ISL_MAX_PROFILES, a.xepoch); }
+                    if (tr) { tr[2] = globaltimer_ns(); tr[3] = tr[2]; }
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) {          // stage the windows as ready-made keys: t << 15 | profile << 11
             const uint32_t wn = s_wn[p], base = s_wbase[p];
             const uint16_t* src = a.q_all + s_qsrc[p];
@@ -800,7 +842,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             for (int k = 0; k < K; ++k) if (reports[k]) s_pop[cprof[k]] = (wa[k] - wa0[k] - 12) >> 2;
             __syncwarp();
             // 5. token for the next segment: heads first, then the flag (release)
-            uint32_t* tok = a.tokens + ((size_t)c * a.n_seg + seg) * kTokStride;
+            uint32_t* tok = a.tokens + (tok_chunk + seg) * kTokStride;
             const bool last = seg == a.n_seg - 1;
             uint32_t* peer = last && a.outbox ? a.outbox + (size_t)c * kTokStride : nullptr;
             if (lane < ISL_MAX_PROFILES) {

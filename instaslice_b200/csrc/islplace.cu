@@ -235,7 +235,10 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         uint32_t total_cand = 0;
         for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) total_cand += e->tab.desc[k][l] >> 31;
         const uint32_t seg_cap = max_segment_for(total_cand);      // queue windows of a segment must fit in shared memory
-        seg = std::min(seg_cap, std::max(64u, (ceil_div(range, 128u) + 63u) / 64u * 64u));
+        uint32_t target = 148;                                       // segments aimed for; ISL_PIPE_SEGMENTS overrides (experiments)
+        if (const char* v = getenv("ISL_PIPE_SEGMENTS")) target = std::max(1u, (uint32_t)strtoul(v, nullptr, 10));
+        target = std::min(target, (uint32_t)std::max(1, e->max_coresident));
+        seg = std::min(seg_cap, std::max(64u, (ceil_div(range, target) + 63u) / 64u * 64u));
         if (seg_cap < 64) { if (ring) return ISL_ERANGE; pipeline = false; seg = 64; }
         n_seg = std::max(1u, ceil_div(range, seg));
         if (e->max_coresident <= 0 || n_seg > (uint32_t)e->max_coresident) { if (ring) return ISL_ERANGE; pipeline = false; }
@@ -279,7 +282,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     if (int rc = grow(e, &e->d_free_acc, &e->cap_free, (size_t)n_batches * (free_stride / 4), 1)) return rc;
     {   // token flags carry the call epoch: a (re)allocated buffer must not hold stale flags of an earlier owner
         const uint32_t before = e->cap_tokens;
-        if (int rc = grow(e, &e->d_tokens, &e->cap_tokens, (size_t)n_chunks * n_seg, kTokStride)) return rc;
+        if (int rc = grow(e, &e->d_tokens, &e->cap_tokens, (size_t)n_chunks * (n_seg + 1), kTokStride)) return rc;
         if (e->cap_tokens != before) ISL_CUDA(e, cudaMemsetAsync(e->d_tokens, 0, (size_t)e->cap_tokens * kTokStride * sizeof(uint32_t), e->stream));
     }
     if (n_tiles_total > ceil_div(e->cfg.max_batch, kTile) + 4096) return ISL_ERANGE;

@@ -20,11 +20,14 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         got = eng.place_stream(batches)
         st = eng.stats(); best = min(best, st["ms_total"])
     ok = all(np.array_equal(a, b) for a, b in zip(got, want))
-    print(json.dumps({"chunk": os.environ.get("ISL_PIPE_CHUNK"), "ms_total_best": round(best, 3), "ms_pipeline": round(st["ms_commit"], 3),
+    print(json.dumps({"chunk": os.environ.get("ISL_PIPE_CHUNK"), "segments": os.environ.get("ISL_PIPE_SEGMENTS"), "ms_total_best": round(best, 3), "ms_pipeline": round(st["ms_commit"], 3),
                       "ms_prepare": round(st["ms_free"], 3), "ms_partition": round(st["ms_partition"], 3), "parity": ok, "jumps": st["chain_jumps"]}))
 else:
     import __graft_entry__ as g
     g.build()
     for c in sys.argv[1:] or ["65536", "32768", "16384", "8192", "4096", "2048"]:
-        env = dict(os.environ, ISL_PIPE_CHUNK=c)
+        chunk, _, segs = c.partition(":")
+        env = dict(os.environ, ISL_PIPE_CHUNK=chunk)
+        if segs:
+            env["ISL_PIPE_SEGMENTS"] = segs
         print(subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True).stdout.strip()[-400:])
