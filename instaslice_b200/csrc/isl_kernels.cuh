@@ -882,4 +882,87 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_bestfit: ISL_POLICY_BEST_FIT (extension, SURVEY 8a-ext — no reference counterpart, parity is against
+// oracle/ref_fast.cpp's best-fit).  Among the GPUs on which the profile has a legal start, take the one with the
+// fewest free slices after the placement = the highest popcount of the occupancy byte, ties to the lowest canonical
+// index; the start is the reference's first legal start.  Requests are resolved strictly in order (request-major: a
+// placement can make a GPU the best fit of the very next request, so there is no GPU-major shortcut).
+// State: GPUs grouped by occupancy byte (256 classes); per class a two-level bitmap (32 GPUs per word, 1024 per
+// summary bit) and its minimum member.  One warp: lane = a few classes, key = (8 - popcount) << 24 | class minimum,
+// redux.min picks the GPU; lane 0 moves it to its new class.  One CTA; all threads build the class structure.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kBfThreads = 1024;
+constexpr uint32_t kBfMaxGpus = 65536;              // 2048 words + 64 summary words per class
+constexpr uint32_t kBfSmemGpus = 4096;              // up to here the class bitmaps live in shared memory (132 KiB)
+
+__global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uint2* __restrict__ in, uint2* __restrict__ out, uint8_t* __restrict__ occ,
+                                                           uint32_t lo, uint32_t hi, const uint8_t* __restrict__ lut, DevProfiles prof,
+                                                           uint32_t* __restrict__ g_bitmaps, Ctrl* ctrl) {
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    __shared__ uint32_t s_min[256];
+    __shared__ uint8_t s_lut[ISL_MAX_PROFILES * 256];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t Gr = hi - lo, W0 = (Gr + 31) / 32, W1 = (W0 + 31) / 32, stride = W0 + W1;   // words per class
+    uint32_t* bm = Gr <= kBfSmemGpus ? s_dyn : g_bitmaps;
+    for (uint32_t i = tid; i < 256 * stride; i += kBfThreads) bm[i] = 0;
+    for (uint32_t i = tid; i < ISL_MAX_PROFILES * 256; i += kBfThreads) s_lut[i] = lut[i];
+    if (tid < 256) s_min[tid] = kInf;
+    __syncthreads();
+    for (uint32_t g = tid; g < Gr; g += kBfThreads) {           // build: every GPU joins the class of its occupancy byte
+        const uint32_t o = occ[lo + g];
+        atomicOr(&bm[o * stride + (g >> 5)], 1u << (g & 31u));
+        atomicOr(&bm[o * stride + W0 + (g >> 10)], 1u << ((g >> 5) & 31u));
+        atomicMin(&s_min[o], g);
+    }
+    __syncthreads();
+    if (tid >= 32) return;
+    uint32_t placed = 0;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint2 mine = base + lane < n ? in[base + lane] : make_uint2(0, (uint32_t)ISL_OP_NOOP << 8);
+        const uint32_t cnt = min(32u, n - base);
+        for (uint32_t j = 0; j < cnt; ++j) {
+            const uint32_t w = __shfl_sync(0xFFFFFFFFu, mine.y, j);
+            const uint32_t p = w & 0xFFu, op = (w >> 8) & 0xFFu;
+            if (op != ISL_OP_ALLOC || p >= prof.n) continue;    // defaults / frees were written by k_prepare
+            uint32_t key = kInf;
+#pragma unroll
+            for (uint32_t r = 0; r < 8; ++r) {                  // lane l looks at classes l, l+32, ...
+                const uint32_t o = r * 32 + lane;
+                const uint32_t mn = s_min[o];
+                if (mn != kInf && s_lut[p * 256 + o] != ISL_START_NONE) key = min(key, ((8u - __popc(o)) << 24) | mn);
+            }
+            const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, key);
+            if (m == kInf) continue;                            // stays NO_CAPACITY
+            const uint32_t g = m & 0xFFFFFFu;
+            if (lane == 0) {
+                const uint32_t o = occ[lo + g];
+                const uint32_t start = s_lut[p * 256 + o], size = prof.rows[p].size;
+                const uint32_t o2 = o | ((((1u << size) - 1u) << start) & 0xFFu);
+                occ[lo + g] = (uint8_t)o2;
+                out[base + j] = pack_result(lo + g, start, size, ISL_ST_PLACED);
+                // leave class o: clear the bit, fix the summary, find the new minimum (g was the minimum)
+                uint32_t* c0 = bm + o * stride;
+                const uint32_t w0 = c0[g >> 5] & ~(1u << (g & 31u));
+                c0[g >> 5] = w0;
+                if (w0 == 0) c0[W0 + (g >> 10)] &= ~(1u << ((g >> 5) & 31u));
+                uint32_t mn = kInf;
+                for (uint32_t k = g >> 10; k < W1; ++k) {
+                    const uint32_t sw = c0[W0 + k];
+                    if (sw) { const uint32_t wi = k * 32 + __ffs(sw) - 1; mn = wi * 32 + __ffs(c0[wi]) - 1; break; }
+                }
+                s_min[o] = mn;
+                // join class o2
+                uint32_t* c1 = bm + o2 * stride;
+                c1[g >> 5] |= 1u << (g & 31u);
+                c1[W0 + (g >> 10)] |= 1u << ((g >> 5) & 31u);
+                if (g < s_min[o2]) s_min[o2] = g;
+                ++placed;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) { atomicAdd(&ctrl->placed, (unsigned long long)placed); atomicAdd(&ctrl->steps, (unsigned long long)placed); }
+}
+
 }  // namespace isl

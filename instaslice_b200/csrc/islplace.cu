@@ -45,6 +45,7 @@ struct isl_engine {
     uint32_t* d_tile_counts = nullptr;
     uint32_t* d_cand = nullptr;
     uint2* d_log = nullptr;          // decision log of one chunk (chain -> commit)
+    uint32_t* d_bf_bitmaps = nullptr; // best-fit class bitmaps for inventories beyond the shared-memory size
     uint32_t* d_sweep_counts = nullptr;
     Ctrl* d_ctrl = nullptr;
     uint8_t* d_scratch = nullptr;    // eval_starts / free_batch staging
@@ -117,8 +118,43 @@ int launch_chain(isl_engine* e, uint2* d_out_chunk, const uint32_t* d_heads_in, 
 }
 
 // Resolve n requests that already sit in device memory.  Enqueues only; the caller synchronises.
+// ISL_POLICY_BEST_FIT: frees + defaults, then the request-major class-bitmap kernel (one CTA).
+int run_bestfit(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out) {
+    if (n == 0) return ISL_OK;
+    const uint32_t Gr = e->hi - e->lo;
+    if (Gr == 0 || Gr > kBfMaxGpus) return ISL_ERANGE;
+    const uint32_t W0 = (Gr + 31) / 32, W1 = (W0 + 31) / 32, stride = W0 + W1;
+    const bool in_smem = Gr <= kBfSmemGpus;
+    const size_t smem = in_smem ? (size_t)256 * stride * sizeof(uint32_t) : 0;
+    if (!in_smem && !e->d_bf_bitmaps) ISL_CUDA(e, cudaMalloc(&e->d_bf_bitmaps, (size_t)256 * (kBfMaxGpus / 32 + kBfMaxGpus / 1024) * sizeof(uint32_t)));
+    static bool attr_set[8] = {false};
+    if (!attr_set[e->device & 7]) {
+        ISL_CUDA(e, cudaFuncSetAttribute(k_bestfit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(256 * (kBfSmemGpus / 32 + kBfSmemGpus / 1024) * sizeof(uint32_t))));
+        attr_set[e->device & 7] = true;
+    }
+    const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
+    if (timing) cudaEventRecord(e->ev[0], e->stream);
+    k_prepare<<<ceil_div(n, kTile), kTileThreads, 0, e->stream>>>(n, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi,
+                                                                  e->prof, e->d_tile_counts, e->d_ctrl, nullptr, nullptr, 0);
+    if (int rc = check_launch(e, "k_prepare")) return rc;
+    if (timing) cudaEventRecord(e->ev[1], e->stream);
+    k_bestfit<<<1, kBfThreads, smem, e->stream>>>(n, d_in, d_out, e->d_occ, e->lo, e->hi, e->d_lut, e->prof, e->d_bf_bitmaps, e->d_ctrl);
+    if (int rc = check_launch(e, "k_bestfit")) return rc;
+    if (timing) {
+        cudaEventRecord(e->ev[2], e->stream);
+        cudaEventSynchronize(e->ev[2]);
+        float t;
+        cudaEventElapsedTime(&t, e->ev[0], e->ev[1]); e->st.ms_free += t;
+        cudaEventElapsedTime(&t, e->ev[1], e->ev[2]); e->st.ms_commit += t;
+        cudaEventElapsedTime(&t, e->ev[0], e->ev[2]); e->st.ms_total += t;
+    }
+    ++e->st.batches; e->st.requests += n;
+    return ISL_OK;
+}
+
 int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const uint32_t* d_heads_in, uint32_t* d_heads_out) {
     if (n == 0) return ISL_OK;
+    if (e->cfg.policy == ISL_POLICY_BEST_FIT) return run_bestfit(e, n, d_in, d_out);
     const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
     const uint32_t tiles = ceil_div(n, kTile);
     if (timing) cudaEventRecord(e->ev[0], e->stream);
@@ -227,7 +263,8 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     const uint32_t range = e->hi - e->lo;
     const bool ring = xepoch != 0;      // partitioned inventory: tokens cross ranks through peer memory, pipeline mandatory
     if (ring && n_chunks > kMaxStreamChunks) return ISL_ERANGE;
-    const bool legacy_token = d_heads_in || d_heads_out;   // isl_place_batch_partitioned: host-carried token, kChunk layout
+    if (e->cfg.policy == ISL_POLICY_BEST_FIT && (d_heads_in || d_heads_out || xepoch)) return ISL_EINVAL;   // best-fit does not partition
+    const bool legacy_token = d_heads_in || d_heads_out || e->cfg.policy == ISL_POLICY_BEST_FIT;   // isl_place_batch_partitioned: host-carried token, kChunk layout
     bool pipeline = ring || (!legacy_token && !(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE)));
     uint32_t seg = 0, n_seg = 0;
     if (pipeline) {
@@ -334,7 +371,6 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
 int validate_ready(isl_engine* e, uint32_t n) {
     if (!e->have_profiles || !e->have_inventory) return ISL_ESTATE;
     if (n > e->cfg.max_batch) return ISL_ERANGE;
-    if (e->cfg.policy != ISL_POLICY_FIRST_FIT) return ISL_EINVAL;
     return ISL_OK;
 }
 
@@ -363,7 +399,8 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
     *out = nullptr;
     if (cfg->abi_version != ISL_ABI_VERSION) return ISL_EINVAL;
     if (cfg->max_gpus == 0 || cfg->max_gpus > ISL_MAX_GPUS || cfg->max_batch == 0) return ISL_EINVAL;
-    if (cfg->policy != ISL_POLICY_FIRST_FIT) return ISL_EINVAL;      // best-fit: see DESIGN.md "What comes next"
+    if (cfg->policy != ISL_POLICY_FIRST_FIT && cfg->policy != ISL_POLICY_BEST_FIT) return ISL_EINVAL;
+    if (cfg->policy == ISL_POLICY_BEST_FIT && cfg->max_gpus > kBfMaxGpus) return ISL_ERANGE;
     if (cfg->quirks & ~ISL_QUIRKS_REF_EXACT) return ISL_EINVAL;
     isl_engine* e = new (std::nothrow) isl_engine;
     if (!e) return ISL_ENOMEM;
@@ -416,7 +453,7 @@ int isl_destroy(isl_engine* e) {
         cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens);
         cudaFree(e->d_free_acc); cudaFree(e->d_tiles);
         if (e->d_outbox && !e->outbox_local) cudaIpcCloseMemHandle(e->d_outbox);
-        cudaFree(e->d_inbox); cudaFree(e->d_trace);
+        cudaFree(e->d_inbox); cudaFree(e->d_trace); cudaFree(e->d_bf_bitmaps);
         for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
         if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     }

@@ -405,3 +405,60 @@ def test_partitioned_ring_on_one_gpu(n_ranks):
         assert np.array_equal(merged, np.concatenate(want))
         occ = np.concatenate([eng.read_occupancy()[lo:hi] for eng, (lo, hi) in zip(engines, bounds)])
         assert np.array_equal(occ, ref.occupancy())
+
+
+# ---- best-fit (extension, SURVEY 8a-ext: no reference counterpart; parity against oracle/ref_fast.cpp best-fit) -----------
+def check_best_fit(node_off, occ, rows, batches, quirks=E.QUIRKS_REF_EXACT):
+    eng = E.Engine(max_gpus=max(4096, len(occ)), max_batch=1 << 20, quirks=quirks, policy=E.POLICY_BEST_FIT)
+    eng.load_profiles(rows)
+    eng.load_inventory(node_off, occ)
+    ref = oracle.Fast(node_off, rows, quirks, policy=1)
+    ref.load(occ)
+    for i, req in enumerate(batches):
+        got, want = eng.place_batch(req), ref.place(req)
+        bad = np.flatnonzero(got != want)
+        assert len(bad) == 0, (i, bad[:5], got[bad[:5]], want[bad[:5]])
+        assert np.array_equal(eng.read_occupancy(), ref.occupancy()), i
+    return eng
+
+
+def test_best_fit_config3():
+    node_off, occ, rows, req = W.config3(n=30_000)           # 4096 GPUs: class bitmaps in shared memory
+    check_best_fit(node_off, occ, rows, [req])
+
+
+@pytest.mark.parametrize("G", [37, 4096, 12288])
+def test_best_fit_random_with_frees(G):
+    rows = E.make_profiles(tables.H100_80GB)
+    rng = W.SplitMix64(G)
+    node_off = np.concatenate([[0], np.cumsum(np.full((G + 7) // 8, 8))]).astype(np.uint32)
+    node_off[-1] = G
+    occ = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+    ref = oracle.Fast(node_off, rows, 0, policy=1)
+    ref.load(occ)
+    batches, live = [], []
+    for b in range(4):
+        n = 800 + 400 * b
+        req = W.alloc_requests((rng.next(n) % np.uint64(len(rows))).astype(np.uint8))
+        for i in range(min(len(live), n // 3)):
+            g, s, z = live.pop(int(rng.next1() % len(live)))
+            req[int(rng.next1() % n)] = (g, 0, E.OP_FREE, s, z)
+        res = ref.place(req)
+        for r in res[(req["op"] == E.OP_ALLOC) & (res["status"] == E.ST_PLACED)]:
+            live.append((int(r["gpu"]), int(r["start"]), int(r["size"])))
+        batches.append(req)
+    check_best_fit(node_off, occ, rows, batches, quirks=0)
+
+
+def test_best_fit_prefers_tightest_gpu():
+    """Hand-checkable: a 1g request goes to the fullest GPU that still has a free slice, not to the first one."""
+    rows = E.make_profiles(tables.A100_40GB)
+    eng = E.Engine(max_gpus=4096, max_batch=64, policy=E.POLICY_BEST_FIT)
+    eng.load_profiles(rows)
+    eng.load_inventory(W.node_offsets(1, 4), np.array([0x00, 0x0F, 0x3F, 0x7F], dtype=np.uint8))
+    res = eng.place_batch(W.alloc_requests(np.array([0, 0, 1], dtype=np.uint8)))     # 1g, 1g, 2g
+    ref = oracle.Fast(W.node_offsets(1, 4), rows, 3, policy=1)
+    ref.load(np.array([0x00, 0x0F, 0x3F, 0x7F], dtype=np.uint8))
+    want = ref.place(W.alloc_requests(np.array([0, 0, 1], dtype=np.uint8)))
+    assert np.array_equal(res, want)
+    assert (int(res["gpu"][0]), int(res["start"][0])) == (2, 6) and (int(res["gpu"][1]), int(res["start"][1])) == (1, 4)
