@@ -275,7 +275,8 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         uint32_t target = 148;                                       // segments aimed for; ISL_PIPE_SEGMENTS overrides (experiments)
         if (const char* v = getenv("ISL_PIPE_SEGMENTS")) target = std::max(1u, (uint32_t)strtoul(v, nullptr, 10));
         target = std::min(target, (uint32_t)std::max(1, e->max_coresident));
-        seg = std::min(seg_cap, std::max(64u, (ceil_div(range, target) + 63u) / 64u * 64u));
+        // segment size from the WHOLE inventory: a partitioned rank keeps the global pipeline depth (~target stages over all ranks)
+        seg = std::min(seg_cap, std::max(64u, (ceil_div(e->G, target) + 63u) / 64u * 64u));
         if (seg_cap < 64) { if (ring) return ISL_ERANGE; pipeline = false; seg = 64; }
         n_seg = std::max(1u, ceil_div(range, seg));
         if (e->max_coresident <= 0 || n_seg > (uint32_t)e->max_coresident) { if (ring) return ISL_ERANGE; pipeline = false; }
