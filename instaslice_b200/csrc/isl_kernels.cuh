@@ -628,7 +628,21 @@ __device__ __forceinline__ uint32_t lds_u32_if(bool pred, uint32_t sa, uint32_t 
     return keep;
 }
 
-template <int K>
+// Rare path of the decision chain, kept out of line so that the hot loop stays free of divergence-capable constructs:
+// first candidate index >= from + 2 on which a profile of `alive` fits, or kInf.
+__device__ __noinline__ uint32_t pipeline_skip(uint32_t sa_cand, const uint16_t* s_feas, uint32_t n_cand, uint32_t cur_plus2, uint32_t alive, uint32_t lane) {
+    alive = __reduce_or_sync(0xFFFFFFFFu, alive);
+    uint32_t j = cur_plus2;                      // record index of (current + 2)
+    while (alive && j < n_cand) {
+        const uint32_t cr = j + lane < n_cand ? lds_u32(sa_cand + 4 * (j + lane)) : kInf;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, cr != kInf && (s_feas[cr & 0xFFu] & alive) != 0);
+        if (b) return j + __ffs(b) - 1;
+        j += 32;
+    }
+    return kInf;
+}
+
+template <int K, bool kP15>
 __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t* s_occ32 = reinterpret_cast<uint32_t*>(smem);                       // kSegMax occupancy bytes
@@ -789,7 +803,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 tnn[k] = two ? lds_u32(wa0[k] + 8) : kInf;
                 wa[k] = wa0[k] + 12;                                            // next entry to load on a pop
             }
-            uint32_t i0 = 0, la = sa_log, ca = sa_cand + 8;                     // ca: address of candidate record i0 + 2
+            uint32_t la = sa_log, ca = sa_cand + 8;                             // ca: shared address of candidate record (current + 2)
             uint32_t o0 = lds_u8(sa_cand), o1 = lds_u8(sa_cand + 4), o2 = lds_u8(sa_cand + 8);
             while (true) {
                 uint32_t key = kInf;
@@ -803,33 +817,24 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     uint32_t alive = 0;
 #pragma unroll
                     for (int k = 0; k < K; ++k) alive |= tcur[k] != kInf ? 1u << cprof[k] : 0u;
-                    alive = __reduce_or_sync(0xFFFFFFFFu, alive);
-                    uint32_t j = i0 + 2;
-                    bool found = false;
-                    while (alive && j < n_cand) {
-                        const uint32_t cr = j + lane < n_cand ? s_cand[j + lane] : kInf;
-                        const uint32_t b = __ballot_sync(0xFFFFFFFFu, cr != kInf && (s_feas[cr & 0xFFu] & alive) != 0);
-                        if (b) { j += __ffs(b) - 1; found = true; break; }
-                        j += 32;
-                    }
+                    const uint32_t j = pipeline_skip(sa_cand, s_feas, n_cand, ((ca - sa_cand) >> 2), alive, lane);
                     ++st_jumps;
-                    if (!found) break;
-                    i0 = j; ca = sa_cand + 4 * (i0 + 2);
+                    if (j == kInf) break;
+                    ca = sa_cand + 4 * (j + 2);
                     o0 = lds_u8(ca - 8); o1 = lds_u8(ca - 4); o2 = lds_u8(ca);
                     continue;
                 }
                 const uint32_t sel = m >> 31;
-                i0 += sel;
-                sts_v2_if(lane == 0, la, m, i0);                    // decision log: (key, candidate index it landed on)
+                ca += sel * 4;
+                sts_v2_if(lane == 0, la, m, ca);                    // decision log: (key, address of the record two past the GPU it landed on)
                 la += 8;
                 o0 = (sel ? o1 : o0) | (m & 0xFFu);
                 o1 = sel ? o2 : o1;
-                ca += sel * 4;
                 o2 = lds_u8(ca);
-                const uint32_t mm = m & 0x7FFFF800u;                // t and profile of the winner, without sel
 #pragma unroll
-                for (int k = 0; k < K; ++k) {       // lanes of the winning profile pop their window (INF never matches: bit 31)
-                    const bool adv = ((mm ^ tcur[k]) & 0xFFFFF800u) == 0;
+                for (int k = 0; k < K; ++k) {       // lanes of the winning profile (same t, same profile) pop their window
+                    // INF never matches a real key: bit 31 unless profile index 15 is in use (kP15), then the t/profile fields alone could
+                    const bool adv = kP15 ? (((m & 0x7FFFF800u) ^ tcur[k]) & 0xFFFFF800u) == 0 : ((m ^ tcur[k]) & 0x7FFFF800u) == 0;
                     tcur[k] = adv ? tnext[k] : tcur[k];
                     tnext[k] = adv ? (tnn[k] | klow[k]) : tnext[k];
                     tnn[k] = lds_u32_if(adv, wa[k], tnn[k]);        // consumed at the earliest one pop later
@@ -837,7 +842,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 }
             }
             const uint32_t nlog = (la - sa_log) >> 3;
-            st_steps += nlog; st_visited += i0;
+            st_steps += nlog; st_visited += ((ca - sa_cand) >> 2) - 2;
 #pragma unroll
             for (int k = 0; k < K; ++k) if (reports[k]) s_pop[cprof[k]] = (wa[k] - wa0[k] - 12) >> 2;
             __syncwarp();
@@ -865,7 +870,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             const uint32_t nlog = s_nlog;
             for (uint32_t j = tid; j < nlog; j += kPipeThreads) {
                 const uint2 e = s_log[j];
-                const uint32_t l = s_cand[e.y] >> 8, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
+                const uint32_t l = s_cand[((e.y - sa_cand) >> 2) - 2] >> 8, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
                 a.out[cd.req_off + t] = pack_result(lo_s + l, __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
                 atomicOr(&s_occ32[l >> 2], mask << ((l & 3u) * 8u));
             }

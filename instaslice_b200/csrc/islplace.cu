@@ -217,15 +217,15 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
 }
 
 
-template <int K>
+template <int K, bool kP15>
 int launch_pipeline(isl_engine* e, PipeArgs& args) {
     static bool attr_set[8] = {false};
     if (!attr_set[e->device & 7]) {
-        ISL_CUDA(e, cudaFuncSetAttribute(k_pipeline<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+        ISL_CUDA(e, cudaFuncSetAttribute(k_pipeline<K, kP15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
         attr_set[e->device & 7] = true;
     }
     void* params[] = {&e->tab, &args};
-    ISL_CUDA(e, cudaLaunchCooperativeKernel((void*)k_pipeline<K>, dim3(args.n_seg), dim3(kPipeThreads), params, kPipeSmem, e->stream));
+    ISL_CUDA(e, cudaLaunchCooperativeKernel((void*)k_pipeline<K, kP15>, dim3(args.n_seg), dim3(kPipeThreads), params, kPipeSmem, e->stream));
     ++e->st.kernel_launches;
     return ISL_OK;
 }
@@ -235,8 +235,8 @@ int query_coresident(isl_engine* e) {
     int per_sm = 0, sms = 0, coop = 0;
     ISL_CUDA(e, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
     ISL_CUDA(e, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
-    ISL_CUDA(e, cudaFuncSetAttribute(k_pipeline<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
-    ISL_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline<1>, kPipeThreads, kPipeSmem));
+    ISL_CUDA(e, cudaFuncSetAttribute(k_pipeline<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+    ISL_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline<4, true>, kPipeThreads, kPipeSmem));
     e->max_coresident = coop ? std::max(1, per_sm * sms) : -1;
     return ISL_OK;
 }
@@ -349,10 +349,11 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     args.trace = (e->cfg.flags & ISL_FLAG_TRACE) ? e->d_trace : nullptr;
     args.inbox = ring && e->has_prev ? e->d_inbox : nullptr; args.outbox = ring ? e->d_outbox : nullptr; args.xepoch = xepoch;
     int rc;
+    const bool p15 = e->prof.n == ISL_MAX_PROFILES;      // profile index 15 in use: the pop test needs the slower, INF-safe form
     switch (e->n_cand_slots) {
-        case 1: rc = launch_pipeline<1>(e, args); break;
-        case 2: rc = launch_pipeline<2>(e, args); break;
-        default: rc = launch_pipeline<4>(e, args); break;
+        case 1: rc = p15 ? launch_pipeline<1, true>(e, args) : launch_pipeline<1, false>(e, args); break;
+        case 2: rc = p15 ? launch_pipeline<2, true>(e, args) : launch_pipeline<2, false>(e, args); break;
+        default: rc = p15 ? launch_pipeline<4, true>(e, args) : launch_pipeline<4, false>(e, args); break;
     }
     if (rc) return rc;
     if (timing) {
