@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
     auto ldc = [&](uint32_t idx) -> uint32_t { return idx < n_cand ? cand[idx] : kInf; };   // past the end: occupancy 0xFF, nothing fits
     uint32_t fill = 0, pending;
     auto reload = [&](uint32_t at) {       // synchronous (re)fill of 5 blocks starting at the block that holds `at`
+        __syncwarp();                          // every lane is done reading the slots that are about to be overwritten
         fill = at & ~31u;
         for (int b = 0; b < 5; ++b) { s_ring[(fill + lane) & (kRing - 1)] = ldc(fill + lane); fill += 32; }
         pending = ldc(fill + lane);
@@ -482,6 +483,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
             ++i0;
             o2 = s_ring[(i0 + 2) & (kRing - 1)] & 0xFFu;
             if ((i0 & 31u) == 0 && fill < i0 + 224) {
+                __syncwarp();
                 s_ring[(fill + lane) & (kRing - 1)] = pending;
                 fill += 32;
                 pending = ldc(fill + lane);
@@ -940,6 +942,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
             const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, key);
             if (m == kInf) continue;                            // stays NO_CAPACITY
             const uint32_t g = m & 0xFFFFFFu;
+            __syncwarp();                                       // all lanes have read the class minima before lane 0 rewrites them
             if (lane == 0) {
                 const uint32_t o = occ[lo + g];
                 const uint32_t start = s_lut[p * 256 + o], size = prof.rows[p].size;

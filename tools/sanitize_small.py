@@ -1,0 +1,37 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): both device paths, frees, stream, best-fit."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import oracle
+from instaslice_b200 import engine as E, tables, workloads as W
+rows = E.make_profiles(tables.H100_80GB)
+rng = W.SplitMix64(5)
+G = 2048
+node_off = W.node_offsets(G // 8, 8)
+occ = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+ref = oracle.Fast(node_off, rows); ref.load(occ)
+batches, live = [], []
+for b in range(3):
+    n = 1500
+    req = W.alloc_requests(W.mix_profiles(rng, n))
+    for i in range(min(len(live), n // 3)):
+        g, s, z = live.pop(int(rng.next1() % len(live)))
+        req[int(rng.next1() % n)] = (g, 0, E.OP_FREE, s, z)
+    res = ref.place(req)
+    for r in res[(req["op"] == E.OP_ALLOC) & (res["status"] == E.ST_PLACED)]:
+        live.append((int(r["gpu"]), int(r["start"]), int(r["size"])))
+    batches.append((req, res))
+for flags in (E.FLAG_NO_PIPELINE, E.FLAG_FORCE_PIPELINE):
+    eng = E.Engine(max_gpus=4096, max_batch=1 << 16, flags=flags)
+    eng.load_profiles(rows); eng.load_inventory(node_off, occ)
+    for req, res in batches:
+        assert np.array_equal(eng.place_batch(req), res)
+eng = E.Engine(max_gpus=4096, max_batch=1 << 16)
+eng.load_profiles(rows); eng.load_inventory(node_off, occ)
+got = eng.place_stream([b[0] for b in batches])
+assert all(np.array_equal(g, b[1]) for g, b in zip(got, batches))
+bf = E.Engine(max_gpus=4096, max_batch=1 << 16, policy=E.POLICY_BEST_FIT)
+bf.load_profiles(rows); bf.load_inventory(node_off, occ)
+rb = oracle.Fast(node_off, rows, 3, policy=1); rb.load(occ)
+assert np.array_equal(bf.place_batch(batches[0][0]), rb.place(batches[0][0]))
+print("sanitize run ok")
