@@ -462,3 +462,23 @@ def test_best_fit_prefers_tightest_gpu():
     want = ref.place(W.alloc_requests(np.array([0, 0, 1], dtype=np.uint8)))
     assert np.array_equal(res, want)
     assert (int(res["gpu"][0]), int(res["start"][0])) == (2, 6) and (int(res["gpu"][1]), int(res["start"][1])) == (1, 4)
+
+
+def test_large_inventory_falls_back_to_single_chain():
+    """300k GPUs need more pipeline segments than can be co-resident: the engine must take the multi-CTA sweep +
+    single-chain path on its own (also for a stream call) and stay bit-exact."""
+    rows = E.make_profiles(tables.H100_80GB)
+    rng = W.SplitMix64(300)
+    G = 300_000
+    node_off = W.node_offsets(G // 8, 8)
+    occ = ((rng.next(G) | rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)       # ~75 % busy: long infeasible runs to skip
+    batches = [W.alloc_requests(W.mix_profiles(rng, 70_000)), W.alloc_requests(W.mix_profiles(rng, 20_000))]
+    ref = oracle.Fast(node_off, rows)
+    ref.load(occ)
+    want = [ref.place(b) for b in batches]
+    eng = make_engine(node_off, occ, rows)
+    got = eng.place_stream(batches)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert np.array_equal(eng.read_occupancy(), ref.occupancy())
+    assert eng.gpu_to_node(G - 1) == G // 8 - 1
