@@ -182,6 +182,10 @@ int  isl_load_profiles(isl_engine* e, uint32_t n, const isl_profile* rows);
  * occ has node_off[n_nodes] bytes.  This is also "resume": the CR is the checkpoint. */
 int  isl_load_inventory(isl_engine* e, uint32_t n_nodes, const uint32_t* node_off, const uint8_t* occ);
 int  isl_read_occupancy(isl_engine* e, uint8_t* out /* G bytes */);
+/* Incremental sync: overwrite the occupancy bytes of canonical GPUs [first_gpu, first_gpu + n) — what the shim does
+ * when ONE Instaslice object changed (an Allocations / Prepared entry appeared or disappeared) instead of re-listing
+ * every node (the reference deep-copies the whole list on every reconcile, :85). */
+int  isl_write_occupancy(isl_engine* e, uint32_t first_gpu, uint32_t n, const uint8_t* occ);
 uint32_t isl_num_gpus(const isl_engine* e);
 /* node that owns canonical GPU index `gpu` (binary search over node_off), or ISL_GPU_NONE */
 uint32_t isl_gpu_to_node(const isl_engine* e, uint32_t gpu);

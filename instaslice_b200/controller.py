@@ -132,6 +132,25 @@ class InstasliceReconciler:
             p.get("podUUID", "") != "" and p["podUUID"] not in it["spec"].get("allocations", {})
             for it in self.items for p in it["spec"].get("prepared", {}).values())
 
+    def update_node(self, instaslice: dict):
+        """Incremental sync after ONE Instaslice object changed (an Allocations / Prepared entry appeared, changed or was
+        deleted by the daemonset): recompute the occupancy bytes of that node's GPUs only and overwrite them in the engine.
+        Falls back to a full ``sync`` when the node's GPU set or profile table changed."""
+        n = next((i for i, it in enumerate(self.items) if it["metadata"]["name"] == instaslice["metadata"]["name"]), None)
+        if n is None:
+            self.items.append(instaslice)
+            return self.sync()
+        lo, hi = int(self.node_off[n]), int(self.node_off[n + 1])
+        uuids = sorted(instaslice["spec"].get("MigGPUUUID", {}))
+        if uuids != self.gpu_uuid[lo:hi] or instaslice["spec"].get("migplacement", []) != self.items[0]["spec"].get("migplacement", []):
+            self.items[n] = instaslice
+            return self.sync()
+        self.items[n] = instaslice
+        self._engine.write_occupancy(lo, np.array([occupancy_byte(instaslice, u) for u in uuids], dtype=np.uint8))
+        self._has_orphans = any(
+            p.get("podUUID", "") != "" and p["podUUID"] not in it["spec"].get("allocations", {})
+            for it in self.items for p in it["spec"].get("prepared", {}).values())
+
     @property
     def engine(self) -> E.Engine:
         return self._engine

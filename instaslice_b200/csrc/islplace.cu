@@ -545,6 +545,18 @@ int isl_read_occupancy(isl_engine* e, uint8_t* out) {
     return ISL_OK;
 }
 
+int isl_write_occupancy(isl_engine* e, uint32_t first_gpu, uint32_t n, const uint8_t* occ) {
+    if (!e || (n && !occ)) return ISL_EINVAL;
+    if (!e->have_inventory) return ISL_ESTATE;
+    if ((uint64_t)first_gpu + n > e->G) return ISL_ERANGE;
+    if (n == 0) return ISL_OK;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_occ + first_gpu, occ, n, cudaMemcpyHostToDevice, e->stream));
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ISL_OK;
+}
+
 uint32_t isl_num_gpus(const isl_engine* e) { return e ? e->G : 0; }
 
 uint32_t isl_gpu_to_node(const isl_engine* e, uint32_t gpu) {

@@ -56,7 +56,7 @@ class Stats(C.Structure):
 
 # every symbol include/islplace.h declares; tests check that the library exports all of them
 EXPORTED_SYMBOLS = [
-    "isl_create", "isl_destroy", "isl_set_stream", "isl_synchronize", "isl_load_profiles", "isl_load_inventory", "isl_read_occupancy",
+    "isl_create", "isl_destroy", "isl_set_stream", "isl_synchronize", "isl_load_profiles", "isl_load_inventory", "isl_read_occupancy", "isl_write_occupancy",
     "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_place_stream", "isl_place_stream_device", "isl_free_batch",
     "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_ipc_inbox_handle", "isl_ipc_connect", "isl_connect_local", "isl_place_stream_partitioned", "isl_device_occupancy", "isl_get_stats", "isl_read_trace",
     "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
@@ -82,6 +82,7 @@ def load_library(path: str = LIB_PATH):
         "isl_load_profiles": (C.c_int, [p, C.c_uint32, p]),
         "isl_load_inventory": (C.c_int, [p, C.c_uint32, p, p]),
         "isl_read_occupancy": (C.c_int, [p, p]),
+        "isl_write_occupancy": (C.c_int, [p, C.c_uint32, C.c_uint32, p]),
         "isl_num_gpus": (C.c_uint32, [p]),
         "isl_gpu_to_node": (C.c_uint32, [p, C.c_uint32]),
         "isl_place_batch": (C.c_int, [p, C.c_uint32, p, p]),
@@ -188,6 +189,10 @@ class Engine:
         out = np.empty(self.num_gpus, dtype=np.uint8)
         self._check(self._lib.isl_read_occupancy(self._h, _ptr(out)), "isl_read_occupancy")
         return out
+
+    def write_occupancy(self, first_gpu: int, occ):
+        occ = np.ascontiguousarray(occ, dtype=np.uint8)
+        self._check(self._lib.isl_write_occupancy(self._h, first_gpu, len(occ), _ptr(occ)), "isl_write_occupancy")
 
     @property
     def num_gpus(self) -> int:

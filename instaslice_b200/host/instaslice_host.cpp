@@ -90,6 +90,24 @@ void InstasliceReconciler::Sync(const InstasliceList& list) {
     check(isl_load_inventory(h_, (uint32_t)list.Items.size(), nodeOff_.data(), occ.data()), h_, "isl_load_inventory");
 }
 
+void InstasliceReconciler::UpdateNode(const InstasliceList& list, size_t node) {
+    if (node + 1 >= nodeOff_.size()) { Sync(list); return; }
+    const Instaslice& is = list.Items[node];
+    const uint32_t lo = nodeOff_[node], hi = nodeOff_[node + 1];
+    if (is.Spec.MigGPUUUID.size() != hi - lo) { Sync(list); return; }
+    std::vector<uint8_t> occ;
+    uint32_t g = lo;
+    for (const auto& kv : is.Spec.MigGPUUUID) {
+        if (kv.first != gpuUUID_[g++]) { Sync(list); return; }
+        occ.push_back(occupancyByte(is, kv.first));
+    }
+    check(isl_write_occupancy(h_, lo, (uint32_t)occ.size(), occ.data()), h_, "isl_write_occupancy");
+    orphans_ = false;
+    for (const Instaslice& it : list.Items)
+        for (const auto& kv : it.Spec.Prepared)
+            if (!kv.second.PodUUID.empty() && !it.Spec.Allocations.count(kv.second.PodUUID)) orphans_ = true;
+}
+
 uint32_t InstasliceReconciler::getStartIndexFromPreparedState(const Instaslice& is, const std::string& gpuUUID, const std::string& profileName) {
     auto it = profiles_.find(profileName);
     if (it == profiles_.end()) return ISL_START_NONE;

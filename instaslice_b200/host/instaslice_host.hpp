@@ -82,6 +82,9 @@ public:
     // Rebuild the flat inventory from the listed custom resources (the CR is the checkpoint).  Throws std::runtime_error
     // on what makes the reference panic and on engine errors.
     void Sync(const InstasliceList& list);
+    // Incremental sync after ONE Instaslice object (list.Items[node]) changed: only that node's occupancy bytes are rewritten.
+    // Falls back to Sync when the node's GPU set changed.
+    void UpdateNode(const InstasliceList& list, size_t node);
 
     static uint8_t occupancyByte(const Instaslice& is, const std::string& gpuUUID);                        // :306-328
     uint32_t getStartIndexFromPreparedState(const Instaslice& is, const std::string& gpuUUID, const std::string& profileName);   // :303-384

@@ -482,3 +482,30 @@ def test_large_inventory_falls_back_to_single_chain():
         assert np.array_equal(g, w)
     assert np.array_equal(eng.read_occupancy(), ref.occupancy())
     assert eng.gpu_to_node(G - 1) == G // 8 - 1
+
+
+def test_incremental_node_update_equals_full_sync():
+    """after one Instaslice object changes, rewriting only that node's occupancy bytes gives the same
+    placements as rebuilding the whole inventory from the custom resources."""
+    gold = load("regress_crd.json")
+    case = gold["cases"][5]
+    items = copy.deepcopy(case["instaslices"])
+    r = ctl.InstasliceReconciler(items, quirks=case["quirks"])
+    pods = [{"uid": p["uid"], "name": p["uid"], "profile": p["profile"]} for p in case["pods"]]
+    first = r.place_pending_pods(pods[:6])
+    # the daemonset deletes two realised allocations on one node, a new dangling slice shows up on another
+    victim = next(a for v, a in first if a)
+    node = next(it for it in items if it["metadata"]["name"] == victim["nodename"])
+    node["spec"]["allocations"].pop(victim["podUUID"])
+    r.update_node(node)
+    other = items[-1]
+    uuid = sorted(other["spec"]["MigGPUUUID"])[0]
+    if ctl.occupancy_byte(other, uuid) & 0x40 == 0:
+        other["spec"].setdefault("prepared", {})["MIG-new"] = {"profile": "1g", "start": 6, "size": 1, "parent": uuid, "podUUID": "", "giinfo": 0, "ciinfo": 0}
+        r.update_node(other)
+    inc = r.engine.read_occupancy().copy()
+    full = ctl.InstasliceReconciler(copy.deepcopy(items), quirks=case["quirks"])
+    assert np.array_equal(inc, full.engine.read_occupancy())
+    a = r.place_pending_pods(copy.deepcopy(pods[6:]))
+    b = full.place_pending_pods(copy.deepcopy(pods[6:]))
+    assert [(v, x and (x["gpuUUID"], x["start"])) for v, x in a] == [(v, x and (x["gpuUUID"], x["start"])) for v, x in b]
