@@ -133,6 +133,27 @@ def make_profiles(table) -> np.ndarray:
     return rows
 
 
+def make_profile_tables(table_list):
+    """Several per-node tables (heterogeneous cluster) -> (profile names, isl_profile records [n_tables][n_names]).
+
+    The name list is the union of the tables' profile names in order of first appearance; a table that has no row
+    of a name gets ``n_starts == 0`` there (the reference finds no Migplacement row on such a node and returns 9)."""
+    names = []
+    for table in table_list:
+        for name, *_ in table:
+            if name not in names:
+                names.append(name)
+    rows = np.zeros((len(table_list), len(names)), dtype=PROFILE_DTYPE)
+    for t, table in enumerate(table_list):
+        seen = set()
+        for row in table:
+            if row[0] in seen:            # the start search uses the FIRST row with a name (:332-340)
+                continue
+            seen.add(row[0])
+            rows[t, names.index(row[0])] = make_profiles([row])[0]
+    return names, rows
+
+
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 

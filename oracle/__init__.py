@@ -35,6 +35,8 @@ def lib():
         p = C.c_void_p
         L.orc_start_for.restype, L.orc_start_for.argtypes = C.c_uint8, [p, C.c_uint32, C.c_uint8]
         L.orc_f_new.restype, L.orc_f_new.argtypes = p, [C.c_uint32, p, C.c_uint32, p, C.c_uint32]
+        L.orc_f_new_tables.restype, L.orc_f_new_tables.argtypes = p, [C.c_uint32, p, C.c_uint32, C.c_uint32, p, p, C.c_uint32]
+        L.orc_fast_new_tables.restype, L.orc_fast_new_tables.argtypes = p, [C.c_uint32, p, C.c_uint32, C.c_uint32, p, p, C.c_uint32, C.c_uint32]
         L.orc_f_delete.restype, L.orc_f_delete.argtypes = None, [p]
         L.orc_f_add_prepared.restype, L.orc_f_add_prepared.argtypes = C.c_int, [p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64]
         L.orc_f_add_allocation.restype, L.orc_f_add_allocation.argtypes = C.c_int, [p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
@@ -63,11 +65,17 @@ def start_for(row: np.ndarray, quirks: int, occ: int) -> int:
 class Fast:
     """ref_fast.cpp: bitmask + per-profile cursor; first-fit (reference) or best-fit (extension)."""
 
-    def __init__(self, node_off, rows, quirks=3, policy=0):
+    def __init__(self, node_off, rows, quirks=3, policy=0, node_table=None):
+        """``rows`` is [n_profiles] or, for a heterogeneous cluster, [n_tables][n_profiles] with ``node_table`` [n_nodes]."""
         self.node_off = np.ascontiguousarray(node_off, dtype=np.uint32)
         self.rows = np.ascontiguousarray(rows, dtype=PROFILE_DTYPE)
         self.G = int(self.node_off[-1])
-        self._h = lib().orc_fast_new(len(self.node_off) - 1, _ptr(self.node_off), len(self.rows), _ptr(self.rows), quirks, policy)
+        if self.rows.ndim == 1:
+            self._h = lib().orc_fast_new(len(self.node_off) - 1, _ptr(self.node_off), len(self.rows), _ptr(self.rows), quirks, policy)
+        else:
+            self.node_table = np.ascontiguousarray(node_table, dtype=np.uint8)
+            self._h = lib().orc_fast_new_tables(len(self.node_off) - 1, _ptr(self.node_off), self.rows.shape[0], self.rows.shape[1],
+                                                _ptr(self.rows), _ptr(self.node_table), quirks, policy)
 
     def load(self, occ):
         occ = np.ascontiguousarray(occ, dtype=np.uint8)
@@ -94,11 +102,16 @@ class Fast:
 class Faithful:
     """ref_faithful.cpp: string-keyed CRD objects, rescans per pod — the reference as written."""
 
-    def __init__(self, node_off, rows, quirks=3):
+    def __init__(self, node_off, rows, quirks=3, node_table=None):
         self.node_off = np.ascontiguousarray(node_off, dtype=np.uint32)
         self.rows = np.ascontiguousarray(rows, dtype=PROFILE_DTYPE)
         self.G = int(self.node_off[-1])
-        self._h = lib().orc_f_new(len(self.node_off) - 1, _ptr(self.node_off), len(self.rows), _ptr(self.rows), quirks)
+        if self.rows.ndim == 1:
+            self._h = lib().orc_f_new(len(self.node_off) - 1, _ptr(self.node_off), len(self.rows), _ptr(self.rows), quirks)
+        else:
+            self.node_table = np.ascontiguousarray(node_table, dtype=np.uint8)
+            self._h = lib().orc_f_new_tables(len(self.node_off) - 1, _ptr(self.node_off), self.rows.shape[0], self.rows.shape[1],
+                                             _ptr(self.rows), _ptr(self.node_table), quirks)
 
     def add_prepared(self, gpu, start, size, pod_id=-1):
         return lib().orc_f_add_prepared(self._h, gpu, start, size, pod_id)

@@ -36,6 +36,9 @@ uint8_t orc_start_for(const isl_profile* row, uint32_t quirks, uint8_t occ);
 typedef struct orc_faithful orc_faithful;
 orc_faithful* orc_f_new(uint32_t n_nodes, const uint32_t* node_off,
                         uint32_t n_profiles, const isl_profile* rows, uint32_t quirks);
+/* heterogeneous cluster: rows[t * n_profiles + p] (n_starts == 0: table t has no row of that name), node n uses table node_table[n] */
+orc_faithful* orc_f_new_tables(uint32_t n_nodes, const uint32_t* node_off, uint32_t n_tables, uint32_t n_profiles, const isl_profile* rows,
+                               const uint8_t* node_table, uint32_t quirks);
 void     orc_f_delete(orc_faithful* h);
 /* Spec.Prepared entry on canonical GPU `gpu`; pod_id < 0 => PodUUID == "" (dangling, counted as busy, :313) */
 int      orc_f_add_prepared(orc_faithful* h, uint32_t gpu, uint32_t start, uint32_t size, int64_t pod_id);
@@ -51,6 +54,8 @@ uint64_t orc_f_num_allocations(orc_faithful* h);
 typedef struct orc_fast orc_fast;
 orc_fast* orc_fast_new(uint32_t n_nodes, const uint32_t* node_off,
                        uint32_t n_profiles, const isl_profile* rows, uint32_t quirks, uint32_t policy);
+orc_fast* orc_fast_new_tables(uint32_t n_nodes, const uint32_t* node_off, uint32_t n_tables, uint32_t n_profiles, const isl_profile* rows,
+                              const uint8_t* node_table, uint32_t quirks, uint32_t policy);
 void     orc_fast_delete(orc_fast* h);
 void     orc_fast_load(orc_fast* h, const uint8_t* occ);
 int      orc_fast_place(orc_fast* h, uint32_t n, const isl_request* in, isl_result* out);

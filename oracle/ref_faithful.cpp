@@ -180,7 +180,15 @@ struct orc_faithful {
 
 extern "C" {
 
+orc_faithful* orc_f_new_tables(uint32_t n_nodes, const uint32_t* node_off, uint32_t n_tables, uint32_t n_profiles, const isl_profile* rows_all,
+                               const uint8_t* node_table, uint32_t quirks);
 orc_faithful* orc_f_new(uint32_t n_nodes, const uint32_t* node_off, uint32_t n_profiles, const isl_profile* rows, uint32_t quirks) {
+    return orc_f_new_tables(n_nodes, node_off, 1, n_profiles, rows, nullptr, quirks);
+}
+// Every node publishes its OWN Migplacement (instaslice_daemonset.go:588-664): node n gets the rows of table node_table[n].
+orc_faithful* orc_f_new_tables(uint32_t n_nodes, const uint32_t* node_off, uint32_t n_tables, uint32_t n_profiles, const isl_profile* rows_all,
+                               const uint8_t* node_table, uint32_t quirks) {
+    (void)n_tables;
     orc_faithful* h = new orc_faithful;
     h->quirks = quirks;
     h->node_off.assign(node_off, node_off + n_nodes + 1);
@@ -197,6 +205,7 @@ orc_faithful* orc_f_new(uint32_t n_nodes, const uint32_t* node_off, uint32_t n_p
             h->gpu_node[g] = n;
             is.Spec.MigGPUUUID[h->gpu_uuid[g]] = "NVIDIA A100-SXM4-40GB";
         }
+        const isl_profile* rows = rows_all + (size_t)(node_table ? node_table[n] : 0) * n_profiles;
         for (uint32_t p = 0; p < n_profiles; ++p) {                 // one Mig row per profile (daemonset :642-658)
             if (rows[p].n_starts == 0) continue;                    // Placements[0] on an empty list panics (:334, Q7): never emitted
             Mig m; m.Profile = h->profile_names[p];
@@ -277,7 +286,9 @@ int orc_f_place(orc_faithful* h, uint32_t n, const isl_request* in, isl_result* 
         if (veto && !podHasNodeAllocation) r.status = ORC_ST_VETO_REQUEUE;
         if (!podHasNodeAllocation && in[i].profile < h->profile_names.size()) {
             // report the size the profile row would have used, like the engine does
-            int size, gi, ci, cieng; extractGpuProfile(h->items[0], profileName, &size, &gi, &ci, &cieng); r.size = (uint8_t)size;
+            int size = 0, gi, ci, cieng;
+            for (const Instaslice& is : h->items) { extractGpuProfile(is, profileName, &size, &gi, &ci, &cieng); if (size) break; }
+            r.size = (uint8_t)size;
         }
         out[i] = r;
     }

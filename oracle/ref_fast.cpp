@@ -43,26 +43,41 @@ extern "C" uint8_t orc_start_for(const isl_profile* row, uint32_t quirks, uint8_
 }
 
 struct orc_fast {
-    uint32_t G = 0, P = 0, quirks = 0, policy = 0;
-    std::vector<isl_profile> rows;
+    uint32_t G = 0, P = 0, T = 1, quirks = 0, policy = 0;
+    std::vector<isl_profile> rows;     // [t*P + p]; n_starts == 0: the node's Migplacement has no row with that name
     std::vector<uint8_t> occ;
-    std::vector<uint8_t> lut;          // [p*256 + occ] -> start or 9
+    std::vector<uint8_t> gtab;         // table of the node that owns the GPU (every node publishes its own Migplacement)
+    std::vector<uint8_t> lut;          // [(t*P + p)*256 + occ] -> start or 9
     std::vector<uint32_t> cursor;      // first GPU that may still take profile p
+    std::vector<uint8_t> default_size; // size reported for an unplaced request: the first table that knows the name
 };
 
 extern "C" {
 
+orc_fast* orc_fast_new_tables(uint32_t n_nodes, const uint32_t* node_off, uint32_t n_tables, uint32_t n_profiles, const isl_profile* rows,
+                              const uint8_t* node_table, uint32_t quirks, uint32_t policy) {
+    orc_fast* h = new orc_fast;
+    h->G = node_off[n_nodes]; h->P = n_profiles; h->T = n_tables; h->quirks = quirks; h->policy = policy;
+    h->rows.assign(rows, rows + (size_t)n_tables * n_profiles);
+    h->occ.assign(h->G, 0);
+    h->gtab.assign(h->G, 0);
+    for (uint32_t n = 0; n < n_nodes; ++n)
+        for (uint32_t g = node_off[n]; g < node_off[n + 1]; ++g) h->gtab[g] = node_table ? node_table[n] : 0;
+    h->lut.resize((size_t)n_tables * n_profiles * 256);
+    for (uint32_t r = 0; r < n_tables * n_profiles; ++r)
+        for (uint32_t o = 0; o < 256; ++o) h->lut[(size_t)r * 256 + o] = orc_start_for(&rows[r], quirks, (uint8_t)o);
+    h->cursor.assign(n_profiles, 0);
+    h->default_size.assign(n_profiles, 0);
+    for (uint32_t p = 0; p < n_profiles; ++p)       // first node in canonical order whose Migplacement has the name
+        for (uint32_t n = 0; n < n_nodes; ++n) {
+            const isl_profile& r = rows[(size_t)(node_table ? node_table[n] : 0) * n_profiles + p];
+            if (r.n_starts) { h->default_size[p] = r.size; break; }
+        }
+    return h;
+}
 orc_fast* orc_fast_new(uint32_t n_nodes, const uint32_t* node_off, uint32_t n_profiles, const isl_profile* rows,
                        uint32_t quirks, uint32_t policy) {
-    orc_fast* h = new orc_fast;
-    h->G = node_off[n_nodes]; h->P = n_profiles; h->quirks = quirks; h->policy = policy;
-    h->rows.assign(rows, rows + n_profiles);
-    h->occ.assign(h->G, 0);
-    h->lut.resize((size_t)n_profiles * 256);
-    for (uint32_t p = 0; p < n_profiles; ++p)
-        for (uint32_t o = 0; o < 256; ++o) h->lut[p * 256 + o] = orc_start_for(&rows[p], quirks, (uint8_t)o);
-    h->cursor.assign(n_profiles, 0);
-    return h;
+    return orc_fast_new_tables(n_nodes, node_off, 1, n_profiles, rows, nullptr, quirks, policy);
 }
 void orc_fast_delete(orc_fast* h) { delete h; }
 void orc_fast_load(orc_fast* h, const uint8_t* occ) {
@@ -85,26 +100,28 @@ int orc_fast_place(orc_fast* h, uint32_t n, const isl_request* in, isl_result* o
         if (in[i].op != ISL_OP_ALLOC) continue;
         const uint32_t p = in[i].profile;
         if (p >= h->P) { out[i] = {ISL_GPU_NONE, (uint8_t)ISL_START_NONE, 0, (uint16_t)ISL_ST_BAD_PROFILE}; continue; }
-        const uint8_t* lut = &h->lut[p * 256];
-        const uint8_t size = h->rows[p].size;
+        // the start table and the size are those of the node that owns the GPU (each node's own Migplacement, :332-340)
+        auto lut_of = [&](uint32_t g) { return &h->lut[((size_t)h->gtab[g] * h->P + p) * 256]; };
         uint32_t hit = ISL_GPU_NONE;
         if (h->policy == ISL_POLICY_FIRST_FIT) {
             uint32_t g = h->cursor[p];
-            while (g < h->G && lut[h->occ[g]] == ISL_START_NONE) ++g;
+            while (g < h->G && lut_of(g)[h->occ[g]] == ISL_START_NONE) ++g;
             h->cursor[p] = g;
             if (g < h->G) hit = g;
         } else {
             int best = 1 << 30;
             for (uint32_t g = 0; g < h->G; ++g) {
-                const uint8_t s = lut[h->occ[g]];
+                const uint8_t s = lut_of(g)[h->occ[g]];
                 if (s == ISL_START_NONE) continue;
-                const uint8_t after = (uint8_t)(h->occ[g] | (((1u << size) - 1u) << s));
+                const uint8_t sz = h->rows[(size_t)h->gtab[g] * h->P + p].size;
+                const uint8_t after = (uint8_t)(h->occ[g] | (((1u << sz) - 1u) << s));
                 const int free_after = 8 - __builtin_popcount(after);
                 if (free_after < best) { best = free_after; hit = g; }
             }
         }
-        if (hit == ISL_GPU_NONE) { out[i] = {ISL_GPU_NONE, (uint8_t)ISL_START_NONE, size, (uint16_t)ISL_ST_NO_CAPACITY}; continue; }
-        const uint8_t s = lut[h->occ[hit]];
+        if (hit == ISL_GPU_NONE) { out[i] = {ISL_GPU_NONE, (uint8_t)ISL_START_NONE, h->default_size[p], (uint16_t)ISL_ST_NO_CAPACITY}; continue; }
+        const uint8_t s = lut_of(hit)[h->occ[hit]];
+        const uint8_t size = h->rows[(size_t)h->gtab[hit] * h->P + p].size;
         h->occ[hit] |= (uint8_t)(((1u << size) - 1u) << s);
         out[i] = {hit, s, size, (uint16_t)ISL_ST_PLACED};
     }
