@@ -49,6 +49,7 @@ extern "C" {
 #define ISL_ABI_VERSION      1u
 #define ISL_MAX_PROFILES     16u          /* NVML_GPU_INSTANCE_PROFILE_COUNT is 0x11 incl. gaps; the reference tables have <= 10 rows */
 #define ISL_MAX_STARTS       8u
+#define ISL_MAX_TABLES       8u           /* distinct per-node Migplacement tables in one cluster (heterogeneous GPU models) */
 #define ISL_SLOTS            8u           /* :306  var gpuAllocatedIndex [8]uint32 */
 #define ISL_START_NONE       9u           /* :248, :343  notValidIndex */
 #define ISL_GPU_NONE         0xFFFFFFFFu
@@ -177,6 +178,13 @@ int  isl_synchronize(isl_engine* e);
 /* Replaces reading instaslice.Spec.Migplacement (:332-340, :288-298). Builds the
  * per-(profile, occupancy byte) first-start table on the device. */
 int  isl_load_profiles(isl_engine* e, uint32_t n, const isl_profile* rows);
+/* Heterogeneous cluster: every node publishes its OWN Migplacement (instaslice_daemonset.go:588-664), and the reference
+ * looks a profile up in the table of the node it is scanning (:332-340).  rows[t * n_profiles + p] is the row of profile
+ * NAME p in table t; n_starts == 0 = that table has no row of the name (the reference then finds nothing on such a node).
+ * Requests name a profile NAME index.  isl_set_node_tables (after isl_load_inventory) says which table each node uses
+ * (default: table 0).  ISL_POLICY_BEST_FIT supports a single table only. */
+int  isl_load_profile_tables(isl_engine* e, uint32_t n_tables, uint32_t n_profiles, const isl_profile* rows);
+int  isl_set_node_tables(isl_engine* e, uint32_t n_nodes, const uint8_t* table_of_node);
 /* Replaces the occupancy rebuild (:306-328) for every GPU of every node.
  * node_off has n_nodes+1 entries (node i owns GPUs [node_off[i], node_off[i+1]));
  * occ has node_off[n_nodes] bytes.  This is also "resume": the CR is the checkpoint. */
@@ -205,7 +213,7 @@ int  isl_place_batch_device(isl_engine* e, uint32_t n, const void* d_in, void* d
 /* Releases spans (Allocations entries deleted by the daemonset). */
 int  isl_free_batch(isl_engine* e, uint32_t n, const isl_span* spans);
 /* getStartIndexFromPreparedState's search (:343-383) for n arbitrary occupancy
- * bytes and one profile row, evaluated by the device table: out[i] in {0..7, 9}. */
+ * bytes and one profile row, evaluated by the device table: out[i] in {0..7, 9}.  `profile` = name index | table << 8. */
 int  isl_eval_starts(isl_engine* e, uint32_t profile, uint32_t n, const uint8_t* occ, uint8_t* out);
 
 /* ---- partitioned inventory (BASELINE config 4; DESIGN.md "Multi-GPU") ---- */

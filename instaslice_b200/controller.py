@@ -108,11 +108,26 @@ class InstasliceReconciler:
         """Rebuild the flat inventory from the custom resources (the CR is the checkpoint)."""
         if not self.items:
             raise ValueError("no Instaslice objects")
-        mig0 = self.items[0]["spec"].get("migplacement", [])
-        for it in self.items[1:]:
-            if it["spec"].get("migplacement", []) != mig0:
-                raise NotImplementedError("per-node profile tables differ: heterogeneous clusters are a DESIGN.md 'next' item")
-        self.rows, self.profile_names = profile_rows(mig0)
+        # every node publishes its own Migplacement (instaslice_daemonset.go:588-664): group identical tables
+        self._tables, self.node_table = [], []
+        for it in self.items:
+            mig = it["spec"].get("migplacement", [])
+            if mig not in self._tables:
+                if len(self._tables) >= 8:
+                    raise ValueError("more than 8 distinct per-node profile tables")
+                self._tables.append(mig)
+            self.node_table.append(self._tables.index(mig))
+        per_table = [profile_rows(mig) for mig in self._tables]
+        self.profile_names = {}
+        for _rows, names in per_table:                       # profile NAME index = order of first appearance over the tables
+            for name in names:
+                self.profile_names.setdefault(name, len(self.profile_names))
+        if len(self.profile_names) > E.MAX_PROFILES:
+            raise ValueError("more than %d distinct profile names" % E.MAX_PROFILES)
+        self.rows = np.zeros((len(self._tables), len(self.profile_names)), dtype=E.PROFILE_DTYPE)
+        for t, (rows, names) in enumerate(per_table):
+            for name, idx in names.items():
+                self.rows[t, self.profile_names[name]] = rows[idx]
         self.gpu_uuid, node_off, occ = [], [0], []
         self.node_of_uuid = {}
         for n, it in enumerate(self.items):
@@ -125,8 +140,9 @@ class InstasliceReconciler:
         self.gpu_index = {u: i for i, u in enumerate(self.gpu_uuid)}
         if self._engine is None:
             self._engine = E.Engine(max_gpus=max(4096, len(self.gpu_uuid)), max_batch=self._max_batch, quirks=self.quirks)
-        self._engine.load_profiles(self.rows)
+        self._engine.load_profile_tables(self.rows)
         self._engine.load_inventory(self.node_off, np.asarray(occ, dtype=np.uint8))
+        self._engine.set_node_tables(np.asarray(self.node_table, dtype=np.uint8))
         # spans of realised slices whose Allocations entry is gone: only these can trigger the veto (:198-203)
         self._has_orphans = any(
             p.get("podUUID", "") != "" and p["podUUID"] not in it["spec"].get("allocations", {})
@@ -142,7 +158,7 @@ class InstasliceReconciler:
             return self.sync()
         lo, hi = int(self.node_off[n]), int(self.node_off[n + 1])
         uuids = sorted(instaslice["spec"].get("MigGPUUUID", {}))
-        if uuids != self.gpu_uuid[lo:hi] or instaslice["spec"].get("migplacement", []) != self.items[0]["spec"].get("migplacement", []):
+        if uuids != self.gpu_uuid[lo:hi] or instaslice["spec"].get("migplacement", []) != self._tables[self.node_table[n]]:
             self.items[n] = instaslice
             return self.sync()
         self.items[n] = instaslice
@@ -184,7 +200,8 @@ class InstasliceReconciler:
         if row is None:
             return NOT_VALID_INDEX
         occ = np.array([occupancy_byte(instaslice, gpuUUID)], dtype=np.uint8)
-        return int(self._engine.eval_starts(row, occ)[0])
+        n = next(i for i, it in enumerate(self.items) if it is instaslice or it["metadata"]["name"] == instaslice["metadata"]["name"])
+        return int(self._engine.eval_starts(row | (self.node_table[n] << 8), occ)[0])       # the node's own table
 
     def findDeviceForASlice(self, instaslice: dict, profileName: str, policy, pod: dict) -> dict:
         """:240-262 — first GPU of ONE node with a valid start; raises AllocationError(:261) when none.
@@ -192,7 +209,7 @@ class InstasliceReconciler:
         Like the reference this does not write the allocation into the CR (:257 is commented out there); the engine's
         occupancy is left untouched as well (the tentative commit is released again).
         """
-        n = self.items.index(instaslice)
+        n = next(i for i, it in enumerate(self.items) if it is instaslice)
         lo, hi = int(self.node_off[n]), int(self.node_off[n + 1])
         res = self._place([profileName], lo, hi)[0]
         if res["status"] != E.ST_PLACED:

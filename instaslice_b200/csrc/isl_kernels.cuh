@@ -37,6 +37,12 @@ constexpr uint32_t kSkip = 0xFFu;          // partition key of a request that is
 constexpr uint32_t kInf = 0xFFFFFFFFu;
 constexpr uint32_t kMaxCand = ISL_MAX_PROFILES * ISL_MAX_STARTS;   // 128 (profile,start) candidates
 constexpr uint32_t kChainThreads = 256;
+constexpr uint32_t kMaxTables = ISL_MAX_TABLES;   // per-node profile tables (heterogeneous clusters)
+
+// The chain's occupancy word is 16 bits: the busy slices in the low byte and, in the high byte, every table bit set EXCEPT
+// the one of the table the GPU's node publishes.  A candidate of table t carries bit (8 + t) in its mask, so `(occ16 & mask) == 0`
+// holds only on GPUs of its own table — no extra instruction per decision.
+__host__ __device__ inline uint32_t table_tag(uint32_t table) { return ((~(1u << table)) & 0xFFu) << 8; }
 
 struct DevProfiles {            // kernel parameter (by value)
     uint32_t n;
@@ -45,7 +51,7 @@ struct DevProfiles {            // kernel parameter (by value)
 };
 
 // One (profile, start) candidate of the chain: bits  [3:0] profile | [6:4] order in the row |
-// [10:7] start | [14:11] size | [23:16] slot mask | [31] valid
+// [10:7] start | [14:11] size | [23:16] slot mask | [26:24] table | [31] valid
 struct CandTab {                // kernel parameter (by value): slot k of lane l is desc[k][l]
     uint32_t desc[4][32];
 };
@@ -79,7 +85,8 @@ __host__ __device__ inline uint32_t candidate_mask(uint32_t size, uint32_t v, ui
 // Device table: lut[p][occ] = first legal start of profile p on a GPU with occupancy byte occ
 // (or 9), feas[occ] = bitmask of profiles that have a legal start.  256 threads, one per byte.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_build_lut(DevProfiles prof, uint8_t* __restrict__ lut, uint16_t* __restrict__ feas) {
+__global__ void __launch_bounds__(256) k_build_lut(DevProfiles prof, uint32_t table, uint8_t* __restrict__ lut, uint16_t* __restrict__ feas) {
+    lut += (size_t)table * ISL_MAX_PROFILES * 256; feas += (size_t)table * 256;        // lut[table][profile][occ], feas[table][occ]
     const uint32_t occ = threadIdx.x;
     uint32_t fmask = 0;
     for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) {
@@ -280,29 +287,29 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
     return r;
 }
 
-__device__ __forceinline__ uint32_t sweep_mask16(const uint4 v, const uint16_t* s_feas, uint32_t active, uint32_t g0, uint32_t lo, uint32_t hi) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+__device__ __forceinline__ uint32_t sweep_mask16(const uint4 v, const uint4 tv, const uint16_t* s_feas, uint32_t active, uint32_t g0, uint32_t lo, uint32_t hi) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
     uint32_t mask = 0;
 #pragma unroll
     for (uint32_t j = 0; j < 16; ++j) {
-        const uint32_t o = (w[j >> 2] >> ((j & 3u) * 8u)) & 0xFFu;
+        const uint32_t o = (w[j >> 2] >> ((j & 3u) * 8u)) & 0xFFu, t = (tw[j >> 2] >> ((j & 3u) * 8u)) & (kMaxTables - 1);
         const uint32_t g = g0 + j;
-        if ((s_feas[o] & active) && g >= lo && g < hi) mask |= 1u << j;
+        if ((s_feas[t * 256 + o] & active) && g >= lo && g < hi) mask |= 1u << j;
     }
     return mask;
 }
 
-__global__ void __launch_bounds__(kSweepThreads) k_sweep_count(const uint4* __restrict__ occ16, const uint16_t* __restrict__ feas,
+__global__ void __launch_bounds__(kSweepThreads) k_sweep_count(const uint4* __restrict__ occ16, const uint4* __restrict__ gtab16, const uint16_t* __restrict__ feas,
                                                                 uint32_t first_block, uint32_t lo, uint32_t hi,
                                                                 const Ctrl* __restrict__ ctrl, uint32_t* __restrict__ counts) {
-    __shared__ uint16_t s_feas[256];
+    __shared__ uint16_t s_feas[kMaxTables * 256];
     __shared__ uint32_t s_warp[kSweepThreads / 32];
-    s_feas[threadIdx.x] = feas[threadIdx.x];
+    for (uint32_t i = threadIdx.x; i < kMaxTables * 256; i += kSweepThreads) s_feas[i] = feas[i];
     __syncthreads();
     const uint32_t active = ctrl->active;
     const uint32_t g0 = (first_block + blockIdx.x) * kSweepBlock + threadIdx.x * kSweepPerThread;
     uint32_t c = 0;
-    if (active && g0 < hi && g0 + kSweepPerThread > lo) c = __popc(sweep_mask16(ld_nc_v4(&occ16[g0 >> 4]), s_feas, active, g0, lo, hi));
+    if (active && g0 < hi && g0 + kSweepPerThread > lo) c = __popc(sweep_mask16(ld_nc_v4(&occ16[g0 >> 4]), ld_nc_v4(&gtab16[g0 >> 4]), s_feas, active, g0, lo, hi));
 #pragma unroll
     for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
     if ((threadIdx.x & 31u) == 0) s_warp[threadIdx.x >> 5] = c;
@@ -314,15 +321,16 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_count(const uint4* __re
     }
 }
 
-__global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __restrict__ occ16, const uint16_t* __restrict__ feas,
+__global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __restrict__ occ16, const uint4* __restrict__ gtab16, const uint16_t* __restrict__ feas,
                                                                   uint32_t first_block, uint32_t lo, uint32_t hi, Ctrl* ctrl,
-                                                                  const uint32_t* __restrict__ counts, uint32_t* __restrict__ cand) {
-    __shared__ uint16_t s_feas[256];
+                                                                  const uint32_t* __restrict__ counts, uint32_t* __restrict__ cand,
+                                                                  uint16_t* __restrict__ cand_o16) {
+    __shared__ uint16_t s_feas[kMaxTables * 256];
     __shared__ uint32_t s_warp[kSweepThreads / 32];
     __shared__ uint32_t s_red[kSweepThreads / 32];
     __shared__ uint32_t s_base;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    s_feas[tid] = feas[tid];
+    for (uint32_t i = tid; i < kMaxTables * 256; i += kSweepThreads) s_feas[i] = feas[i];
     // base = number of candidates in the CTAs before this one (and the grand total for the last CTA)
     uint32_t pre = 0;
     for (uint32_t b = tid; b < blockIdx.x; b += kSweepThreads) pre += counts[b];
@@ -333,9 +341,9 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __
     if (tid == 0) { uint32_t t = 0; for (uint32_t w = 0; w < kSweepThreads / 32; ++w) t += s_red[w]; s_base = t; }
     const uint32_t active = ctrl->active;
     const uint32_t g0 = (first_block + blockIdx.x) * kSweepBlock + tid * kSweepPerThread;
-    uint4 v = make_uint4(0, 0, 0, 0);
+    uint4 v = make_uint4(0, 0, 0, 0), tv = make_uint4(0, 0, 0, 0);
     uint32_t mask = 0;
-    if (active && g0 < hi && g0 + kSweepPerThread > lo) { v = ld_nc_v4(&occ16[g0 >> 4]); mask = sweep_mask16(v, s_feas, active, g0, lo, hi); }
+    if (active && g0 < hi && g0 + kSweepPerThread > lo) { v = ld_nc_v4(&occ16[g0 >> 4]); tv = ld_nc_v4(&gtab16[g0 >> 4]); mask = sweep_mask16(v, tv, s_feas, active, g0, lo, hi); }
     const uint32_t c = __popc(mask);
     uint32_t incl = c;                                  // inclusive warp scan of the per-thread counts
 #pragma unroll
@@ -344,12 +352,13 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __
     __syncthreads();
     uint32_t off = s_base + incl - c;
     for (uint32_t w = 0; w < warp; ++w) off += s_warp[w];
-    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t wv[4] = {v.x, v.y, v.z, v.w}, twv[4] = {tv.x, tv.y, tv.z, tv.w};
     uint32_t m = mask;
     while (m) {
         const uint32_t j = __ffs(m) - 1; m &= m - 1;
-        const uint32_t o = (wv[j >> 2] >> ((j & 3u) * 8u)) & 0xFFu;
-        cand[off++] = ((g0 + j) << 8) | o;
+        const uint32_t o = (wv[j >> 2] >> ((j & 3u) * 8u)) & 0xFFu, t = (twv[j >> 2] >> ((j & 3u) * 8u)) & (kMaxTables - 1);
+        cand_o16[off] = (uint16_t)(o | table_tag(t));          // what the chain needs: occupancy + table tag
+        cand[off++] = ((g0 + j) << 8) | o;                       // what the commit needs: the GPU
     }
     if (blockIdx.x == gridDim.x - 1 && tid == kSweepThreads - 1) ctrl->n_cand = off;
 }
@@ -381,18 +390,18 @@ constexpr uint32_t kRing = 256;
 
 template <int K>
 __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* ctrl, const uint16_t* __restrict__ q_global,
-                                                             const uint32_t* __restrict__ cand, const uint16_t* __restrict__ feas,
+                                                             const uint16_t* __restrict__ cand_o16, const uint16_t* __restrict__ feas,
                                                              uint2* __restrict__ log, const uint32_t* __restrict__ heads_in,
                                                              uint32_t* __restrict__ heads_out) {
     extern __shared__ __align__(16) uint16_t s_q[];
     __shared__ uint32_t s_ring[kRing];
-    __shared__ uint16_t s_feas[256];
+    __shared__ uint16_t s_feas[kMaxTables * 256];
     const uint32_t q_total = ctrl->qoff[ISL_MAX_PROFILES];
     {   // stage every queue of the chunk: <= 129 KB, 16-byte vector copies
         const uint4* src = reinterpret_cast<const uint4*>(q_global);
         uint4* dst = reinterpret_cast<uint4*>(s_q);
         for (uint32_t i = threadIdx.x; i < (q_total + 7) / 8; i += kChainThreads) dst[i] = src[i];
-        s_feas[threadIdx.x] = feas[threadIdx.x];
+        for (uint32_t i = threadIdx.x; i < kMaxTables * 256; i += kChainThreads) s_feas[i] = feas[i];
     }
     __syncthreads();
     if (threadIdx.x >= 32) return;
@@ -421,8 +430,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
         const uint32_t d = tab.desc[k][lane];
         const bool valid = d >> 31;
         const uint32_t p = d & 15u;
-        cmask[k] = valid ? (d >> 16) & 0xFFu : 0xFFu;
-        keylow[k] = (p << 11) | (((d >> 4) & 7u) << 8) | cmask[k];
+        cmask[k] = valid ? ((d >> 16) & 0xFFu) | (1u << (8 + ((d >> 24) & 7u))) : 0xFFFFu;      // slot mask + own-table bit
+        keylow[k] = (p << 11) | (((d >> 4) & 7u) << 8) | (cmask[k] & 0xFFu);
         pbit[k] = valid ? 1u << p : 0u;
         reports[k] = valid && ((d >> 4) & 7u) == 0;       // first candidate of the row reports the head
         const uint32_t qb = ctrl->qoff[p], end = valid ? ctrl->qcnt[p] : 0u;
@@ -432,7 +441,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
         tcur[k] = left[k] > 0 ? ((uint32_t)s_q[qa[k]] << 15) | keylow[k] : kInf;
         tnext[k] = left[k] > 1 ? ((uint32_t)s_q[qa[k] + 1] << 15) | keylow[k] : kInf;
     }
-    auto ldc = [&](uint32_t idx) -> uint32_t { return idx < n_cand ? cand[idx] : kInf; };   // past the end: occupancy 0xFF, nothing fits
+    auto ldc = [&](uint32_t idx) -> uint32_t { return idx < n_cand ? (uint32_t)cand_o16[idx] : 0xFFFFu; };   // past the end: nothing fits
     uint32_t fill = 0, pending;
     auto reload = [&](uint32_t at) {       // synchronous (re)fill of 5 blocks starting at the block that holds `at`
         __syncwarp();                          // every lane is done reading the slots that are about to be overwritten
@@ -443,7 +452,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
     };
     reload(0);
     uint32_t i0 = 0;
-    uint32_t o0 = s_ring[0] & 0xFFu, o1 = s_ring[1] & 0xFFu, o2 = s_ring[2] & 0xFFu;
+    uint32_t o0 = s_ring[0], o1 = s_ring[1], o2 = s_ring[2];
     uint32_t jumps = 0;
     uint2* lp = log;
     while (rem) {
@@ -464,8 +473,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
             uint32_t j = i0 + 2;
             bool found = false;
             while (j < n_cand) {
-                const uint32_t c = ldc(j + lane);
-                const uint32_t b = __ballot_sync(0xFFFFFFFFu, (s_feas[c & 0xFFu] & alive) != 0 && c != kInf);
+                const uint32_t c = ldc(j + lane);                 // table = the one cleared bit of the tag
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, c != 0xFFFFu && (s_feas[(__ffs(~(c >> 8) & 0xFFu) - 1) * 256 + (c & 0xFFu)] & alive) != 0);
                 if (b) { j += __ffs(b) - 1; found = true; break; }
                 j += 32;
             }
@@ -473,7 +482,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
             if (!found) break;
             i0 = j;
             if (i0 + 64 > fill) reload(i0);
-            o0 = s_ring[i0 & (kRing - 1)] & 0xFFu; o1 = s_ring[(i0 + 1) & (kRing - 1)] & 0xFFu; o2 = s_ring[(i0 + 2) & (kRing - 1)] & 0xFFu;
+            o0 = s_ring[i0 & (kRing - 1)]; o1 = s_ring[(i0 + 1) & (kRing - 1)]; o2 = s_ring[(i0 + 2) & (kRing - 1)];
             continue;
         }
         const uint32_t sel = m >> 31;
@@ -481,7 +490,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
         if (sel) {      // warp-uniform: the current GPU is finished, the next one becomes current
             o0 = o1 | (m & 0xFFu); o1 = o2;
             ++i0;
-            o2 = s_ring[(i0 + 2) & (kRing - 1)] & 0xFFu;
+            o2 = s_ring[(i0 + 2) & (kRing - 1)];
             if ((i0 & 31u) == 0 && fill < i0 + 224) {
                 __syncwarp();
                 s_ring[(fill + lane) & (kRing - 1)] = pending;
@@ -581,6 +590,7 @@ struct PipeArgs {
     uint32_t q_stride, free_stride;
     uint32_t* tokens;               // [chunk][segment + 1][kTokStride]; slot n_seg = 'everything placeable is placed' broadcast
     uint8_t* occ;
+    const uint8_t* gtab;            // table id of every GPU's node
     uint2* out;
     const uint16_t* feas;
     Ctrl* stats;
@@ -621,7 +631,7 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
 }
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
 __device__ __forceinline__ void sts_v2_if(bool pred, uint32_t sa, uint32_t x, uint32_t y) {
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.v2.u32 [%1], {%2, %3}; }" ::"r"((uint32_t)pred), "r"(sa), "r"(x), "r"(y) : "memory");
 }
@@ -637,7 +647,7 @@ __device__ __noinline__ uint32_t pipeline_skip(uint32_t sa_cand, const uint16_t*
     uint32_t j = cur_plus2;                      // record index of (current + 2)
     while (alive && j < n_cand) {
         const uint32_t cr = j + lane < n_cand ? lds_u32(sa_cand + 4 * (j + lane)) : kInf;
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, cr != kInf && (s_feas[cr & 0xFFu] & alive) != 0);
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, cr != kInf && (s_feas[(__ffs(~(cr >> 8) & 0xFFu) - 1) * 256 + (cr & 0xFFu)] & alive) != 0);
         if (b) return j + __ffs(b) - 1;
         j += 32;
     }
@@ -648,10 +658,11 @@ template <int K, bool kP15>
 __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t* s_occ32 = reinterpret_cast<uint32_t*>(smem);                       // kSegMax occupancy bytes
-    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + kPipeOffCand);         // records (local gpu << 8 | occ) + sentinels
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + kPipeOffCand);         // records (local gpu << 16 | table tag | occ) + sentinels
     uint2* s_log = reinterpret_cast<uint2*>(smem + kPipeOffLog);                 // (key, candidate index) per decision
     uint32_t* s_wkey = reinterpret_cast<uint32_t*>(smem + kPipeOffWin);          // per-profile windows of ready-made keys t<<15 | p<<11
-    __shared__ uint16_t s_feas[256];
+    __shared__ uint16_t s_feas[kMaxTables * 256];
+    __shared__ uint8_t s_tab[kSegMax];                                           // table of every local GPU
     __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_wbase[ISL_MAX_PROFILES], s_qsrc[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
     __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_warp[kPipeThreads / 32], s_ncand, s_nlog, s_src, s_idle;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
@@ -660,7 +671,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     const uint32_t sa_wkey = (uint32_t)__cvta_generic_to_shared(s_wkey);
 
     for (uint32_t i = tid; i < kSegMax / 4; i += kPipeThreads) s_occ32[i] = 0xFFFFFFFFu;
-    s_feas[tid] = a.feas[tid];
+    for (uint32_t i = tid; i < kMaxTables * 256; i += kPipeThreads) s_feas[i] = a.feas[i];
+    for (uint32_t i = tid; i < kSegMax; i += kPipeThreads) s_tab[i] = i < n_g ? a.gtab[lo_s + i] & (kMaxTables - 1) : 0;
     if (tid < ISL_MAX_PROFILES) {
         uint32_t n = 0;
         for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) { const uint32_t d = tab.desc[k][l]; n += (d >> 31) && (d & 15u) == tid; }
@@ -678,8 +690,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         const uint32_t d = tab.desc[k][lane];
         valid[k] = d >> 31;
         cprof[k] = d & 15u;
-        cmask[k] = valid[k] ? (d >> 16) & 0xFFu : 0xFFu;
-        klow[k] = (((d >> 4) & 7u) << 8) | cmask[k];            // order-in-row and slot mask; t and profile come from the window key
+        cmask[k] = valid[k] ? ((d >> 16) & 0xFFu) | (1u << (8 + ((d >> 24) & 7u))) : 0xFFFFu;   // slot mask + own-table bit
+        klow[k] = (((d >> 4) & 7u) << 8) | (cmask[k] & 0xFFu);            // order-in-row and slot mask; t and profile come from the window key
         reports[k] = valid[k] && ((d >> 4) & 7u) == 0;
     }
     unsigned long long st_steps = 0, st_jumps = 0, st_visited = 0;
@@ -699,7 +711,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         {   // 2. local sweep: thread t owns local GPUs 2t and 2t+1; ordered compaction
             const uint32_t w = reinterpret_cast<uint16_t*>(s_occ32)[tid];
             const uint32_t oa = w & 0xFFu, ob = w >> 8;
-            const bool fa = 2 * tid < n_g && (s_feas[oa] & active), fb = 2 * tid + 1 < n_g && (s_feas[ob] & active);
+            const uint32_t ta = s_tab[2 * tid], tb = s_tab[2 * tid + 1];
+            const bool fa = 2 * tid < n_g && (s_feas[ta * 256 + oa] & active), fb = 2 * tid + 1 < n_g && (s_feas[tb * 256 + ob] & active);
             const uint32_t cnt = (fa ? 1u : 0u) + (fb ? 1u : 0u);
             uint32_t incl = cnt;
 #pragma unroll
@@ -708,8 +721,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             __syncthreads();
             uint32_t off = incl - cnt;
             for (uint32_t x = 0; x < warp; ++x) off += s_warp[x];
-            if (fa) s_cand[off++] = ((2 * tid) << 8) | oa;
-            if (fb) s_cand[off++] = ((2 * tid + 1) << 8) | ob;
+            if (fa) s_cand[off++] = ((2 * tid) << 16) | table_tag(ta) | oa;
+            if (fb) s_cand[off++] = ((2 * tid + 1) << 16) | table_tag(tb) | ob;
             if (tid == kPipeThreads - 1) { s_ncand = off; for (uint32_t x = 0; x < 8; ++x) s_cand[off + x] = kInf; }   // sentinels: nothing fits
         }
         // 3. token of the previous segment
@@ -806,7 +819,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 wa[k] = wa0[k] + 12;                                            // next entry to load on a pop
             }
             uint32_t la = sa_log, ca = sa_cand + 8;                             // ca: shared address of candidate record (current + 2)
-            uint32_t o0 = lds_u8(sa_cand), o1 = lds_u8(sa_cand + 4), o2 = lds_u8(sa_cand + 8);
+            uint32_t o0 = lds_u16(sa_cand), o1 = lds_u16(sa_cand + 4), o2 = lds_u16(sa_cand + 8);
             while (true) {
                 uint32_t key = kInf;
 #pragma unroll
@@ -823,7 +836,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     ++st_jumps;
                     if (j == kInf) break;
                     ca = sa_cand + 4 * (j + 2);
-                    o0 = lds_u8(ca - 8); o1 = lds_u8(ca - 4); o2 = lds_u8(ca);
+                    o0 = lds_u16(ca - 8); o1 = lds_u16(ca - 4); o2 = lds_u16(ca);
                     continue;
                 }
                 const uint32_t sel = m >> 31;
@@ -832,7 +845,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 la += 8;
                 o0 = (sel ? o1 : o0) | (m & 0xFFu);
                 o1 = sel ? o2 : o1;
-                o2 = lds_u8(ca);
+                o2 = lds_u16(ca);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {       // lanes of the winning profile (same t, same profile) pop their window
                     // INF never matches a real key: bit 31 unless profile index 15 is in use (kP15), then the t/profile fields alone could
@@ -872,7 +885,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             const uint32_t nlog = s_nlog;
             for (uint32_t j = tid; j < nlog; j += kPipeThreads) {
                 const uint2 e = s_log[j];
-                const uint32_t l = s_cand[((e.y - sa_cand) >> 2) - 2] >> 8, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
+                const uint32_t l = s_cand[((e.y - sa_cand) >> 2) - 2] >> 16, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
                 a.out[cd.req_off + t] = pack_result(lo_s + l, __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
                 atomicOr(&s_occ32[l >> 2], mask << ((l & 3u) * 8u));
             }

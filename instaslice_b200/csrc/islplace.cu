@@ -33,6 +33,12 @@ struct isl_engine {
 
     uint32_t G = 0, lo = 0, hi = 0;
     std::vector<uint32_t> node_off;
+    // per-node profile tables (heterogeneous clusters): rows_all[t][p], n_starts == 0 = table t has no row of name p
+    uint32_t n_tables = 1;
+    isl_profile rows_all[ISL_MAX_TABLES][ISL_MAX_PROFILES] = {};
+    std::vector<uint8_t> node_table;     // table of every node (empty = all 0)
+    uint8_t* d_gtab = nullptr;           // table of every GPU's node, one byte per GPU
+    uint16_t* d_cand_o16 = nullptr;      // single-chain path: occupancy + table tag of every candidate
 
     // device buffers
     uint8_t* d_occ = nullptr;        // one byte per GPU, padded to whole sweep blocks with 0xFF
@@ -111,7 +117,7 @@ int launch_chain(isl_engine* e, uint2* d_out_chunk, const uint32_t* d_heads_in, 
         ISL_CUDA(e, cudaFuncSetAttribute(k_chain<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[e->device & 7] = true;
     }
-    k_chain<K><<<1, kChainThreads, smem, e->stream>>>(e->tab, e->d_ctrl, e->d_q, e->d_cand, e->d_feas, e->d_log, d_heads_in, d_heads_out);
+    k_chain<K><<<1, kChainThreads, smem, e->stream>>>(e->tab, e->d_ctrl, e->d_q, e->d_cand_o16, e->d_feas, e->d_log, d_heads_in, d_heads_out);
     if (int rc = check_launch(e, "k_chain")) return rc;
     k_commit<<<kChunk / 256, 256, 0, e->stream>>>(e->d_ctrl, e->d_log, e->d_cand, reinterpret_cast<uint32_t*>(e->d_occ), d_out_chunk);
     return check_launch(e, "k_commit");
@@ -154,7 +160,7 @@ int run_bestfit(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out) {
 
 int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const uint32_t* d_heads_in, uint32_t* d_heads_out) {
     if (n == 0) return ISL_OK;
-    if (e->cfg.policy == ISL_POLICY_BEST_FIT) return run_bestfit(e, n, d_in, d_out);
+    if (e->cfg.policy == ISL_POLICY_BEST_FIT) return e->n_tables == 1 ? run_bestfit(e, n, d_in, d_out) : ISL_EINVAL;
     const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
     const uint32_t tiles = ceil_div(n, kTile);
     if (timing) cudaEventRecord(e->ev[0], e->stream);
@@ -174,11 +180,11 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
         if (int rc = check_launch(e, "k_partition")) return rc;
         if (timing) cudaEventRecord(e->ev[3], e->stream);
         if (sweep_blocks) {
-            k_sweep_count<<<sweep_blocks, kSweepThreads, 0, e->stream>>>(reinterpret_cast<const uint4*>(e->d_occ), e->d_feas, first_block, e->lo, e->hi,
+            k_sweep_count<<<sweep_blocks, kSweepThreads, 0, e->stream>>>(reinterpret_cast<const uint4*>(e->d_occ), reinterpret_cast<const uint4*>(e->d_gtab), e->d_feas, first_block, e->lo, e->hi,
                                                                          e->d_ctrl, e->d_sweep_counts);
             if (int rc = check_launch(e, "k_sweep_count")) return rc;
-            k_sweep_scatter<<<sweep_blocks, kSweepThreads, 0, e->stream>>>(reinterpret_cast<const uint4*>(e->d_occ), e->d_feas, first_block, e->lo, e->hi,
-                                                                           e->d_ctrl, e->d_sweep_counts, e->d_cand);
+            k_sweep_scatter<<<sweep_blocks, kSweepThreads, 0, e->stream>>>(reinterpret_cast<const uint4*>(e->d_occ), reinterpret_cast<const uint4*>(e->d_gtab), e->d_feas, first_block, e->lo, e->hi,
+                                                                           e->d_ctrl, e->d_sweep_counts, e->d_cand, e->d_cand_o16);
             if (int rc = check_launch(e, "k_sweep_scatter")) return rc;
         }
         if (timing) cudaEventRecord(e->ev[4], e->stream);
@@ -339,7 +345,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     PipeArgs args{};
     args.n_chunks = n_chunks; args.n_seg = n_seg; args.seg = seg; args.lo = e->lo; args.hi = e->hi; args.epoch = ++e->epoch;
     args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
-    args.q_stride = q_stride; args.free_stride = free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.out = d_out; args.feas = e->d_feas; args.stats = e->d_ctrl;
+    args.q_stride = q_stride; args.free_stride = free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab; args.out = d_out; args.feas = e->d_feas; args.stats = e->d_ctrl;
     args.heads_in = d_heads_in; args.heads_out = d_heads_out;
     if (e->cfg.flags & ISL_FLAG_TRACE) {
         if (int rc = grow(e, &e->d_trace, &e->cap_trace, (size_t)n_chunks * n_seg, 4)) return rc;
@@ -426,8 +432,12 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
     e->occ_bytes = ((size_t)cfg->max_gpus + kSweepBlock - 1) / kSweepBlock * kSweepBlock;
     const uint32_t max_tiles = ceil_div(cfg->max_batch, kTile) + 4096;   // + one partial tile per batch of a stream
     ISL_TRY(cudaMalloc(&e->d_occ, e->occ_bytes));
-    ISL_TRY(cudaMalloc(&e->d_lut, ISL_MAX_PROFILES * 256));
-    ISL_TRY(cudaMalloc(&e->d_feas, 256 * sizeof(uint16_t)));
+    ISL_TRY(cudaMalloc(&e->d_lut, ISL_MAX_TABLES * ISL_MAX_PROFILES * 256));
+    ISL_TRY(cudaMalloc(&e->d_feas, ISL_MAX_TABLES * 256 * sizeof(uint16_t)));
+    ISL_TRY(cudaMemset(e->d_feas, 0, ISL_MAX_TABLES * 256 * sizeof(uint16_t)));
+    ISL_TRY(cudaMalloc(&e->d_gtab, e->occ_bytes));
+    ISL_TRY(cudaMemset(e->d_gtab, 0, e->occ_bytes));
+    ISL_TRY(cudaMalloc(&e->d_cand_o16, e->occ_bytes * sizeof(uint16_t)));
     ISL_TRY(cudaMalloc(&e->d_req, (size_t)cfg->max_batch * sizeof(uint2)));
     ISL_TRY(cudaMalloc(&e->d_res, (size_t)cfg->max_batch * sizeof(uint2)));
     ISL_TRY(cudaMalloc(&e->d_q, (size_t)kQCap * sizeof(uint16_t)));
@@ -449,6 +459,7 @@ int isl_destroy(isl_engine* e) {
     {
         DeviceGuard guard(e->device);
         if (e->stream) cudaStreamSynchronize(e->stream);
+        cudaFree(e->d_gtab); cudaFree(e->d_cand_o16);
         cudaFree(e->d_occ); cudaFree(e->d_lut); cudaFree(e->d_feas); cudaFree(e->d_req); cudaFree(e->d_res);
         cudaFree(e->d_q); cudaFree(e->d_tile_counts); cudaFree(e->d_cand); cudaFree(e->d_log); cudaFree(e->d_sweep_counts);
         cudaFree(e->d_ctrl); cudaFree(e->d_scratch);
@@ -481,39 +492,84 @@ int isl_synchronize(isl_engine* e) {
     return ISL_OK;
 }
 
-int isl_load_profiles(isl_engine* e, uint32_t n, const isl_profile* rows) {
-    if (!e || !rows || n == 0 || n > ISL_MAX_PROFILES) return ISL_EINVAL;
+// shared by isl_load_profiles (one table, every row must have placements) and isl_load_profile_tables
+static int load_tables(isl_engine* e, uint32_t n_tables, uint32_t n, const isl_profile* rows, bool allow_absent) {
+    if (!e || !rows || n == 0 || n > ISL_MAX_PROFILES || n_tables == 0 || n_tables > ISL_MAX_TABLES) return ISL_EINVAL;
     // Validate what would make the reference panic: empty Placements (:334), start >= 8 (:345).
-    for (uint32_t p = 0; p < n; ++p) {
-        if (rows[p].n_starts == 0 || rows[p].n_starts > ISL_MAX_STARTS) return ISL_EINVAL;
-        for (uint32_t k = 0; k < rows[p].n_starts; ++k) {
-            if (rows[p].starts[k] >= ISL_SLOTS) return ISL_EINVAL;
-            for (uint32_t j = 0; j < k; ++j) if (rows[p].starts[j] == rows[p].starts[k]) return ISL_EINVAL;   // shim de-duplicates
+    uint32_t total_cand = 0;
+    for (uint32_t r = 0; r < n_tables * n; ++r) {
+        if (rows[r].n_starts == 0 && !allow_absent) return ISL_EINVAL;
+        if (rows[r].n_starts > ISL_MAX_STARTS) return ISL_EINVAL;
+        for (uint32_t k = 0; k < rows[r].n_starts; ++k) {
+            if (rows[r].starts[k] >= ISL_SLOTS) return ISL_EINVAL;
+            for (uint32_t j = 0; j < k; ++j) if (rows[r].starts[j] == rows[r].starts[k]) return ISL_EINVAL;   // shim de-duplicates
+            total_cand += candidate_mask(rows[r].size, rows[r].starts[k], e->cfg.quirks) != 0;
         }
     }
+    if (total_cand > kMaxCand) return ISL_EINVAL;          // more (table, profile, start) candidates than the chain's 4 x 32 lane slots
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
+    e->n_tables = n_tables;
+    memset(e->rows_all, 0, sizeof(e->rows_all));
+    for (uint32_t t = 0; t < n_tables; ++t) memcpy(e->rows_all[t], rows + (size_t)t * n, n * sizeof(isl_profile));
     e->prof.n = n; e->prof.quirks = e->cfg.quirks;
     memset(e->prof.rows, 0, sizeof(e->prof.rows));
-    memcpy(e->prof.rows, rows, n * sizeof(isl_profile));
-    // chain candidates: every (profile, start) the search can ever return, in row order
+    // default row of a name (its size is what an unplaced result reports) = the row of the first NODE in canonical order
+    // that knows the name; until isl_set_node_tables every node uses table 0
+    for (uint32_t p = 0; p < n; ++p) e->prof.rows[p] = e->rows_all[0][p];
+    // chain candidates: every (table, profile, start) the search can ever return, in row order
     memset(&e->tab, 0, sizeof(e->tab));
     uint32_t c = 0; e->cand_profiles = 0;
-    for (uint32_t p = 0; p < n; ++p) {
-        uint32_t ord = 0;
-        for (uint32_t k = 0; k < rows[p].n_starts; ++k) {
-            const uint32_t m = candidate_mask(rows[p].size, rows[p].starts[k], e->cfg.quirks);
-            if (!m) continue;
-            e->tab.desc[c / 32][c % 32] = p | (ord << 4) | ((uint32_t)rows[p].starts[k] << 7) | ((uint32_t)rows[p].size << 11) | (m << 16) | (1u << 31);
-            ++c; ++ord;
-            e->cand_profiles |= 1u << p;
+    for (uint32_t t = 0; t < n_tables; ++t)
+        for (uint32_t p = 0; p < n; ++p) {
+            const isl_profile& row = e->rows_all[t][p];
+            uint32_t ord = 0;
+            for (uint32_t k = 0; k < row.n_starts; ++k) {
+                const uint32_t m = candidate_mask(row.size, row.starts[k], e->cfg.quirks);
+                if (!m) continue;
+                e->tab.desc[c / 32][c % 32] = p | (ord << 4) | ((uint32_t)row.starts[k] << 7) | ((uint32_t)row.size << 11) | (m << 16) | (t << 24) | (1u << 31);
+                ++c; ++ord;
+                e->cand_profiles |= 1u << p;
+            }
         }
-    }
     e->n_cand_slots = c <= 32 ? 1 : (c <= 64 ? 2 : 4);
-    k_build_lut<<<1, 256, 0, e->stream>>>(e->prof, e->d_lut, e->d_feas);
-    if (int rc = check_launch(e, "k_build_lut")) return rc;
+    ISL_CUDA(e, cudaMemsetAsync(e->d_feas, 0, ISL_MAX_TABLES * 256 * sizeof(uint16_t), e->stream));
+    for (uint32_t t = 0; t < n_tables; ++t) {
+        DevProfiles dp{};
+        dp.n = n; dp.quirks = e->cfg.quirks;
+        memcpy(dp.rows, e->rows_all[t], sizeof(dp.rows));
+        k_build_lut<<<1, 256, 0, e->stream>>>(dp, t, e->d_lut, e->d_feas);
+        if (int rc = check_launch(e, "k_build_lut")) return rc;
+    }
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     e->have_profiles = true;
+    return ISL_OK;
+}
+
+int isl_load_profiles(isl_engine* e, uint32_t n, const isl_profile* rows) { return load_tables(e, 1, n, rows, false); }
+
+int isl_load_profile_tables(isl_engine* e, uint32_t n_tables, uint32_t n_profiles, const isl_profile* rows) {
+    return load_tables(e, n_tables, n_profiles, rows, true);
+}
+
+int isl_set_node_tables(isl_engine* e, uint32_t n_nodes, const uint8_t* table_of_node) {
+    if (!e || !table_of_node) return ISL_EINVAL;
+    if (!e->have_inventory || !e->have_profiles) return ISL_ESTATE;
+    if (n_nodes + 1 != e->node_off.size()) return ISL_EINVAL;
+    for (uint32_t n = 0; n < n_nodes; ++n) if (table_of_node[n] >= e->n_tables) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    e->node_table.assign(table_of_node, table_of_node + n_nodes);
+    std::vector<uint8_t> gtab(e->G);
+    for (uint32_t n = 0; n < n_nodes; ++n)
+        for (uint32_t g = e->node_off[n]; g < e->node_off[n + 1]; ++g) gtab[g] = table_of_node[n];
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_gtab, gtab.data(), e->G, cudaMemcpyHostToDevice, e->stream));
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (uint32_t p = 0; p < e->prof.n; ++p) {              // size reported for an unplaced request: first node (canonical order) that knows the name
+        e->prof.rows[p] = isl_profile{};
+        for (uint32_t n = 0; n < n_nodes; ++n)
+            if (e->rows_all[table_of_node[n]][p].n_starts) { e->prof.rows[p] = e->rows_all[table_of_node[n]][p]; break; }
+    }
     return ISL_OK;
 }
 
@@ -529,6 +585,9 @@ int isl_load_inventory(isl_engine* e, uint32_t n_nodes, const uint32_t* node_off
     e->node_off.assign(node_off, node_off + n_nodes + 1);
     e->G = G; e->lo = 0; e->hi = G;
     ISL_CUDA(e, cudaMemsetAsync(e->d_occ, 0xFF, e->occ_bytes, e->stream));
+    ISL_CUDA(e, cudaMemsetAsync(e->d_gtab, 0, e->occ_bytes, e->stream));        // every node uses table 0 until isl_set_node_tables
+    e->node_table.clear();
+    for (uint32_t p = 0; p < e->prof.n; ++p) e->prof.rows[p] = e->rows_all[0][p];
     ISL_CUDA(e, cudaMemcpyAsync(e->d_occ, occ, G, cudaMemcpyHostToDevice, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     e->have_inventory = true;
@@ -710,13 +769,15 @@ int isl_free_batch(isl_engine* e, uint32_t n, const isl_span* spans) {
 int isl_eval_starts(isl_engine* e, uint32_t profile, uint32_t n, const uint8_t* occ, uint8_t* out) {
     if (!e || (n && (!occ || !out))) return ISL_EINVAL;
     if (!e->have_profiles) return ISL_ESTATE;
-    if (profile >= e->prof.n) return ISL_EINVAL;
+    const uint32_t table = profile >> 8;
+    profile &= 0xFFu;
+    if (profile >= e->prof.n || table >= e->n_tables) return ISL_EINVAL;
     if (n == 0) return ISL_OK;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
     if (int rc = ensure_scratch(e, (size_t)n * 2)) return rc;
     ISL_CUDA(e, cudaMemcpyAsync(e->d_scratch, occ, n, cudaMemcpyHostToDevice, e->stream));
-    k_eval_starts<<<std::min(ceil_div(n, 256), 1184u), 256, 0, e->stream>>>(e->d_lut, profile, n, e->d_scratch, e->d_scratch + n);
+    k_eval_starts<<<std::min(ceil_div(n, 256), 1184u), 256, 0, e->stream>>>(e->d_lut + (size_t)table * ISL_MAX_PROFILES * 256, profile, n, e->d_scratch, e->d_scratch + n);
     if (int rc = check_launch(e, "k_eval_starts")) return rc;
     ISL_CUDA(e, cudaMemcpyAsync(out, e->d_scratch + n, n, cudaMemcpyDeviceToHost, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));

@@ -56,7 +56,7 @@ class Stats(C.Structure):
 
 # every symbol include/islplace.h declares; tests check that the library exports all of them
 EXPORTED_SYMBOLS = [
-    "isl_create", "isl_destroy", "isl_set_stream", "isl_synchronize", "isl_load_profiles", "isl_load_inventory", "isl_read_occupancy", "isl_write_occupancy",
+    "isl_create", "isl_destroy", "isl_set_stream", "isl_synchronize", "isl_load_profiles", "isl_load_profile_tables", "isl_set_node_tables", "isl_load_inventory", "isl_read_occupancy", "isl_write_occupancy",
     "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_place_stream", "isl_place_stream_device", "isl_free_batch",
     "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_ipc_inbox_handle", "isl_ipc_connect", "isl_connect_local", "isl_place_stream_partitioned", "isl_device_occupancy", "isl_get_stats", "isl_read_trace",
     "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
@@ -80,6 +80,8 @@ def load_library(path: str = LIB_PATH):
         "isl_set_stream": (C.c_int, [p, p]),
         "isl_synchronize": (C.c_int, [p]),
         "isl_load_profiles": (C.c_int, [p, C.c_uint32, p]),
+        "isl_load_profile_tables": (C.c_int, [p, C.c_uint32, C.c_uint32, p]),
+        "isl_set_node_tables": (C.c_int, [p, C.c_uint32, p]),
         "isl_load_inventory": (C.c_int, [p, C.c_uint32, p, p]),
         "isl_read_occupancy": (C.c_int, [p, p]),
         "isl_write_occupancy": (C.c_int, [p, C.c_uint32, C.c_uint32, p]),
@@ -199,6 +201,15 @@ class Engine:
     def load_profiles(self, rows: np.ndarray):
         rows = np.ascontiguousarray(rows, dtype=PROFILE_DTYPE)
         self._check(self._lib.isl_load_profiles(self._h, len(rows), _ptr(rows)), "isl_load_profiles")
+
+    def load_profile_tables(self, rows2d: np.ndarray):
+        """[n_tables][n_profile_names] rows of a heterogeneous cluster (``make_profile_tables``)."""
+        rows2d = np.ascontiguousarray(rows2d, dtype=PROFILE_DTYPE)
+        self._check(self._lib.isl_load_profile_tables(self._h, rows2d.shape[0], rows2d.shape[1], _ptr(rows2d)), "isl_load_profile_tables")
+
+    def set_node_tables(self, node_table):
+        node_table = np.ascontiguousarray(node_table, dtype=np.uint8)
+        self._check(self._lib.isl_set_node_tables(self._h, len(node_table), _ptr(node_table)), "isl_set_node_tables")
 
     def load_inventory(self, node_off, occ):
         node_off = np.ascontiguousarray(node_off, dtype=np.uint32)

@@ -55,23 +55,52 @@ void InstasliceReconciler::extractGpuProfile(const Instaslice& is, const std::st
 
 void InstasliceReconciler::Sync(const InstasliceList& list) {
     if (list.Items.empty()) throw std::runtime_error("no Instaslice objects");
-    std::vector<isl_profile> rows;
-    profiles_.clear();
-    for (const Mig& m : list.Items[0].Spec.Migplacement) {          // FIRST row with a name serves the start search (:332-340)
-        if (profiles_.count(m.Profile)) continue;
-        if (m.Placements.empty()) throw std::runtime_error("profile " + m.Profile + " has no placements (reference panics, :334)");
-        if (rows.size() >= ISL_MAX_PROFILES) throw std::runtime_error("too many profiles");
-        isl_profile r{};
-        r.size = (uint8_t)m.Placements[0].Size;
-        for (const Placement& p : m.Placements) {
-            bool dup = false;
-            for (uint32_t k = 0; k < r.n_starts; ++k) dup = dup || r.starts[k] == p.Start;
-            if (!dup && r.n_starts < ISL_MAX_STARTS) r.starts[r.n_starts++] = (uint8_t)p.Start;
+    // every node publishes its own Migplacement (instaslice_daemonset.go:588-664): group identical tables, name index = first appearance
+    auto same = [](const std::vector<Mig>& a, const std::vector<Mig>& b) {
+        if (a.size() != b.size()) return false;
+        for (size_t i = 0; i < a.size(); ++i) {
+            if (a[i].Profile != b[i].Profile || a[i].Giprofileid != b[i].Giprofileid || a[i].Placements.size() != b[i].Placements.size()) return false;
+            for (size_t k = 0; k < a[i].Placements.size(); ++k)
+                if (a[i].Placements[k].Size != b[i].Placements[k].Size || a[i].Placements[k].Start != b[i].Placements[k].Start) return false;
         }
-        r.gi_profile_id = m.Giprofileid; r.ci_profile_id = m.CIProfileID; r.ci_eng_profile_id = m.CIEngProfileID;
-        profiles_[m.Profile] = (uint8_t)rows.size();
-        rows.push_back(r);
+        return true;
+    };
+    std::vector<const std::vector<Mig>*> tables;
+    nodeTable_.clear();
+    profiles_.clear();
+    for (const Instaslice& is : list.Items) {
+        size_t t = 0;
+        while (t < tables.size() && !same(*tables[t], is.Spec.Migplacement)) ++t;
+        if (t == tables.size()) {
+            if (tables.size() >= ISL_MAX_TABLES) throw std::runtime_error("more than 8 distinct per-node profile tables");
+            tables.push_back(&is.Spec.Migplacement);
+            for (const Mig& m : is.Spec.Migplacement) {
+                if (m.Placements.empty()) throw std::runtime_error("profile " + m.Profile + " has no placements (reference panics, :334)");
+                if (!profiles_.count(m.Profile)) { const uint8_t idx = (uint8_t)profiles_.size(); profiles_[m.Profile] = idx; }
+            }
+        }
+        nodeTable_.push_back((uint8_t)t);
     }
+    if (profiles_.size() > ISL_MAX_PROFILES) throw std::runtime_error("too many profile names");
+    const size_t P = profiles_.size();
+    std::vector<isl_profile> rows(tables.size() * P);          // rows[t * P + name]; n_starts == 0: no row of that name in table t
+    for (size_t t = 0; t < tables.size(); ++t) {
+        std::map<std::string, bool> seen;
+        for (const Mig& m : *tables[t]) {                       // FIRST row with a name serves the start search (:332-340)
+            if (seen[m.Profile]) continue;
+            seen[m.Profile] = true;
+            isl_profile r{};
+            r.size = (uint8_t)m.Placements[0].Size;
+            for (const Placement& p : m.Placements) {
+                bool dup = false;
+                for (uint32_t k = 0; k < r.n_starts; ++k) dup = dup || r.starts[k] == p.Start;
+                if (!dup && r.n_starts < ISL_MAX_STARTS) r.starts[r.n_starts++] = (uint8_t)p.Start;
+            }
+            r.gi_profile_id = m.Giprofileid; r.ci_profile_id = m.CIProfileID; r.ci_eng_profile_id = m.CIEngProfileID;
+            rows[t * P + profiles_[m.Profile]] = r;
+        }
+    }
+    nTables_ = (uint32_t)tables.size();
     gpuUUID_.clear(); gpuNode_.clear(); gpuIndex_.clear(); nodeOff_.assign(1, 0); orphans_ = false;
     std::vector<uint8_t> occ;
     for (size_t n = 0; n < list.Items.size(); ++n) {
@@ -86,8 +115,9 @@ void InstasliceReconciler::Sync(const InstasliceList& list) {
             if (!kv.second.PodUUID.empty() && !is.Spec.Allocations.count(kv.second.PodUUID)) orphans_ = true;
     }
     if (gpuUUID_.empty()) throw std::runtime_error("no GPUs");
-    check(isl_load_profiles(h_, (uint32_t)rows.size(), rows.data()), h_, "isl_load_profiles");
+    check(isl_load_profile_tables(h_, nTables_, (uint32_t)P, rows.data()), h_, "isl_load_profile_tables");
     check(isl_load_inventory(h_, (uint32_t)list.Items.size(), nodeOff_.data(), occ.data()), h_, "isl_load_inventory");
+    check(isl_set_node_tables(h_, (uint32_t)nodeTable_.size(), nodeTable_.data()), h_, "isl_set_node_tables");
 }
 
 void InstasliceReconciler::UpdateNode(const InstasliceList& list, size_t node) {
@@ -113,7 +143,10 @@ uint32_t InstasliceReconciler::getStartIndexFromPreparedState(const Instaslice& 
     if (it == profiles_.end()) return ISL_START_NONE;
     const uint8_t occ = occupancyByte(is, gpuUUID);
     uint8_t start = ISL_START_NONE;
-    check(isl_eval_starts(h_, it->second, 1, &occ, &start), h_, "isl_eval_starts");
+    uint32_t table = 0;                                         // the table of the node that owns the GPU
+    auto gi = gpuIndex_.find(gpuUUID);
+    if (gi != gpuIndex_.end()) table = nodeTable_[gpuNode_[gi->second]];
+    check(isl_eval_starts(h_, it->second | (table << 8), 1, &occ, &start), h_, "isl_eval_starts");
     return start;
 }
 

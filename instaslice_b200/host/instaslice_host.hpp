@@ -103,6 +103,8 @@ private:
     std::vector<std::string> gpuUUID_;
     std::vector<size_t> gpuNode_;
     std::vector<uint32_t> nodeOff_;
+    std::vector<uint8_t> nodeTable_;      // per-node profile table (heterogeneous clusters)
+    uint32_t nTables_ = 1;
     std::map<std::string, uint8_t> profiles_;
     std::map<std::string, uint32_t> gpuIndex_;
     bool orphans_ = false;
