@@ -635,6 +635,15 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t sa) { uint32_t v; asm volat
 __device__ __forceinline__ void sts_v2_if(bool pred, uint32_t sa, uint32_t x, uint32_t y) {
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.v2.u32 [%1], {%2, %3}; }" ::"r"((uint32_t)pred), "r"(sa), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ uint32_t add_if(bool pred, uint32_t x, uint32_t inc) {         // one predicated add instead of select + move
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p add.u32 %0, %0, %2; }" : "+r"(x) : "r"((uint32_t)pred), "r"(inc));
+    return x;
+}
+__device__ __forceinline__ uint32_t redux_min_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
 __device__ __forceinline__ uint32_t lds_u32_if(bool pred, uint32_t sa, uint32_t keep) {   // predicated load: keeps `keep` when !pred
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p ld.shared.u32 %0, [%2]; }" : "+r"(keep) : "r"((uint32_t)pred), "r"(sa));
     return keep;
@@ -827,7 +836,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     const uint32_t kk = (o0 & cmask[k]) == 0 ? tcur[k] : ((o1 & cmask[k]) == 0 ? tcur[k] | 0x80000000u : kInf);
                     key = min(key, kk);
                 }
-                const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, key);
+                const uint32_t m = redux_min_u32(key);
                 if (__builtin_expect(m == kInf, 0)) {   // neither GPU takes anything: ballot to the next candidate a pending profile fits on
                     uint32_t alive = 0;
 #pragma unroll
@@ -840,7 +849,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     continue;
                 }
                 const uint32_t sel = m >> 31;
-                ca += sel * 4;
+                asm volatile("{ .reg .pred p; setp.lt.s32 p, %1, 0; @p add.u32 %0, %0, 4; }" : "+r"(ca) : "r"(m));   // ca += sel * 4
                 sts_v2_if(lane == 0, la, m, ca);                    // decision log: (key, address of the record two past the GPU it landed on)
                 la += 8;
                 o0 = (sel ? o1 : o0) | (m & 0xFFu);
@@ -853,7 +862,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     tcur[k] = adv ? tnext[k] : tcur[k];
                     tnext[k] = adv ? (tnn[k] | klow[k]) : tnext[k];
                     tnn[k] = lds_u32_if(adv, wa[k], tnn[k]);        // consumed at the earliest one pop later
-                    wa[k] += adv ? 4u : 0u;
+                    wa[k] = add_if(adv, wa[k], 4u);
                 }
             }
             const uint32_t nlog = (la - sa_log) >> 3;
