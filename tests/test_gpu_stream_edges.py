@@ -1,0 +1,81 @@
+"""Edge cases of the stream / segment-pipeline path.  Needs a B200."""
+import numpy as np
+import pytest
+
+import oracle
+from instaslice_b200 import engine as E
+from instaslice_b200 import tables, workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def churn_batches(rng, ref, sizes, n_profiles):
+    batches, live = [], []
+    for n in sizes:
+        req = W.alloc_requests((rng.next(n) % np.uint64(n_profiles)).astype(np.uint8)) if n else np.zeros(0, dtype=E.REQUEST_DTYPE)
+        for i in range(min(len(live), n // 3)):
+            g, s, z = live.pop(int(rng.next1() % len(live)))
+            req[int(rng.next1() % n)] = (g, 0, E.OP_FREE, s, z)
+        res = ref.place(req)
+        for r in res[(req["op"] == E.OP_ALLOC) & (res["status"] == E.ST_PLACED)]:
+            live.append((int(r["gpu"]), int(r["start"]), int(r["size"])))
+        batches.append((req, res))
+    return batches
+
+
+def test_stream_with_empty_and_tiny_batches():
+    """300 batches of 0..40 requests (empty ones included) in ONE call: one pipeline chunk per non-empty batch."""
+    rows = E.make_profiles(tables.H100_80GB)
+    rng = W.SplitMix64(11)
+    G = 2048
+    node_off = W.node_offsets(G // 8, 8)
+    occ = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+    ref = oracle.Fast(node_off, rows)
+    ref.load(occ)
+    sizes = [int(x) for x in (rng.next(300) % np.uint64(41))]
+    sizes[0] = 0
+    sizes[-1] = 0
+    batches = churn_batches(rng, ref, sizes, len(rows))
+    for flags in (0, E.FLAG_NO_PIPELINE):
+        eng = E.Engine(max_gpus=4096, max_batch=1 << 16, flags=flags)
+        eng.load_profiles(rows)
+        eng.load_inventory(node_off, occ)
+        got = eng.place_stream([b[0] for b in batches])
+        assert len(got) == len(batches)
+        for i, (g_, (_, w)) in enumerate(zip(got, batches)):
+            assert np.array_equal(g_, w), (flags, i)
+        assert np.array_equal(eng.read_occupancy(), ref.occupancy())
+    # a stream made only of empty batches is a no-op
+    assert all(len(x) == 0 for x in eng.place_stream([np.zeros(0, dtype=E.REQUEST_DTYPE)] * 3))
+
+
+def test_engine_reuse_across_inventories_and_tables():
+    """One engine, reloaded with inventories of different size and different tables between stream calls."""
+    eng = E.Engine(max_gpus=1 << 16, max_batch=1 << 18)
+    rng = W.SplitMix64(21)
+    for G, table in ((65536, tables.H100_80GB), (512, tables.A100_40GB), (20000, tables.H100_80GB), (8, tables.A100_40GB)):
+        rows = E.make_profiles(table)
+        node_off = np.concatenate([[0], np.cumsum(np.full((G + 7) // 8, 8))]).astype(np.uint32)
+        node_off[-1] = G
+        occ = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+        ref = oracle.Fast(node_off, rows)
+        ref.load(occ)
+        batches = churn_batches(rng, ref, [5000, 70000, 1, 3000], len(rows))
+        eng.load_profiles(rows)
+        eng.load_inventory(node_off, occ)
+        got = eng.place_stream([b[0] for b in batches])
+        for i, (g_, (_, w)) in enumerate(zip(got, batches)):
+            assert np.array_equal(g_, w), (G, i)
+        assert np.array_equal(eng.read_occupancy(), ref.occupancy()), G
+
+
+def test_stream_capacity_errors():
+    rows = E.make_profiles(tables.H100_80GB)
+    eng = E.Engine(max_gpus=4096, max_batch=1000)
+    eng.load_profiles(rows)
+    eng.load_inventory(W.node_offsets(4, 8), np.zeros(32, dtype=np.uint8))
+    with pytest.raises(E.EngineError) as ei:
+        eng.place_stream([W.alloc_requests(np.zeros(600, dtype=np.uint8)), W.alloc_requests(np.zeros(600, dtype=np.uint8))])
+    assert ei.value.code == E.ERANGE
+    ok = eng.place_stream([W.alloc_requests(np.zeros(500, dtype=np.uint8)), W.alloc_requests(np.zeros(500, dtype=np.uint8))])
+    assert sum(int((r["status"] == E.ST_PLACED).sum()) for r in ok) == 32 * 7
