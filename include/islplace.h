@@ -102,6 +102,7 @@ typedef struct isl_config {
 
 #define ISL_FLAG_TIMING 1u  /* record per-kernel CUDA-event timings (isl_get_stats) */
 #define ISL_FLAG_NO_PIPELINE    2u  /* always resolve chunk after chunk with the single-chain path */
+#define ISL_FLAG_NO_SMALL      16u  /* do not use the fused single-launch kernel for batches of <= 1024 requests (tests) */
 #define ISL_FLAG_TRACE          8u  /* record per (chunk, segment) timestamps of the segment pipeline (isl_read_trace) */
 #define ISL_FLAG_FORCE_PIPELINE 4u  /* use the segment pipeline even for a single chunk (tests) */
 

@@ -388,26 +388,14 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kRing = 256;
 
+// The chain itself, run by ONE warp (shared by k_chain and k_small).  qoff / qcnt: queue layout of the chunk; s_q: the
+// queues in shared memory; cand_o16: occupancy + table tag of every candidate GPU in canonical order (global memory,
+// streamed through s_ring); log: one (key, candidate index) record per decision.  Returns the number of decisions.
 template <int K>
-__global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* ctrl, const uint16_t* __restrict__ q_global,
-                                                             const uint16_t* __restrict__ cand_o16, const uint16_t* __restrict__ feas,
-                                                             uint2* __restrict__ log, const uint32_t* __restrict__ heads_in,
-                                                             uint32_t* __restrict__ heads_out) {
-    extern __shared__ __align__(16) uint16_t s_q[];
-    __shared__ uint32_t s_ring[kRing];
-    __shared__ uint16_t s_feas[kMaxTables * 256];
-    const uint32_t q_total = ctrl->qoff[ISL_MAX_PROFILES];
-    {   // stage every queue of the chunk: <= 129 KB, 16-byte vector copies
-        const uint4* src = reinterpret_cast<const uint4*>(q_global);
-        uint4* dst = reinterpret_cast<uint4*>(s_q);
-        for (uint32_t i = threadIdx.x; i < (q_total + 7) / 8; i += kChainThreads) dst[i] = src[i];
-        for (uint32_t i = threadIdx.x; i < kMaxTables * 256; i += kChainThreads) s_feas[i] = feas[i];
-    }
-    __syncthreads();
-    if (threadIdx.x >= 32) return;
-    const uint32_t lane = threadIdx.x;
-    const uint32_t n_cand = ctrl->n_cand;
-
+__device__ __forceinline__ uint32_t chain_warp(const CandTab& tab, const uint32_t* qoff, const uint32_t* qcnt, const uint16_t* s_q, uint32_t* s_ring,
+                                               const uint16_t* s_feas, const uint16_t* __restrict__ cand_o16, uint32_t n_cand, uint2* log,
+                                               const uint32_t* __restrict__ heads_in, uint32_t* __restrict__ heads_out, uint32_t lane,
+                                               uint32_t* visited_out, uint32_t* jumps_out) {
     uint32_t cmask[K], keylow[K], pbit[K], head[K], left[K], qa[K], tcur[K], tnext[K];
     bool reports[K];
     uint32_t rem = 0;                       // requests still pending over all profiles that have a candidate (warp-uniform)
@@ -420,7 +408,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
                 const uint32_t p = d & 15u;
                 if ((seen >> p) & 1u) continue;
                 seen |= 1u << p;
-                const uint32_t h = heads_in ? heads_in[p] : 0u, e = ctrl->qcnt[p];
+                const uint32_t h = heads_in ? heads_in[p] : 0u, e = qcnt[p];
                 rem += e > h ? e - h : 0u;
             }
     }
@@ -434,14 +422,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
         keylow[k] = (p << 11) | (((d >> 4) & 7u) << 8) | (cmask[k] & 0xFFu);
         pbit[k] = valid ? 1u << p : 0u;
         reports[k] = valid && ((d >> 4) & 7u) == 0;       // first candidate of the row reports the head
-        const uint32_t qb = ctrl->qoff[p], end = valid ? ctrl->qcnt[p] : 0u;
+        const uint32_t qb = qoff[p], end = valid ? qcnt[p] : 0u;
         head[k] = heads_in ? heads_in[p] : 0u;
         left[k] = end > head[k] ? end - head[k] : 0u;      // requests of this profile not yet popped
         qa[k] = qb + head[k];                              // shared-memory index of the current head entry
         tcur[k] = left[k] > 0 ? ((uint32_t)s_q[qa[k]] << 15) | keylow[k] : kInf;
         tnext[k] = left[k] > 1 ? ((uint32_t)s_q[qa[k] + 1] << 15) | keylow[k] : kInf;
     }
-    auto ldc = [&](uint32_t idx) -> uint32_t { return idx < n_cand ? (uint32_t)cand_o16[idx] : 0xFFFFu; };   // past the end: nothing fits
+    auto ldc = [&](uint32_t idx) -> uint32_t { return idx < n_cand ? (uint32_t)__ldcg(cand_o16 + idx) : 0xFFFFu; };   // past the end: nothing fits
     uint32_t fill = 0, pending;
     auto reload = [&](uint32_t at) {       // synchronous (re)fill of 5 blocks starting at the block that holds `at`
         __syncwarp();                          // every lane is done reading the slots that are about to be overwritten
@@ -486,7 +474,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
             continue;
         }
         const uint32_t sel = m >> 31;
-        *lp++ = make_uint2(m, i0 + sel);                  // decision log: (key, candidate index it landed on)
+        if (lane == 0) *lp = make_uint2(m, i0 + sel);     // decision log: (key, candidate index it landed on)
+        ++lp;
         if (sel) {      // warp-uniform: the current GPU is finished, the next one becomes current
             o0 = o1 | (m & 0xFFu); o1 = o2;
             ++i0;
@@ -515,16 +504,177 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
         }
         --rem;
     }
-    const uint32_t steps = rem0 - rem;
 #pragma unroll
     for (int k = 0; k < K; ++k)
-        if (reports[k] && heads_out) heads_out[(keylow[k] >> 11) & 15u] = ctrl->qcnt[(keylow[k] >> 11) & 15u] - left[k];
-    if (lane == 0) {
+        if (reports[k] && heads_out) heads_out[(keylow[k] >> 11) & 15u] = qcnt[(keylow[k] >> 11) & 15u] - left[k];
+    *visited_out = i0; *jumps_out = jumps;
+    return rem0 - rem;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* ctrl, const uint16_t* __restrict__ q_global,
+                                                             const uint16_t* __restrict__ cand_o16, const uint16_t* __restrict__ feas,
+                                                             uint2* __restrict__ log, const uint32_t* __restrict__ heads_in,
+                                                             uint32_t* __restrict__ heads_out) {
+    extern __shared__ __align__(16) uint16_t s_q[];
+    __shared__ uint32_t s_ring[kRing];
+    __shared__ uint16_t s_feas[kMaxTables * 256];
+    const uint32_t q_total = ctrl->qoff[ISL_MAX_PROFILES];
+    {   // stage every queue of the chunk: <= 129 KB, 16-byte vector copies
+        const uint4* src = reinterpret_cast<const uint4*>(q_global);
+        uint4* dst = reinterpret_cast<uint4*>(s_q);
+        for (uint32_t i = threadIdx.x; i < (q_total + 7) / 8; i += kChainThreads) dst[i] = src[i];
+        for (uint32_t i = threadIdx.x; i < kMaxTables * 256; i += kChainThreads) s_feas[i] = feas[i];
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    uint32_t visited, jumps;
+    const uint32_t steps = chain_warp<K>(tab, ctrl->qoff, ctrl->qcnt, s_q, s_ring, s_feas, cand_o16, ctrl->n_cand, log, heads_in, heads_out, threadIdx.x,
+                                         &visited, &jumps);
+    if (threadIdx.x == 0) {
         ctrl->n_log = steps;
         atomicAdd(&ctrl->placed, (unsigned long long)steps);
         atomicAdd(&ctrl->steps, (unsigned long long)steps);
-        atomicAdd(&ctrl->visited, (unsigned long long)i0);
+        atomicAdd(&ctrl->visited, (unsigned long long)visited);
         atomicAdd(&ctrl->jumps, (unsigned long long)jumps);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_small<K>: the whole hot path of ONE small batch (<= 1024 requests) in ONE launch of ONE CTA — the latency path
+// (BASELINE config 5: a reconciler handing over one or two pods at a time).  Same steps as the big path:
+//   A  frees / default results / stable partition of the ALLOC requests into per-profile queues (shared memory)
+//   B  vectorised sweep of the inventory with ordered compaction of the candidate GPUs (16 GPUs per thread and round)
+//   C  the decision chain (warp 0)
+//   D  commit of the logged decisions
+// Tiny batches (<= 64 requests) arrive as kernel parameters and their results go straight to mapped pinned host memory,
+// so the call is one launch and one stream synchronisation.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kSmallThreads = 1024;
+constexpr uint32_t kSmallMax = 1024;              // requests: one per thread in phase A
+constexpr uint32_t kSmallInline = 64;             // requests that travel as kernel parameters
+struct SmallReqs { uint2 r[kSmallInline]; };
+
+template <int K>
+__global__ void __launch_bounds__(kSmallThreads, 1) k_small(CandTab tab, DevProfiles prof, uint32_t n, const uint2* __restrict__ in, SmallReqs inl,
+                                                             uint2* __restrict__ out, uint8_t* __restrict__ occ, const uint8_t* __restrict__ gtab,
+                                                             const uint16_t* __restrict__ feas, uint32_t G, uint32_t lo, uint32_t hi,
+                                                             uint32_t cand_profiles, uint32_t* __restrict__ cand, uint16_t* __restrict__ cand_o16, Ctrl* stats) {
+    __shared__ uint16_t s_q[kSmallMax + kQPad * ISL_MAX_PROFILES];
+    __shared__ uint32_t s_ring[kRing];
+    __shared__ uint16_t s_feas[kMaxTables * 256];
+    __shared__ uint32_t s_seg[32][ISL_MAX_PROFILES];
+    __shared__ uint32_t s_qoff[ISL_MAX_PROFILES + 1], s_qcnt[ISL_MAX_PROFILES], s_scan[32], s_active, s_base, s_nlog, s_freed;
+    __shared__ uint2 s_log[kSmallMax];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t* occ32 = reinterpret_cast<uint32_t*>(occ);
+    for (uint32_t i = tid; i < kMaxTables * 256; i += kSmallThreads) s_feas[i] = feas[i];
+    if (tid < 32 * ISL_MAX_PROFILES) (&s_seg[0][0])[tid] = 0;
+    if (tid == 0) { s_base = 0; s_freed = 0; }
+    __syncthreads();
+    // ---- A: one request per thread
+    uint32_t key = kSkip, rank = 0;
+    if (tid < n) {
+        const uint2 rq = in ? in[tid] : inl.r[tid];
+        const uint32_t handle = rq.x, profile = rq.y & 0xFFu, op = (rq.y >> 8) & 0xFFu, start = (rq.y >> 16) & 0xFFu, size = rq.y >> 24;
+        if (op == ISL_OP_ALLOC) {
+            if (profile < prof.n) { key = profile; out[tid] = pack_result(ISL_GPU_NONE, ISL_START_NONE, prof.rows[profile].size, ISL_ST_NO_CAPACITY); }
+            else out[tid] = pack_result(ISL_GPU_NONE, ISL_START_NONE, 0, ISL_ST_BAD_PROFILE);
+        } else if (op == ISL_OP_FREE) {
+            if (handle >= G || size == 0 || start + size > ISL_SLOTS) out[tid] = pack_result(handle, start, size, ISL_ST_BAD_SPAN);
+            else {
+                if (handle >= lo && handle < hi) { atomicAnd(&occ32[handle >> 2], ~((((1u << size) - 1u) << start) << ((handle & 3u) * 8u))); atomicAdd(&s_freed, 1u); }
+                out[tid] = pack_result(handle, start, size, ISL_ST_FREED);
+            }
+        } else out[tid] = pack_result(ISL_GPU_NONE, ISL_START_NONE, 0, ISL_ST_NOOP);
+    }
+    {
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        rank = __popc(peers & ((1u << lane) - 1u));
+        if (key != kSkip && lane == (uint32_t)(__ffs(peers) - 1)) s_seg[warp][key] = __popc(peers);
+    }
+    __syncthreads();
+    if (tid < ISL_MAX_PROFILES) {           // exclusive scan over the 32 warps, in request order
+        uint32_t run = 0;
+        for (uint32_t w = 0; w < 32; ++w) { const uint32_t c = s_seg[w][tid]; s_seg[w][tid] = run; run += c; }
+        s_qcnt[tid] = run;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t off = 0, active = 0, allocs = 0;
+        for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) {
+            s_qoff[p] = off;
+            if (s_qcnt[p] && ((cand_profiles >> p) & 1u)) active |= 1u << p;
+            allocs += s_qcnt[p];
+            off += (s_qcnt[p] + kQPad - 1) & ~(kQPad - 1);
+        }
+        s_qoff[ISL_MAX_PROFILES] = off; s_active = active;
+        if (allocs) atomicAdd(&stats->allocs, (unsigned long long)allocs);
+        if (s_freed) atomicAdd(&stats->freed, (unsigned long long)s_freed);
+    }
+    __threadfence();                        // the frees must be visible to the sweep's loads
+    __syncthreads();
+    if (key != kSkip) s_q[s_qoff[key] + s_seg[warp][key] + rank] = (uint16_t)tid;
+    // ---- B: sweep, 16 GPUs per thread and round, ordered compaction into cand / cand_o16
+    const uint32_t active = s_active;
+    if (active) {
+        for (uint32_t base = lo / (kSmallThreads * 16u) * (kSmallThreads * 16u); base < hi; base += kSmallThreads * 16u) {
+            const uint32_t g0 = base + tid * 16u;
+            uint4 v = make_uint4(0, 0, 0, 0), tv = make_uint4(0, 0, 0, 0);
+            uint32_t mask = 0;
+            if (g0 < hi && g0 + 16u > lo) {
+                v = __ldcg(reinterpret_cast<const uint4*>(occ) + (g0 >> 4)); tv = __ldcg(reinterpret_cast<const uint4*>(gtab) + (g0 >> 4));
+                mask = sweep_mask16(v, tv, s_feas, active, g0, lo, hi);
+            }
+            const uint32_t c = __popc(mask);
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {                    // exclusive scan of the 32 warp totals
+                const uint32_t t = s_scan[lane];
+                uint32_t x = t;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if ((int)lane >= d) x += y; }
+                s_scan[lane] = x - t;
+                if (lane == 31) s_nlog = x;     // round total (s_nlog is reused as scratch here)
+            }
+            __syncthreads();
+            uint32_t off = s_base + s_scan[warp] + incl - c;
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w}, twv[4] = {tv.x, tv.y, tv.z, tv.w};
+            uint32_t m = mask;
+            while (m) {
+                const uint32_t j = __ffs(m) - 1; m &= m - 1;
+                const uint32_t o = (wv[j >> 2] >> ((j & 3u) * 8u)) & 0xFFu, t = (twv[j >> 2] >> ((j & 3u) * 8u)) & (kMaxTables - 1);
+                cand_o16[off] = (uint16_t)(o | table_tag(t));
+                cand[off++] = ((g0 + j) << 8) | o;
+            }
+            __syncthreads();
+            if (tid == 0) s_base += s_nlog;
+            __syncthreads();
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    // ---- C: the chain
+    if (warp == 0) {
+        uint32_t visited = 0, jumps = 0;
+        const uint32_t steps = active ? chain_warp<K>(tab, s_qoff, s_qcnt, s_q, s_ring, s_feas, cand_o16, s_base, s_log, nullptr, nullptr, lane, &visited, &jumps) : 0u;
+        if (lane == 0) {
+            s_nlog = steps;
+            if (steps) { atomicAdd(&stats->placed, (unsigned long long)steps); atomicAdd(&stats->steps, (unsigned long long)steps); }
+            if (visited) atomicAdd(&stats->visited, (unsigned long long)visited);
+            if (jumps) atomicAdd(&stats->jumps, (unsigned long long)jumps);
+        }
+    }
+    __syncthreads();
+    // ---- D: commit
+    for (uint32_t j = tid; j < s_nlog; j += kSmallThreads) {
+        const uint2 e = s_log[j];
+        const uint32_t g = __ldcg(cand + e.y) >> 8, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
+        out[t] = pack_result(g, __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
+        atomicOr(&occ32[g >> 2], mask << ((g & 3u) * 8u));
     }
 }
 

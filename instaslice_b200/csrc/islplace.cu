@@ -52,6 +52,8 @@ struct isl_engine {
     uint32_t* d_cand = nullptr;
     uint2* d_log = nullptr;          // decision log of one chunk (chain -> commit)
     uint32_t* d_bf_bitmaps = nullptr; // best-fit class bitmaps for inventories beyond the shared-memory size
+    uint2* h_small_out = nullptr;     // mapped pinned results of tiny batches (k_small writes them over PCIe directly)
+    uint2* d_small_out = nullptr;     // device alias of h_small_out
     uint32_t* d_sweep_counts = nullptr;
     Ctrl* d_ctrl = nullptr;
     uint8_t* d_scratch = nullptr;    // eval_starts / free_batch staging
@@ -124,6 +126,36 @@ int launch_chain(isl_engine* e, uint2* d_out_chunk, const uint32_t* d_heads_in, 
 }
 
 // Resolve n requests that already sit in device memory.  Enqueues only; the caller synchronises.
+// The latency path: one launch of one CTA resolves a batch of <= 1024 requests (k_small).
+bool small_eligible(const isl_engine* e, uint32_t n) {
+    return n > 0 && n <= kSmallMax && e->cfg.policy == ISL_POLICY_FIRST_FIT && !(e->cfg.flags & (ISL_FLAG_NO_SMALL | ISL_FLAG_FORCE_PIPELINE)) &&
+           e->hi > e->lo && e->hi - e->lo <= (1u << 18);
+}
+
+int run_small(isl_engine* e, uint32_t n, const uint2* d_in, const SmallReqs* inl, uint2* d_out) {
+    static const SmallReqs zero{};
+    const SmallReqs& params = inl ? *inl : zero;
+    const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
+    if (timing) cudaEventRecord(e->ev[0], e->stream);
+    switch (e->n_cand_slots) {
+        case 1: k_small<1><<<1, kSmallThreads, 0, e->stream>>>(e->tab, e->prof, n, d_in, params, d_out, e->d_occ, e->d_gtab, e->d_feas, e->G, e->lo, e->hi,
+                                                               e->cand_profiles, e->d_cand, e->d_cand_o16, e->d_ctrl); break;
+        case 2: k_small<2><<<1, kSmallThreads, 0, e->stream>>>(e->tab, e->prof, n, d_in, params, d_out, e->d_occ, e->d_gtab, e->d_feas, e->G, e->lo, e->hi,
+                                                               e->cand_profiles, e->d_cand, e->d_cand_o16, e->d_ctrl); break;
+        default: k_small<4><<<1, kSmallThreads, 0, e->stream>>>(e->tab, e->prof, n, d_in, params, d_out, e->d_occ, e->d_gtab, e->d_feas, e->G, e->lo, e->hi,
+                                                                e->cand_profiles, e->d_cand, e->d_cand_o16, e->d_ctrl); break;
+    }
+    if (int rc = check_launch(e, "k_small")) return rc;
+    if (timing) {
+        cudaEventRecord(e->ev[1], e->stream);
+        cudaEventSynchronize(e->ev[1]);
+        float t;
+        cudaEventElapsedTime(&t, e->ev[0], e->ev[1]); e->st.ms_commit += t; e->st.ms_total += t;
+    }
+    ++e->st.batches; e->st.requests += n;
+    return ISL_OK;
+}
+
 // ISL_POLICY_BEST_FIT: frees + defaults, then the request-major class-bitmap kernel (one CTA).
 int run_bestfit(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out) {
     if (n == 0) return ISL_OK;
@@ -269,6 +301,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     const uint32_t range = e->hi - e->lo;
     const bool ring = xepoch != 0;      // partitioned inventory: tokens cross ranks through peer memory, pipeline mandatory
     if (ring && n_chunks > kMaxStreamChunks) return ISL_ERANGE;
+    if (n_batches == 1 && !d_heads_in && !d_heads_out && !xepoch && small_eligible(e, sizes[0])) return run_small(e, sizes[0], d_in, nullptr, d_out);
     if (e->cfg.policy == ISL_POLICY_BEST_FIT && (d_heads_in || d_heads_out || xepoch)) return ISL_EINVAL;   // best-fit does not partition
     const bool legacy_token = d_heads_in || d_heads_out || e->cfg.policy == ISL_POLICY_BEST_FIT;   // isl_place_batch_partitioned: host-carried token, kChunk layout
     bool pipeline = ring || (!legacy_token && !(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE)));
@@ -449,6 +482,8 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
     ISL_TRY(cudaMemset(e->d_ctrl, 0, sizeof(Ctrl)));
     ISL_TRY(cudaMemset(e->d_occ, 0xFF, e->occ_bytes));
     for (auto& ev : e->ev) ISL_TRY(cudaEventCreate(&ev));
+    ISL_TRY(cudaHostAlloc(&e->h_small_out, kSmallInline * sizeof(uint2), cudaHostAllocMapped));
+    ISL_TRY(cudaHostGetDevicePointer(&e->d_small_out, e->h_small_out, 0));
 #undef ISL_TRY
     *out = e;
     return ISL_OK;
@@ -467,6 +502,7 @@ int isl_destroy(isl_engine* e) {
         cudaFree(e->d_free_acc); cudaFree(e->d_tiles);
         if (e->d_outbox && !e->outbox_local) cudaIpcCloseMemHandle(e->d_outbox);
         cudaFree(e->d_inbox); cudaFree(e->d_trace); cudaFree(e->d_bf_bitmaps);
+        if (e->h_small_out) cudaFreeHost(e->h_small_out);
         for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
         if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     }
@@ -630,6 +666,14 @@ int isl_place_batch(isl_engine* e, uint32_t n, const isl_request* in, isl_result
     if (n == 0) return ISL_OK;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
+    if (n <= kSmallInline && small_eligible(e, n)) {        // requests as kernel parameters, results into mapped pinned memory: 1 launch + 1 sync
+        SmallReqs inl{};
+        memcpy(inl.r, in, (size_t)n * sizeof(isl_request));
+        if (int rc = run_small(e, n, nullptr, &inl, e->d_small_out)) return rc;
+        ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+        memcpy(out, e->h_small_out, (size_t)n * sizeof(isl_result));
+        return ISL_OK;
+    }
     ISL_CUDA(e, cudaMemcpyAsync(e->d_req, in, (size_t)n * sizeof(isl_request), cudaMemcpyHostToDevice, e->stream));
     if (int rc = run_stream(e, 1, &n, e->d_req, e->d_res, nullptr, nullptr)) return rc;
     ISL_CUDA(e, cudaMemcpyAsync(out, e->d_res, (size_t)n * sizeof(isl_result), cudaMemcpyDeviceToHost, e->stream));

@@ -27,7 +27,7 @@ QUIRK_STRICT_BOUND, QUIRK_POW2_ONLY = 1, 2
 QUIRKS_REF_EXACT, QUIRKS_FIXED = 3, 0
 OP_ALLOC, OP_FREE, OP_NOOP = 0, 1, 2
 ST_PLACED, ST_NO_CAPACITY, ST_BAD_PROFILE, ST_FREED, ST_BAD_SPAN, ST_NOOP = 0, 1, 2, 3, 4, 5
-FLAG_TIMING, FLAG_NO_PIPELINE, FLAG_FORCE_PIPELINE, FLAG_TRACE = 1, 2, 4, 8
+FLAG_TIMING, FLAG_NO_PIPELINE, FLAG_FORCE_PIPELINE, FLAG_TRACE, FLAG_NO_SMALL = 1, 2, 4, 8, 16
 
 # ---- record layouts -------------------------------------------------------------------------
 REQUEST_DTYPE = np.dtype([("handle", "<u4"), ("profile", "u1"), ("op", "u1"), ("start", "u1"), ("size", "u1")])

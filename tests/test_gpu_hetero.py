@@ -45,7 +45,7 @@ def test_mixed_tables_vs_oracle(n_nodes, quirks):
     ref.load(occ)
     want = [ref.place(b) for b in batches]
     final = ref.occupancy()
-    for flags in (E.FLAG_NO_PIPELINE, E.FLAG_FORCE_PIPELINE, 0):
+    for flags in (E.FLAG_NO_PIPELINE | E.FLAG_NO_SMALL, E.FLAG_FORCE_PIPELINE, 0):
         eng = E.Engine(max_gpus=max(4096, G), max_batch=1 << 20, quirks=quirks, flags=flags)
         eng.load_profile_tables(rows2d)
         eng.load_inventory(node_off, occ)

@@ -36,7 +36,7 @@ def check_against_fast(node_off, occ, rows, batches, quirks=E.QUIRKS_REF_EXACT):
     ref.load(occ)
     want = [ref.place(req) for req in batches]
     final = ref.occupancy()
-    for flags in (E.FLAG_NO_PIPELINE, E.FLAG_FORCE_PIPELINE):
+    for flags in (E.FLAG_NO_PIPELINE | E.FLAG_NO_SMALL, E.FLAG_FORCE_PIPELINE, 0):
         eng = make_engine(node_off, occ, rows, quirks, flags=flags)
         for i, req in enumerate(batches):
             got = eng.place_batch(req)
@@ -171,7 +171,7 @@ def test_regress_crd_batched_equals_pod_by_pod():
 
 
 # ---- randomised parity, edge cases ------------------------------------------------------------------------
-@pytest.mark.parametrize("flags", [E.FLAG_NO_PIPELINE, E.FLAG_FORCE_PIPELINE])
+@pytest.mark.parametrize("flags", [E.FLAG_NO_PIPELINE | E.FLAG_NO_SMALL, E.FLAG_FORCE_PIPELINE, 0])
 @pytest.mark.parametrize("quirks", [3, 0])
 @pytest.mark.parametrize("tname", ["a100-40gb", "h100-80gb"])
 def test_random_occupancy_and_frees(tname, quirks, flags):

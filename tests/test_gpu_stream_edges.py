@@ -36,7 +36,7 @@ def test_stream_with_empty_and_tiny_batches():
     sizes[0] = 0
     sizes[-1] = 0
     batches = churn_batches(rng, ref, sizes, len(rows))
-    for flags in (0, E.FLAG_NO_PIPELINE):
+    for flags in (0, E.FLAG_NO_PIPELINE | E.FLAG_NO_SMALL):
         eng = E.Engine(max_gpus=4096, max_batch=1 << 16, flags=flags)
         eng.load_profiles(rows)
         eng.load_inventory(node_off, occ)

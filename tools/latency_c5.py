@@ -21,7 +21,7 @@ arrivals = np.cumsum(-np.log1p(-u) / RATE)
 life = -np.log1p(-(rng.next(n) >> np.uint64(11)).astype(np.float64) / float(1 << 53)) * MEAN_LIFE
 prof = tables.profile_index(tables.A100_40GB, "3g.20gb")
 G = 4096
-eng = E.Engine(max_gpus=G, max_batch=65536)
+eng = E.Engine(max_gpus=G, max_batch=65536, flags=int(os.environ.get("C5_FLAGS", "0")))
 eng.load_profiles(E.make_profiles(tables.A100_40GB))
 eng.load_inventory(W.node_offsets(G // 8, 8), np.zeros(G, dtype=np.uint8))
 for _ in range(200):                                   # warm the path (kernels loaded, buffers allocated)
