@@ -164,6 +164,7 @@ typedef struct isl_stats {
     double   ms_sweep;
     double   ms_commit;
     double   ms_total;             /* first kernel start -> last kernel end, per batch, summed */
+    uint64_t scan_placed;          /* placements committed by the parallel capacity scan (single-profile chunks), no chain */
 } isl_stats;
 
 /* ---- lifetime ---------------------------------------------------------- */

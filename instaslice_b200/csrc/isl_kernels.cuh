@@ -63,7 +63,7 @@ struct Ctrl {                   // device-resident control block, rewritten per 
     uint32_t n_cand;                       // candidate GPUs found by the sweep
     uint32_t heads_out[ISL_MAX_PROFILES];  // queue heads after the chain (token for the next rank)
     uint32_t n_log;                        // decisions logged by the chain of this chunk
-    unsigned long long placed, freed, bad, steps, visited, allocs, jumps;
+    unsigned long long placed, freed, bad, steps, visited, allocs, jumps, scanned;
 };
 
 // The one rule both the device table and the chain candidates come from: slot mask of placing a
@@ -85,8 +85,10 @@ __host__ __device__ inline uint32_t candidate_mask(uint32_t size, uint32_t v, ui
 // Device table: lut[p][occ] = first legal start of profile p on a GPU with occupancy byte occ
 // (or 9), feas[occ] = bitmask of profiles that have a legal start.  256 threads, one per byte.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_build_lut(DevProfiles prof, uint32_t table, uint8_t* __restrict__ lut, uint16_t* __restrict__ feas) {
+__global__ void __launch_bounds__(256) k_build_lut(DevProfiles prof, uint32_t table, uint8_t* __restrict__ lut, uint16_t* __restrict__ feas,
+                                                   uint8_t* __restrict__ capn, uint32_t* __restrict__ seq) {
     lut += (size_t)table * ISL_MAX_PROFILES * 256; feas += (size_t)table * 256;        // lut[table][profile][occ], feas[table][occ]
+    capn += (size_t)table * ISL_MAX_PROFILES * 256; seq += (size_t)table * ISL_MAX_PROFILES * 256;
     const uint32_t occ = threadIdx.x;
     uint32_t fmask = 0;
     for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) {
@@ -100,6 +102,23 @@ __global__ void __launch_bounds__(256) k_build_lut(DevProfiles prof, uint32_t ta
         }
         lut[p * 256 + occ] = (uint8_t)found;
         if (found != ISL_START_NONE) fmask |= 1u << p;
+        // how many requests of this profile the GPU takes IN A ROW from this occupancy, and at which starts (4 bits each):
+        // the single-profile scan commit (k_sweep_* in scan mode) places whole GPUs at once from these two tables
+        uint32_t o = occ, cnt = 0, packed = 0;
+        if (p < prof.n) {
+            const isl_profile& row = prof.rows[p];
+            while (cnt < 8) {
+                uint32_t st = ISL_START_NONE, mk = 0;
+                for (uint32_t k = 0; k < row.n_starts; ++k) {
+                    const uint32_t m = candidate_mask(row.size, row.starts[k], prof.quirks);
+                    if (m != 0 && (o & m) == 0) { st = row.starts[k]; mk = m; break; }
+                }
+                if (st == ISL_START_NONE) break;
+                packed |= st << (4 * cnt); o |= mk; ++cnt;
+            }
+        }
+        capn[p * 256 + occ] = (uint8_t)cnt;
+        seq[p * 256 + occ] = packed;
     }
     feas[occ] = (uint16_t)fmask;
 }
@@ -299,9 +318,24 @@ __device__ __forceinline__ uint32_t sweep_mask16(const uint4 v, const uint4 tv, 
     return mask;
 }
 
+// Scan mode (exactly ONE placeable profile in the chunk, e.g. a burst of replicas of one Deployment): there is nothing
+// to interleave, GPU g simply takes the next capn[occ_g] requests of the queue.  The two sweep passes then compute the
+// device-wide exclusive scan of those capacities and commit results and occupancy directly — fully parallel, no chain.
+__device__ __forceinline__ uint32_t scan_capacity16(const uint4 v, const uint4 tv, const uint8_t* __restrict__ capn, uint32_t p, uint32_t g0, uint32_t lo, uint32_t hi) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) {
+        const uint32_t o = (w[j >> 2] >> ((j & 3u) * 8u)) & 0xFFu, t = (tw[j >> 2] >> ((j & 3u) * 8u)) & (kMaxTables - 1);
+        const uint32_t g = g0 + j;
+        if (g >= lo && g < hi) c += capn[(t * ISL_MAX_PROFILES + p) * 256 + o];
+    }
+    return c;
+}
+
 __global__ void __launch_bounds__(kSweepThreads) k_sweep_count(const uint4* __restrict__ occ16, const uint4* __restrict__ gtab16, const uint16_t* __restrict__ feas,
                                                                 uint32_t first_block, uint32_t lo, uint32_t hi,
-                                                                const Ctrl* __restrict__ ctrl, uint32_t* __restrict__ counts) {
+                                                                const Ctrl* __restrict__ ctrl, uint32_t* __restrict__ counts, const uint8_t* __restrict__ capn) {
     __shared__ uint16_t s_feas[kMaxTables * 256];
     __shared__ uint32_t s_warp[kSweepThreads / 32];
     for (uint32_t i = threadIdx.x; i < kMaxTables * 256; i += kSweepThreads) s_feas[i] = feas[i];
@@ -309,7 +343,10 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_count(const uint4* __re
     const uint32_t active = ctrl->active;
     const uint32_t g0 = (first_block + blockIdx.x) * kSweepBlock + threadIdx.x * kSweepPerThread;
     uint32_t c = 0;
-    if (active && g0 < hi && g0 + kSweepPerThread > lo) c = __popc(sweep_mask16(ld_nc_v4(&occ16[g0 >> 4]), ld_nc_v4(&gtab16[g0 >> 4]), s_feas, active, g0, lo, hi));
+    if (active && g0 < hi && g0 + kSweepPerThread > lo) {
+        const uint4 v = ld_nc_v4(&occ16[g0 >> 4]), tv = ld_nc_v4(&gtab16[g0 >> 4]);
+        c = __popc(active) == 1 ? scan_capacity16(v, tv, capn, __ffs(active) - 1, g0, lo, hi) : __popc(sweep_mask16(v, tv, s_feas, active, g0, lo, hi));
+    }
 #pragma unroll
     for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
     if ((threadIdx.x & 31u) == 0) s_warp[threadIdx.x >> 5] = c;
@@ -324,7 +361,9 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_count(const uint4* __re
 __global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __restrict__ occ16, const uint4* __restrict__ gtab16, const uint16_t* __restrict__ feas,
                                                                   uint32_t first_block, uint32_t lo, uint32_t hi, Ctrl* ctrl,
                                                                   const uint32_t* __restrict__ counts, uint32_t* __restrict__ cand,
-                                                                  uint16_t* __restrict__ cand_o16) {
+                                                                  uint16_t* __restrict__ cand_o16, const uint8_t* __restrict__ capn, const uint32_t* __restrict__ seq,
+                                                                  const uint16_t* __restrict__ q, uint8_t* __restrict__ occ8, uint2* __restrict__ out_chunk,
+                                                                  const uint32_t* __restrict__ heads_in, uint32_t* __restrict__ heads_out, const uint8_t* __restrict__ sizes) {
     __shared__ uint16_t s_feas[kMaxTables * 256];
     __shared__ uint32_t s_warp[kSweepThreads / 32];
     __shared__ uint32_t s_red[kSweepThreads / 32];
@@ -343,8 +382,15 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __
     const uint32_t g0 = (first_block + blockIdx.x) * kSweepBlock + tid * kSweepPerThread;
     uint4 v = make_uint4(0, 0, 0, 0), tv = make_uint4(0, 0, 0, 0);
     uint32_t mask = 0;
-    if (active && g0 < hi && g0 + kSweepPerThread > lo) { v = ld_nc_v4(&occ16[g0 >> 4]); tv = ld_nc_v4(&gtab16[g0 >> 4]); mask = sweep_mask16(v, tv, s_feas, active, g0, lo, hi); }
-    const uint32_t c = __popc(mask);
+    const bool scan_mode = __popc(active) == 1;
+    const uint32_t sp = scan_mode ? __ffs(active) - 1 : 0u;
+    uint32_t cap_sum = 0;
+    if (active && g0 < hi && g0 + kSweepPerThread > lo) {
+        v = ld_nc_v4(&occ16[g0 >> 4]); tv = ld_nc_v4(&gtab16[g0 >> 4]);
+        if (scan_mode) cap_sum = scan_capacity16(v, tv, capn, sp, g0, lo, hi);
+        else mask = sweep_mask16(v, tv, s_feas, active, g0, lo, hi);
+    }
+    const uint32_t c = scan_mode ? cap_sum : __popc(mask);
     uint32_t incl = c;                                  // inclusive warp scan of the per-thread counts
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
@@ -353,6 +399,36 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __
     uint32_t off = s_base + incl - c;
     for (uint32_t w = 0; w < warp; ++w) off += s_warp[w];
     const uint32_t wv[4] = {v.x, v.y, v.z, v.w}, twv[4] = {tv.x, tv.y, tv.z, tv.w};
+    if (scan_mode) {        // `off` is the exclusive scan of the capacities = queue position this thread's first GPU starts at
+        const uint32_t h0 = heads_in ? heads_in[sp] : 0u, n_p = ctrl->qcnt[sp];
+        const uint16_t* qp = q + ctrl->qoff[sp];
+        uint32_t pos = h0 + off;
+        if (cap_sum && pos < n_p) {
+#pragma unroll 1
+            for (uint32_t j = 0; j < 16 && pos < n_p; ++j) {
+                const uint32_t g = g0 + j;
+                if (g < lo || g >= hi) continue;
+                const uint32_t o = (wv[j >> 2] >> ((j & 3u) * 8u)) & 0xFFu, t = (twv[j >> 2] >> ((j & 3u) * 8u)) & (kMaxTables - 1);
+                const uint32_t row = (t * ISL_MAX_PROFILES + sp) * 256 + o;
+                const uint32_t cg = capn[row], size = sizes[t * ISL_MAX_PROFILES + sp];
+                if (!cg) continue;
+                uint32_t starts = seq[row], o2 = o;
+                for (uint32_t k = 0; k < cg && pos < n_p; ++k, ++pos) {
+                    const uint32_t st = (starts >> (4 * k)) & 15u;
+                    out_chunk[qp[pos]] = pack_result(g, st, size, ISL_ST_PLACED);
+                    o2 |= (((1u << size) - 1u) << st) & 0xFFu;
+                }
+                occ8[g] = (uint8_t)o2;
+            }
+        }
+        if (blockIdx.x == gridDim.x - 1 && tid == kSweepThreads - 1) {      // `off + cap_sum` = total capacity of the range
+            const uint32_t total = off + cap_sum, left = n_p > h0 ? n_p - h0 : 0u, placed = min(total, left);
+            ctrl->n_cand = 0; ctrl->n_log = 0;                              // the chain and k_commit have nothing to do
+            if (heads_out) heads_out[sp] = h0 + placed;
+            if (placed) { atomicAdd(&ctrl->placed, (unsigned long long)placed); atomicAdd(&ctrl->scanned, (unsigned long long)placed); }
+        }
+        return;
+    }
     uint32_t m = mask;
     while (m) {
         const uint32_t j = __ffs(m) - 1; m &= m - 1;
@@ -519,6 +595,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
     extern __shared__ __align__(16) uint16_t s_q[];
     __shared__ uint32_t s_ring[kRing];
     __shared__ uint16_t s_feas[kMaxTables * 256];
+    if (__popc(ctrl->active) == 1) {        // single-profile chunk: the sweep kernels committed it in scan mode, nothing to chain
+        if (threadIdx.x == 0) ctrl->n_log = 0;
+        return;
+    }
     const uint32_t q_total = ctrl->qoff[ISL_MAX_PROFILES];
     {   // stage every queue of the chunk: <= 129 KB, 16-byte vector copies
         const uint4* src = reinterpret_cast<const uint4*>(q_global);

@@ -38,6 +38,9 @@ struct isl_engine {
     isl_profile rows_all[ISL_MAX_TABLES][ISL_MAX_PROFILES] = {};
     std::vector<uint8_t> node_table;     // table of every node (empty = all 0)
     uint8_t* d_gtab = nullptr;           // table of every GPU's node, one byte per GPU
+    uint8_t* d_capn = nullptr;           // [table][profile][occ]: placements of the profile the GPU takes in a row
+    uint32_t* d_seq = nullptr;           // [table][profile][occ]: their starts, 4 bits each
+    uint8_t* d_sizes = nullptr;          // [table][profile]: slices per placement
     uint16_t* d_cand_o16 = nullptr;      // single-chain path: occupancy + table tag of every candidate
 
     // device buffers
@@ -211,15 +214,6 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
                                                              n_tiles, e->cand_profiles, e->d_q, e->d_ctrl, nullptr, 0);
         if (int rc = check_launch(e, "k_partition")) return rc;
         if (timing) cudaEventRecord(e->ev[3], e->stream);
-        if (sweep_blocks) {
-            k_sweep_count<<<sweep_blocks, kSweepThreads, 0, e->stream>>>(reinterpret_cast<const uint4*>(e->d_occ), reinterpret_cast<const uint4*>(e->d_gtab), e->d_feas, first_block, e->lo, e->hi,
-                                                                         e->d_ctrl, e->d_sweep_counts);
-            if (int rc = check_launch(e, "k_sweep_count")) return rc;
-            k_sweep_scatter<<<sweep_blocks, kSweepThreads, 0, e->stream>>>(reinterpret_cast<const uint4*>(e->d_occ), reinterpret_cast<const uint4*>(e->d_gtab), e->d_feas, first_block, e->lo, e->hi,
-                                                                           e->d_ctrl, e->d_sweep_counts, e->d_cand, e->d_cand_o16);
-            if (int rc = check_launch(e, "k_sweep_scatter")) return rc;
-        }
-        if (timing) cudaEventRecord(e->ev[4], e->stream);
         // the heads token of a chunk: first chunk of a partitioned call chains from the previous rank
         const uint32_t* h_in = d_heads_in ? d_heads_in + (size_t)(c0 / kChunk) * ISL_MAX_PROFILES : nullptr;
         uint32_t* h_out = d_heads_out ? d_heads_out + (size_t)(c0 / kChunk) * ISL_MAX_PROFILES : nullptr;
@@ -227,6 +221,16 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
             if (h_in) ISL_CUDA(e, cudaMemcpyAsync(h_out, h_in, ISL_MAX_PROFILES * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
             else ISL_CUDA(e, cudaMemsetAsync(h_out, 0, ISL_MAX_PROFILES * sizeof(uint32_t), e->stream));
         }
+        if (sweep_blocks) {     // candidate compaction — or, for a single-profile chunk, the capacity scan that commits directly
+            k_sweep_count<<<sweep_blocks, kSweepThreads, 0, e->stream>>>(reinterpret_cast<const uint4*>(e->d_occ), reinterpret_cast<const uint4*>(e->d_gtab), e->d_feas, first_block, e->lo, e->hi,
+                                                                         e->d_ctrl, e->d_sweep_counts, e->d_capn);
+            if (int rc = check_launch(e, "k_sweep_count")) return rc;
+            k_sweep_scatter<<<sweep_blocks, kSweepThreads, 0, e->stream>>>(reinterpret_cast<const uint4*>(e->d_occ), reinterpret_cast<const uint4*>(e->d_gtab), e->d_feas, first_block, e->lo, e->hi,
+                                                                           e->d_ctrl, e->d_sweep_counts, e->d_cand, e->d_cand_o16, e->d_capn, e->d_seq, e->d_q, e->d_occ,
+                                                                           d_out + c0, h_in, h_out, e->d_sizes);
+            if (int rc = check_launch(e, "k_sweep_scatter")) return rc;
+        }
+        if (timing) cudaEventRecord(e->ev[4], e->stream);
         int rc;
         switch (e->n_cand_slots) {
             case 1: rc = launch_chain<1>(e, d_out + c0, h_in, h_out); break;
@@ -468,6 +472,9 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
     ISL_TRY(cudaMalloc(&e->d_lut, ISL_MAX_TABLES * ISL_MAX_PROFILES * 256));
     ISL_TRY(cudaMalloc(&e->d_feas, ISL_MAX_TABLES * 256 * sizeof(uint16_t)));
     ISL_TRY(cudaMemset(e->d_feas, 0, ISL_MAX_TABLES * 256 * sizeof(uint16_t)));
+    ISL_TRY(cudaMalloc(&e->d_capn, ISL_MAX_TABLES * ISL_MAX_PROFILES * 256));
+    ISL_TRY(cudaMalloc(&e->d_seq, ISL_MAX_TABLES * ISL_MAX_PROFILES * 256 * sizeof(uint32_t)));
+    ISL_TRY(cudaMalloc(&e->d_sizes, ISL_MAX_TABLES * ISL_MAX_PROFILES));
     ISL_TRY(cudaMalloc(&e->d_gtab, e->occ_bytes));
     ISL_TRY(cudaMemset(e->d_gtab, 0, e->occ_bytes));
     ISL_TRY(cudaMalloc(&e->d_cand_o16, e->occ_bytes * sizeof(uint16_t)));
@@ -494,7 +501,7 @@ int isl_destroy(isl_engine* e) {
     {
         DeviceGuard guard(e->device);
         if (e->stream) cudaStreamSynchronize(e->stream);
-        cudaFree(e->d_gtab); cudaFree(e->d_cand_o16);
+        cudaFree(e->d_gtab); cudaFree(e->d_cand_o16); cudaFree(e->d_capn); cudaFree(e->d_seq); cudaFree(e->d_sizes);
         cudaFree(e->d_occ); cudaFree(e->d_lut); cudaFree(e->d_feas); cudaFree(e->d_req); cudaFree(e->d_res);
         cudaFree(e->d_q); cudaFree(e->d_tile_counts); cudaFree(e->d_cand); cudaFree(e->d_log); cudaFree(e->d_sweep_counts);
         cudaFree(e->d_ctrl); cudaFree(e->d_scratch);
@@ -574,8 +581,13 @@ static int load_tables(isl_engine* e, uint32_t n_tables, uint32_t n, const isl_p
         DevProfiles dp{};
         dp.n = n; dp.quirks = e->cfg.quirks;
         memcpy(dp.rows, e->rows_all[t], sizeof(dp.rows));
-        k_build_lut<<<1, 256, 0, e->stream>>>(dp, t, e->d_lut, e->d_feas);
+        k_build_lut<<<1, 256, 0, e->stream>>>(dp, t, e->d_lut, e->d_feas, e->d_capn, e->d_seq);
         if (int rc = check_launch(e, "k_build_lut")) return rc;
+    }
+    {
+        uint8_t sizes[ISL_MAX_TABLES * ISL_MAX_PROFILES] = {0};
+        for (uint32_t t = 0; t < n_tables; ++t) for (uint32_t p = 0; p < n; ++p) sizes[t * ISL_MAX_PROFILES + p] = e->rows_all[t][p].size;
+        ISL_CUDA(e, cudaMemcpyAsync(e->d_sizes, sizes, sizeof(sizes), cudaMemcpyHostToDevice, e->stream));
     }
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     e->have_profiles = true;
@@ -848,7 +860,7 @@ int isl_get_stats(isl_engine* e, isl_stats* out) {
     Ctrl c;
     ISL_CUDA(e, cudaMemcpyAsync(&c, e->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
-    e->st.placed = c.placed; e->st.freed = c.freed; e->st.no_capacity = c.allocs - c.placed; e->st.chain_steps = c.steps; e->st.chain_gpus_visited = c.visited; e->st.chain_jumps = c.jumps;
+    e->st.placed = c.placed; e->st.freed = c.freed; e->st.no_capacity = c.allocs - c.placed; e->st.chain_steps = c.steps; e->st.chain_gpus_visited = c.visited; e->st.chain_jumps = c.jumps; e->st.scan_placed = c.scanned;
     *out = e->st;
     return ISL_OK;
 }
@@ -860,7 +872,7 @@ int isl_reset_stats(isl_engine* e) {
     const uint64_t launches = e->st.kernel_launches;
     e->st = isl_stats{};
     e->st.kernel_launches = launches;      // launches are counted since creation
-    ISL_CUDA(e, cudaMemsetAsync(&e->d_ctrl->placed, 0, 7 * sizeof(unsigned long long), e->stream));
+    ISL_CUDA(e, cudaMemsetAsync(&e->d_ctrl->placed, 0, 8 * sizeof(unsigned long long), e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     return ISL_OK;
 }

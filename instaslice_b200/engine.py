@@ -48,7 +48,7 @@ class Stats(C.Structure):
     _fields_ = [("batches", C.c_uint64), ("requests", C.c_uint64), ("placed", C.c_uint64), ("no_capacity", C.c_uint64),
                 ("freed", C.c_uint64), ("kernel_launches", C.c_uint64), ("chain_steps", C.c_uint64),
                 ("chain_gpus_visited", C.c_uint64), ("chain_jumps", C.c_uint64), ("ms_free", C.c_double), ("ms_partition", C.c_double),
-                ("ms_sweep", C.c_double), ("ms_commit", C.c_double), ("ms_total", C.c_double)]
+                ("ms_sweep", C.c_double), ("ms_commit", C.c_double), ("ms_total", C.c_double), ("scan_placed", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
