@@ -267,7 +267,12 @@ int launch_pipeline(isl_engine* e, PipeArgs& args) {
         attr_set[e->device & 7] = true;
     }
     void* params[] = {&e->tab, &args};
-    ISL_CUDA(e, cudaLaunchCooperativeKernel((void*)k_pipeline<K, kP15>, dim3(args.n_seg), dim3(kPipeThreads), params, kPipeSmem, e->stream));
+    const cudaError_t err = cudaLaunchCooperativeKernel((void*)k_pipeline<K, kP15>, dim3(args.n_seg), dim3(kPipeThreads), params, kPipeSmem, e->stream);
+    if (err == cudaErrorCooperativeLaunchTooLarge || err == cudaErrorLaunchOutOfResources) {   // e.g. the GPU is shared: not all CTAs can be co-resident
+        cudaGetLastError();
+        return ISL_ESTATE;          // caller falls back to the chunk-by-chunk path
+    }
+    if (err != cudaSuccess) { snprintf(e->cuda_err, sizeof(e->cuda_err), "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(err)); return ISL_ECUDA; }
     ++e->st.kernel_launches;
     return ISL_OK;
 }
@@ -397,6 +402,15 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         case 1: rc = p15 ? launch_pipeline<1, true>(e, args) : launch_pipeline<1, false>(e, args); break;
         case 2: rc = p15 ? launch_pipeline<2, true>(e, args) : launch_pipeline<2, false>(e, args); break;
         default: rc = p15 ? launch_pipeline<4, true>(e, args) : launch_pipeline<4, false>(e, args); break;
+    }
+    if (rc == ISL_ESTATE) {         // the pre-pass above did not touch the occupancy (frees went to the free masks): redo batch by batch
+        e->max_coresident = -1;     // and do not try the pipeline again on this engine
+        uint64_t boff = 0;
+        for (uint32_t b = 0; b < n_batches; ++b) {
+            if (int rc2 = run_batch(e, sizes[b], d_in + boff, d_out + boff, nullptr, nullptr)) return rc2;
+            boff += sizes[b];
+        }
+        return ISL_OK;
     }
     if (rc) return rc;
     if (timing) {
