@@ -403,6 +403,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         case 2: rc = p15 ? launch_pipeline<2, true>(e, args) : launch_pipeline<2, false>(e, args); break;
         default: rc = p15 ? launch_pipeline<4, true>(e, args) : launch_pipeline<4, false>(e, args); break;
     }
+    if (rc == ISL_ESTATE && ring) return ISL_ERANGE;    // a partitioned run cannot leave the pipeline: the token ring lives inside it
     if (rc == ISL_ESTATE) {         // the pre-pass above did not touch the occupancy (frees went to the free masks): redo batch by batch
         e->max_coresident = -1;     // and do not try the pipeline again on this engine
         uint64_t boff = 0;
