@@ -19,6 +19,7 @@ import "C"
 
 import (
 	"fmt"
+	"reflect"
 	"sort"
 	"unsafe"
 
@@ -33,6 +34,7 @@ type PlacementEngine struct {
 	gpuNode  []int             // canonical GPU index -> index into the Instaslice list
 	profiles map[string]uint8  // profile name -> row index (FIRST Migplacement row with that name, :332-340)
 	orphans  bool              // a realised slice outlived its allocation: the :198-203 veto can fire
+	nodeOff  []C.uint32_t      // node index -> first canonical GPU index
 }
 
 func NewPlacementEngine(maxGPUs, maxBatch uint32) (*PlacementEngine, error) {
@@ -76,29 +78,57 @@ func (e *PlacementEngine) Sync(list *inferencev1alpha1.InstasliceList) error {
 	if len(list.Items) == 0 {
 		return fmt.Errorf("no Instaslice objects")
 	}
-	// profile rows from the first node's Migplacement (all nodes must publish the same table today)
-	rows := make([]C.isl_profile, 0, 16)
+	// every node publishes its OWN Migplacement (instaslice_daemonset.go:588-664): group identical tables (<= 8), profile NAME
+	// index = order of first appearance; rows[t*P + name] with n_starts == 0 when table t has no row of that name
+	type tableT = []inferencev1alpha1.Mig
+	tables := []tableT{}
+	nodeTable := make([]C.uint8_t, len(list.Items))
 	e.profiles = map[string]uint8{}
-	for _, m := range list.Items[0].Spec.Migplacement {
-		if _, dup := e.profiles[m.Profile]; dup {
-			continue
-		}
-		if len(m.Placements) == 0 {
-			return fmt.Errorf("profile %s has no placements", m.Profile) // the reference panics at :334
-		}
-		var r C.isl_profile
-		r.size = C.uint8_t(m.Placements[0].Size)
-		seen := map[int]bool{}
-		for _, p := range m.Placements {
-			if !seen[p.Start] {
-				seen[p.Start] = true
-				r.starts[r.n_starts] = C.uint8_t(p.Start)
-				r.n_starts++
+	for n := range list.Items {
+		mig := list.Items[n].Spec.Migplacement
+		t := 0
+		for ; t < len(tables); t++ {
+			if reflect.DeepEqual(tables[t], tableT(mig)) {
+				break
 			}
 		}
-		r.gi_profile_id, r.ci_profile_id, r.ci_eng_profile_id = C.int32_t(m.Giprofileid), C.int32_t(m.CIProfileID), C.int32_t(m.CIEngProfileID)
-		e.profiles[m.Profile] = uint8(len(rows))
-		rows = append(rows, r)
+		if t == len(tables) {
+			if len(tables) >= int(C.ISL_MAX_TABLES) {
+				return fmt.Errorf("more than %d distinct per-node profile tables", int(C.ISL_MAX_TABLES))
+			}
+			tables = append(tables, mig)
+			for _, m := range mig {
+				if len(m.Placements) == 0 {
+					return fmt.Errorf("profile %s has no placements", m.Profile) // the reference panics at :334
+				}
+				if _, ok := e.profiles[m.Profile]; !ok {
+					e.profiles[m.Profile] = uint8(len(e.profiles))
+				}
+			}
+		}
+		nodeTable[n] = C.uint8_t(t)
+	}
+	P := len(e.profiles)
+	rows := make([]C.isl_profile, len(tables)*P)
+	for t, mig := range tables {
+		seenName := map[string]bool{}
+		for _, m := range mig {
+			if seenName[m.Profile] { // the start search uses the FIRST row with a name (:332-340)
+				continue
+			}
+			seenName[m.Profile] = true
+			r := &rows[t*P+int(e.profiles[m.Profile])]
+			r.size = C.uint8_t(m.Placements[0].Size)
+			seen := map[int]bool{}
+			for _, p := range m.Placements {
+				if !seen[p.Start] {
+					seen[p.Start] = true
+					r.starts[r.n_starts] = C.uint8_t(p.Start)
+					r.n_starts++
+				}
+			}
+			r.gi_profile_id, r.ci_profile_id, r.ci_eng_profile_id = C.int32_t(m.Giprofileid), C.int32_t(m.CIProfileID), C.int32_t(m.CIEngProfileID)
+		}
 	}
 	nodeOff := []C.uint32_t{0}
 	occ := []C.uint8_t{}
@@ -126,11 +156,40 @@ func (e *PlacementEngine) Sync(list *inferencev1alpha1.InstasliceList) error {
 			}
 		}
 	}
-	if rc := C.isl_load_profiles(e.h, C.uint32_t(len(rows)), &rows[0]); rc != C.ISL_OK {
-		return fmt.Errorf("isl_load_profiles: %s", C.GoString(C.isl_strerror(rc)))
+	if rc := C.isl_load_profile_tables(e.h, C.uint32_t(len(tables)), C.uint32_t(P), &rows[0]); rc != C.ISL_OK {
+		return fmt.Errorf("isl_load_profile_tables: %s", C.GoString(C.isl_strerror(rc)))
 	}
 	if rc := C.isl_load_inventory(e.h, C.uint32_t(len(list.Items)), &nodeOff[0], &occ[0]); rc != C.ISL_OK {
 		return fmt.Errorf("isl_load_inventory: %s", C.GoString(C.isl_strerror(rc)))
+	}
+	if rc := C.isl_set_node_tables(e.h, C.uint32_t(len(list.Items)), &nodeTable[0]); rc != C.ISL_OK {
+		return fmt.Errorf("isl_set_node_tables: %s", C.GoString(C.isl_strerror(rc)))
+	}
+	e.nodeOff = nodeOff
+	return nil
+}
+
+// UpdateNode is the incremental sync after ONE Instaslice object changed (an Allocations / Prepared entry appeared or was
+// deleted): only that node's occupancy bytes are rewritten (isl_write_occupancy) instead of re-listing the cluster (:85).
+func (e *PlacementEngine) UpdateNode(list *inferencev1alpha1.InstasliceList, n int) error {
+	is := &list.Items[n]
+	lo, hi := int(e.nodeOff[n]), int(e.nodeOff[n+1])
+	if len(is.Spec.MigGPUUUID) != hi-lo {
+		return e.Sync(list)
+	}
+	occ := make([]C.uint8_t, 0, hi-lo)
+	for g := lo; g < hi; g++ {
+		if _, ok := is.Spec.MigGPUUUID[e.gpuUUID[g]]; !ok {
+			return e.Sync(list)
+		}
+		b, err := occupancyByte(is, e.gpuUUID[g])
+		if err != nil {
+			return err
+		}
+		occ = append(occ, C.uint8_t(b))
+	}
+	if rc := C.isl_write_occupancy(e.h, C.uint32_t(lo), C.uint32_t(len(occ)), &occ[0]); rc != C.ISL_OK {
+		return fmt.Errorf("isl_write_occupancy: %s", C.GoString(C.isl_strerror(rc)))
 	}
 	return nil
 }
