@@ -314,6 +314,8 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     if (e->cfg.policy == ISL_POLICY_BEST_FIT && (d_heads_in || d_heads_out || xepoch)) return ISL_EINVAL;   // best-fit does not partition
     const bool legacy_token = d_heads_in || d_heads_out || e->cfg.policy == ISL_POLICY_BEST_FIT;   // isl_place_batch_partitioned: host-carried token, kChunk layout
     bool pipeline = ring || (!legacy_token && !(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE)));
+    // the stream path keeps one free-mask byte per GPU and batch: very long streams over large inventories go batch by batch
+    if (pipeline && (uint64_t)n_batches * e->occ_bytes > (256ull << 20)) { if (ring) return ISL_ERANGE; pipeline = false; }
     uint32_t seg = 0, n_seg = 0;
     if (pipeline) {
         if (int rc = query_coresident(e)) return rc;
@@ -360,7 +362,6 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     if (ring && n_chunks > kMaxStreamChunks) return ISL_ERANGE;
     const uint32_t q_stride = pc + kQPad * ISL_MAX_PROFILES;
     const uint32_t free_stride = (uint32_t)e->occ_bytes;           // bytes per batch
-    if ((uint64_t)n_batches * free_stride > (256ull << 20)) return ISL_ERANGE;
     if (int rc = grow(e, &e->d_chunks, &e->cap_chunks, n_chunks, 1)) return rc;
     if (int rc = grow(e, &e->d_cctl, &e->cap_cctl, n_chunks, 1)) return rc;
     if (int rc = grow(e, &e->d_qall, &e->cap_qall, (size_t)n_chunks * q_stride, 1)) return rc;
