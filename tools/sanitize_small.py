@@ -34,4 +34,26 @@ bf = E.Engine(max_gpus=4096, max_batch=1 << 16, policy=E.POLICY_BEST_FIT)
 bf.load_profiles(rows); bf.load_inventory(node_off, occ)
 rb = oracle.Fast(node_off, rows, 3, policy=1); rb.load(occ)
 assert np.array_equal(bf.place_batch(batches[0][0]), rb.place(batches[0][0]))
+# fused small-batch kernel, scan mode, heterogeneous tables
+small = E.Engine(max_gpus=4096, max_batch=1 << 16)
+small.load_profiles(rows); small.load_inventory(node_off, occ)
+rs = oracle.Fast(node_off, rows); rs.load(occ)
+for n in (1, 40, 700):
+    rq = W.alloc_requests(W.mix_profiles(rng, n))
+    assert np.array_equal(small.place_batch(rq), rs.place(rq))
+scan = E.Engine(max_gpus=4096, max_batch=1 << 16, flags=E.FLAG_NO_PIPELINE | E.FLAG_NO_SMALL)
+scan.load_profiles(rows); scan.load_inventory(node_off, occ)
+rs.load(occ)
+rq = W.alloc_requests(np.zeros(5000, dtype=np.uint8))
+assert np.array_equal(scan.place_batch(rq), rs.place(rq)) and scan.stats()["scan_placed"] > 0
+names, rows2d = E.make_profile_tables([tables.A100_40GB, tables.H100_80GB])
+nt = (rng.next(G // 8) % np.uint64(2)).astype(np.uint8)
+rh = oracle.Fast(node_off, rows2d, 3, node_table=nt); rh.load(occ)
+bh = [W.alloc_requests((rng.next(n) % np.uint64(len(names))).astype(np.uint8)) for n in (3000, 900, 70000)]
+wh = [rh.place(b) for b in bh]
+for flags in (E.FLAG_NO_PIPELINE | E.FLAG_NO_SMALL, 0):
+    he = E.Engine(max_gpus=4096, max_batch=1 << 17, flags=flags)
+    he.load_profile_tables(rows2d); he.load_inventory(node_off, occ); he.set_node_tables(nt)
+    gh = he.place_stream(bh) if flags == 0 else [he.place_batch(b) for b in bh]
+    assert all(np.array_equal(a, b) for a, b in zip(gh, wh))
 print("sanitize run ok")
