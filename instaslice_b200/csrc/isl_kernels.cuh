@@ -799,7 +799,7 @@ constexpr uint32_t kTokStride = 32;                 // uint32 per token: heads[1
 // shared memory: occupancy bytes | candidate records (+8 sentinels) | decision log | queue-window keys
 constexpr uint32_t kPipeOffCand = kSegMax;
 constexpr uint32_t kPipeOffLog = kPipeOffCand + 4 * (kSegMax + 8);
-constexpr uint32_t kPipeOffWin = kPipeOffLog + 8 * kLogCap;
+constexpr uint32_t kPipeOffWin = kPipeOffLog + 8 * (kLogCap + 1);      // + 1: the pseudo-decision the loop logs before it sees 'nothing fits'
 constexpr uint32_t kPipeSmem = kPipeOffWin + 4 * (kWinTotal + 4 * ISL_MAX_PROFILES);
 
 // largest segment whose worst-case queue windows (every candidate GPU accepting every legal start of every
@@ -830,9 +830,14 @@ struct PipeArgs {
     const uint32_t* inbox;          // local [chunk][kTokStride], written by the previous rank's last segment (nullptr = first rank)
     uint32_t* outbox;               // the next rank's inbox, peer-mapped (nullptr = last rank)
     uint32_t xepoch;                // stream id shared by all ranks
-    unsigned long long* trace;      // optional [chunk][segment][4] globaltimer ns: sweep done, token in, chain done, commit done
+    unsigned long long* trace;      // optional [chunk][segment][kTraceWords]: globaltimer ns of sweep done, token in, token out, commit done, chain start, chain end; decisions; jumps
 };
 
+constexpr uint32_t kTraceWords = 8;
+#ifndef ISL_UNROLL
+#define ISL_UNROLL 4
+#endif
+constexpr int kUnroll = ISL_UNROLL;          // decisions per trip of the decision loop
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -965,7 +970,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             if (tid == kPipeThreads - 1) { s_ncand = off; for (uint32_t x = 0; x < 8; ++x) s_cand[off + x] = kInf; }   // sentinels: nothing fits
         }
         // 3. token of the previous segment
-        unsigned long long* tr = a.trace ? a.trace + ((size_t)c * a.n_seg + seg) * 4 : nullptr;
+        unsigned long long* tr = a.trace ? a.trace + ((size_t)c * a.n_seg + seg) * kTraceWords : nullptr;
         const size_t tok_chunk = (size_t)c * (a.n_seg + 1);
         if (tid == 0) {
             if (tr) tr[0] = globaltimer_ns();
@@ -1059,43 +1064,64 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             }
             uint32_t la = sa_log, ca = sa_cand + 8;                             // ca: shared address of candidate record (current + 2)
             uint32_t o0 = lds_u16(sa_cand), o1 = lds_u16(sa_cand + 4), o2 = lds_u16(sa_cand + 8);
+            const unsigned long long jumps0 = st_jumps;
+            if (tr && lane == 0) tr[4] = globaltimer_ns();
+            // The updates are issued unconditionally and the "nothing fits" test comes LAST: a branch is not speculated, so a test
+            // in front of the updates would put its resolution on the loop-carried path of every decision.  m == INF behaves like
+            // a decision that lands on the next GPU and pops only exhausted lanes (no real key has all-ones t / profile fields unless
+            // profile 15 is in use, kP15); the rare path rewinds the cursors, the occupancy registers are reloaded after the jump anyway.
             while (true) {
-                uint32_t key = kInf;
+                bool none = false;
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const uint32_t kk = (o0 & cmask[k]) == 0 ? tcur[k] : ((o1 & cmask[k]) == 0 ? tcur[k] | 0x80000000u : kInf);
-                    key = min(key, kk);
-                }
-                const uint32_t m = redux_min_u32(key);
-                if (__builtin_expect(m == kInf, 0)) {   // neither GPU takes anything: ballot to the next candidate a pending profile fits on
-                    uint32_t alive = 0;
+                for (int u = 0; u < kUnroll; ++u) {     // unrolled: one taken branch per kUnroll decisions
+                    uint32_t key = kInf;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) alive |= tcur[k] != kInf ? 1u << cprof[k] : 0u;
-                    const uint32_t j = pipeline_skip(sa_cand, s_feas, n_cand, ((ca - sa_cand) >> 2), alive, lane);
-                    ++st_jumps;
-                    if (j == kInf) break;
-                    ca = sa_cand + 4 * (j + 2);
-                    o0 = lds_u16(ca - 8); o1 = lds_u16(ca - 4); o2 = lds_u16(ca);
-                    continue;
-                }
-                const uint32_t sel = m >> 31;
-                asm volatile("{ .reg .pred p; setp.lt.s32 p, %1, 0; @p add.u32 %0, %0, 4; }" : "+r"(ca) : "r"(m));   // ca += sel * 4
-                sts_v2_if(lane == 0, la, m, ca);                    // decision log: (key, address of the record two past the GPU it landed on)
-                la += 8;
-                o0 = (sel ? o1 : o0) | (m & 0xFFu);
-                o1 = sel ? o2 : o1;
-                o2 = lds_u16(ca);
+                    for (int k = 0; k < K; ++k) {
+                        const uint32_t kk = (o0 & cmask[k]) == 0 ? tcur[k] : ((o1 & cmask[k]) == 0 ? tcur[k] | 0x80000000u : kInf);
+                        key = min(key, kk);
+                    }
+                    const uint32_t m = redux_min_u32(key);
+                    if (kP15) { none = m == kInf; if (none) break; }
+                    const uint32_t sel = m >> 31;
+                    asm volatile("{ .reg .pred p; setp.lt.s32 p, %1, 0; @p add.u32 %0, %0, 4; }" : "+r"(ca) : "r"(m));   // ca += sel * 4
+                    sts_v2_if(lane == 0, la, m, ca);                    // decision log: (key, address of the record two past the GPU it landed on)
+                    la += 8;
+                    o0 = (sel ? o1 : o0) | (m & 0xFFu);
+                    o1 = sel ? o2 : o1;
+                    o2 = lds_u16(ca);
 #pragma unroll
-                for (int k = 0; k < K; ++k) {       // lanes of the winning profile (same t, same profile) pop their window
-                    // INF never matches a real key: bit 31 unless profile index 15 is in use (kP15), then the t/profile fields alone could
-                    const bool adv = kP15 ? (((m & 0x7FFFF800u) ^ tcur[k]) & 0xFFFFF800u) == 0 : ((m ^ tcur[k]) & 0x7FFFF800u) == 0;
-                    tcur[k] = adv ? tnext[k] : tcur[k];
-                    tnext[k] = adv ? (tnn[k] | klow[k]) : tnext[k];
-                    tnn[k] = lds_u32_if(adv, wa[k], tnn[k]);        // consumed at the earliest one pop later
-                    wa[k] = add_if(adv, wa[k], 4u);
+                    for (int k = 0; k < K; ++k) {       // lanes of the winning profile (same t, same profile) pop their window
+                        const bool adv = kP15 ? (((m & 0x7FFFF800u) ^ tcur[k]) & 0xFFFFF800u) == 0 : ((m ^ tcur[k]) & 0x7FFFF800u) == 0;
+                        tcur[k] = adv ? tnext[k] : tcur[k];
+                        tnext[k] = adv ? (tnn[k] | klow[k]) : tnext[k];
+                        tnn[k] = lds_u32_if(adv, wa[k], tnn[k]);        // consumed at the earliest one pop later
+                        wa[k] = add_if(adv, wa[k], 4u);
+                    }
+                    if (!kP15) {
+                        none = m == kInf;
+                        if (__builtin_expect(none, 0)) {
+                            ca -= 4; la -= 8;                           // rewind the pseudo-decision
+                            // m == INF matched exactly the exhausted lanes (tcur == INF; their tnext was the second INF sentinel): undo their pop
+#pragma unroll
+                            for (int k = 0; k < K; ++k)
+                                if (tcur[k] == kInf) { tnext[k] = kInf; wa[k] -= 4; }
+                            break;
+                        }
+                    }
                 }
+                if (__builtin_expect(!none, 1)) continue;
+                // neither GPU takes anything: ballot to the next candidate a pending profile fits on
+                uint32_t alive = 0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) alive |= tcur[k] != kInf ? 1u << cprof[k] : 0u;
+                const uint32_t j = pipeline_skip(sa_cand, s_feas, n_cand, ((ca - sa_cand) >> 2), alive, lane);
+                ++st_jumps;
+                if (j == kInf) break;
+                ca = sa_cand + 4 * (j + 2);
+                o0 = lds_u16(ca - 8); o1 = lds_u16(ca - 4); o2 = lds_u16(ca);
             }
             const uint32_t nlog = (la - sa_log) >> 3;
+            if (tr && lane == 0) { tr[5] = globaltimer_ns(); tr[6] = nlog; tr[7] = (st_jumps - jumps0) | ((unsigned long long)(((ca - sa_cand) >> 2) - 2) << 32); }
             st_steps += nlog; st_visited += ((ca - sa_cand) >> 2) - 2;
 #pragma unroll
             for (int k = 0; k < K; ++k) if (reports[k]) s_pop[cprof[k]] = (wa[k] - wa0[k] - 12) >> 2;

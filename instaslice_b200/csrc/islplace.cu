@@ -391,8 +391,8 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     args.q_stride = q_stride; args.free_stride = free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab; args.out = d_out; args.feas = e->d_feas; args.stats = e->d_ctrl;
     args.heads_in = d_heads_in; args.heads_out = d_heads_out;
     if (e->cfg.flags & ISL_FLAG_TRACE) {
-        if (int rc = grow(e, &e->d_trace, &e->cap_trace, (size_t)n_chunks * n_seg, 4)) return rc;
-        ISL_CUDA(e, cudaMemsetAsync(e->d_trace, 0, (size_t)n_chunks * n_seg * 4 * sizeof(unsigned long long), e->stream));
+        if (int rc = grow(e, &e->d_trace, &e->cap_trace, (size_t)n_chunks * n_seg, kTraceWords)) return rc;
+        ISL_CUDA(e, cudaMemsetAsync(e->d_trace, 0, (size_t)n_chunks * n_seg * kTraceWords * sizeof(unsigned long long), e->stream));
         e->trace_chunks = n_chunks; e->trace_seg = n_seg;
     }
     args.trace = (e->cfg.flags & ISL_FLAG_TRACE) ? e->d_trace : nullptr;
@@ -861,7 +861,7 @@ int isl_read_trace(isl_engine* e, uint64_t* out, uint32_t max_words, uint32_t* n
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
     *n_chunks = e->trace_chunks; *n_seg = e->trace_seg;
-    const size_t words = (size_t)e->trace_chunks * e->trace_seg * 4;
+    const size_t words = (size_t)e->trace_chunks * e->trace_seg * kTraceWords;
     if (!out || words == 0) return ISL_OK;
     if (words > max_words) return ISL_ERANGE;
     ISL_CUDA(e, cudaMemcpyAsync(out, e->d_trace, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
