@@ -247,8 +247,9 @@ void* isl_device_occupancy(isl_engine* e);
 
 /* ---- diagnostics ------------------------------------------------------- */
 int         isl_get_stats(isl_engine* e, isl_stats* out);
-/* ISL_FLAG_TRACE: uint64 [chunk][segment][8] of the last stream call = globaltimer ns of local sweep done, token arrived,
- * token published, commit done, decision loop start, decision loop end; decisions of the cell; jumps | GPUs visited << 32.
+/* ISL_FLAG_TRACE: uint64 [chunk][segment][12] of the last stream call = globaltimer ns of local sweep done, token arrived,
+ * token published, commit done, decision loop start, decision loop end; decisions of the cell; jumps | GPUs visited << 32;
+ * ns of heads computed, queue windows staged; two spare words.
  * out may be NULL to query the dimensions. */
 int         isl_read_trace(isl_engine* e, uint64_t* out, uint32_t max_words, uint32_t* n_chunks, uint32_t* n_seg);
 int         isl_reset_stats(isl_engine* e);

@@ -830,10 +830,10 @@ struct PipeArgs {
     const uint32_t* inbox;          // local [chunk][kTokStride], written by the previous rank's last segment (nullptr = first rank)
     uint32_t* outbox;               // the next rank's inbox, peer-mapped (nullptr = last rank)
     uint32_t xepoch;                // stream id shared by all ranks
-    unsigned long long* trace;      // optional [chunk][segment][kTraceWords]: globaltimer ns of sweep done, token in, token out, commit done, chain start, chain end; decisions; jumps
+    unsigned long long* trace;      // optional [chunk][segment][kTraceWords]: globaltimer ns of sweep done, token in, token out, commit done, chain start, chain end; decisions; jumps | visited << 32; ns of heads done, windows staged; 2 spare
 };
 
-constexpr uint32_t kTraceWords = 8;
+constexpr uint32_t kTraceWords = 12;
 #ifndef ISL_UNROLL
 #define ISL_UNROLL 4
 #endif
@@ -842,6 +842,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
+}
+// Trace stamp without a branch: a divergent `if (lane == 0)` in front of the decision loop can leave warp 0 split for good, and
+// every redux of the loop then takes the BRA.DIV emulation path (measured: 4x slower decisions).  `p` may be any address when !pred.
+__device__ __forceinline__ void stamp_if(bool pred, unsigned long long* p) {
+    asm volatile("{ .reg .pred q; .reg .u64 t; setp.ne.u32 q, %0, 0; mov.u64 t, %%globaltimer; @q st.global.u64 [%1], t; }" ::"r"((uint32_t)pred), "l"(p) : "memory");
+}
+__device__ __forceinline__ void store_if(bool pred, unsigned long long* p, unsigned long long v) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.u64 [%1], %2; }" ::"r"((uint32_t)pred), "l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     uint32_t v;
@@ -908,7 +916,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     __shared__ uint16_t s_feas[kMaxTables * 256];
     __shared__ uint8_t s_tab[kSegMax];                                           // table of every local GPU
     __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_wbase[ISL_MAX_PROFILES], s_qsrc[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
-    __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_warp[kPipeThreads / 32], s_ncand, s_nlog, s_src, s_idle;
+    __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_minsize[ISL_MAX_PROFILES], s_usable[kMaxTables], s_warp[kPipeThreads / 32], s_ncand, s_nfree, s_nlog, s_src, s_idle, s_wtotal;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     const uint32_t lo_s = min(a.hi, a.lo + seg * a.seg), hi_s = min(a.hi, lo_s + a.seg), n_g = hi_s - lo_s;
     const uint32_t sa_cand = (uint32_t)__cvta_generic_to_shared(s_cand), sa_log = (uint32_t)__cvta_generic_to_shared(s_log);
@@ -918,9 +926,21 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     for (uint32_t i = tid; i < kMaxTables * 256; i += kPipeThreads) s_feas[i] = a.feas[i];
     for (uint32_t i = tid; i < kSegMax; i += kPipeThreads) s_tab[i] = i < n_g ? a.gtab[lo_s + i] & (kMaxTables - 1) : 0;
     if (tid < ISL_MAX_PROFILES) {
-        uint32_t n = 0;
-        for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) { const uint32_t d = tab.desc[k][l]; n += (d >> 31) && (d & 15u) == tid; }
+        uint32_t n = 0, sz = 8;
+        for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) {
+            const uint32_t d = tab.desc[k][l];
+            if ((d >> 31) && (d & 15u) == tid) { ++n; sz = min(sz, (uint32_t)__popc((d >> 16) & 0xFFu)); }
+        }
         s_maxacc[tid] = n;
+        s_minsize[tid] = max(sz, 1u);           // smallest span of the profile over all tables
+    }
+    if (tid >= 32 && tid < 32 + kMaxTables) {   // slices any candidate of the table can ever cover (REF_EXACT 80GB-class tables: 0x7F)
+        uint32_t u = 0;
+        for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) {
+            const uint32_t d = tab.desc[k][l];
+            if ((d >> 31) && ((d >> 24) & 7u) == tid - 32) u |= (d >> 16) & 0xFFu;
+        }
+        s_usable[tid - 32] = u;
     }
     __syncthreads();
     for (uint32_t i = tid; i < n_g; i += kPipeThreads) reinterpret_cast<uint8_t*>(s_occ32)[i] = a.occ[lo_s + i];
@@ -957,7 +977,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             const uint32_t oa = w & 0xFFu, ob = w >> 8;
             const uint32_t ta = s_tab[2 * tid], tb = s_tab[2 * tid + 1];
             const bool fa = 2 * tid < n_g && (s_feas[ta * 256 + oa] & active), fb = 2 * tid + 1 < n_g && (s_feas[tb * 256 + ob] & active);
-            const uint32_t cnt = (fa ? 1u : 0u) + (fb ? 1u : 0u);
+            // one scan carries both counts: candidates (low half) and free slices on the candidates (high half) — the latter
+            // bounds what the segment can accept: a profile of span z pops at most free / z requests here
+            const uint32_t cnt = ((fa ? 1u : 0u) + (fb ? 1u : 0u)) | (((fa ? __popc(~oa & s_usable[ta]) : 0u) + (fb ? __popc(~ob & s_usable[tb]) : 0u)) << 16);
             uint32_t incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
@@ -965,9 +987,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             __syncthreads();
             uint32_t off = incl - cnt;
             for (uint32_t x = 0; x < warp; ++x) off += s_warp[x];
+            const uint32_t nfree = (off + cnt) >> 16;
+            off &= 0xFFFFu;
             if (fa) s_cand[off++] = ((2 * tid) << 16) | table_tag(ta) | oa;
             if (fb) s_cand[off++] = ((2 * tid + 1) << 16) | table_tag(tb) | ob;
-            if (tid == kPipeThreads - 1) { s_ncand = off; for (uint32_t x = 0; x < 8; ++x) s_cand[off + x] = kInf; }   // sentinels: nothing fits
+            if (tid == kPipeThreads - 1) { s_ncand = off; s_nfree = nfree; for (uint32_t x = 0; x < 8; ++x) s_cand[off + x] = kInf; }   // sentinels: nothing fits
         }
         // 3. token of the previous segment
         unsigned long long* tr = a.trace ? a.trace + ((size_t)c * a.n_seg + seg) * kTraceWords : nullptr;
@@ -1001,7 +1025,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 else h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
                 const uint32_t qc = cc->qcnt[tid];
                 left = ((active >> tid) & 1u) && qc > h ? qc - h : 0u;
-                wn = min(left, s_ncand * s_maxacc[tid]);            // no more pops than that are possible here
+                wn = min(left, min(s_ncand * s_maxacc[tid], s_nfree / s_minsize[tid]));   // no more pops than that are possible here
                 s_heads[tid] = h; s_wn[tid] = wn; s_pop[tid] = 0;
                 s_qsrc[tid] = c * a.q_stride + cc->qoff[tid] + h;
             }
@@ -1018,8 +1042,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
 #pragma unroll
             for (int d = 1; d < 16; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
             if (tid < ISL_MAX_PROFILES) s_wbase[tid] = incl - (wn + 2);
+            if (tid == ISL_MAX_PROFILES - 1) s_wtotal = incl;
         }
         __syncthreads();
+        stamp_if(tr && tid == 0, tr + 8);
         if (s_idle) {       // pass-through: the token (unchanged heads) still reaches the next rank / the caller from the last segment
             if (warp == 0) {
                 const bool last = seg == a.n_seg - 1;
@@ -1042,13 +1068,37 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             __syncthreads();
             continue;
         }
-        for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) {          // stage the windows as ready-made keys: t << 15 | profile << 11
-            const uint32_t wn = s_wn[p], base = s_wbase[p];
-            const uint16_t* src = a.q_all + s_qsrc[p];
-            for (uint32_t i = tid; i < wn; i += kPipeThreads) s_wkey[base + i] = ((uint32_t)src[i] << 15) | (p << 11);
-            if (tid < 2) s_wkey[base + wn + tid] = kInf;
+        {   // stage the windows as ready-made keys t << 15 | profile << 11, each closed by two INF sentinels.  One flat index space
+            // over all profiles, four entries per thread and round with the loads issued back to back: one L2 round trip per round
+            const uint32_t total = s_wtotal;
+            uint32_t base[ISL_MAX_PROFILES];
+#pragma unroll
+            for (uint32_t q = 0; q < ISL_MAX_PROFILES; ++q) base[q] = s_wbase[q];
+            for (uint32_t i0 = tid; i0 < total; i0 += 4 * kPipeThreads) {
+                uint32_t v[4], pp[4];
+                bool real[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = i0 + u * kPipeThreads;
+                    uint32_t p = 0, b = 0;
+#pragma unroll
+                    for (uint32_t q = 1; q < ISL_MAX_PROFILES; ++q) { const bool ge = i >= base[q]; p += ge ? 1u : 0u; b = ge ? base[q] : b; }   // bases are non-decreasing
+                    const uint32_t jj = i - b;
+                    real[u] = i < total && jj < s_wn[p];
+                    pp[u] = p;
+                    v[u] = __ldg(a.q_all + (real[u] ? s_qsrc[p] + jj : 0u));        // unconditional (clamped) so that the four loads overlap; written by k_partition
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = i0 + u * kPipeThreads;
+                    if (i < total) s_wkey[i] = real[u] ? (v[u] << 15) | (pp[u] << 11) : kInf;
+                }
+            }
         }
+        store_if(tr && tid == 0, tr + 10, s_wtotal | ((unsigned long long)s_nfree << 32));
+        stamp_if(tr && tid == 0, tr + 11);
         __syncthreads();
+        stamp_if(tr && tid == 0, tr + 9);
         if (warp == 0) {                    // 4. the decision chain (see k_chain), tuned for the shortest loop-carried path
             const uint32_t n_cand = s_ncand;
             uint32_t tcur[K], tnext[K], tnn[K], wa[K], wa0[K];
@@ -1065,7 +1115,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             uint32_t la = sa_log, ca = sa_cand + 8;                             // ca: shared address of candidate record (current + 2)
             uint32_t o0 = lds_u16(sa_cand), o1 = lds_u16(sa_cand + 4), o2 = lds_u16(sa_cand + 8);
             const unsigned long long jumps0 = st_jumps;
-            if (tr && lane == 0) tr[4] = globaltimer_ns();
+            stamp_if(tr && lane == 0, tr + 4);
             // The updates are issued unconditionally and the "nothing fits" test comes LAST: a branch is not speculated, so a test
             // in front of the updates would put its resolution on the loop-carried path of every decision.  m == INF behaves like
             // a decision that lands on the next GPU and pops only exhausted lanes (no real key has all-ones t / profile fields unless
@@ -1121,7 +1171,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 o0 = lds_u16(ca - 8); o1 = lds_u16(ca - 4); o2 = lds_u16(ca);
             }
             const uint32_t nlog = (la - sa_log) >> 3;
-            if (tr && lane == 0) { tr[5] = globaltimer_ns(); tr[6] = nlog; tr[7] = (st_jumps - jumps0) | ((unsigned long long)(((ca - sa_cand) >> 2) - 2) << 32); }
+            stamp_if(tr && lane == 0, tr + 5);
+            store_if(tr && lane == 0, tr + 6, nlog);
+            store_if(tr && lane == 0, tr + 7, (st_jumps - jumps0) | ((unsigned long long)(((ca - sa_cand) >> 2) - 2) << 32));
             st_steps += nlog; st_visited += ((ca - sa_cand) >> 2) - 2;
 #pragma unroll
             for (int k = 0; k < K; ++k) if (reports[k]) s_pop[cprof[k]] = (wa[k] - wa0[k] - 12) >> 2;

@@ -302,11 +302,11 @@ class Engine:
 
     # -- diagnostics
     def read_trace(self) -> np.ndarray:
-        """[chunk][segment][8] of the last stream call (FLAG_TRACE): globaltimer ns of sweep done, token in, token out, commit done,
-        chain start, chain end; then the decisions of the cell and jumps | visited << 32."""
+        """[chunk][segment][12] of the last stream call (FLAG_TRACE): globaltimer ns of sweep done, token in, token out, commit done,
+        chain start, chain end; the decisions of the cell; jumps | visited << 32; ns of heads done, windows staged; 2 spare."""
         nc, ns = C.c_uint32(), C.c_uint32()
         self._check(self._lib.isl_read_trace(self._h, None, 0, C.byref(nc), C.byref(ns)), "isl_read_trace")
-        out = np.zeros((nc.value, ns.value, 8), dtype=np.uint64)
+        out = np.zeros((nc.value, ns.value, 12), dtype=np.uint64)
         if out.size:
             self._check(self._lib.isl_read_trace(self._h, _ptr(out), out.size, C.byref(nc), C.byref(ns)), "isl_read_trace")
         return out

@@ -46,7 +46,7 @@ print("chain_us = %.2f + %.4f * decisions   (%.1f ns per decision; %.0f cycles a
 (a2, b2), *_ = np.linalg.lstsq(A, commit[busy], rcond=None)
 print("commit_us = %.2f + %.4f * decisions" % (a2, b2))
 print("idle cell hop (token in -> token out) us: mean %.2f" % float(chain[~busy].mean()))
-print("kernel span us %.1f; sum of busy-cell chain for chunk 0: %.1f; chunk 8: %.1f" % ((tr[:, :, :6].max() - tr[:, :, :6][tr[:, :, :6] > 0].min()) / 1e3, chain[0][busy[0]].sum(), chain[8][busy[8]].sum()))
+print("kernel span us %.1f; sum of busy-cell chain for chunk 0: %.1f; chunk 8: %.1f" % ((tr[:, :, :4].max() - tr[:, :, :4][tr[:, :, :4] > 0].min()) / 1e3, chain[0][busy[0]].sum(), chain[8][busy[8]].sum()))
 print("per-chunk: decisions", dec.sum(axis=1).tolist())
 print("per-chunk busy segments", busy.sum(axis=1).tolist())
 # finer split of a busy cell (trace words 4..7)
@@ -56,6 +56,11 @@ jumps, visited = jv & 0xFFFFFFFF, jv >> 32
 assert (ndec[busy] == dec[busy]).all(), "trace decision counts disagree with the results"
 pre = (t_cs - t_in)[busy] / 1e3; loop = (t_ce - t_cs)[busy] / 1e3; post = (t_out - t_ce)[busy] / 1e3
 print("busy cell: token in -> loop start %.2f us | loop %.2f us | loop end -> token out %.2f us (means)" % (pre.mean(), loop.mean(), post.mean()))
+t_h, t_st = tr[:, :, 8], tr[:, :, 9]
+print("  token in -> heads %.2f us -> windows staged %.2f us -> loop start %.2f us" % (((t_h - t_in)[busy] / 1e3).mean(), ((t_st - t_h)[busy] / 1e3).mean(), ((t_cs - t_st)[busy] / 1e3).mean()))
+wt = tr[:, :, 10]
+print("  staged entries per busy cell: mean %.0f max %d; free slices on candidates mean %.0f; thread 0 done staging %.2f us after heads" %
+      ((wt & 0xFFFFFFFF)[busy].mean(), (wt & 0xFFFFFFFF)[busy].max(), (wt >> 32)[busy].mean(), ((tr[:, :, 11] - t_h)[busy] / 1e3).mean()))
 B = np.stack([np.ones(busy.sum()), dec[busy], jumps[busy], visited[busy]], axis=1)
 coef, *_ = np.linalg.lstsq(B, loop, rcond=None)
 print("loop_us = %.3f + %.4f*decisions + %.4f*jumps + %.4f*visited" % tuple(coef))
