@@ -793,13 +793,14 @@ __global__ void __launch_bounds__(256) k_commit(const Ctrl* __restrict__ ctrl, c
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kSegMax = 512;                   // GPUs per segment (2 per thread in the local sweep)
 constexpr uint32_t kPipeThreads = 256;
-constexpr uint32_t kWinTotal = 16384;               // 32-bit queue-window keys a segment can stage for all profiles together
 constexpr uint32_t kLogCap = 8 * kSegMax;           // a GPU accepts at most 8 placements
 constexpr uint32_t kTokStride = 32;                 // uint32 per token: heads[16], flag at [16]
-// shared memory: occupancy bytes | candidate records (+8 sentinels) | decision log | queue-window keys
+// shared memory: occupancy bytes | candidate records (+8 sentinels) | decision log (+1 pseudo-decision) | the chunk's queues (uint16) | queue-window keys
 constexpr uint32_t kPipeOffCand = kSegMax;
 constexpr uint32_t kPipeOffLog = kPipeOffCand + 4 * (kSegMax + 8);
-constexpr uint32_t kPipeOffWin = kPipeOffLog + 8 * (kLogCap + 1);      // + 1: the pseudo-decision the loop logs before it sees 'nothing fits'
+constexpr uint32_t kPipeOffQ = (kPipeOffLog + 8 * (kLogCap + 1) + 15u) & ~15u;
+constexpr uint32_t kPipeOffWin = kPipeOffQ + 2 * kQCap + 16;
+constexpr uint32_t kWinTotal = 14336;               // 32-bit queue-window keys a segment can stage for all profiles together
 constexpr uint32_t kPipeSmem = kPipeOffWin + 4 * (kWinTotal + 4 * ISL_MAX_PROFILES);
 
 // largest segment whose worst-case queue windows (every candidate GPU accepting every legal start of every
@@ -887,6 +888,10 @@ __device__ __forceinline__ uint32_t redux_min_u32(uint32_t v) {
     asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
     return r;
 }
+__device__ __forceinline__ uint32_t lds_u16_if(bool pred, uint32_t sa, uint32_t keep) {   // predicated load: keeps `keep` when !pred
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p ld.shared.u16 %0, [%2]; }" : "+r"(keep) : "r"((uint32_t)pred), "r"(sa));
+    return keep;
+}
 __device__ __forceinline__ uint32_t lds_u32_if(bool pred, uint32_t sa, uint32_t keep) {   // predicated load: keeps `keep` when !pred
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p ld.shared.u32 %0, [%2]; }" : "+r"(keep) : "r"((uint32_t)pred), "r"(sa));
     return keep;
@@ -912,14 +917,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     uint32_t* s_occ32 = reinterpret_cast<uint32_t*>(smem);                       // kSegMax occupancy bytes
     uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + kPipeOffCand);         // records (local gpu << 16 | table tag | occ) + sentinels
     uint2* s_log = reinterpret_cast<uint2*>(smem + kPipeOffLog);                 // (key, candidate index) per decision
-    uint32_t* s_wkey = reinterpret_cast<uint32_t*>(smem + kPipeOffWin);          // per-profile windows of ready-made keys t<<15 | p<<11
     __shared__ uint16_t s_feas[kMaxTables * 256];
     __shared__ uint8_t s_tab[kSegMax];                                           // table of every local GPU
-    __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_wbase[ISL_MAX_PROFILES], s_qsrc[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
-    __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_minsize[ISL_MAX_PROFILES], s_usable[kMaxTables], s_warp[kPipeThreads / 32], s_ncand, s_nfree, s_nlog, s_src, s_idle, s_wtotal;
+    __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_wbase[ISL_MAX_PROFILES], s_qbeg[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
+    __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_minsize[ISL_MAX_PROFILES], s_usable[kMaxTables], s_plist[ISL_MAX_PROFILES], s_nplist;
+    __shared__ uint32_t s_warp[kPipeThreads / 32], s_ncand, s_nfree, s_nlog, s_src, s_idle;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     const uint32_t lo_s = min(a.hi, a.lo + seg * a.seg), hi_s = min(a.hi, lo_s + a.seg), n_g = hi_s - lo_s;
     const uint32_t sa_cand = (uint32_t)__cvta_generic_to_shared(s_cand), sa_log = (uint32_t)__cvta_generic_to_shared(s_log);
+    const uint32_t sa_q = (uint32_t)__cvta_generic_to_shared(smem + kPipeOffQ);     // the chunk's queues: uint16 in-chunk request indices
+    uint32_t* s_wkey = reinterpret_cast<uint32_t*>(smem + kPipeOffWin);          // per-profile windows of ready-made keys t<<15 | p<<11
     const uint32_t sa_wkey = (uint32_t)__cvta_generic_to_shared(s_wkey);
 
     for (uint32_t i = tid; i < kSegMax / 4; i += kPipeThreads) s_occ32[i] = 0xFFFFFFFFu;
@@ -933,6 +940,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         }
         s_maxacc[tid] = n;
         s_minsize[tid] = max(sz, 1u);           // smallest span of the profile over all tables
+        const uint32_t have = __ballot_sync(0xFFFFu, n != 0);      // profiles that own at least one candidate: only these get a window
+        if (n) s_plist[__popc(have & ((1u << tid) - 1u))] = tid;
+        if (tid == 0) s_nplist = __popc(have);
     }
     if (tid >= 32 && tid < 32 + kMaxTables) {   // slices any candidate of the table can ever cover (REF_EXACT 80GB-class tables: 0x7F)
         uint32_t u = 0;
@@ -960,6 +970,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     }
     unsigned long long st_steps = 0, st_jumps = 0, st_visited = 0;
 
+    // The queues of a chunk (k_partition wrote them before this kernel started) are copied into shared memory with cp.async
+    // while the segment still waits for the chunk's token: they do not depend on the heads, so nothing is staged on the
+    // critical path between 'token in' and the first decision.  Offset -> thread mapping is the same for every chunk, so a
+    // thread's own wait_group orders its copies of consecutive chunks.
+    auto queue_load_async = [&](uint32_t chunk) {
+        const char* src = reinterpret_cast<const char*>(a.q_all + (size_t)chunk * a.q_stride);
+        const uint32_t bytes = (a.cctl[chunk].qoff[ISL_MAX_PROFILES] * 2u + 15u) & ~15u;
+        for (uint32_t off = tid * 16u; off < bytes; off += kPipeThreads * 16u)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa_q + off), "l"(src + off) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    queue_load_async(0);
+
     for (uint32_t c = 0; c < a.n_chunks; ++c) {
         const ChunkDesc cd = a.chunks[c];
         const Ctrl* cc = a.cctl + c;
@@ -977,7 +1000,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             const uint32_t oa = w & 0xFFu, ob = w >> 8;
             const uint32_t ta = s_tab[2 * tid], tb = s_tab[2 * tid + 1];
             const bool fa = 2 * tid < n_g && (s_feas[ta * 256 + oa] & active), fb = 2 * tid + 1 < n_g && (s_feas[tb * 256 + ob] & active);
-            // one scan carries both counts: candidates (low half) and free slices on the candidates (high half) — the latter
+            // one scan carries both counts: candidates (low half) and free usable slices on the candidates (high half) — the latter
             // bounds what the segment can accept: a profile of span z pops at most free / z requests here
             const uint32_t cnt = ((fa ? 1u : 0u) + (fb ? 1u : 0u)) | (((fa ? __popc(~oa & s_usable[ta]) : 0u) + (fb ? __popc(~ob & s_usable[tb]) : 0u)) << 16);
             uint32_t incl = cnt;
@@ -1014,6 +1037,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             s_src = src;
             if (tr) tr[1] = globaltimer_ns();
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");       // my share of the chunk's queues has landed (long ago, as a rule)
         __syncthreads();
         if (tid < 32) {     // heads, window sizes and the compact window layout (exclusive scan over the 16 profiles)
             uint32_t h = 0, wn = 0, left = 0;
@@ -1023,11 +1047,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 else if (src == 3) h = __ldcg(a.tokens + (tok_chunk + a.n_seg) * kTokStride + tid);
                 else if (src == 2) h = ld_relaxed_sys(a.inbox + (size_t)c * kTokStride + tid);
                 else h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
-                const uint32_t qc = cc->qcnt[tid];
+                const uint32_t qc = cc->qcnt[tid], qo = cc->qoff[tid];
                 left = ((active >> tid) & 1u) && qc > h ? qc - h : 0u;
                 wn = min(left, min(s_ncand * s_maxacc[tid], s_nfree / s_minsize[tid]));   // no more pops than that are possible here
                 s_heads[tid] = h; s_wn[tid] = wn; s_pop[tid] = 0;
-                s_qsrc[tid] = c * a.q_stride + cc->qoff[tid] + h;
+                s_qbeg[tid] = qo + h;                                           // first pending entry in the shared copy of the queues
             }
             // nothing placeable is pending any more: tell every later segment at once instead of relaying hop by hop
             const bool idle = __ballot_sync(0xFFFFFFFFu, left != 0) == 0;
@@ -1042,7 +1066,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
 #pragma unroll
             for (int d = 1; d < 16; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
             if (tid < ISL_MAX_PROFILES) s_wbase[tid] = incl - (wn + 2);
-            if (tid == ISL_MAX_PROFILES - 1) s_wtotal = incl;
         }
         __syncthreads();
         stamp_if(tr && tid == 0, tr + 8);
@@ -1066,37 +1089,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 }
             }
             __syncthreads();
+            if (c + 1 < a.n_chunks) queue_load_async(c + 1);
             continue;
         }
-        {   // stage the windows as ready-made keys t << 15 | profile << 11, each closed by two INF sentinels.  One flat index space
-            // over all profiles, four entries per thread and round with the loads issued back to back: one L2 round trip per round
-            const uint32_t total = s_wtotal;
-            uint32_t base[ISL_MAX_PROFILES];
-#pragma unroll
-            for (uint32_t q = 0; q < ISL_MAX_PROFILES; ++q) base[q] = s_wbase[q];
-            for (uint32_t i0 = tid; i0 < total; i0 += 4 * kPipeThreads) {
-                uint32_t v[4], pp[4];
-                bool real[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t i = i0 + u * kPipeThreads;
-                    uint32_t p = 0, b = 0;
-#pragma unroll
-                    for (uint32_t q = 1; q < ISL_MAX_PROFILES; ++q) { const bool ge = i >= base[q]; p += ge ? 1u : 0u; b = ge ? base[q] : b; }   // bases are non-decreasing
-                    const uint32_t jj = i - b;
-                    real[u] = i < total && jj < s_wn[p];
-                    pp[u] = p;
-                    v[u] = __ldg(a.q_all + (real[u] ? s_qsrc[p] + jj : 0u));        // unconditional (clamped) so that the four loads overlap; written by k_partition
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t i = i0 + u * kPipeThreads;
-                    if (i < total) s_wkey[i] = real[u] ? (v[u] << 15) | (pp[u] << 11) : kInf;
-                }
+        {   // windows of ready-made keys t << 15 | profile << 11, each closed by two INF sentinels — converted from the shared copy of
+            // the queues (a shared-memory round trip per round instead of an L2 one), only for profiles that own candidates
+            const uint32_t npl = s_nplist;
+            for (uint32_t x = 0; x < npl; ++x) {
+                const uint32_t p = s_plist[x], wn = s_wn[p], base = s_wbase[p], src = sa_q + 2 * s_qbeg[p];
+                for (uint32_t i = tid; i < wn + 2; i += kPipeThreads) s_wkey[base + i] = i < wn ? (lds_u16(src + 2 * i) << 15) | (p << 11) : kInf;
             }
         }
-        store_if(tr && tid == 0, tr + 10, s_wtotal | ((unsigned long long)s_nfree << 32));
-        stamp_if(tr && tid == 0, tr + 11);
         __syncthreads();
         stamp_if(tr && tid == 0, tr + 9);
         if (warp == 0) {                    // 4. the decision chain (see k_chain), tuned for the shortest loop-carried path
@@ -1198,6 +1201,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             }
         }
         __syncthreads();
+        if (c + 1 < a.n_chunks) queue_load_async(c + 1);        // the chain is done with the queues: fetch the next chunk's behind the commit
         {   // 6. commit
             const uint32_t nlog = s_nlog;
             for (uint32_t j = tid; j < nlog; j += kPipeThreads) {
@@ -1210,6 +1214,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         __syncthreads();
         if (tr && tid == 0) tr[3] = globaltimer_ns();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     for (uint32_t i = tid; i < n_g; i += kPipeThreads) a.occ[lo_s + i] = reinterpret_cast<uint8_t*>(s_occ32)[i];
     if (tid == 0 && st_steps + st_jumps) {
         atomicAdd(&a.stats->placed, st_steps);
