@@ -1095,10 +1095,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         {   // windows of ready-made keys t << 15 | profile << 11, each closed by two INF sentinels — converted from the shared copy of
             // the queues (a shared-memory round trip per round instead of an L2 one), only for profiles that own candidates
             const uint32_t npl = s_nplist;
+            const uint16_t* __restrict__ sq = reinterpret_cast<const uint16_t*>(smem + kPipeOffQ);
             for (uint32_t x = 0; x < npl; ++x) {
-                const uint32_t p = s_plist[x], wn = s_wn[p], base = s_wbase[p], src = sa_q + 2 * s_qbeg[p];
-                for (uint32_t i = tid; i < wn + 2; i += kPipeThreads) s_wkey[base + i] = i < wn ? (lds_u16(src + 2 * i) << 15) | (p << 11) : kInf;
+                const uint32_t p = s_plist[x], wn = s_wn[p], pk = p << 11, qb = s_qbeg[p];
+                uint32_t* __restrict__ dst = s_wkey + s_wbase[p];
+                // plain, unconditional (clamped) accesses: the loads of a round overlap instead of queueing behind each other
+                for (uint32_t i = tid; i < wn + 2; i += kPipeThreads) { const uint32_t v = sq[qb + min(i, wn)]; dst[i] = i < wn ? (v << 15) | pk : kInf; }
             }
+            stamp_if(tr && tid == 0, tr + 10);
+            store_if(tr && tid == 0, tr + 11, s_wn[s_plist[0]] | ((unsigned long long)s_nfree << 32));
         }
         __syncthreads();
         stamp_if(tr && tid == 0, tr + 9);

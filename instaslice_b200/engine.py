@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libislplace.so")
+LIB_PATH = os.environ.get("ISL_LIB") or os.path.join(_HERE, "libislplace.so")      # ISL_LIB: A/B builds of the same ABI (tools/)
 
 # ---- constants (mirror include/islplace.h) -------------------------------------------------
 ABI_VERSION = 1

@@ -58,9 +58,9 @@ pre = (t_cs - t_in)[busy] / 1e3; loop = (t_ce - t_cs)[busy] / 1e3; post = (t_out
 print("busy cell: token in -> loop start %.2f us | loop %.2f us | loop end -> token out %.2f us (means)" % (pre.mean(), loop.mean(), post.mean()))
 t_h, t_st = tr[:, :, 8], tr[:, :, 9]
 print("  token in -> heads %.2f us -> windows staged %.2f us -> loop start %.2f us" % (((t_h - t_in)[busy] / 1e3).mean(), ((t_st - t_h)[busy] / 1e3).mean(), ((t_cs - t_st)[busy] / 1e3).mean()))
-wt = tr[:, :, 10]
-print("  staged entries per busy cell: mean %.0f max %d; free slices on candidates mean %.0f; thread 0 done staging %.2f us after heads" %
-      ((wt & 0xFFFFFFFF)[busy].mean(), (wt & 0xFFFFFFFF)[busy].max(), (wt >> 32)[busy].mean(), ((tr[:, :, 11] - t_h)[busy] / 1e3).mean()))
+wt = tr[:, :, 11]
+print("  warp 0 done converting its window %.2f us after heads (window of the first profile: mean %.0f entries; free usable slices on candidates: mean %.0f)" %
+      (((tr[:, :, 10] - t_h)[busy] / 1e3).mean(), (wt & 0xFFFFFFFF)[busy].mean(), (wt >> 32)[busy].mean()))
 B = np.stack([np.ones(busy.sum()), dec[busy], jumps[busy], visited[busy]], axis=1)
 coef, *_ = np.linalg.lstsq(B, loop, rcond=None)
 print("loop_us = %.3f + %.4f*decisions + %.4f*jumps + %.4f*visited" % tuple(coef))
