@@ -164,14 +164,16 @@ struct TileDesc {
 __global__ void __launch_bounds__(kTileThreads) k_prepare(uint32_t n, const uint2* __restrict__ in, uint2* __restrict__ out,
                                                            uint32_t* __restrict__ occ32, uint32_t G, uint32_t lo, uint32_t hi,
                                                            DevProfiles prof, uint32_t* __restrict__ tile_counts, Ctrl* ctrl,
-                                                           const TileDesc* __restrict__ descs, uint32_t* __restrict__ free_acc, uint32_t free_stride) {
+                                                           const TileDesc* __restrict__ descs, uint32_t* __restrict__ free_acc, uint32_t free_stride,
+                                                           uint32_t tile_base) {
     // descs != nullptr (stream mode): the tile's batch comes from the table, and FREEs are not applied here but ORed
     // into the batch's free-mask array (one byte per GPU); the segment pipeline clears them in batch order inside the
-    // segment that owns the GPU.
-    uint32_t tile = blockIdx.x;
+    // segment that owns the GPU.  tile_base: first global tile of this launch (a stream may be fed batch by batch).
+    const uint32_t bid = blockIdx.x + tile_base;
+    uint32_t tile = bid;
     if (descs) {
-        const TileDesc d = descs[blockIdx.x];
-        n = d.batch_n; in += d.batch_off; out += d.batch_off; tile = blockIdx.x - d.batch_first_tile;
+        const TileDesc d = descs[bid];
+        n = d.batch_n; in += d.batch_off; out += d.batch_off; tile = bid - d.batch_first_tile;
         free_acc += (size_t)d.batch * free_stride;
     }
     __shared__ uint32_t s_cnt[ISL_MAX_PROFILES];
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(kTileThreads) k_prepare(uint32_t n, const uint
         if (key != kSkip && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_cnt[key], (uint32_t)__popc(peers));
     }
     __syncthreads();
-    if (threadIdx.x < ISL_MAX_PROFILES) tile_counts[blockIdx.x * ISL_MAX_PROFILES + threadIdx.x] = s_cnt[threadIdx.x];
+    if (threadIdx.x < ISL_MAX_PROFILES) tile_counts[bid * ISL_MAX_PROFILES + threadIdx.x] = s_cnt[threadIdx.x];
     if (threadIdx.x == 0) {
         if (s_freed) atomicAdd(&ctrl->freed, (unsigned long long)s_freed);
         uint32_t allocs = 0;
@@ -226,14 +228,15 @@ __global__ void __launch_bounds__(kTileThreads) k_prepare(uint32_t n, const uint
 __global__ void __launch_bounds__(kTileThreads) k_partition(uint32_t n_chunk, const uint2* __restrict__ in_chunk, uint32_t n_profiles,
                                                              const uint32_t* __restrict__ tile_counts_chunk, uint32_t n_tiles,
                                                              uint32_t cand_profiles, uint16_t* __restrict__ q, Ctrl* ctrl,
-                                                             const TileDesc* __restrict__ descs, uint32_t q_stride) {
+                                                             const TileDesc* __restrict__ descs, uint32_t q_stride, uint32_t tile_base) {
     // descs != nullptr (stream mode): in_chunk / tile_counts_chunk / q / ctrl are the bases of the whole stream and
     // the tile's chunk comes from the table.
-    uint32_t tile = blockIdx.x;
+    const uint32_t bid = blockIdx.x + tile_base;
+    uint32_t tile = bid;
     if (descs) {
-        const TileDesc d = descs[blockIdx.x];
+        const TileDesc d = descs[bid];
         n_chunk = d.chunk_n; in_chunk += d.chunk_off; tile_counts_chunk += (size_t)d.chunk_first_tile * ISL_MAX_PROFILES;
-        n_tiles = d.chunk_tiles; tile = blockIdx.x - d.chunk_first_tile; q += (size_t)d.chunk * q_stride; ctrl += d.chunk;
+        n_tiles = d.chunk_tiles; tile = bid - d.chunk_first_tile; q += (size_t)d.chunk * q_stride; ctrl += d.chunk;
     }
     __shared__ uint32_t s_part[16][ISL_MAX_PROFILES][2];   // [j][p][0]=total, [1]=prefix before this tile
     __shared__ uint32_t s_base[ISL_MAX_PROFILES];
@@ -291,6 +294,12 @@ __global__ void __launch_bounds__(kTileThreads) k_partition(uint32_t n_chunk, co
         const uint32_t i = tile * kTile + r * kTileThreads + tid;
         q[s_base[key[r]] + s_seg[r * 8 + warp][key[r]] + rank[r]] = (uint16_t)i;
     }
+}
+
+// one word, stream-ordered: "the pre-pass of this batch is complete" for a segment pipeline that is already running
+__global__ void k_set_flag(uint32_t* flag, uint32_t value) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -831,6 +840,10 @@ struct PipeArgs {
     const uint32_t* inbox;          // local [chunk][kTokStride], written by the previous rank's last segment (nullptr = first rank)
     uint32_t* outbox;               // the next rank's inbox, peer-mapped (nullptr = last rank)
     uint32_t xepoch;                // stream id shared by all ranks
+    // host-buffer streams (isl_place_stream): the batches are fed while the pipeline runs, the results leave chunk by chunk
+    const uint32_t* ready;          // [batch] == epoch once the batch's requests are in HBM and its pre-pass is done (nullptr = all ready)
+    uint32_t* done_cnt;             // [chunk] segments that have committed the chunk (zeroed per call; nullptr = no copier CTA)
+    uint2* host_out;                // mapped pinned result array of the caller: CTA n_seg copies every complete chunk there
     unsigned long long* trace;      // optional [chunk][segment][kTraceWords]: globaltimer ns of sweep done, token in, token out, commit done, chain start, chain end; decisions; jumps | visited << 32; ns of heads done, windows staged; 2 spare
 };
 
@@ -923,6 +936,25 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_minsize[ISL_MAX_PROFILES], s_usable[kMaxTables], s_plist[ISL_MAX_PROFILES], s_nplist;
     __shared__ uint32_t s_warp[kPipeThreads / 32], s_ncand, s_nfree, s_nlog, s_src, s_idle;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
+    if (seg == a.n_seg) {       // the extra CTA of a host-buffer stream: every chunk all segments have committed goes to the caller's
+                                // (mapped, pinned) result array right away, so the D2H of the results hides behind the rest of the stream
+        for (uint32_t c = 0; c < a.n_chunks; ++c) {
+            const ChunkDesc cd = a.chunks[c];
+            if (tid == 0) while (ld_acquire_gpu(a.done_cnt + c) < a.n_seg) __nanosleep(256);
+            __syncthreads();
+            const uint2* __restrict__ src = a.out + cd.req_off;
+            uint2* __restrict__ dst = a.host_out + cd.req_off;
+            const uint32_t head = min(cd.n, cd.req_off & 1u), pairs = (cd.n - head) >> 1;       // 16-byte body, 8-byte head / tail
+            if (tid == 0 && head) dst[0] = __ldcg(src);
+            const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src + head);
+            uint4* __restrict__ d4 = reinterpret_cast<uint4*>(dst + head);
+#pragma unroll 4
+            for (uint32_t i = tid; i < pairs; i += kPipeThreads) d4[i] = __ldcg(s4 + i);
+            if (tid == 0 && ((cd.n - head) & 1u)) dst[cd.n - 1] = __ldcg(src + cd.n - 1);
+        }
+        __threadfence_system();
+        return;
+    }
     const uint32_t lo_s = min(a.hi, a.lo + seg * a.seg), hi_s = min(a.hi, lo_s + a.seg), n_g = hi_s - lo_s;
     const uint32_t sa_cand = (uint32_t)__cvta_generic_to_shared(s_cand), sa_log = (uint32_t)__cvta_generic_to_shared(s_log);
     const uint32_t sa_q = (uint32_t)__cvta_generic_to_shared(smem + kPipeOffQ);     // the chunk's queues: uint16 in-chunk request indices
@@ -981,6 +1013,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa_q + off), "l"(src + off) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // fed streams: the requests of a batch may still be on their way (H2D + pre-pass on the feed stream) when the pipeline gets there
+    auto wait_ready = [&](uint32_t chunk) {
+        if (!a.ready) return;
+        if (tid == 0) { const uint32_t* f = a.ready + a.chunks[chunk].batch; while (ld_acquire_gpu(f) != a.epoch) __nanosleep(128); }
+        __syncthreads();
+    };
+    auto chunk_done = [&](uint32_t chunk) {     // after the barrier that ends the chunk's commit
+        if (a.done_cnt && tid == 0) { __threadfence(); atomicAdd(a.done_cnt + chunk, 1u); }
+    };
+    wait_ready(0);
     queue_load_async(0);
 
     for (uint32_t c = 0; c < a.n_chunks; ++c) {
@@ -1089,7 +1131,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 }
             }
             __syncthreads();
-            if (c + 1 < a.n_chunks) queue_load_async(c + 1);
+            chunk_done(c);
+            if (c + 1 < a.n_chunks) { wait_ready(c + 1); queue_load_async(c + 1); }
             continue;
         }
         {   // windows of ready-made keys t << 15 | profile << 11, each closed by two INF sentinels — converted from the shared copy of
@@ -1206,7 +1249,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             }
         }
         __syncthreads();
-        if (c + 1 < a.n_chunks) queue_load_async(c + 1);        // the chain is done with the queues: fetch the next chunk's behind the commit
+        if (c + 1 < a.n_chunks && !a.ready) queue_load_async(c + 1);    // the chain is done with the queues: fetch the next chunk's behind the commit
         {   // 6. commit
             const uint32_t nlog = s_nlog;
             for (uint32_t j = tid; j < nlog; j += kPipeThreads) {
@@ -1218,6 +1261,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         }
         __syncthreads();
         if (tr && tid == 0) tr[3] = globaltimer_ns();
+        chunk_done(c);
+        if (c + 1 < a.n_chunks && a.ready) { wait_ready(c + 1); queue_load_async(c + 1); }   // fed stream: the next batch may not have arrived yet
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     for (uint32_t i = tid; i < n_g; i += kPipeThreads) a.occ[lo_s + i] = reinterpret_cast<uint8_t*>(s_occ32)[i];

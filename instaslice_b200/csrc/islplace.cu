@@ -72,6 +72,11 @@ struct isl_engine {
     bool has_prev = false, outbox_local = false;
     unsigned long long* d_trace = nullptr; uint32_t cap_trace = 0, trace_chunks = 0, trace_seg = 0;
     int max_coresident = 0;          // CTAs of k_pipeline that can be resident at once (0 = not queried)
+    // host-buffer streams: batches are fed on their own stream while the pipeline runs; results leave chunk by chunk
+    cudaStream_t feed_stream = nullptr; cudaEvent_t ev_feed = nullptr, ev_feed_done = nullptr;
+    uint32_t* d_ready = nullptr; uint32_t cap_ready = 0;      // [batch] epoch flag
+    uint32_t* d_done_cnt = nullptr; uint32_t cap_done = 0;    // [chunk] committed segments
+    bool delivered = false;          // the last run_stream call already put the results into the caller's host buffer
     size_t scratch_bytes = 0;
 
     // stats
@@ -97,6 +102,7 @@ struct DeviceGuard {
 };
 
 inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+constexpr uint32_t kFeedReserve = 16;      // SMs a fed stream keeps free for its pre-pass kernels
 
 int check_launch(isl_engine* e, const char* what) {
     cudaError_t err = cudaGetLastError();
@@ -176,7 +182,7 @@ int run_bestfit(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out) {
     const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
     if (timing) cudaEventRecord(e->ev[0], e->stream);
     k_prepare<<<ceil_div(n, kTile), kTileThreads, 0, e->stream>>>(n, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi,
-                                                                  e->prof, e->d_tile_counts, e->d_ctrl, nullptr, nullptr, 0);
+                                                                  e->prof, e->d_tile_counts, e->d_ctrl, nullptr, nullptr, 0, 0);
     if (int rc = check_launch(e, "k_prepare")) return rc;
     if (timing) cudaEventRecord(e->ev[1], e->stream);
     k_bestfit<<<1, kBfThreads, smem, e->stream>>>(n, d_in, d_out, e->d_occ, e->lo, e->hi, e->d_lut, e->prof, e->d_bf_bitmaps, e->d_ctrl);
@@ -200,7 +206,7 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
     const uint32_t tiles = ceil_div(n, kTile);
     if (timing) cudaEventRecord(e->ev[0], e->stream);
     k_prepare<<<tiles, kTileThreads, 0, e->stream>>>(n, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi,
-                                                     e->prof, e->d_tile_counts, e->d_ctrl, nullptr, nullptr, 0);
+                                                     e->prof, e->d_tile_counts, e->d_ctrl, nullptr, nullptr, 0, 0);
     if (int rc = check_launch(e, "k_prepare")) return rc;
     if (timing) cudaEventRecord(e->ev[1], e->stream);
     const uint32_t first_block = e->lo / kSweepBlock;
@@ -211,7 +217,7 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
         const uint32_t first_tile = c0 / kTile, n_tiles = ceil_div(n_chunk, kTile);
         if (timing) cudaEventRecord(e->ev[2], e->stream);
         k_partition<<<n_tiles, kTileThreads, 0, e->stream>>>(n_chunk, d_in + c0, e->prof.n, e->d_tile_counts + (size_t)first_tile * ISL_MAX_PROFILES,
-                                                             n_tiles, e->cand_profiles, e->d_q, e->d_ctrl, nullptr, 0);
+                                                             n_tiles, e->cand_profiles, e->d_q, e->d_ctrl, nullptr, 0, 0);
         if (int rc = check_launch(e, "k_partition")) return rc;
         if (timing) cudaEventRecord(e->ev[3], e->stream);
         // the heads token of a chunk: first chunk of a partitioned call chains from the previous rank
@@ -267,7 +273,7 @@ int launch_pipeline(isl_engine* e, PipeArgs& args) {
         attr_set[e->device & 7] = true;
     }
     void* params[] = {&e->tab, &args};
-    const cudaError_t err = cudaLaunchCooperativeKernel((void*)k_pipeline<K, kP15>, dim3(args.n_seg), dim3(kPipeThreads), params, kPipeSmem, e->stream);
+    const cudaError_t err = cudaLaunchCooperativeKernel((void*)k_pipeline<K, kP15>, dim3(args.n_seg + (args.host_out ? 1u : 0u)), dim3(kPipeThreads), params, kPipeSmem, e->stream);
     if (err == cudaErrorCooperativeLaunchTooLarge || err == cudaErrorLaunchOutOfResources) {   // e.g. the GPU is shared: not all CTAs can be co-resident
         cudaGetLastError();
         return ISL_ESTATE;          // caller falls back to the chunk-by-chunk path
@@ -300,8 +306,12 @@ int grow(isl_engine* e, T** buf, uint32_t* cap, size_t need, size_t elems_per_un
 }
 
 // Resolve a stream of batches (semantics: one batch after the other).  Enqueues only.
+// h_in / h_out (isl_place_stream): the caller's host buffers.  With the segment pipeline the batches are copied and pre-passed one
+// by one on a second stream while the pipeline already runs (it waits per batch on a device flag), and an extra CTA copies every
+// finished chunk's results straight into h_out when that is mapped pinned memory (e->delivered) — H2D and D2H hide behind the kernel.
 int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const uint2* d_in, uint2* d_out,
-               const uint32_t* d_heads_in, uint32_t* d_heads_out, uint32_t xepoch = 0) {
+               const uint32_t* d_heads_in, uint32_t* d_heads_out, uint32_t xepoch = 0, const uint2* h_in = nullptr, uint2* h_out = nullptr) {
+    e->delivered = false;
     uint64_t total = 0;
     uint32_t n_chunks = 0;
     for (uint32_t b = 0; b < n_batches; ++b) { total += sizes[b]; n_chunks += ceil_div(sizes[b], e->pipe_chunk); }
@@ -310,7 +320,14 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     const uint32_t range = e->hi - e->lo;
     const bool ring = xepoch != 0;      // partitioned inventory: tokens cross ranks through peer memory, pipeline mandatory
     if (ring && n_chunks > kMaxStreamChunks) return ISL_ERANGE;
-    if (n_batches == 1 && !d_heads_in && !d_heads_out && !xepoch && small_eligible(e, sizes[0])) return run_small(e, sizes[0], d_in, nullptr, d_out);
+    auto copy_in_whole = [&]() -> int {       // paths that do not feed batch by batch: one H2D copy up front
+        if (h_in) ISL_CUDA(e, cudaMemcpyAsync(const_cast<uint2*>(d_in), h_in, (size_t)total * sizeof(uint2), cudaMemcpyHostToDevice, e->stream));
+        return ISL_OK;
+    };
+    if (n_batches == 1 && !d_heads_in && !d_heads_out && !xepoch && small_eligible(e, sizes[0])) {
+        if (int rc = copy_in_whole()) return rc;
+        return run_small(e, sizes[0], d_in, nullptr, d_out);
+    }
     if (e->cfg.policy == ISL_POLICY_BEST_FIT && (d_heads_in || d_heads_out || xepoch)) return ISL_EINVAL;   // best-fit does not partition
     const bool legacy_token = d_heads_in || d_heads_out || e->cfg.policy == ISL_POLICY_BEST_FIT;   // isl_place_batch_partitioned: host-carried token, kChunk layout
     bool pipeline = ring || (!legacy_token && !(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE)));
@@ -325,6 +342,9 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         uint32_t target = 148;                                       // segments aimed for; ISL_PIPE_SEGMENTS overrides (experiments)
         if (const char* v = getenv("ISL_PIPE_SEGMENTS")) target = std::max(1u, (uint32_t)strtoul(v, nullptr, 10));
         target = std::min(target, (uint32_t)std::max(1, e->max_coresident));
+        // fed host streams run their per-batch pre-pass kernels WHILE the pipeline is resident: keep kFeedReserve SMs free of pipeline
+        // CTAs (one CTA fills an SM's shared memory, and kernels with another shared-memory carve-out cannot join it there)
+        if (h_in && h_out && n_batches >= 2 && !ring && e->max_coresident > 2 * (int)kFeedReserve) target = std::min(target, (uint32_t)e->max_coresident - 1u - kFeedReserve);
         // segment size from the WHOLE inventory: a partitioned rank keeps the global pipeline depth (~target stages over all ranks)
         seg = std::min(seg_cap, std::max(64u, (ceil_div(e->G, target) + 63u) / 64u * 64u));
         if (seg_cap < 64) { if (ring) return ISL_ERANGE; pipeline = false; seg = 64; }
@@ -332,6 +352,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         if (e->max_coresident <= 0 || n_seg > (uint32_t)e->max_coresident) { if (ring) return ISL_ERANGE; pipeline = false; }
     }
     if (!pipeline) {       // one batch after the other through the single-chain path
+        if (int rc = copy_in_whole()) return rc;
         uint64_t off = 0;
         uint32_t hoff = 0;
         for (uint32_t b = 0; b < n_batches; ++b) {
@@ -373,20 +394,68 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         if (e->cap_tokens != before) ISL_CUDA(e, cudaMemsetAsync(e->d_tokens, 0, (size_t)e->cap_tokens * kTokStride * sizeof(uint32_t), e->stream));
     }
     if (n_tiles_total > ceil_div(e->cfg.max_batch, kTile) + 4096) return ISL_ERANGE;
-    ISL_CUDA(e, cudaMemcpyAsync(e->d_chunks, e->h_chunks.data(), n_chunks * sizeof(ChunkDesc), cudaMemcpyHostToDevice, e->stream));
-    ISL_CUDA(e, cudaMemcpyAsync(e->d_tiles, e->h_tiles.data(), n_tiles_total * sizeof(TileDesc), cudaMemcpyHostToDevice, e->stream));
-    ISL_CUDA(e, cudaMemsetAsync(e->d_free_acc, 0, (size_t)n_batches * free_stride, e->stream));
+    // feed mode: host buffers, more than one batch, no timing / tracing of the phases, and room for the copier CTA
+    bool feed = h_in && h_out && n_batches >= 2 && !timing && !(e->cfg.flags & ISL_FLAG_TRACE) && !ring && !getenv("ISL_NO_FEED");
+    uint2* h_out_dev = nullptr;
+    if (feed) {
+        if (n_seg + 1 + kFeedReserve > (uint32_t)e->max_coresident) feed = false;       // the pre-pass could starve behind a full house of pipeline CTAs
+    }
+    if (feed) {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, h_out) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) h_out_dev = static_cast<uint2*>(pa.devicePointer);
+        cudaGetLastError();
+        if (!e->feed_stream) {
+            ISL_CUDA(e, cudaStreamCreateWithFlags(&e->feed_stream, cudaStreamNonBlocking));
+            ISL_CUDA(e, cudaEventCreateWithFlags(&e->ev_feed, cudaEventDisableTiming));
+            ISL_CUDA(e, cudaEventCreateWithFlags(&e->ev_feed_done, cudaEventDisableTiming));
+        }
+        if (int rc = grow(e, &e->d_ready, &e->cap_ready, n_batches, 1)) return rc;
+        if (int rc = grow(e, &e->d_done_cnt, &e->cap_done, n_chunks, 1)) return rc;
+    }
+    const cudaStream_t pre = feed ? e->feed_stream : e->stream;     // the stream the tables and the pre-pass go to
+    if (feed) {     // the feed stream starts behind whatever the engine's stream still holds (earlier calls, load_inventory)
+        ISL_CUDA(e, cudaEventRecord(e->ev_feed, e->stream));
+        ISL_CUDA(e, cudaStreamWaitEvent(e->feed_stream, e->ev_feed, 0));
+        ISL_CUDA(e, cudaMemsetAsync(e->d_done_cnt, 0, (size_t)n_chunks * sizeof(uint32_t), pre));
+    } else if (int rc = copy_in_whole()) return rc;
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_chunks, e->h_chunks.data(), n_chunks * sizeof(ChunkDesc), cudaMemcpyHostToDevice, pre));
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_tiles, e->h_tiles.data(), n_tiles_total * sizeof(TileDesc), cudaMemcpyHostToDevice, pre));
+    ISL_CUDA(e, cudaMemsetAsync(e->d_free_acc, 0, (size_t)n_batches * free_stride, pre));
+    const uint32_t epoch = ++e->epoch;
+    // pre-pass of the tiles [t0, t1): defaults + free masks + histograms, then the stable partition into per-profile queues
+    auto prepass = [&](uint32_t t0, uint32_t t1) -> int {
+        k_prepare<<<t1 - t0, kTileThreads, 0, pre>>>(0, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi, e->prof,
+                                                     e->d_tile_counts, e->d_ctrl, e->d_tiles, e->d_free_acc, free_stride / 4, t0);
+        if (int rc = check_launch(e, "k_prepare")) return rc;
+        if (timing) cudaEventRecord(e->ev[1], e->stream);
+        k_partition<<<t1 - t0, kTileThreads, 0, pre>>>(0, d_in, e->prof.n, e->d_tile_counts, 0, e->cand_profiles, e->d_qall, e->d_cctl,
+                                                       e->d_tiles, q_stride, t0);
+        return check_launch(e, "k_partition");
+    };
+    // batch b of a fed stream: H2D of its requests, its pre-pass, its ready flag — all on the feed stream
+    std::vector<uint32_t> batch_tile0(n_batches + 1, n_tiles_total);
+    for (uint32_t t = n_tiles_total; t-- > 0;) batch_tile0[e->h_tiles[t].batch] = t;
+    for (uint32_t b = n_batches; b-- > 0;) if (batch_tile0[b] == n_tiles_total) batch_tile0[b] = batch_tile0[b + 1];   // empty batch: no tiles
+    uint64_t fed_off = 0;
+    auto feed_batch = [&](uint32_t b) -> int {
+        if (sizes[b]) {
+            ISL_CUDA(e, cudaMemcpyAsync(const_cast<uint2*>(d_in) + fed_off, h_in + fed_off, (size_t)sizes[b] * sizeof(uint2), cudaMemcpyHostToDevice, pre));
+            if (int rc = prepass(batch_tile0[b], batch_tile0[b + 1])) return rc;
+        }
+        k_set_flag<<<1, 1, 0, pre>>>(e->d_ready + b, epoch);
+        fed_off += sizes[b];
+        return check_launch(e, "k_set_flag");
+    };
     if (timing) cudaEventRecord(e->ev[0], e->stream);
-    k_prepare<<<n_tiles_total, kTileThreads, 0, e->stream>>>(0, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi, e->prof,
-                                                             e->d_tile_counts, e->d_ctrl, e->d_tiles, e->d_free_acc, free_stride / 4);
-    if (int rc = check_launch(e, "k_prepare")) return rc;
-    if (timing) cudaEventRecord(e->ev[1], e->stream);
-    k_partition<<<n_tiles_total, kTileThreads, 0, e->stream>>>(0, d_in, e->prof.n, e->d_tile_counts, 0, e->cand_profiles, e->d_qall, e->d_cctl,
-                                                               e->d_tiles, q_stride);
-    if (int rc = check_launch(e, "k_partition")) return rc;
+    if (feed) {
+        if (int rc = feed_batch(0)) return rc;
+        ISL_CUDA(e, cudaEventRecord(e->ev_feed, pre));                  // tables + first batch are on their way: the pipeline may start
+        ISL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_feed, 0));
+    } else if (int rc = prepass(0, n_tiles_total)) return rc;
     if (timing) cudaEventRecord(e->ev[2], e->stream);
     PipeArgs args{};
-    args.n_chunks = n_chunks; args.n_seg = n_seg; args.seg = seg; args.lo = e->lo; args.hi = e->hi; args.epoch = ++e->epoch;
+    args.n_chunks = n_chunks; args.n_seg = n_seg; args.seg = seg; args.lo = e->lo; args.hi = e->hi; args.epoch = epoch;
+    args.ready = feed ? e->d_ready : nullptr; args.done_cnt = h_out_dev ? e->d_done_cnt : nullptr; args.host_out = h_out_dev;
     args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
     args.q_stride = q_stride; args.free_stride = free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab; args.out = d_out; args.feas = e->d_feas; args.stats = e->d_ctrl;
     args.heads_in = d_heads_in; args.heads_out = d_heads_out;
@@ -407,6 +476,11 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     if (rc == ISL_ESTATE && ring) return ISL_ERANGE;    // a partitioned run cannot leave the pipeline: the token ring lives inside it
     if (rc == ISL_ESTATE) {         // the pre-pass above did not touch the occupancy (frees went to the free masks): redo batch by batch
         e->max_coresident = -1;     // and do not try the pipeline again on this engine
+        if (feed) {                 // only batch 0 was fed: bring the whole stream in behind it
+            ISL_CUDA(e, cudaEventRecord(e->ev_feed_done, pre));
+            ISL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_feed_done, 0));
+            if (int rc2 = copy_in_whole()) return rc2;
+        }
         uint64_t boff = 0;
         for (uint32_t b = 0; b < n_batches; ++b) {
             if (int rc2 = run_batch(e, sizes[b], d_in + boff, d_out + boff, nullptr, nullptr)) return rc2;
@@ -415,6 +489,12 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         return ISL_OK;
     }
     if (rc) return rc;
+    if (feed) {     // the remaining batches, while the pipeline works on the first ones
+        for (uint32_t b = 1; b < n_batches; ++b) if (int rc2 = feed_batch(b)) return rc2;
+        ISL_CUDA(e, cudaEventRecord(e->ev_feed_done, pre));
+        ISL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_feed_done, 0));
+        e->delivered = h_out_dev != nullptr;
+    }
     if (timing) {
         cudaEventRecord(e->ev[3], e->stream);
         cudaEventSynchronize(e->ev[3]);
@@ -524,7 +604,10 @@ int isl_destroy(isl_engine* e) {
         cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens);
         cudaFree(e->d_free_acc); cudaFree(e->d_tiles);
         if (e->d_outbox && !e->outbox_local) cudaIpcCloseMemHandle(e->d_outbox);
-        cudaFree(e->d_inbox); cudaFree(e->d_trace); cudaFree(e->d_bf_bitmaps);
+        cudaFree(e->d_inbox); cudaFree(e->d_trace); cudaFree(e->d_bf_bitmaps); cudaFree(e->d_ready); cudaFree(e->d_done_cnt);
+        if (e->feed_stream) cudaStreamDestroy(e->feed_stream);
+        if (e->ev_feed) cudaEventDestroy(e->ev_feed);
+        if (e->ev_feed_done) cudaEventDestroy(e->ev_feed_done);
         if (e->h_small_out) cudaFreeHost(e->h_small_out);
         for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
         if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -719,9 +802,11 @@ int isl_place_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, c
     if (total == 0) return ISL_OK;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
-    ISL_CUDA(e, cudaMemcpyAsync(e->d_req, in, (size_t)total * sizeof(isl_request), cudaMemcpyHostToDevice, e->stream));
-    if (int rc = run_stream(e, n_batches, sizes, e->d_req, e->d_res, nullptr, nullptr)) return rc;
-    ISL_CUDA(e, cudaMemcpyAsync(out, e->d_res, (size_t)total * sizeof(isl_result), cudaMemcpyDeviceToHost, e->stream));
+    if (int rc = run_stream(e, n_batches, sizes, e->d_req, e->d_res, nullptr, nullptr, 0, reinterpret_cast<const uint2*>(in), reinterpret_cast<uint2*>(out))) {
+        if (e->feed_stream) cudaStreamSynchronize(e->feed_stream);
+        return rc;
+    }
+    if (!e->delivered) ISL_CUDA(e, cudaMemcpyAsync(out, e->d_res, (size_t)total * sizeof(isl_result), cudaMemcpyDeviceToHost, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     return ISL_OK;
 }

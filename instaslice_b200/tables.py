@@ -28,7 +28,26 @@ H100_80GB = [
     ("7g.80gb", 8, [0], 4),
 ]
 
-TABLES = {"a100-40gb": A100_40GB, "h100-80gb": H100_80GB}
+# A30-24GB: four memory slices.  The reference's search hard-codes 8 slots (instaslice_controller.go:306) and the strict
+# `start + size < 8` bound (Q1), so a 4-slice GPU needs nothing special: its rows simply never name a start above 3
+# and `4g.24gb` (size 4, start 0) is placeable.  SURVEY 8f-3 "generalised slot width".
+A30_24GB = [
+    ("1g.6gb", 1, [0, 1, 2, 3], 0),
+    ("2g.12gb", 2, [0, 2], 1),
+    ("4g.24gb", 4, [0], 3),
+]
+
+# B200-180GB: same placement geometry as the 80GB class, names as in NVIDIA's MIG user guide (not verifiable offline)
+B200_180GB = [
+    ("1g.23gb", 1, [0, 1, 2, 3, 4, 5, 6], 0),
+    ("1g.45gb", 2, [0, 2, 4, 6], 9),
+    ("2g.45gb", 2, [0, 2, 4], 1),
+    ("3g.90gb", 4, [0, 4], 2),
+    ("4g.90gb", 4, [0], 3),
+    ("7g.180gb", 8, [0], 4),
+]
+
+TABLES = {"a100-40gb": A100_40GB, "h100-80gb": H100_80GB, "a30-24gb": A30_24GB, "b200-180gb": B200_180GB}
 
 
 def migplacement(table):

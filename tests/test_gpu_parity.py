@@ -54,7 +54,7 @@ def check_against_fast(node_off, occ, rows, batches, quirks=E.QUIRKS_REF_EXACT):
 
 # ---- the device table: every (occupancy byte, profile row), both tables, all quirk sets --------------------
 @pytest.mark.parametrize("quirks", [3, 0, 1, 2])
-@pytest.mark.parametrize("tname", ["a100-40gb", "h100-80gb"])
+@pytest.mark.parametrize("tname", ["a100-40gb", "h100-80gb", "a30-24gb", "b200-180gb"])
 def test_device_table_exhaustive(tname, quirks):
     rows = E.make_profiles(tables.TABLES[tname])
     eng = E.Engine(max_gpus=4096, max_batch=1024, quirks=quirks)
@@ -173,7 +173,7 @@ def test_regress_crd_batched_equals_pod_by_pod():
 # ---- randomised parity, edge cases ------------------------------------------------------------------------
 @pytest.mark.parametrize("flags", [E.FLAG_NO_PIPELINE | E.FLAG_NO_SMALL, E.FLAG_FORCE_PIPELINE, 0])
 @pytest.mark.parametrize("quirks", [3, 0])
-@pytest.mark.parametrize("tname", ["a100-40gb", "h100-80gb"])
+@pytest.mark.parametrize("tname", ["a100-40gb", "h100-80gb", "a30-24gb", "b200-180gb"])
 def test_random_occupancy_and_frees(tname, quirks, flags):
     table = tables.TABLES[tname]
     rows = E.make_profiles(table)

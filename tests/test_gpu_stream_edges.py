@@ -79,3 +79,36 @@ def test_stream_capacity_errors():
     assert ei.value.code == E.ERANGE
     ok = eng.place_stream([W.alloc_requests(np.zeros(500, dtype=np.uint8)), W.alloc_requests(np.zeros(500, dtype=np.uint8))])
     assert sum(int((r["status"] == E.ST_PLACED).sum()) for r in ok) == 32 * 7
+
+
+@pytest.mark.parametrize("sizes", [[70001, 0, 513, 65536, 3, 99999], [1500, 1500], [65537, 65535, 1]])
+def test_stream_from_pinned_host_buffers(sizes):
+    """isl_place_stream with pinned host buffers: the batches are fed while the pipeline runs and an extra CTA writes every finished
+    chunk into the caller's array (odd offsets, empty batches, multi-chunk batches); same answers as pageable buffers and the oracle."""
+    import torch
+    rows = E.make_profiles(tables.H100_80GB)
+    rng = W.SplitMix64(31 + len(sizes))
+    G = 30000
+    node_off = np.concatenate([[0], np.cumsum(np.full((G + 7) // 8, 8))]).astype(np.uint32)
+    node_off[-1] = G
+    occ = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+    ref = oracle.Fast(node_off, rows)
+    ref.load(occ)
+    batches = churn_batches(rng, ref, sizes, len(rows))
+    want = np.concatenate([b[1] for b in batches])
+    req = np.concatenate([b[0] for b in batches])
+    h_in = torch.from_numpy(req.view(np.uint64).copy()).pin_memory()
+    h_out = torch.zeros_like(h_in).pin_memory()
+    eng = E.Engine(max_gpus=1 << 15, max_batch=1 << 19)
+    eng.load_profiles(rows)
+    for rep in range(2):        # twice: flags and counters of the first call must not leak into the second
+        eng.load_inventory(node_off, occ)
+        h_out.zero_()
+        eng.place_stream_ptr(np.array(sizes, dtype=np.uint32), h_in.data_ptr(), h_out.data_ptr(), device=False)
+        got = h_out.numpy().view(E.RESULT_DTYPE)
+        bad = np.flatnonzero(got != want)
+        assert len(bad) == 0, (rep, bad[:5], got[bad[:5]], want[bad[:5]])
+        assert np.array_equal(eng.read_occupancy(), ref.occupancy())
+    eng.load_inventory(node_off, occ)
+    pageable = eng.place_stream([b[0] for b in batches])
+    assert np.array_equal(np.concatenate(pageable), want)
