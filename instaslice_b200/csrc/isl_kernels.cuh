@@ -1016,7 +1016,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     // fed streams: the requests of a batch may still be on their way (H2D + pre-pass on the feed stream) when the pipeline gets there
     auto wait_ready = [&](uint32_t chunk) {
         if (!a.ready) return;
-        if (tid == 0) { const uint32_t* f = a.ready + a.chunks[chunk].batch; while (ld_acquire_gpu(f) != a.epoch) __nanosleep(128); }
+        if (tid == 0) {
+            const uint32_t* f = a.ready + a.chunks[chunk].batch;
+            const unsigned long long t0 = globaltimer_ns();
+            // the feed kernels are launched AFTER this one; a tool that serialises kernels would starve the wait (the host side switches
+            // feeding off when it detects one, ISL_NO_FEED=1 forces it) — fail loudly after 20 s instead of hanging the GPU
+            while (ld_acquire_gpu(f) != a.epoch) { __nanosleep(128); if (globaltimer_ns() - t0 > 20000000000ull) __trap(); }
+        }
         __syncthreads();
     };
     auto chunk_done = [&](uint32_t chunk) {     // after the barrier that ends the chunk's commit

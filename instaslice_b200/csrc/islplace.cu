@@ -333,6 +333,11 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     bool pipeline = ring || (!legacy_token && !(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE)));
     // the stream path keeps one free-mask byte per GPU and batch: very long streams over large inventories go batch by batch
     if (pipeline && (uint64_t)n_batches * e->occ_bytes > (256ull << 20)) { if (ring) return ISL_ERANGE; pipeline = false; }
+    // feed mode (below): host buffers, more than one batch, no timing / tracing of the phases, no kernel-serialising tool around
+    // (ncu, compute-sanitizer, CUDA_LAUNCH_BLOCKING would starve a pipeline that waits for kernels launched after it: they inject
+    // through CUDA_INJECTION64_PATH; ISL_NO_FEED=1 switches feeding off by hand)
+    const bool want_feed = h_in && h_out && n_batches >= 2 && !(e->cfg.flags & (ISL_FLAG_TIMING | ISL_FLAG_TRACE)) && !ring && !getenv("ISL_NO_FEED") &&
+                           !getenv("CUDA_INJECTION64_PATH") && !getenv("CUDA_LAUNCH_BLOCKING") && !getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
     uint32_t seg = 0, n_seg = 0;
     if (pipeline) {
         if (int rc = query_coresident(e)) return rc;
@@ -344,7 +349,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         target = std::min(target, (uint32_t)std::max(1, e->max_coresident));
         // fed host streams run their per-batch pre-pass kernels WHILE the pipeline is resident: keep kFeedReserve SMs free of pipeline
         // CTAs (one CTA fills an SM's shared memory, and kernels with another shared-memory carve-out cannot join it there)
-        if (h_in && h_out && n_batches >= 2 && !ring && e->max_coresident > 2 * (int)kFeedReserve) target = std::min(target, (uint32_t)e->max_coresident - 1u - kFeedReserve);
+        if (want_feed && e->max_coresident > 2 * (int)kFeedReserve) target = std::min(target, (uint32_t)e->max_coresident - 1u - kFeedReserve);
         // segment size from the WHOLE inventory: a partitioned rank keeps the global pipeline depth (~target stages over all ranks)
         seg = std::min(seg_cap, std::max(64u, (ceil_div(e->G, target) + 63u) / 64u * 64u));
         if (seg_cap < 64) { if (ring) return ISL_ERANGE; pipeline = false; seg = 64; }
@@ -394,8 +399,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         if (e->cap_tokens != before) ISL_CUDA(e, cudaMemsetAsync(e->d_tokens, 0, (size_t)e->cap_tokens * kTokStride * sizeof(uint32_t), e->stream));
     }
     if (n_tiles_total > ceil_div(e->cfg.max_batch, kTile) + 4096) return ISL_ERANGE;
-    // feed mode: host buffers, more than one batch, no timing / tracing of the phases, and room for the copier CTA
-    bool feed = h_in && h_out && n_batches >= 2 && !timing && !(e->cfg.flags & ISL_FLAG_TRACE) && !ring && !getenv("ISL_NO_FEED");
+    bool feed = want_feed;       // and room for the copier CTA plus the reserve
     uint2* h_out_dev = nullptr;
     if (feed) {
         if (n_seg + 1 + kFeedReserve > (uint32_t)e->max_coresident) feed = false;       // the pre-pass could starve behind a full house of pipeline CTAs
