@@ -9,13 +9,15 @@ pre-filled state (64 KiB device copy, inside the timed region) and the 16 record
 1 x 16 960 operations) are resolved in order.  The recording itself (which allocation each FREE names depends
 on earlier placements) is made once, untimed, by running the generator through the engine.
 
-value   whole-job placements/s with requests and results resident in HBM (isl_place_batch_device)
-e2e     the same through isl_place_batch with pinned HOST buffers: H2D of every batch and D2H of every result
-        array are inside the timed region
-N > 1   the inventory is partitioned over the ranks (contiguous GPU ranges); every rank holds the request
-        batches; the per-profile queue-head token travels rank -> rank per batch (NCCL send/recv), results are
-        combined with an all-reduce(MIN) over the 8-byte records and the occupancy shards are all-gathered.
-        Strong scaling (the job is fixed).
+value   whole-job placements/s with requests and results resident in HBM (isl_place_stream_device: ONE call per step, the
+        engine pipelines the 16 batches over inventory segments inside one cooperative kernel)
+e2e     the same through isl_place_stream with pinned HOST buffers: the H2D copy of every batch and the delivery of every
+        result record into the caller's host array are inside the timed region (batches are fed on a second stream while the
+        pipeline runs; an extra CTA writes finished chunks into the pinned result array)
+N > 1   the inventory is partitioned over the ranks (contiguous GPU ranges); every rank holds the request stream and runs the
+        segment pipeline over its own range; the per-profile queue-head token of every chunk crosses ranks INSIDE the running
+        kernels (peer store into the next rank's inbox over NVLink, CUDA IPC); results are combined with an NCCL
+        all-reduce(MIN) over the 8-byte records and the occupancy shards are all-gathered.  Strong scaling (the job is fixed).
 
 The CPU oracle is used only for the cpu_baseline leg (timed baseline + parity check of the same sample) and
 for --impl reference.
@@ -254,7 +256,7 @@ def run_own(args):
                 eng.place_batch_ptr(len(b), h_in_all.data_ptr() + 8 * int(offs[i]), h_out_all.data_ptr() + 8 * int(offs[i]))
         ms_pb = timed(step_per_batch, args.steps, 1)
         e2e = {"value": n_ops * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n_ops, "d2h_bytes_per_step": 8 * n_ops,
-               "ms_per_step": ms_e2e / args.steps, "api": "isl_place_stream (16 batches per call)",
+               "ms_per_step": ms_e2e / args.steps, "api": "isl_place_stream (16 batches per call; batches fed and results delivered while the pipeline runs)",
                "per_batch_calls_value": n_ops * args.steps / (ms_pb / 1e3), "per_batch_calls_note": "isl_place_batch once per batch, synchronous"}
 
     roofline = cpu = None
@@ -283,7 +285,7 @@ def run_own(args):
         roofline = {"bound": "hbm", "kernel": "k_pipeline", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic(), "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": ms_pipe, "launches": 1,
-                    "note": "latency-bound exact commit chain pipelined over 128 inventory segments (one CTA each); inventory, queues and candidates "
+                    "note": "latency-bound exact commit chain pipelined over ~148 inventory segments (one CTA per SM); inventory, queues and candidates "
                             "are shared-memory / L2 resident by construction, so DRAM traffic stays below the algorithmic bytes",
                     "phase_ms_per_step": {"prepare": st["ms_free"], "partition": st["ms_partition"], "pipeline": st["ms_commit"], "total": st["ms_total"]},
                     "single_chain_path_ms_per_step": {"prepare": sst["ms_free"], "partition": sst["ms_partition"], "sweep": sst["ms_sweep"],

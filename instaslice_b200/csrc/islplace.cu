@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -344,7 +345,16 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         uint32_t total_cand = 0;
         for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) total_cand += e->tab.desc[k][l] >> 31;
         const uint32_t seg_cap = max_segment_for(total_cand);      // queue windows of a segment must fit in shared memory
-        uint32_t target = 148;                                       // segments aimed for; ISL_PIPE_SEGMENTS overrides (experiments)
+        // Segments aimed for.  A batch's decisions form ONE sequential chain over the inventory, only different chunks overlap, so a
+        // stream of B chunks over S stages takes about (S + B - 1) x (D x t_dec / S + t_fix), D = decisions of a chunk (tools/chain_cost.py:
+        // t_dec 41 ns, t_fix ~2.3 us per busy cell).  The minimum is at S = sqrt((B - 1) x D x t_dec / t_fix); D is estimated by the
+        // smaller of the chunk size and ~3.5 placements per GPU.  ISL_PIPE_SEGMENTS overrides (experiments).
+        uint32_t target = 148;
+        {
+            const double d_est = std::min((double)total / n_chunks, 3.5 * (double)e->G);
+            const double s_opt = std::sqrt(std::max(1.0, (double)(n_chunks - 1)) * d_est * (0.041 / 2.3));
+            target = (uint32_t)std::min(148.0, std::max(1.0, std::floor(s_opt + 0.5)));
+        }
         if (const char* v = getenv("ISL_PIPE_SEGMENTS")) target = std::max(1u, (uint32_t)strtoul(v, nullptr, 10));
         target = std::min(target, (uint32_t)std::max(1, e->max_coresident));
         // fed host streams run their per-batch pre-pass kernels WHILE the pipeline is resident: keep kFeedReserve SMs free of pipeline
