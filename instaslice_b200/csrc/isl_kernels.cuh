@@ -1316,26 +1316,34 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
     __syncthreads();
     if (tid >= 32) return;
     uint32_t placed = 0;
+    uint32_t dead = 0;              // profiles that found no GPU: occupancy only grows inside a batch's ALLOC phase, so they never will again
     for (uint32_t base = 0; base < n; base += 32) {
         const uint2 mine = base + lane < n ? in[base + lane] : make_uint2(0, (uint32_t)ISL_OP_NOOP << 8);
         const uint32_t cnt = min(32u, n - base);
+        {   // whole block without a live ALLOC (frees, unknown or dead profiles): nothing to decide
+            const uint32_t wp = mine.y & 0xFFu, wop = (mine.y >> 8) & 0xFFu;
+            if (__ballot_sync(0xFFFFFFFFu, wop == ISL_OP_ALLOC && wp < prof.n && !((dead >> wp) & 1u)) == 0) continue;
+        }
         for (uint32_t j = 0; j < cnt; ++j) {
             const uint32_t w = __shfl_sync(0xFFFFFFFFu, mine.y, j);
             const uint32_t p = w & 0xFFu, op = (w >> 8) & 0xFFu;
-            if (op != ISL_OP_ALLOC || p >= prof.n) continue;    // defaults / frees were written by k_prepare
-            uint32_t key = kInf;
+            if (op != ISL_OP_ALLOC || p >= prof.n || ((dead >> p) & 1u)) continue;    // defaults / frees were written by k_prepare
+            uint32_t key = kInf, ko = 0;
 #pragma unroll
             for (uint32_t r = 0; r < 8; ++r) {                  // lane l looks at classes l, l+32, ...
                 const uint32_t o = r * 32 + lane;
                 const uint32_t mn = s_min[o];
-                if (mn != kInf && s_lut[p * 256 + o] != ISL_START_NONE) key = min(key, ((8u - __popc(o)) << 24) | mn);
+                if (mn != kInf && s_lut[p * 256 + o] != ISL_START_NONE) {
+                    const uint32_t k2 = ((8u - __popc(o)) << 24) | mn;
+                    if (k2 < key) { key = k2; ko = o; }
+                }
             }
             const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, key);
-            if (m == kInf) continue;                            // stays NO_CAPACITY
+            if (m == kInf) { dead |= 1u << p; continue; }      // stays NO_CAPACITY, and so does every later request of the profile
             const uint32_t g = m & 0xFFFFFFu;
-            __syncwarp();                                       // all lanes have read the class minima before lane 0 rewrites them
+            const uint32_t o_win = __shfl_sync(0xFFFFFFFFu, ko, __ffs(__ballot_sync(0xFFFFFFFFu, key == m)) - 1);   // the class IS the occupancy byte
             if (lane == 0) {
-                const uint32_t o = occ[lo + g];
+                const uint32_t o = o_win;
                 const uint32_t start = s_lut[p * 256 + o], size = prof.rows[p].size;
                 const uint32_t o2 = o | ((((1u << size) - 1u) << start) & 0xFFu);
                 occ[lo + g] = (uint8_t)o2;
