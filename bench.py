@@ -297,7 +297,8 @@ def run_own(args):
         line = {"metric": METRIC, "value": n_ops * args.steps / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "ops_per_step": n_ops, "batches_per_step": len(batches), "gpus_in_inventory": G,
+                "config": {"workload": WORKLOAD, "ops_per_step": n_ops, "alloc_requests_per_step": int(sum(int((b["op"] == E.OP_ALLOC).sum()) for b in batches)),
+                           "ops_counted": "every request resolved: ALLOC decisions (placed or no-capacity) and FREEs", "batches_per_step": len(batches), "gpus_in_inventory": G,
                            "policy": "first-fit", "quirks": "REF_EXACT",
                            "parallelism": "segment pipeline, 1 GPU" if world == 1 else "inventory partitioned over %d ranks: peer-memory token ring + NCCL all-reduce(MIN) of results + NCCL all-gather of occupancy" % world,
                            "l2": "flushed between timed steps (256 MiB write)", "timing": "cuda events per step, max over ranks"},
@@ -400,7 +401,8 @@ def run_reference(args):
                       "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                       "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
                       "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                                       "note": "single reconcile worker like the reference (controller-runtime default); the Go binary cannot be built in this image"},
+                                       "note": "single reconcile worker like the reference (controller-runtime default); the Go binary cannot be built in this image; "
+                                               "counts ALLOC decisions only (a FREE is a map delete by the daemonset in the reference), the GPU arm's ops are ~50% FREEs"},
                       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
     return 0
 

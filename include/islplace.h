@@ -207,7 +207,10 @@ uint32_t isl_gpu_to_node(const isl_engine* e, uint32_t gpu);
 int  isl_place_batch(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out);
 /* A STREAM of batches in one call: batch i has sizes[i] requests, `in`/`out` hold the batches back to back.
  * Semantics are exactly those of calling isl_place_batch once per batch in order; the engine pipelines the
- * batches over inventory segments (DESIGN.md "Segment pipeline").  Sum of sizes <= isl_config.max_batch. */
+ * batches over inventory segments (DESIGN.md "Segment pipeline").  Sum of sizes <= isl_config.max_batch.
+ * With PINNED host buffers (cudaHostAlloc / cudaHostRegister) the batches are copied and pre-passed while the pipeline
+ * already runs and finished chunks are written straight into `out`; pageable buffers work without that overlap.
+ * Environment: ISL_NO_FEED=1 switches the overlap off (the library does so itself under kernel-serialising tools). */
 int  isl_place_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const isl_request* in, isl_result* out);
 int  isl_place_stream_device(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const void* d_in, void* d_out);
 /* Same, requests and results already resident in device memory (CUdeviceptr as void*). */

@@ -120,12 +120,15 @@ class EngineError(RuntimeError):
         self.code = code
 
 
-def make_profiles(table) -> np.ndarray:
-    """``tables.A100_40GB``-style rows -> isl_profile records (duplicate starts dropped, order kept)."""
+def make_profiles(table, right_to_left: bool = False) -> np.ndarray:
+    """``tables.A100_40GB``-style rows -> isl_profile records (duplicate starts dropped, order kept).
+
+    ``right_to_left``: the start search takes the first legal start in ROW order (:343-383), so a right-to-left placement inside a
+    GPU (the policy the reference only stubs, :464-469) is the same engine fed with the rows reversed — SURVEY 8f-4."""
     rows = np.zeros(len(table), dtype=PROFILE_DTYPE)
     for i, (_name, size, starts, gi) in enumerate(table):
         uniq = []
-        for s in starts:
+        for s in (list(starts)[::-1] if right_to_left else starts):
             if s not in uniq:
                 uniq.append(s)
         rows[i]["size"] = size

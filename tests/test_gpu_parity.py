@@ -509,3 +509,29 @@ def test_incremental_node_update_equals_full_sync():
     a = r.place_pending_pods(copy.deepcopy(pods[6:]))
     b = full.place_pending_pods(copy.deepcopy(pods[6:]))
     assert [(v, x and (x["gpuUUID"], x["start"])) for v, x in a] == [(v, x and (x["gpuUUID"], x["start"])) for v, x in b]
+
+
+@pytest.mark.parametrize("quirks", [3, 0])
+def test_right_to_left_rows(quirks):
+    """the reference's RightToLeftPolicy is a stub (:464-469).  The start search honours ROW order (:343-383), so a
+    right-to-left policy is the engine fed with reversed rows; the oracle, which walks the rows the same way, is the checker."""
+    rows = E.make_profiles(tables.H100_80GB, right_to_left=True)
+    assert list(rows[0]["starts"][:7]) == [6, 5, 4, 3, 2, 1, 0]
+    rng = W.SplitMix64(5 + quirks)
+    G = 3000
+    node_off = np.concatenate([[0], np.cumsum(np.full((G + 7) // 8, 8))]).astype(np.uint32)
+    node_off[-1] = G
+    occ = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+    ref = oracle.Fast(node_off, rows, quirks)
+    ref.load(occ)
+    batches = [W.alloc_requests(W.mix_profiles(rng, n)) for n in (900, 70000, 40)] + [W.alloc_requests(np.zeros(5000, dtype=np.uint8))]   # last: scan mode
+    want = [ref.place(b) for b in batches]
+    # one empty GPU, one 1g request: lands on slice 6, not 0
+    assert oracle.start_for(rows[0], quirks, 0x00) == 6
+    for flags in (E.FLAG_NO_PIPELINE | E.FLAG_NO_SMALL, 0):
+        eng = E.Engine(max_gpus=4096, max_batch=1 << 18, quirks=quirks, flags=flags)
+        eng.load_profiles(rows)
+        eng.load_inventory(node_off, occ)
+        got = eng.place_stream(batches) if flags == 0 else [eng.place_batch(b) for b in batches]
+        assert all(np.array_equal(a, b) for a, b in zip(got, want)), flags
+        assert np.array_equal(eng.read_occupancy(), ref.occupancy())
