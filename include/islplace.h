@@ -196,6 +196,11 @@ int  isl_read_occupancy(isl_engine* e, uint8_t* out /* G bytes */);
  * when ONE Instaslice object changed (an Allocations / Prepared entry appeared or disappeared) instead of re-listing
  * every node (the reference deep-copies the whole list on every reconcile, :85). */
 int  isl_write_occupancy(isl_engine* e, uint32_t first_gpu, uint32_t n, const uint8_t* occ);
+/* What-if queries (defragmentation planning): isl_snapshot_occupancy keeps a device-side copy of the whole
+ * occupancy, any number of isl_place_* / isl_free_batch calls then run against the live state, isl_restore_occupancy puts the
+ * snapshot back (a 1-byte-per-GPU device copy, no host round trip).  ISL_ESTATE if there is no inventory / no snapshot. */
+int  isl_snapshot_occupancy(isl_engine* e);
+int  isl_restore_occupancy(isl_engine* e);
 uint32_t isl_num_gpus(const isl_engine* e);
 /* node that owns canonical GPU index `gpu` (binary search over node_off), or ISL_GPU_NONE */
 uint32_t isl_gpu_to_node(const isl_engine* e, uint32_t gpu);

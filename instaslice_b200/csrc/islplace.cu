@@ -77,6 +77,7 @@ struct isl_engine {
     cudaStream_t feed_stream = nullptr; cudaEvent_t ev_feed = nullptr, ev_feed_done = nullptr;
     uint32_t* d_ready = nullptr; uint32_t cap_ready = 0;      // [batch] epoch flag
     uint32_t* d_done_cnt = nullptr; uint32_t cap_done = 0;    // [chunk] committed segments
+    uint8_t* d_occ_snap = nullptr; size_t snap_bytes = 0; uint32_t snap_G = 0;      // isl_snapshot_occupancy / isl_restore_occupancy
     bool delivered = false;          // the last run_stream call already put the results into the caller's host buffer
     size_t scratch_bytes = 0;
 
@@ -618,7 +619,7 @@ int isl_destroy(isl_engine* e) {
         cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens);
         cudaFree(e->d_free_acc); cudaFree(e->d_tiles);
         if (e->d_outbox && !e->outbox_local) cudaIpcCloseMemHandle(e->d_outbox);
-        cudaFree(e->d_inbox); cudaFree(e->d_trace); cudaFree(e->d_bf_bitmaps); cudaFree(e->d_ready); cudaFree(e->d_done_cnt);
+        cudaFree(e->d_inbox); cudaFree(e->d_trace); cudaFree(e->d_bf_bitmaps); cudaFree(e->d_ready); cudaFree(e->d_done_cnt); cudaFree(e->d_occ_snap);
         if (e->feed_stream) cudaStreamDestroy(e->feed_stream);
         if (e->ev_feed) cudaEventDestroy(e->ev_feed);
         if (e->ev_feed_done) cudaEventDestroy(e->ev_feed_done);
@@ -745,6 +746,7 @@ int isl_load_inventory(isl_engine* e, uint32_t n_nodes, const uint32_t* node_off
     DeviceGuard guard(e->device);
     e->node_off.assign(node_off, node_off + n_nodes + 1);
     e->G = G; e->lo = 0; e->hi = G;
+    e->snap_G = 0;                  // a snapshot belongs to the inventory it was taken from
     ISL_CUDA(e, cudaMemsetAsync(e->d_occ, 0xFF, e->occ_bytes, e->stream));
     ISL_CUDA(e, cudaMemsetAsync(e->d_gtab, 0, e->occ_bytes, e->stream));        // every node uses table 0 until isl_set_node_tables
     e->node_table.clear();
@@ -774,6 +776,31 @@ int isl_write_occupancy(isl_engine* e, uint32_t first_gpu, uint32_t n, const uin
     DeviceGuard guard(e->device);
     ISL_CUDA(e, cudaMemcpyAsync(e->d_occ + first_gpu, occ, n, cudaMemcpyHostToDevice, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ISL_OK;
+}
+
+int isl_snapshot_occupancy(isl_engine* e) {
+    if (!e) return ISL_EINVAL;
+    if (!e->have_inventory) return ISL_ESTATE;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    if (e->snap_bytes < e->occ_bytes) {
+        if (e->d_occ_snap) cudaFree(e->d_occ_snap);
+        e->d_occ_snap = nullptr; e->snap_bytes = 0;
+        ISL_CUDA(e, cudaMalloc(&e->d_occ_snap, e->occ_bytes));
+        e->snap_bytes = e->occ_bytes;
+    }
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_occ_snap, e->d_occ, e->occ_bytes, cudaMemcpyDeviceToDevice, e->stream));
+    e->snap_G = e->G;
+    return ISL_OK;
+}
+
+int isl_restore_occupancy(isl_engine* e) {
+    if (!e) return ISL_EINVAL;
+    if (!e->have_inventory || !e->d_occ_snap || e->snap_G != e->G) return ISL_ESTATE;     // a snapshot belongs to the inventory it was taken from
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_occ, e->d_occ_snap, e->occ_bytes, cudaMemcpyDeviceToDevice, e->stream));
     return ISL_OK;
 }
 

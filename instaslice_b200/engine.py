@@ -57,7 +57,7 @@ class Stats(C.Structure):
 # every symbol include/islplace.h declares; tests check that the library exports all of them
 EXPORTED_SYMBOLS = [
     "isl_create", "isl_destroy", "isl_set_stream", "isl_synchronize", "isl_load_profiles", "isl_load_profile_tables", "isl_set_node_tables", "isl_load_inventory", "isl_read_occupancy", "isl_write_occupancy",
-    "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_place_stream", "isl_place_stream_device", "isl_free_batch",
+    "isl_snapshot_occupancy", "isl_restore_occupancy", "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_place_stream", "isl_place_stream_device", "isl_free_batch",
     "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_ipc_inbox_handle", "isl_ipc_connect", "isl_connect_local", "isl_place_stream_partitioned", "isl_device_occupancy", "isl_get_stats", "isl_read_trace",
     "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
 ]
@@ -78,6 +78,8 @@ def load_library(path: str = LIB_PATH):
         "isl_create": (C.c_int, [C.POINTER(Config), C.POINTER(p)]),
         "isl_destroy": (C.c_int, [p]),
         "isl_set_stream": (C.c_int, [p, p]),
+        "isl_snapshot_occupancy": (C.c_int, [p]),
+        "isl_restore_occupancy": (C.c_int, [p]),
         "isl_synchronize": (C.c_int, [p]),
         "isl_load_profiles": (C.c_int, [p, C.c_uint32, p]),
         "isl_load_profile_tables": (C.c_int, [p, C.c_uint32, C.c_uint32, p]),
@@ -302,6 +304,14 @@ class Engine:
 
     def device_occupancy(self) -> int:
         return int(self._lib.isl_device_occupancy(self._h) or 0)
+
+    def snapshot_occupancy(self):
+        """What-if queries: keep a device-side copy of the occupancy ... (see restore_occupancy)."""
+        self._check(self._lib.isl_snapshot_occupancy(self._h), "isl_snapshot_occupancy")
+
+    def restore_occupancy(self):
+        """... and put it back after any number of placement calls (defragmentation planning)."""
+        self._check(self._lib.isl_restore_occupancy(self._h), "isl_restore_occupancy")
 
     # -- diagnostics
     def read_trace(self) -> np.ndarray:

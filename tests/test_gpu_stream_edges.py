@@ -112,3 +112,32 @@ def test_stream_from_pinned_host_buffers(sizes):
     eng.load_inventory(node_off, occ)
     pageable = eng.place_stream([b[0] for b in batches])
     assert np.array_equal(np.concatenate(pageable), want)
+
+
+def test_what_if_snapshot_and_restore():
+    """SURVEY 8f-4 what-if queries: snapshot, try a placement plan (frees + allocs), restore — the live state is untouched,
+    and a snapshot does not survive a new inventory."""
+    rows = E.make_profiles(tables.H100_80GB)
+    rng = W.SplitMix64(41)
+    G = 5000
+    node_off = np.concatenate([[0], np.cumsum(np.full((G + 7) // 8, 8))]).astype(np.uint32)
+    node_off[-1] = G
+    occ = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+    eng = E.Engine(max_gpus=1 << 13, max_batch=1 << 18)
+    eng.load_profiles(rows)
+    with pytest.raises(E.EngineError):
+        eng.restore_occupancy()                       # nothing loaded, nothing snapshotted
+    eng.load_inventory(node_off, occ)
+    with pytest.raises(E.EngineError):
+        eng.restore_occupancy()
+    eng.snapshot_occupancy()
+    plan = [W.alloc_requests(W.mix_profiles(rng, n)) for n in (3000, 70000)]
+    first = eng.place_stream(plan)
+    assert not np.array_equal(eng.read_occupancy(), occ)
+    eng.restore_occupancy()
+    assert np.array_equal(eng.read_occupancy(), occ)
+    again = eng.place_stream(plan)                    # the same question gets the same answer
+    assert all(np.array_equal(a, b) for a, b in zip(first, again))
+    eng.load_inventory(node_off, occ)
+    with pytest.raises(E.EngineError):
+        eng.restore_occupancy()
