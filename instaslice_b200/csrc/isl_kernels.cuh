@@ -1170,40 +1170,69 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 wa[k] = wa0[k] + 12;                                            // next entry to load on a pop
             }
             uint32_t la = sa_log, ca = sa_cand + 8;                             // ca: shared address of candidate record (current + 2)
-            uint32_t o0 = lds_u16(sa_cand), o1 = lds_u16(sa_cand + 4), o2 = lds_u16(sa_cand + 8);
+            // Per slot the loop carries conflict words z = occupancy & candidate mask of the current / next / next-but-one candidate GPU
+            // and g = "fits on that GPU ? sel bit : nothing" as a ready OR mask; the key of the NEXT decision is formed at the end of the
+            // body.  Loop-carried path behind the redux: sign mask of `sel` -> bitwise mux of z -> fold the winner's slices in and test
+            // (one LOP3 with a predicate output) -> pick the key: four ALU levels (a freshly updated occupancy register tested through
+            // ISETP / SEL needs five; measured 41 -> 35 ns per decision, and ISETP + SEL behind the redux costs ~10 cycles more than
+            // shift + LOP3 mux: tools/microbench_pred.cu).
+            // The updates are issued unconditionally and the "nothing fits" test comes LAST: a branch is not speculated, so a test in
+            // front of the updates would put its resolution on the loop-carried path of every decision.  m == INF behaves like a decision
+            // that lands on the next GPU and pops only exhausted lanes (no real key has all-ones t / profile fields unless profile 15
+            // is in use, kP15); the rare path rewinds the cursors and reloads the conflict words after the jump.
+            uint32_t z0[K], z1[K], z2[K], g1[K], g2[K], cm8[K];
+            auto reload_z = [&]() {
+                const uint32_t a0 = lds_u16(ca - 8), a1 = lds_u16(ca - 4), a2 = lds_u16(ca);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    z0[k] = a0 & cmask[k]; z1[k] = a1 & cmask[k]; z2[k] = a2 & cmask[k];
+                    g1[k] = z1[k] == 0 ? 0x80000000u : kInf; g2[k] = z2[k] == 0 ? 0x80000000u : kInf;
+                }
+            };
+#pragma unroll
+            for (int k = 0; k < K; ++k) cm8[k] = cmask[k] & 0xFFu;
+            reload_z();
+            uint32_t key = kInf, a2 = lds_u16(ca);
+            auto first_key = [&]() {
+                key = kInf;
+#pragma unroll
+                for (int k = 0; k < K; ++k) key = min(key, z0[k] == 0 ? tcur[k] : (tcur[k] | g1[k]));
+            };
+            first_key();
             const unsigned long long jumps0 = st_jumps;
             stamp_if(tr && lane == 0, tr + 4);
-            // The updates are issued unconditionally and the "nothing fits" test comes LAST: a branch is not speculated, so a test
-            // in front of the updates would put its resolution on the loop-carried path of every decision.  m == INF behaves like
-            // a decision that lands on the next GPU and pops only exhausted lanes (no real key has all-ones t / profile fields unless
-            // profile 15 is in use, kP15); the rare path rewinds the cursors, the occupancy registers are reloaded after the jump anyway.
             while (true) {
                 bool none = false;
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {     // unrolled: one taken branch per kUnroll decisions
-                    uint32_t key = kInf;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const uint32_t kk = (o0 & cmask[k]) == 0 ? tcur[k] : ((o1 & cmask[k]) == 0 ? tcur[k] | 0x80000000u : kInf);
-                        key = min(key, kk);
-                    }
                     const uint32_t m = redux_min_u32(key);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {       // in the shadow of the redux: the record fetched by the previous decision (the same one again if it did not advance)
+                        z2[k] = a2 & cmask[k];
+                        g2[k] = z2[k] == 0 ? 0x80000000u : kInf;
+                    }
                     if (kP15) { none = m == kInf; if (none) break; }
-                    // `sel` as a sign mask and bitwise muxes instead of a predicate and selects: the shift reads the redux result straight
-                    // from its uniform register, no UR -> R move on the loop-carried path (tools/microbench_pred.cu: 48 -> 38 cycles)
-                    uint32_t ks, ot;
+                    uint32_t ks;
                     asm("shr.s32 %0, %1, 31;" : "=r"(ks) : "r"(m));                                            // all ones: landed on the next GPU
                     asm("mad.lo.s32 %0, %1, -4, %0;" : "+r"(ca) : "r"(ks));                                     // ca += sel * 4
                     sts_v2_if(lane == 0, la, m, ca);                    // decision log: (key, address of the record two past the GPU it landed on)
                     la += 8;
-                    asm("lop3.b32 %0, %1, %2, %3, 0xca;" : "=r"(ot) : "r"(ks), "r"(o1), "r"(o0));             // sel ? o1 : o0
-                    o0 = ot | (m & 0xFFu);
-                    asm("lop3.b32 %0, %1, %2, %3, 0xca;" : "=r"(o1) : "r"(ks), "r"(o2), "r"(o1));             // sel ? o2 : o1
-                    o2 = lds_u16(ca);
+                    a2 = lds_u16(ca);
+                    key = kInf;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {       // lanes of the winning profile (same t, same profile) pop their window
+                    for (int k = 0; k < K; ++k) {
                         const bool adv = kP15 ? (((m & 0x7FFFF800u) ^ tcur[k]) & 0xFFFFF800u) == 0 : ((m ^ tcur[k]) & 0x7FFFF800u) == 0;
-                        tcur[k] = adv ? tnext[k] : tcur[k];
+                        const uint32_t tn = adv ? tnext[k] : tcur[k];
+                        uint32_t zs, gn, kk;
+                        asm("lop3.b32 %0, %1, %2, %3, 0xca;" : "=r"(zs) : "r"(ks), "r"(z1[k]), "r"(z0[k]));       // sel ? z1 : z0
+                        asm("lop3.b32 %0, %1, %2, %3, 0xca;" : "=r"(gn) : "r"(ks), "r"(g2[k]), "r"(g1[k]));       // sel ? g2 : g1
+                        asm("{ .reg .pred p; .reg .b32 t; lop3.b32 t, %1, %2, %3, 0xF8; setp.eq.u32 p, t, 0; selp.b32 %0, %4, %5, p; }"
+                            : "=r"(kk) : "r"(zs), "r"(m), "r"(cm8[k]), "r"(tn), "r"(tn | gn));
+                        key = min(key, kk);
+                        z0[k] = zs | (m & cm8[k]);
+                        g1[k] = gn;
+                        asm("lop3.b32 %0, %1, %2, %3, 0xca;" : "=r"(z1[k]) : "r"(ks), "r"(z2[k]), "r"(z1[k]));    // sel ? z2 : z1
+                        tcur[k] = tn;
                         tnext[k] = adv ? (tnn[k] | klow[k]) : tnext[k];
                         tnn[k] = lds_u32_if(adv, wa[k], tnn[k]);        // consumed at the earliest one pop later
                         wa[k] = add_if(adv, wa[k], 4u);
@@ -1212,7 +1241,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                         none = m == kInf;
                         if (__builtin_expect(none, 0)) {
                             ca -= 4; la -= 8;                           // rewind the pseudo-decision
-                            // m == INF matched exactly the exhausted lanes (tcur == INF; their tnext was the second INF sentinel): undo their pop
 #pragma unroll
                             for (int k = 0; k < K; ++k)
                                 if (tcur[k] == kInf) { tnext[k] = kInf; wa[k] -= 4; }
@@ -1221,7 +1249,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     }
                 }
                 if (__builtin_expect(!none, 1)) continue;
-                // neither GPU takes anything: ballot to the next candidate a pending profile fits on
                 uint32_t alive = 0;
 #pragma unroll
                 for (int k = 0; k < K; ++k) alive |= tcur[k] != kInf ? 1u << cprof[k] : 0u;
@@ -1229,7 +1256,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 ++st_jumps;
                 if (j == kInf) break;
                 ca = sa_cand + 4 * (j + 2);
-                o0 = lds_u16(ca - 8); o1 = lds_u16(ca - 4); o2 = lds_u16(ca);
+                reload_z();
+                a2 = lds_u16(ca);
+                first_key();
             }
             const uint32_t nlog = (la - sa_log) >> 3;
             stamp_if(tr && lane == 0, tr + 5);
