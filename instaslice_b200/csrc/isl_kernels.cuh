@@ -881,6 +881,14 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -934,7 +942,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     __shared__ uint8_t s_tab[kSegMax];                                           // table of every local GPU
     __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_wbase[ISL_MAX_PROFILES], s_qbeg[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
     __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_minsize[ISL_MAX_PROFILES], s_usable[kMaxTables], s_plist[ISL_MAX_PROFILES], s_nplist;
-    __shared__ uint32_t s_warp[kPipeThreads / 32], s_ncand, s_nfree, s_nlog, s_src, s_idle;
+    __shared__ uint32_t s_warp[kPipeThreads / 32], s_ncand, s_nfree, s_nlog, s_idle;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     if (seg == a.n_seg) {       // the extra CTA of a host-buffer stream: every chunk all segments have committed goes to the caller's
                                 // (mapped, pinned) result array right away, so the D2H of the results hides behind the rest of the stream
@@ -1064,37 +1072,39 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             if (fb) s_cand[off++] = ((2 * tid + 1) << 16) | table_tag(tb) | ob;
             if (tid == kPipeThreads - 1) { s_ncand = off; s_nfree = nfree; for (uint32_t x = 0; x < 8; ++x) s_cand[off + x] = kInf; }   // sentinels: nothing fits
         }
+        __syncthreads();                    // s_ncand / s_nfree of the sweep are visible to warp 0
         // 3. token of the previous segment
         unsigned long long* tr = a.trace ? a.trace + ((size_t)c * a.n_seg + seg) * kTraceWords : nullptr;
         const size_t tok_chunk = (size_t)c * (a.n_seg + 1);
-        if (tid == 0) {
-            if (tr) tr[0] = globaltimer_ns();
-            uint32_t src = 0;                                       // 0: heads_in / zeros, 1: previous segment, 2: peer inbox, 3: done broadcast
-            if (seg > 0) {
-                const uint32_t* flag = a.tokens + (tok_chunk + seg - 1) * kTokStride + ISL_MAX_PROFILES;
-                const uint32_t* done = a.tokens + (tok_chunk + a.n_seg) * kTokStride + ISL_MAX_PROFILES;
-                while (true) {
-                    if (ld_acquire_gpu(flag) == a.epoch) { src = 1; break; }
-                    if (ld_acquire_gpu(done) == a.epoch) { src = 3; break; }
-                }
-            } else if (a.inbox) {       // first segment of a rank that has a predecessor: the token comes over NVLink
-                const uint32_t* flag = a.inbox + (size_t)c * kTokStride + ISL_MAX_PROFILES;
-                while (ld_acquire_sys(flag) != a.xepoch) { }
-                src = 2;
-            }
-            s_src = src;
-            if (tr) tr[1] = globaltimer_ns();
-        }
+        // Inside a GPU a token is self-validating: every head word carries the call's 15-bit epoch tag above its 17 bits of payload
+        // (heads <= 65 536), so there is no separate flag, no fence on the producer side and no second round trip on this side —
+        // lanes 0..15 of warp 0 each poll their own word of the previous segment's token or of the chunk's 'done' record (whichever
+        // is valid first: when both are, they hold the same heads).  Across GPUs (inbox) the flag + system-scope release stays.
         asm volatile("cp.async.wait_group 0;" ::: "memory");       // my share of the chunk's queues has landed (long ago, as a rule)
-        __syncthreads();
         if (tid < 32) {     // heads, window sizes and the compact window layout (exclusive scan over the 16 profiles)
             uint32_t h = 0, wn = 0, left = 0;
-            const uint32_t src = s_src;
+            bool from_done = false;
+            const uint32_t tag = a.epoch & 0x7FFFu;
+            stamp_if(tr && tid == 0, tr + 0);
+            if (seg > 0) {
+                const uint32_t* pt = a.tokens + (tok_chunk + seg - 1) * kTokStride + (tid & 15u);
+                const uint32_t* pd = a.tokens + (tok_chunk + a.n_seg) * kTokStride + (tid & 15u);
+                bool ok = tid >= ISL_MAX_PROFILES;
+                while (!__all_sync(0xFFFFFFFFu, ok)) {
+                    if (!ok) {
+                        uint32_t v = ld_relaxed_gpu(pt);
+                        if ((v >> 17) == tag) { h = v & 0x1FFFFu; ok = true; }
+                        else { v = ld_relaxed_gpu(pd); if ((v >> 17) == tag) { h = v & 0x1FFFFu; ok = true; from_done = true; } }
+                    }
+                }
+            } else if (a.inbox) {       // first segment of a rank that has a predecessor: the token comes over NVLink
+                if (tid == 0) { const uint32_t* flag = a.inbox + (size_t)c * kTokStride + ISL_MAX_PROFILES; while (ld_acquire_sys(flag) != a.xepoch) { } }
+                __syncwarp();
+                if (tid < ISL_MAX_PROFILES) h = ld_relaxed_sys(a.inbox + (size_t)c * kTokStride + tid);
+            } else if (tid < ISL_MAX_PROFILES) h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
+            stamp_if(tr && tid == 0, tr + 1);
+            const bool all_done = __all_sync(0xFFFFFFFFu, from_done || tid >= ISL_MAX_PROFILES);
             if (tid < ISL_MAX_PROFILES) {
-                if (src == 1) h = __ldcg(a.tokens + (tok_chunk + seg - 1) * kTokStride + tid);
-                else if (src == 3) h = __ldcg(a.tokens + (tok_chunk + a.n_seg) * kTokStride + tid);
-                else if (src == 2) h = ld_relaxed_sys(a.inbox + (size_t)c * kTokStride + tid);
-                else h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
                 const uint32_t qc = cc->qcnt[tid], qo = cc->qoff[tid];
                 left = ((active >> tid) & 1u) && qc > h ? qc - h : 0u;
                 wn = min(left, min(s_ncand * s_maxacc[tid], s_nfree / s_minsize[tid]));   // no more pops than that are possible here
@@ -1103,12 +1113,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             }
             // nothing placeable is pending any more: tell every later segment at once instead of relaying hop by hop
             const bool idle = __ballot_sync(0xFFFFFFFFu, left != 0) == 0;
-            if (idle && src != 3) {
-                uint32_t* done = a.tokens + (tok_chunk + a.n_seg) * kTokStride;
-                if (tid < ISL_MAX_PROFILES) done[tid] = h;
-                __syncwarp();
-                if (tid == 0) { __threadfence(); st_release_gpu(done + ISL_MAX_PROFILES, a.epoch); }
-            }
+            if (idle && !all_done && tid < ISL_MAX_PROFILES) st_relaxed_gpu(a.tokens + (tok_chunk + a.n_seg) * kTokStride + tid, (tag << 17) | h);
             if (tid == 0) s_idle = idle ? 1u : 0u;
             uint32_t incl = wn + 2;                             // two INF sentinels close every window
 #pragma unroll
@@ -1124,14 +1129,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 uint32_t* peer = last && a.outbox ? a.outbox + (size_t)c * kTokStride : nullptr;
                 if (lane < ISL_MAX_PROFILES) {
                     const uint32_t h = s_heads[lane];
-                    tok[lane] = h;
+                    st_relaxed_gpu(tok + lane, ((a.epoch & 0x7FFFu) << 17) | h);
                     if (last && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + lane] = h;
                     if (peer) peer[lane] = h;
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    __threadfence();
-                    st_release_gpu(tok + ISL_MAX_PROFILES, a.epoch);
                     if (peer) { __threadfence_system(); st_release_sys(peer + ISL_MAX_PROFILES, a.xepoch); }
                     if (tr) { tr[2] = globaltimer_ns(); tr[3] = tr[2]; }
                 }
@@ -1274,14 +1277,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             uint32_t* peer = last && a.outbox ? a.outbox + (size_t)c * kTokStride : nullptr;
             if (lane < ISL_MAX_PROFILES) {
                 const uint32_t h = s_heads[lane] + s_pop[lane];
-                tok[lane] = h;
+                st_relaxed_gpu(tok + lane, ((a.epoch & 0x7FFFu) << 17) | h);       // the next segment starts
                 if (last && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + lane] = h;
                 if (peer) peer[lane] = h;
             }
             __syncwarp();
             if (lane == 0) {
-                __threadfence();
-                st_release_gpu(tok + ISL_MAX_PROFILES, a.epoch);
                 if (peer) { __threadfence_system(); st_release_sys(peer + ISL_MAX_PROFILES, a.xepoch); }
                 s_nlog = nlog;
                 if (tr) tr[2] = globaltimer_ns();

@@ -436,7 +436,10 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     ISL_CUDA(e, cudaMemcpyAsync(e->d_chunks, e->h_chunks.data(), n_chunks * sizeof(ChunkDesc), cudaMemcpyHostToDevice, pre));
     ISL_CUDA(e, cudaMemcpyAsync(e->d_tiles, e->h_tiles.data(), n_tiles_total * sizeof(TileDesc), cudaMemcpyHostToDevice, pre));
     ISL_CUDA(e, cudaMemsetAsync(e->d_free_acc, 0, (size_t)n_batches * free_stride, pre));
-    const uint32_t epoch = ++e->epoch;
+    uint32_t epoch = ++e->epoch;
+    if ((epoch & 0x7FFFu) == 0) epoch = ++e->epoch;      // the token words carry the low 15 bits as a tag; tag 0 is what a cleared buffer holds
+    if ((epoch & 0x7FFFu) == 1 && epoch != 1 && e->d_tokens)    // tag wrap-around: no stale word of 32 768 calls ago may look current
+        ISL_CUDA(e, cudaMemsetAsync(e->d_tokens, 0, (size_t)e->cap_tokens * kTokStride * sizeof(uint32_t), e->stream));
     // pre-pass of the tiles [t0, t1): defaults + free masks + histograms, then the stable partition into per-profile queues
     auto prepass = [&](uint32_t t0, uint32_t t1) -> int {
         k_prepare<<<t1 - t0, kTileThreads, 0, pre>>>(0, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi, e->prof,
