@@ -1376,6 +1376,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
             if (m == kInf) { dead |= 1u << p; continue; }      // stays NO_CAPACITY, and so does every later request of the profile
             const uint32_t g = m & 0xFFFFFFu;
             const uint32_t o_win = __shfl_sync(0xFFFFFFFFu, ko, __ffs(__ballot_sync(0xFFFFFFFFu, key == m)) - 1);   // the class IS the occupancy byte
+            __syncwarp();                                       // all lanes have read the class minima before lane 0 rewrites them
             if (lane == 0) {
                 const uint32_t o = o_win;
                 const uint32_t start = s_lut[p * 256 + o], size = prof.rows[p].size;
