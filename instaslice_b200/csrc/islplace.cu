@@ -312,7 +312,8 @@ int grow(isl_engine* e, T** buf, uint32_t* cap, size_t need, size_t elems_per_un
 // by one on a second stream while the pipeline already runs (it waits per batch on a device flag), and an extra CTA copies every
 // finished chunk's results straight into h_out when that is mapped pinned memory (e->delivered) — H2D and D2H hide behind the kernel.
 int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const uint2* d_in, uint2* d_out,
-               const uint32_t* d_heads_in, uint32_t* d_heads_out, uint32_t xepoch = 0, const uint2* h_in = nullptr, uint2* h_out = nullptr) {
+               const uint32_t* d_heads_in, uint32_t* d_heads_out, uint32_t xepoch = 0, const uint2* h_in = nullptr, uint2* h_out = nullptr,
+               bool mixed_single_chunk = false) {
     e->delivered = false;
     uint64_t total = 0;
     uint32_t n_chunks = 0;
@@ -332,7 +333,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     }
     if (e->cfg.policy == ISL_POLICY_BEST_FIT && (d_heads_in || d_heads_out || xepoch)) return ISL_EINVAL;   // best-fit does not partition
     const bool legacy_token = d_heads_in || d_heads_out || e->cfg.policy == ISL_POLICY_BEST_FIT;   // isl_place_batch_partitioned: host-carried token, kChunk layout
-    bool pipeline = ring || (!legacy_token && !(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE)));
+    bool pipeline = ring || (!legacy_token && !(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || mixed_single_chunk || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE)));
     // the stream path keeps one free-mask byte per GPU and batch: very long streams over large inventories go batch by batch
     if (pipeline && (uint64_t)n_batches * e->occ_bytes > (256ull << 20)) { if (ring) return ISL_ERANGE; pipeline = false; }
     // feed mode (below): host buffers, more than one batch, no timing / tracing of the phases, no kernel-serialising tool around
@@ -830,7 +831,17 @@ int isl_place_batch(isl_engine* e, uint32_t n, const isl_request* in, isl_result
         return ISL_OK;
     }
     ISL_CUDA(e, cudaMemcpyAsync(e->d_req, in, (size_t)n * sizeof(isl_request), cudaMemcpyHostToDevice, e->stream));
-    if (int rc = run_stream(e, 1, &n, e->d_req, e->d_res, nullptr, nullptr)) return rc;
+    // One large batch that mixes profiles: the segment pipeline's decision loop (35 ns per decision, one launch for the chain of all
+    // segments) beats the single-chain path (~110 ns) although nothing overlaps inside one chunk.  A batch with a single placeable
+    // profile stays on the single-chain path, whose scan mode commits it without any chain.  (The buffer is on the host: a look at
+    // the profile bytes costs microseconds.)
+    bool mixed = false;
+    if (n >= 4096) {
+        uint32_t seen = 0;
+        for (uint32_t i = 0; i < n && !mixed; ++i)
+            if (in[i].op == ISL_OP_ALLOC && in[i].profile < ISL_MAX_PROFILES) { seen |= (1u << in[i].profile) & e->cand_profiles; mixed = (seen & (seen - 1)) != 0; }
+    }
+    if (int rc = run_stream(e, 1, &n, e->d_req, e->d_res, nullptr, nullptr, 0, nullptr, nullptr, mixed)) return rc;
     ISL_CUDA(e, cudaMemcpyAsync(out, e->d_res, (size_t)n * sizeof(isl_result), cudaMemcpyDeviceToHost, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     return ISL_OK;
