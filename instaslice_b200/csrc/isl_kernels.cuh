@@ -849,7 +849,7 @@ struct PipeArgs {
 
 constexpr uint32_t kTraceWords = 12;
 #ifndef ISL_UNROLL
-#define ISL_UNROLL 4
+#define ISL_UNROLL 8
 #endif
 constexpr int kUnroll = ISL_UNROLL;          // decisions per trip of the decision loop
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
