@@ -801,7 +801,11 @@ __global__ void __launch_bounds__(256) k_commit(const Ctrl* __restrict__ ctrl, c
 // Results are bit-identical to resolving the batches one after the other.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kSegMax = 512;                   // GPUs per segment (2 per thread in the local sweep)
-constexpr uint32_t kPipeThreads = 256;
+#ifndef ISL_PIPE_THREADS
+#define ISL_PIPE_THREADS 256
+#endif
+constexpr uint32_t kPipeThreads = ISL_PIPE_THREADS;     // 1 or 2 GPUs per thread in the local sweep
+static_assert(kPipeThreads == kSegMax || 2 * kPipeThreads == kSegMax, "sweep layout");
 constexpr uint32_t kLogCap = 8 * kSegMax;           // a GPU accepts at most 8 placements
 constexpr uint32_t kTokStride = 32;                 // uint32 per token: heads[16], flag at [16]
 // shared memory: occupancy bytes | candidate records (+8 sentinels) | decision log (+1 pseudo-decision) | the chunk's queues (uint16) | queue-window keys
@@ -1051,14 +1055,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             __syncthreads();
         }
         const uint32_t active = cc->active;
-        {   // 2. local sweep: thread t owns local GPUs 2t and 2t+1; ordered compaction
-            const uint32_t w = reinterpret_cast<uint16_t*>(s_occ32)[tid];
-            const uint32_t oa = w & 0xFFu, ob = w >> 8;
-            const uint32_t ta = s_tab[2 * tid], tb = s_tab[2 * tid + 1];
-            const bool fa = 2 * tid < n_g && (s_feas[ta * 256 + oa] & active), fb = 2 * tid + 1 < n_g && (s_feas[tb * 256 + ob] & active);
+        {   // 2. local sweep: thread t owns kSegMax / kPipeThreads consecutive local GPUs; ordered compaction
+            constexpr uint32_t kGpt = kSegMax / kPipeThreads;
+            uint32_t og[kGpt], tg[kGpt];
+            bool fg[kGpt];
             // one scan carries both counts: candidates (low half) and free usable slices on the candidates (high half) — the latter
             // bounds what the segment can accept: a profile of span z pops at most free / z requests here
-            const uint32_t cnt = ((fa ? 1u : 0u) + (fb ? 1u : 0u)) | (((fa ? __popc(~oa & s_usable[ta]) : 0u) + (fb ? __popc(~ob & s_usable[tb]) : 0u)) << 16);
+            uint32_t cnt = 0;
+#pragma unroll
+            for (uint32_t x = 0; x < kGpt; ++x) {
+                const uint32_t g = kGpt * tid + x;
+                og[x] = reinterpret_cast<const uint8_t*>(s_occ32)[g]; tg[x] = s_tab[g];
+                fg[x] = g < n_g && (s_feas[tg[x] * 256 + og[x]] & active);
+                if (fg[x]) cnt += 1u | ((uint32_t)__popc(~og[x] & s_usable[tg[x]]) << 16);
+            }
             uint32_t incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
@@ -1068,8 +1078,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             for (uint32_t x = 0; x < warp; ++x) off += s_warp[x];
             const uint32_t nfree = (off + cnt) >> 16;
             off &= 0xFFFFu;
-            if (fa) s_cand[off++] = ((2 * tid) << 16) | table_tag(ta) | oa;
-            if (fb) s_cand[off++] = ((2 * tid + 1) << 16) | table_tag(tb) | ob;
+#pragma unroll
+            for (uint32_t x = 0; x < kGpt; ++x) if (fg[x]) s_cand[off++] = ((kGpt * tid + x) << 16) | table_tag(tg[x]) | og[x];
             if (tid == kPipeThreads - 1) { s_ncand = off; s_nfree = nfree; for (uint32_t x = 0; x < 8; ++x) s_cand[off + x] = kInf; }   // sentinels: nothing fits
         }
         __syncthreads();                    // s_ncand / s_nfree of the sweep are visible to warp 0
