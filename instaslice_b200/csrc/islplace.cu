@@ -581,6 +581,18 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
 #define ISL_TRY(call) do { if ((call) != cudaSuccess) { return fail(ISL_ECUDA); } } while (0)
     ISL_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->own_stream = true;
+    {   // Load every kernel NOW.  With CUDA's lazy module loading the first launch of a kernel loads it, and that load can wait for the
+        // device to drain — a fed host stream launches k_prepare / k_partition / k_set_flag for batch b WHILE the pipeline kernel is
+        // spinning on ready[b]: a first-ever launch at that moment deadlocks (seen as the 20 s trap of a process whose first call was a
+        // stream with an empty first batch).
+        cudaFuncAttributes fa;
+        const void* kernels[] = {(const void*)k_prepare, (const void*)k_partition, (const void*)k_set_flag, (const void*)k_build_lut, (const void*)k_eval_starts,
+                                 (const void*)k_free_spans, (const void*)k_sweep_count, (const void*)k_sweep_scatter, (const void*)k_commit, (const void*)k_bestfit,
+                                 (const void*)k_chain<1>, (const void*)k_chain<2>, (const void*)k_chain<4>, (const void*)k_small<1>, (const void*)k_small<2>, (const void*)k_small<4>,
+                                 (const void*)k_pipeline<1, false>, (const void*)k_pipeline<1, true>, (const void*)k_pipeline<2, false>, (const void*)k_pipeline<2, true>,
+                                 (const void*)k_pipeline<4, false>, (const void*)k_pipeline<4, true>};
+        for (const void* k : kernels) ISL_TRY(cudaFuncGetAttributes(&fa, k));
+    }
     e->occ_bytes = ((size_t)cfg->max_gpus + kSweepBlock - 1) / kSweepBlock * kSweepBlock;
     const uint32_t max_tiles = ceil_div(cfg->max_batch, kTile) + 4096;   // + one partial tile per batch of a stream
     ISL_TRY(cudaMalloc(&e->d_occ, e->occ_bytes));

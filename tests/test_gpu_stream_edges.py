@@ -141,3 +141,39 @@ def test_what_if_snapshot_and_restore():
     eng.load_inventory(node_off, occ)
     with pytest.raises(E.EngineError):
         eng.restore_occupancy()
+
+
+def test_token_tag_wraps_after_32768_stream_calls():
+    """The token words of the segment pipeline carry the low 15 bits of the call epoch as their validity tag.  33 000 stream calls on one
+    engine cross the wrap-around (tag 0 is skipped, stale tags of 32 768 calls ago are cleared): every call must answer like the first."""
+    rows = E.make_profiles(tables.H100_80GB)
+    G = 1024                                   # two segments: tokens really travel
+    node_off = np.concatenate([[0], np.cumsum(np.full(G // 8, 8))]).astype(np.uint32)
+    rng = W.SplitMix64(51)
+    occ = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+    eng = E.Engine(max_gpus=G, max_batch=1 << 12, flags=E.FLAG_FORCE_PIPELINE)
+    eng.load_profiles(rows)
+    eng.load_inventory(node_off, occ)
+    b1 = W.alloc_requests(np.array([0, 2, 3, 0, 1, 4], dtype=np.uint8))
+    first = eng.place_stream([b1, b1[:1]])
+    placed = np.concatenate(first)
+    placed = placed[placed["status"] == E.ST_PLACED]
+    undo = np.zeros(len(placed), dtype=E.REQUEST_DTYPE)
+    undo["handle"], undo["op"], undo["start"], undo["size"] = placed["gpu"], E.OP_FREE, placed["start"], placed["size"]
+    ref = oracle.Fast(node_off, rows)
+    ref.load(occ)
+    assert np.array_equal(first[0], ref.place(b1))
+    eng.place_stream([undo, undo[:0]])            # back to the loaded occupancy
+    assert np.array_equal(eng.read_occupancy(), occ)
+    sizes = np.array([len(b1), 1, len(undo)], dtype=np.uint32)
+    req = np.concatenate([b1, b1[:1], undo])
+    out = np.empty(len(req), dtype=E.RESULT_DTYPE)
+    want = None
+    for call in range(33000):
+        eng.place_stream_ptr(sizes, req.ctypes.data, out.ctypes.data, device=False)
+        if want is None:
+            want = out.copy()
+            assert np.array_equal(want[:len(b1)], first[0]) and np.array_equal(want[len(b1):len(b1) + 1], first[1])
+        elif not np.array_equal(out, want):
+            raise AssertionError("call %d differs" % call)
+    assert np.array_equal(eng.read_occupancy(), occ)
