@@ -349,7 +349,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         const uint32_t seg_cap = max_segment_for(total_cand);      // queue windows of a segment must fit in shared memory
         // Segments aimed for.  A batch's decisions form ONE sequential chain over the inventory, only different chunks overlap, so a
         // stream of B chunks over S stages takes about (S + B - 1) x (D x t_dec / S + t_fix), D = decisions of a chunk (tools/chain_cost.py:
-        // t_dec 41 ns, t_fix ~2.3 us per busy cell).  The minimum is at S = sqrt((B - 1) x D x t_dec / t_fix); D is estimated by the
+        // t_dec 35-41 ns, t_fix 1.6-2.3 us per busy cell over the round: ratio ~0.018 / us).  Minimum at S = sqrt((B - 1) x D x t_dec / t_fix); D is estimated by the
         // smaller of the chunk size and ~3.5 placements per GPU.  ISL_PIPE_SEGMENTS overrides (experiments).
         uint32_t target = 148;
         {

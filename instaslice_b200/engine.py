@@ -248,7 +248,8 @@ class Engine:
         return out
 
     def place_stream(self, batches: list) -> list:
-        """A stream of batches in one call (host buffers); same results as place_batch per batch, pipelined on the device."""
+        """A stream of batches in one call (host buffers); same results as place_batch per batch, pipelined on the device.
+        (numpy arrays are pageable: the H2D / D2H overlap of isl_place_stream needs pinned buffers, see place_stream_ptr.)"""
         sizes = np.array([len(b) for b in batches], dtype=np.uint32)
         req = np.ascontiguousarray(np.concatenate(batches) if len(batches) else np.zeros(0, dtype=REQUEST_DTYPE), dtype=REQUEST_DTYPE)
         out = np.empty(len(req), dtype=RESULT_DTYPE)
