@@ -791,13 +791,18 @@ __global__ void __launch_bounds__(256) k_commit(const Ctrl* __restrict__ ctrl, c
 //   * inside a segment everything happens in stream order: allocs of chunk c, then the frees of the
 //     next batch, then its allocs (occupancy of the segment lives in this CTA's shared memory), and
 //   * the only state that crosses a segment boundary is the per-profile queue-head token (16 counters).
-// One persistent CTA per segment (cooperative launch, all co-resident).  Per chunk a CTA
+// One persistent CTA per segment (cooperative launch, all co-resident; one CTA fills an SM's shared memory).  Per chunk a CTA
+//   0. has the chunk's queues (uint16 request indices) copied into shared memory by cp.async, issued when the previous
+//      chunk's chain ended: they do not depend on the token
 //   1. applies the batch's frees that fall into its range                      (all threads)
 //   2. sweeps its occupancy bytes into an ordered candidate list               (all threads, before the token arrives)
-//   3. waits for the token of segment s-1 (global flag, acquire), stages the queue windows it may pop
-//   4. runs the decision chain of k_chain on its candidates                    (warp 0)
-//   5. publishes the token for segment s+1 (release) and only then
+//   3. waits for the token of segment s-1 (self-validating words: epoch tag + head, polled by 16 lanes), converts the queue
+//      windows it may pop into ready-made 32-bit keys (shared -> shared)
+//   4. runs the decision chain on its candidates                               (warp 0)
+//   5. publishes the token for segment s+1 and only then
 //   6. commits the logged decisions: result records + occupancy bits           (all threads)
+// Host-buffer streams: the batches are fed by a second stream while this kernel runs (ready flags), an extra CTA delivers
+// finished chunks into the caller's pinned result array (done counters).
 // Results are bit-identical to resolving the batches one after the other.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kSegMax = 512;                   // GPUs per segment (2 per thread in the local sweep)
@@ -807,7 +812,7 @@ constexpr uint32_t kSegMax = 512;                   // GPUs per segment (2 per t
 constexpr uint32_t kPipeThreads = ISL_PIPE_THREADS;     // 1 or 2 GPUs per thread in the local sweep
 static_assert(kPipeThreads == kSegMax || 2 * kPipeThreads == kSegMax, "sweep layout");
 constexpr uint32_t kLogCap = 8 * kSegMax;           // a GPU accepts at most 8 placements
-constexpr uint32_t kTokStride = 32;                 // uint32 per token: heads[16], flag at [16]
+constexpr uint32_t kTokStride = 32;                 // uint32 per token: 16 tagged head words inside a GPU; raw heads[16] + flag at [16] across GPUs
 // shared memory: occupancy bytes | candidate records (+8 sentinels) | decision log (+1 pseudo-decision) | the chunk's queues (uint16) | queue-window keys
 constexpr uint32_t kPipeOffCand = kSegMax;
 constexpr uint32_t kPipeOffLog = kPipeOffCand + 4 * (kSegMax + 8);
@@ -832,7 +837,7 @@ struct PipeArgs {
     const uint16_t* q_all;          // per chunk queues, stride q_stride entries
     const uint8_t* free_acc;        // per batch one byte per GPU: OR of the slot masks its FREEs release (stride free_stride bytes)
     uint32_t q_stride, free_stride;
-    uint32_t* tokens;               // [chunk][segment + 1][kTokStride]; slot n_seg = 'everything placeable is placed' broadcast
+    uint32_t* tokens;               // [chunk][segment + 1][kTokStride] of (epoch tag << 17 | head); slot n_seg = 'everything placeable is placed' broadcast
     uint8_t* occ;
     const uint8_t* gtab;            // table id of every GPU's node
     uint2* out;
@@ -912,10 +917,6 @@ __device__ __forceinline__ uint32_t redux_min_u32(uint32_t v) {
     uint32_t r;
     asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
     return r;
-}
-__device__ __forceinline__ uint32_t lds_u16_if(bool pred, uint32_t sa, uint32_t keep) {   // predicated load: keeps `keep` when !pred
-    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p ld.shared.u16 %0, [%2]; }" : "+r"(keep) : "r"((uint32_t)pred), "r"(sa));
-    return keep;
 }
 __device__ __forceinline__ uint32_t lds_u32_if(bool pred, uint32_t sa, uint32_t keep) {   // predicated load: keeps `keep` when !pred
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p ld.shared.u32 %0, [%2]; }" : "+r"(keep) : "r"((uint32_t)pred), "r"(sa));
