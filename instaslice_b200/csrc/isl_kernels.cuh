@@ -768,6 +768,82 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(CandTab tab, DevProf
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_few: the latency path of a reconciler that hands over one or two pods at a time (BASELINE configs 1 and 5): at most
+// kFewMax requests, an inventory range of at most kFewGpus GPUs, first-fit.  Request-major on purpose — with a handful of
+// requests there is nothing to amortise a partition / sweep / chain over: ONE CTA holds 16 occupancy bytes per thread in
+// registers, the first-start tables in shared memory, and for every ALLOC in order finds the first feasible GPU with a
+// block-wide min (redux + one shared-memory hop) — exactly the reference's scan order (:240-262, :303-384).  Requests travel as
+// kernel parameters, results go straight to mapped pinned host memory: one launch, one stream synchronisation.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kFewThreads = 1024;
+constexpr uint32_t kFewMax = 8;
+constexpr uint32_t kFewGpus = kFewThreads * 16;
+
+__global__ void __launch_bounds__(kFewThreads, 1) k_few(DevProfiles prof, uint32_t n, SmallReqs inl, uint2* __restrict__ out, uint8_t* __restrict__ occ,
+                                                         const uint8_t* __restrict__ gtab, const uint8_t* __restrict__ lut, const uint8_t* __restrict__ sizes,
+                                                         uint32_t n_tables, uint32_t G, uint32_t lo, uint32_t hi, Ctrl* stats) {
+    __shared__ __align__(16) uint8_t s_lut[kMaxTables * ISL_MAX_PROFILES * 256];
+    __shared__ uint8_t s_sizes[kMaxTables * ISL_MAX_PROFILES];
+    __shared__ uint32_t s_red[32], s_win;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t* occ32 = reinterpret_cast<uint32_t*>(occ);
+    for (uint32_t i = tid; i < n_tables * ISL_MAX_PROFILES * 64; i += kFewThreads) reinterpret_cast<uint32_t*>(s_lut)[i] = reinterpret_cast<const uint32_t*>(lut)[i];
+    if (tid < n_tables * ISL_MAX_PROFILES) s_sizes[tid] = sizes[tid];
+    uint32_t freed = 0, allocs = 0;
+    if (tid < n) {          // defaults and FREEs, one request per thread (as k_prepare / k_small phase A)
+        const uint2 rq = inl.r[tid];
+        const uint32_t handle = rq.x, profile = rq.y & 0xFFu, op = (rq.y >> 8) & 0xFFu, start = (rq.y >> 16) & 0xFFu, size = rq.y >> 24;
+        if (op == ISL_OP_ALLOC) {
+            if (profile < prof.n) { out[tid] = pack_result(ISL_GPU_NONE, ISL_START_NONE, prof.rows[profile].size, ISL_ST_NO_CAPACITY); allocs = 1; }
+            else out[tid] = pack_result(ISL_GPU_NONE, ISL_START_NONE, 0, ISL_ST_BAD_PROFILE);
+        } else if (op == ISL_OP_FREE) {
+            if (handle >= G || size == 0 || start + size > ISL_SLOTS) out[tid] = pack_result(handle, start, size, ISL_ST_BAD_SPAN);
+            else {
+                if (handle >= lo && handle < hi) { atomicAnd(&occ32[handle >> 2], ~((((1u << size) - 1u) << start) << ((handle & 3u) * 8u))); freed = 1; }
+                out[tid] = pack_result(handle, start, size, ISL_ST_FREED);
+            }
+        } else out[tid] = pack_result(ISL_GPU_NONE, ISL_START_NONE, 0, ISL_ST_NOOP);
+    }
+    __threadfence();                        // the frees must be visible to the loads below
+    __syncthreads();
+    // 16 GPUs per thread, aligned to 16: the byte of a GPU outside [lo, hi) reads as full
+    const uint32_t g0 = (lo & ~15u) + tid * 16u;
+    uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u), tv = make_uint4(0, 0, 0, 0);
+    if (g0 < hi) { v = __ldcg(reinterpret_cast<const uint4*>(occ) + (g0 >> 4)); if (n_tables > 1) tv = __ldcg(reinterpret_cast<const uint4*>(gtab) + (g0 >> 4)); }
+    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t twv[4] = {tv.x, tv.y, tv.z, tv.w};
+    for (uint32_t r = 0; r < n; ++r) {      // the ALLOCs strictly in request order, each seeing all earlier commits
+        const uint32_t w = inl.r[r].y, p = w & 0xFFu, op = (w >> 8) & 0xFFu;
+        if (op != ISL_OP_ALLOC || p >= prof.n) continue;        // uniform
+        uint32_t best = kInf;
+#pragma unroll
+        for (int j = 15; j >= 0; --j) {     // descending, so the lowest feasible GPU of the thread is what remains
+            const uint32_t g = g0 + j, o = (wv[j >> 2] >> ((j & 3) * 8)) & 0xFFu, t = (twv[j >> 2] >> ((j & 3) * 8)) & (kMaxTables - 1);
+            if (g >= lo && g < hi && s_lut[(t * ISL_MAX_PROFILES + p) * 256 + o] != ISL_START_NONE) best = g;
+        }
+        const uint32_t wm = __reduce_min_sync(0xFFFFFFFFu, best);
+        if (lane == 0) s_red[warp] = wm;
+        __syncthreads();
+        if (warp == 0) { const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, s_red[lane]); if (lane == 0) s_win = m; }
+        __syncthreads();
+        const uint32_t g = s_win;
+        if (g != kInf && g >= g0 && g < g0 + 16u) {             // the owner commits
+            const uint32_t j = g - g0, sh = (j & 3u) * 8u, o = (wv[j >> 2] >> sh) & 0xFFu, t = (twv[j >> 2] >> sh) & (kMaxTables - 1);
+            const uint32_t st = s_lut[(t * ISL_MAX_PROFILES + p) * 256 + o], size = s_sizes[t * ISL_MAX_PROFILES + p];
+            const uint32_t o2 = o | ((((1u << size) - 1u) << st) & 0xFFu);
+            wv[j >> 2] = (wv[j >> 2] & ~(0xFFu << sh)) | (o2 << sh);
+            occ[g] = (uint8_t)o2;
+            out[r] = pack_result(g, st, size, ISL_ST_PLACED);
+            atomicAdd(&stats->placed, 1ull); atomicAdd(&stats->steps, 1ull);
+        }
+        // s_red / s_win are rewritten only after the next request's first barrier has been passed by everybody who read them
+    }
+    // statistics (off the caller's critical path: the results are already on their way)
+    if (freed) atomicAdd(&stats->freed, 1ull);
+    if (allocs) atomicAdd(&stats->allocs, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_commit: one thread per logged decision.  Writes the result record of the request (the fields of
 // AllocationDetails the allocator decides) and ORs the slot mask into the packed occupancy word.
 // Distinct decisions on one GPU have disjoint masks (the chain only accepts free masks): no double

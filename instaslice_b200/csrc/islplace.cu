@@ -167,6 +167,17 @@ int run_small(isl_engine* e, uint32_t n, const uint2* d_in, const SmallReqs* inl
     return ISL_OK;
 }
 
+// The shortest path: <= kFewMax requests against <= kFewGpus GPUs (k_few).  Requests as kernel parameters, results into mapped pinned memory.
+bool few_eligible(const isl_engine* e, uint32_t n) {
+    return n <= kFewMax && small_eligible(e, n) && e->hi - (e->lo & ~15u) <= kFewGpus && !getenv("ISL_NO_FEW");
+}
+int run_few(isl_engine* e, uint32_t n, const SmallReqs& inl, uint2* d_out) {
+    k_few<<<1, kFewThreads, 0, e->stream>>>(e->prof, n, inl, d_out, e->d_occ, e->d_gtab, e->d_lut, e->d_sizes, e->n_tables, e->G, e->lo, e->hi, e->d_ctrl);
+    if (int rc = check_launch(e, "k_few")) return rc;
+    ++e->st.batches; e->st.requests += n;
+    return ISL_OK;
+}
+
 // ISL_POLICY_BEST_FIT: frees + defaults, then the request-major class-bitmap kernel (one CTA).
 int run_bestfit(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out) {
     if (n == 0) return ISL_OK;
@@ -586,7 +597,7 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
         // spinning on ready[b]: a first-ever launch at that moment deadlocks (seen as the 20 s trap of a process whose first call was a
         // stream with an empty first batch).
         cudaFuncAttributes fa;
-        const void* kernels[] = {(const void*)k_prepare, (const void*)k_partition, (const void*)k_set_flag, (const void*)k_build_lut, (const void*)k_eval_starts,
+        const void* kernels[] = {(const void*)k_prepare, (const void*)k_partition, (const void*)k_set_flag, (const void*)k_few, (const void*)k_build_lut, (const void*)k_eval_starts,
                                  (const void*)k_free_spans, (const void*)k_sweep_count, (const void*)k_sweep_scatter, (const void*)k_commit, (const void*)k_bestfit,
                                  (const void*)k_chain<1>, (const void*)k_chain<2>, (const void*)k_chain<4>, (const void*)k_small<1>, (const void*)k_small<2>, (const void*)k_small<4>,
                                  (const void*)k_pipeline<1, false>, (const void*)k_pipeline<1, true>, (const void*)k_pipeline<2, false>, (const void*)k_pipeline<2, true>,
@@ -837,7 +848,7 @@ int isl_place_batch(isl_engine* e, uint32_t n, const isl_request* in, isl_result
     if (n <= kSmallInline && small_eligible(e, n)) {        // requests as kernel parameters, results into mapped pinned memory: 1 launch + 1 sync
         SmallReqs inl{};
         memcpy(inl.r, in, (size_t)n * sizeof(isl_request));
-        if (int rc = run_small(e, n, nullptr, &inl, e->d_small_out)) return rc;
+        if (int rc = few_eligible(e, n) ? run_few(e, n, inl, e->d_small_out) : run_small(e, n, nullptr, &inl, e->d_small_out)) return rc;
         ISL_CUDA(e, cudaStreamSynchronize(e->stream));
         memcpy(out, e->h_small_out, (size_t)n * sizeof(isl_result));
         return ISL_OK;
