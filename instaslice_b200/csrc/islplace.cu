@@ -172,8 +172,16 @@ bool few_eligible(const isl_engine* e, uint32_t n) {
     return n <= kFewMax && small_eligible(e, n) && e->hi - (e->lo & ~15u) <= kFewGpus && !getenv("ISL_NO_FEW");
 }
 int run_few(isl_engine* e, uint32_t n, const SmallReqs& inl, uint2* d_out) {
+    const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
+    if (timing) cudaEventRecord(e->ev[0], e->stream);
     k_few<<<1, kFewThreads, 0, e->stream>>>(e->prof, n, inl, d_out, e->d_occ, e->d_gtab, e->d_lut, e->d_sizes, e->n_tables, e->G, e->lo, e->hi, e->d_ctrl);
     if (int rc = check_launch(e, "k_few")) return rc;
+    if (timing) {
+        cudaEventRecord(e->ev[1], e->stream);
+        cudaEventSynchronize(e->ev[1]);
+        float t;
+        cudaEventElapsedTime(&t, e->ev[0], e->ev[1]); e->st.ms_commit += t; e->st.ms_total += t;
+    }
     ++e->st.batches; e->st.requests += n;
     return ISL_OK;
 }
