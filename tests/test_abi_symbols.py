@@ -47,3 +47,28 @@ def test_argument_validation_without_gpu():
     assert lib.isl_create(ctypes.byref(bad), ctypes.byref(h)) == E.EINVAL
     assert lib.isl_destroy(None) == E.EINVAL
     assert lib.isl_num_gpus(None) == 0
+
+
+def test_header_is_plain_c99(tmp_path):
+    """What cgo includes must be C, not C++: the header alone compiles with gcc -std=c99 -pedantic."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        import pytest
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include "islplace.h"\nint main(void) { isl_config c; isl_request r; isl_result s; (void)c; (void)r; (void)s; return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o",
+                    str(tmp_path / "t.o")], check=True)
+
+
+def test_no_gpu_means_error_not_fallback():
+    """Without a GPU isl_create fails with ISL_ECUDA — there is no CPU path behind the ABI."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    lib = E.load_library()
+    h = ctypes.c_void_p()
+    ok = E.Config(E.ABI_VERSION, 0, 3, -1, 16, 16, 0, 0)
+    assert lib.isl_create(ctypes.byref(ok), ctypes.byref(h)) == E.ECUDA
