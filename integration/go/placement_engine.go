@@ -11,9 +11,12 @@ package controller
 
 /*
 #cgo CFLAGS: -I${SRCDIR}/../../include
-#cgo LDFLAGS: -lislplace
+#cgo LDFLAGS: -lislplace -lcudart
 #include <stdlib.h>
+#include <cuda_runtime_api.h>
 #include "islplace.h"
+static void* isl_pinned(size_t n) { void* p = 0; return cudaHostAlloc(&p, n, cudaHostAllocDefault) == cudaSuccess ? p : 0; }
+static void  isl_unpin(void* p)   { cudaFreeHost(p); }
 */
 import "C"
 
@@ -263,4 +266,82 @@ func (r *InstasliceReconciler) PlacePending(e *PlacementEngine, list *inferencev
 func (e *PlacementEngine) Release(gpuIndex uint32, start, size uint8) {
 	span := C.isl_span{gpu: C.uint32_t(gpuIndex), start: C.uint8_t(start), size: C.uint8_t(size)}
 	C.isl_free_batch(e.h, 1, &span)
+}
+
+// PlaceBacklog resolves several ordered batches (e.g. per-namespace queues drained in turn) with ONE isl_place_stream
+// call: identical answers to PlacePending batch after batch, pipelined on the device.  The request / result arrays are
+// pinned (cudaHostAlloc through the tiny C helper below, or cudaHostRegister on C.malloc'ed arrays kept for the life of
+// the controller): the engine then copies batch b while it already places batch b-1 and writes finished chunks straight
+// into `res`.  Pageable arrays work as well, without that overlap.
+//
+//   // in the cgo preamble:
+//   //   #include <cuda_runtime_api.h>
+//   //   static void* isl_pinned(size_t n) { void* p = 0; return cudaHostAlloc(&p, n, cudaHostAllocDefault) == cudaSuccess ? p : 0; }
+//   //   static void  isl_unpin(void* p)   { cudaFreeHost(p); }
+func (r *InstasliceReconciler) PlaceBacklog(e *PlacementEngine, list *inferencev1alpha1.InstasliceList, policy AllocationPolicy,
+	batches [][]PendingPod) ([][]*inferencev1alpha1.AllocationDetails, error) {
+	total := 0
+	sizes := make([]C.uint32_t, len(batches))
+	for b, pods := range batches {
+		sizes[b] = C.uint32_t(len(pods))
+		total += len(pods)
+	}
+	out := make([][]*inferencev1alpha1.AllocationDetails, len(batches))
+	if total == 0 || e.orphans { // the exact-match veto (:198-203) needs one pod at a time: fall back to PlacePending
+		for b, pods := range batches {
+			one, err := r.PlacePending(e, list, policy, pods)
+			if err != nil {
+				return nil, err
+			}
+			out[b] = one
+		}
+		return out, nil
+	}
+	req := (*[1 << 28]C.isl_request)(C.isl_pinned(C.size_t(total) * C.sizeof_isl_request))[:total:total]
+	res := (*[1 << 28]C.isl_result)(C.isl_pinned(C.size_t(total) * C.sizeof_isl_result))[:total:total]
+	defer C.isl_unpin(unsafe.Pointer(&req[0]))
+	defer C.isl_unpin(unsafe.Pointer(&res[0]))
+	i := 0
+	for _, pods := range batches {
+		for _, p := range pods {
+			row, ok := e.profiles[p.ProfileName]
+			if !ok {
+				row = C.ISL_PROFILE_UNKNOWN
+			}
+			req[i] = C.isl_request{handle: C.uint32_t(i), profile: C.uint8_t(row), op: C.ISL_OP_ALLOC}
+			i++
+		}
+	}
+	if rc := C.isl_place_stream(e.h, C.uint32_t(len(batches)), &sizes[0], &req[0], &res[0]); rc != C.ISL_OK {
+		return nil, fmt.Errorf("isl_place_stream: %s (%s)", C.GoString(C.isl_strerror(rc)), C.GoString(C.isl_last_cuda_error(e.h)))
+	}
+	i = 0
+	for b, pods := range batches {
+		out[b] = make([]*inferencev1alpha1.AllocationDetails, len(pods))
+		for k, p := range pods {
+			if res[i].status == C.ISL_ST_PLACED {
+				gpu := int(res[i].gpu)
+				is := &list.Items[e.gpuNode[gpu]]
+				size, gi, ci, cieng := r.extractGpuProfile(is, p.ProfileName) // :283-300, unchanged
+				out[b][k] = policy.SetAllocationDetails(p.ProfileName, uint32(res[i].start), uint32(size), string(p.Pod.UID), is.Name, "creating",
+					gi, ci, cieng, p.Pod.Namespace, p.Pod.Name, e.gpuUUID[gpu]) // :254-256, unchanged
+			}
+			i++
+		}
+	}
+	return out, nil
+}
+
+// WhatIf runs `plan` against a device-side snapshot of the occupancy and puts the snapshot back: defragmentation planning
+// ("would these pods fit if those slices were released?") without touching the live state (isl_snapshot_occupancy /
+// isl_restore_occupancy: a 1-byte-per-GPU device copy).
+func (e *PlacementEngine) WhatIf(plan func() error) error {
+	if rc := C.isl_snapshot_occupancy(e.h); rc != C.ISL_OK {
+		return fmt.Errorf("isl_snapshot_occupancy: %s", C.GoString(C.isl_strerror(rc)))
+	}
+	err := plan()
+	if rc := C.isl_restore_occupancy(e.h); rc != C.ISL_OK && err == nil {
+		err = fmt.Errorf("isl_restore_occupancy: %s", C.GoString(C.isl_strerror(rc)))
+	}
+	return err
 }
