@@ -1,30 +1,44 @@
 #!/usr/bin/env python
-"""bench.py — MIG placements/s on BASELINE config 4 (1M ops x 65 536 GPUs, 50/50 alloc/free churn).
+"""bench.py — MIG placement decisions/s of the B200 placement engine on the BASELINE configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--config c4] [--gpus N] [--steps K] [--warmup W] [--impl reference] [--min-age A]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over the whole recorded workload: the inventory is reset to the
-pre-filled state (64 KiB device copy, inside the timed region) and the 16 recorded batches (15 x 65 536 +
-1 x 16 960 operations) are resolved in order.  The recording itself (which allocation each FREE names depends
-on earlier placements) is made once, untimed, by running the generator through the engine.
+--config (default c4, the configuration BASELINE.json's metric is quoted on; the others make every BASELINE config
+driver-reachable with the same parity / cpu_baseline / roofline / e2e keys):
+  c1    samples/test-pod.yaml: one 1g.5gb request on one emulated A100-40GB GPU           (isl_place_batch, the k_few path)
+  c2    10 000 x 1g.10gb on 256 GPUs, first-fit                                            (one batch; scan-mode commit)
+  c3    100 000 mixed-profile pods on 4 096 GPUs, first-fit (REF_EXACT parity)             (one batch; segment pipeline)
+  c3bf  the same input, ISL_POLICY_BEST_FIT (extension, parity against the oracle's best-fit)
+  c4    1M operations x 65 536 GPUs, 50/50 alloc/free churn, 16 batches                    (stream of batches; N > 1: partitioned)
+  c5    vLLM-shaped replay (3g.20gb) at 10 000 req/s for 10 s on 4 096 GPUs — p50 / p99 submit -> result latency (native driver)
 
-value   whole-job placements/s with requests and results resident in HBM (isl_place_stream_device: ONE call per step, the
-        engine pipelines the 16 batches over inventory segments inside one cooperative kernel)
-e2e     the same through isl_place_stream with pinned HOST buffers: the H2D copy of every batch and the delivery of every
-        result record into the caller's host array are inside the timed region (batches are fed on a second stream while the
-        pipeline runs; an extra CTA writes finished chunks into the pinned result array)
-N > 1   the inventory is partitioned over the ranks (contiguous GPU ranges); every rank holds the request stream and runs the
-        segment pipeline over its own range; the per-profile queue-head token of every chunk crosses ranks INSIDE the running
-        kernels (peer store into the next rank's inbox over NVLink, CUDA IPC); results are combined with an NCCL
-        all-reduce(MIN) over the 8-byte records and the occupancy shards are all-gathered.  Strong scaling (the job is fixed).
+One "step" = one pass of the hot path over the whole workload of the config, starting from the same inventory (the reset of the
+occupancy bytes is a 64 KiB device copy inside the timed region).
 
-The CPU oracle is used only for the cpu_baseline leg (timed baseline + parity check of the same sample) and
-for --impl reference.
+c4 in detail.  In the churn workload a FREE names an allocation an EARLIER batch placed, so a live caller cannot compose batch b
+before it has seen the results of earlier batches.  The headline therefore is the CAUSAL FEED: the workload variant in which a FREE
+of batch b names an allocation at least A batches old (--min-age A, default 8; a pod outlives a few reconcile batches), submitted
+with at most A batches in flight:
+  value         ALLOC decisions/s, requests and results resident in HBM; the device-side causal window (isl_set_causal_window(A))
+                keeps batch b from starting before every inventory segment has committed batch b - A
+  e2e           the same through the open-stream API (isl_stream_open / _submit / _wait / _close) with pinned HOST buffers: batch b
+                is submitted only after isl_stream_wait returned the results of batch b - A to host memory
+  strict_causal the ORIGINAL config-4 stream (a FREE may name anything live), one batch in flight (A = 1) — what a reconciler that
+                needs every result before composing the next batch gets
+  replay_*      the original stream handed over in one call (all 16 batches up front) — the pipelining ceiling, not causally available
+Every mode is checked byte for byte against the CPU oracle (ref_fast): results of every batch and the final occupancy.
+N > 1: the inventory is partitioned over the ranks (contiguous GPU ranges); the queue-head token of every chunk crosses ranks INSIDE
+the running kernels (peer store into the next rank's inbox over NVLink); the PLACED records go straight into rank 0's result array
+(peer stores from the commit threads — no result collective); the causal window is enforced across ranks by a per-chunk counter on
+rank 0 (peer atomics); the occupancy shards are all-gathered with NCCL.  Strong scaling (the job is fixed).
+
+The CPU oracle is used only for the parity gate, the cpu_baseline leg and --impl reference.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -40,7 +54,14 @@ sys.path.insert(0, ROOT)
 
 METRIC = "placements_per_sec"
 UNIT = "placements/s"
-WORKLOAD = "C4: 8192 nodes x 8 GPUs (65536), H100-80GB table, prefill 50%, 1e6 ops, 50/50 alloc/free, batches of 65536, seed 42"
+WORKLOADS = {
+    "c1": "C1: samples/test-pod.yaml, one 1g.5gb request on 1 node x 1 empty A100-40GB GPU",
+    "c2": "C2: 10000 x 1g.10gb on 32 nodes x 8 GPUs (256), H100-80GB table, first-fit",
+    "c3": "C3: 100000 mixed-profile pods (1g 40 / 2g 25 / 3g 20 / 4g 10 / 7g 5 %) on 512 nodes x 8 GPUs (4096), first-fit, seed 42",
+    "c3bf": "C3: 100000 mixed-profile pods on 4096 GPUs, best-fit with fragmentation score (extension), seed 42",
+    "c4": "C4: 8192 nodes x 8 GPUs (65536), H100-80GB table, prefill 50%, 1e6 ops, 50/50 alloc/free, batches of 65536, seed 42",
+    "c5": "C5: vLLM-shaped replay, Poisson 10000 req/s, 100% 3g.20gb, A100-40GB tables, 4096 GPUs, exp(30 s) lifetimes",
+}
 
 
 def env_int(name, default):
@@ -102,19 +123,351 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
+def ncu_traffic(kernel="k_pipeline"):
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if one has been summarised."""
     try:
         with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            d = json.load(f)
+        return d.get("dram_bytes_per_launch") if d.get("kernel", "k_pipeline").startswith(kernel) else None
     except Exception:
         return None
 
 
-# ------------------------------------------------------------------------------------------------------------
-def record_workload(E, W, torch):
-    """Generate config 4 through the engine (untimed).  Returns (churn object, prefilled occupancy, churn batches, results)."""
-    ch = W.Churn()
+def _device_view(torch, ptr: int, n: int, typestr="|u1"):
+    """torch view of engine-owned device memory (no copy)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+    return torch.as_tensor(h, device="cuda")
+
+
+class Ctx:
+    """What every config needs: torch, ranks, a timing helper, the clock sampler."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank, self.world, self.local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+        # NCCL's own log shows the communicator (ranks, NVLS / P2P) — keep it, but on stderr: rank 0 prints ONE JSON line on stdout
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        import __graft_entry__ as g
+        if self.rank == 0:
+            g.build()
+        if self.world > 1:
+            dist.barrier()
+        self.stream = torch.cuda.Stream()           # a real (non-default) stream: the legacy default stream has handle 0
+        torch.cuda.set_stream(self.stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def timed(self, step_fn, steps, warmup, flush_l2=True):
+        """W untimed steps, then K steps, each bracketed by CUDA events on the stream the engine launches on; barrier + synchronize on
+        both sides; returns (total ms = MAX over ranks, wall seconds of this rank)."""
+        torch, dist = self.torch, self.dist
+        for _ in range(warmup):
+            step_fn()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms, wall = 0.0, 0.0
+        for _ in range(steps):
+            if flush_l2:
+                self.flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            step_fn()
+            e1.record()
+            e1.synchronize()
+            wall += time.perf_counter() - t0
+            total_ms += e0.elapsed_time(e1)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, wall
+
+
+def base_line(ctx, config, value, ms_per_step, config_extra, parity, launches, clocks, scaling="strong"):
+    a = ctx.args
+    cfg = {"workload": WORKLOADS[config], "l2": "flushed between timed steps (256 MiB write)", "timing": "cuda events per step on the launching stream, max over ranks",
+           "quirks": "REF_EXACT"}
+    cfg.update(config_extra)
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+            "parity": "bit-exact vs the CPU oracle (ref_fast): every result record and the final occupancy" if parity else "MISMATCH vs the CPU oracle",
+            "gpu_launches": int(launches), "clocks": clocks}
+
+
+# ---- CPU legs (the only places that execute oracle/) ----------------------------------------------------------------------
+def fast_replay(oracle, node_off, rows, occ0, batches, policy=0, reps=5):
+    """ref_fast on the whole job, best of `reps` (one core).  Returns (results per batch, final occupancy, best seconds)."""
+    best, res, occ = 1e30, None, None
+    for _ in range(reps):
+        f = oracle.Fast(node_off, rows, 3, policy=policy)
+        f.load(occ0)
+        t0 = time.perf_counter()
+        r = [f.place(b) for b in batches]
+        dt = time.perf_counter() - t0
+        if dt < best:
+            best = dt
+        res, occ = r, f.occupancy()
+    return res, occ, best
+
+
+def faithful_from_prefill(oracle, node_off, rows, prefill):
+    """The reference's CR state that corresponds to a pre-filled inventory: one Allocations entry per pre-fill placement."""
+    f = oracle.Faithful(node_off, rows)
+    pod = 0
+    for req, res in prefill:
+        placed = (req["op"] == 0) & (res["status"] == 0)
+        for g, s, z in zip(res["gpu"][placed].tolist(), res["start"][placed].tolist(), res["size"][placed].tolist()):
+            f.add_allocation(g, s, z, pod)
+            pod += 1
+    return f
+
+
+def cpu_baseline_batches(node_off, rows, occ0, batches, got, got_occ, policy=0, faithful=None, faithful_ops=None, faithful_note=""):
+    """ref_fast on the whole job (best of 5) + parity verdicts; ref_faithful (the reference as written, one reconcile worker) on a
+    bounded prefix when `faithful` (a prepared Faithful state) is given."""
+    import oracle
+    from instaslice_b200 import engine as E
+    want, want_occ, t_fast = fast_replay(oracle, node_off, rows, occ0, batches, policy)
+    ok = all(np.array_equal(a, b) for a, b in zip(got, want)) and (got_occ is None or np.array_equal(got_occ, want_occ))
+    n_ops = sum(len(b) for b in batches)
+    n_alloc = int(sum(int((b["op"] == E.OP_ALLOC).sum()) for b in batches))
+    out = {"cores": 1, "kind": "port", "unit": UNIT,
+           "ref_fast_value": n_alloc / t_fast, "ref_fast_ops_per_sec": n_ops / t_fast, "ref_fast_ms": t_fast * 1e3,
+           "ref_fast_note": "bitmask restatement (oracle/ref_fast.cpp), whole job, 1 core, best of 5 — the strong CPU baseline",
+           "parity_full_job_vs_ref_fast": bool(ok)}
+    if faithful is not None:
+        req = np.concatenate(batches)[:faithful_ops] if faithful_ops else np.concatenate(batches)
+        # batch boundaries matter (FREEs first inside a batch): the prefix is cut inside batch 0 or spans whole batches
+        pieces, off = [], 0
+        for b in batches:
+            if off >= len(req):
+                break
+            pieces.append(b[: len(req) - off])
+            off += len(pieces[-1])
+        t0 = time.perf_counter()
+        fres = [faithful.place(p) for p in pieces]
+        dt = time.perf_counter() - t0
+        n_a = int(sum(int((p["op"] == E.OP_ALLOC).sum()) for p in pieces))
+        ok_f = all(np.array_equal(a, b[: len(a)]) for a, b in zip(fres, want))
+        out.update({"value": n_a / dt, "sample": "ref_faithful.cpp (the reference as written: string-keyed CRs, rescans per pod; 1 reconcile worker) on %s: %d ops = %d ALLOC decisions, %.1f s"
+                                                  % (faithful_note, len(req), n_a, dt),
+                    "parity_sample_faithful_vs_fast": bool(ok_f)})
+        ok = ok and ok_f
+    else:
+        out.update({"value": n_alloc / t_fast, "sample": "ref_fast.cpp on the whole job (no reference-as-written counterpart for this policy)"})
+    return out, bool(ok)
+
+
+# ---- configs 1-3: one batch ------------------------------------------------------------------------------------------------
+def run_single_batch(ctx, config):
+    torch = ctx.torch
+    from instaslice_b200 import engine as E
+    from instaslice_b200 import workloads as W
+    a = ctx.args
+    policy = E.POLICY_BEST_FIT if config == "c3bf" else E.POLICY_FIRST_FIT
+    node_off, occ0, rows, req = {"c1": W.config1, "c2": W.config2, "c3": W.config3, "c3bf": W.config3}[config]()
+    G, n = len(occ0), len(req)
+    eng = E.Engine(max_gpus=max(4096, G), max_batch=1 << 20, policy=policy)
+    eng.set_stream(ctx.stream.cuda_stream)
+    eng.load_profiles(rows)
+    eng.load_inventory(node_off, occ0)
+    d_occ0 = torch.from_numpy(occ0).cuda()
+    occ_view = _device_view(torch, eng.device_occupancy(), G)
+    d_in = torch.from_numpy(req.view(np.int64).copy()).cuda()
+    d_out = torch.empty_like(d_in)
+    h_in = torch.from_numpy(req.view(np.int64).copy()).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+
+    def step_device():
+        occ_view.copy_(d_occ0)
+        eng.place_batch_device(n, d_in.data_ptr(), d_out.data_ptr())
+
+    def step_e2e():         # the call the reconciler makes: host buffers in, host buffers out, synchronous
+        occ_view.copy_(d_occ0)
+        eng.place_batch_ptr(n, h_in.data_ptr(), h_out.data_ptr())
+
+    sampler = ClockSampler(ctx.local)
+    if ctx.rank == 0:
+        sampler.start()
+    launches0 = eng.stats()["kernel_launches"]
+    ms_dev, _ = ctx.timed(step_device, a.steps, a.warmup)
+    launches = eng.stats()["kernel_launches"] - launches0
+    got_dev = d_out.cpu().numpy().view(E.RESULT_DTYPE)
+    occ_dev = eng.read_occupancy()
+    ms_e2e, wall_e2e = ctx.timed(step_e2e, a.steps, a.warmup)
+    clocks = sampler.stop() if ctx.rank == 0 else None
+    got_e2e = h_out.numpy().view(E.RESULT_DTYPE).copy()
+    n_alloc = int((req["op"] == E.OP_ALLOC).sum())
+
+    # dominant kernel, timed live with CUDA events on the engine's own stream (timing mode)
+    teng = E.Engine(max_gpus=max(4096, G), max_batch=1 << 20, policy=policy, timing=True)
+    teng.load_profiles(rows)
+    for _ in range(3):
+        teng.load_inventory(node_off, occ0)
+        teng.reset_stats()
+        teng.place_batch_device(n, d_in.data_ptr(), d_out.data_ptr())
+        teng.synchronize()
+    st = teng.stats()
+    teng.close()
+    phases = {"prepare": st["ms_free"], "partition": st["ms_partition"], "sweep": st["ms_sweep"], "commit": st["ms_commit"], "total": st["ms_total"]}
+    dom_name, dom_ms = max(((k, v) for k, v in phases.items() if k != "total"), key=lambda kv: kv[1])
+    kernel = {"c1": "k_few", "c2": "k_sweep_scatter (scan-mode commit)", "c3": "k_pipeline", "c3bf": "k_bestfit"}[config]
+    alg_bytes = 16 * n + 2 * G
+    peak, how = measured_peak()
+    achieved = alg_bytes / (max(dom_ms, 1e-6) / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms, "dominant_phase": dom_name, "phase_ms_per_step": phases,
+                "note": "integer / bitmask work; the inventory (%d B) is on-chip, the request / result arrays stream once; the exact commit is a sequential "
+                        "recurrence over placements and bounds the step, not HBM" % G}
+    parity, cpu = True, None
+    if ctx.rank == 0:
+        import oracle
+        faithful = faithful_ops = None
+        note = ""
+        if policy == E.POLICY_FIRST_FIT:
+            faithful = oracle.Faithful(node_off, rows)
+            faithful.load_occupancy_as_dangling(occ0)
+            faithful_ops = {"c1": None, "c2": None, "c3": 20000}[config]
+            note = "the whole job" if faithful_ops is None else "the first %d requests of the job" % faithful_ops
+        cpu, parity = cpu_baseline_batches(node_off, rows, occ0, [req], [got_dev], occ_dev, policy, faithful, faithful_ops, note)
+        parity = parity and np.array_equal(got_e2e, got_dev)
+    value = n_alloc * a.steps / (ms_dev / 1e3)
+    e2e_ms = max(ms_e2e, wall_e2e * 1e3)
+    line = base_line(ctx, config, value * ctx.world, ms_dev / a.steps,
+                     {"requests_per_step": n, "gpus_in_inventory": G, "policy": "best-fit" if policy else "first-fit",
+                      "parallelism": "1 GPU" if ctx.world == 1 else "%d independent replicas (a single batch does not shard: replicas only)" % ctx.world,
+                      "ops_counted": "ALLOC decisions (placed or definitively no-capacity)"}, parity, launches, clocks,
+                     scaling="strong" if ctx.world == 1 else "weak")
+    line["e2e"] = {"value": n_alloc * a.steps / (e2e_ms / 1e3) * ctx.world, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+                   "ms_per_step": e2e_ms / a.steps, "api": "isl_place_batch (host buffers, synchronous); timed by the host clock around the call and by CUDA events, the larger is reported"}
+    line["roofline"] = roofline
+    if cpu:
+        line["cpu_baseline"] = cpu
+    eng.close()
+    return line, parity
+
+
+# ---- config 5: latency replay -----------------------------------------------------------------------------------------------
+def c5_trace(W, rate, seconds, mean_life=30.0):
+    rng = W.SplitMix64(42)
+    n = int(rate * seconds)
+    u = (rng.next(n) >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+    arrivals = np.cumsum(-np.log1p(-u) / rate)
+    life = -np.log1p(-(rng.next(n) >> np.uint64(11)).astype(np.float64) / float(1 << 53)) * mean_life
+    return n, np.ascontiguousarray(arrivals), np.ascontiguousarray(life)
+
+
+def c5_replay(place_fn_addr, ctx_handle, n, arrivals, life, profile):
+    """instaslice_b200/host/replay_driver.cpp: the native open-loop driver (no Python between the clock and the call)."""
+    from instaslice_b200 import engine as E
+    host = C.CDLL(os.path.join(ROOT, "instaslice_b200", "libislhost.so"))
+    fn = host.islh_replay_open_loop
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint8, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                   C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
+    cap, cap_calls = 4 * n + 1024, 2 * n + 1024
+    lat = np.zeros(n)
+    rec_req, rec_res = np.zeros(cap, dtype=E.REQUEST_DTYPE), np.zeros(cap, dtype=E.RESULT_DTYPE)
+    rec_sizes = np.zeros(cap_calls, dtype=np.uint32)
+    n_calls, n_rec, wall, placed = C.c_uint32(), C.c_uint32(), C.c_double(), C.c_uint32()
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    rc = fn(C.c_void_p(place_fn_addr), ctx_handle, n, p(arrivals), p(life), profile, p(lat), p(rec_req), p(rec_res), cap, p(rec_sizes), cap_calls,
+            C.byref(n_calls), C.byref(n_rec), C.byref(wall), C.byref(placed))
+    if rc != 0:
+        raise RuntimeError("islh_replay_open_loop: %d" % rc)
+    sizes = rec_sizes[: n_calls.value]
+    return lat, rec_req[: n_rec.value], rec_res[: n_rec.value], sizes, wall.value, placed.value
+
+
+def latency_summary(lat):
+    us = lat * 1e6
+    return {k: float(np.percentile(us, q)) for k, q in (("p50", 50), ("p90", 90), ("p99", 99), ("p999", 99.9))} | {"max": float(us.max()), "mean": float(us.mean())}
+
+
+def run_c5(ctx):
+    from instaslice_b200 import engine as E, tables
+    from instaslice_b200 import workloads as W
+    a = ctx.args
+    rate, seconds, G = 10000.0, float(a.seconds), 4096
+    n, arrivals, life = c5_trace(W, rate, seconds)
+    rows = E.make_profiles(tables.A100_40GB)
+    node_off = W.node_offsets(G // 8, 8)
+    prof = tables.profile_index(tables.A100_40GB, "3g.20gb")
+    eng = E.Engine(max_gpus=G, max_batch=65536)
+    eng.load_profiles(rows)
+    eng.load_inventory(node_off, np.zeros(G, dtype=np.uint8))
+    noop = np.array([(0, E.PROFILE_UNKNOWN, E.OP_NOOP, 0, 0)], dtype=E.REQUEST_DTYPE)
+    for _ in range(max(200, a.warmup)):                    # warm the path (kernels loaded, buffers allocated)
+        eng.place_batch(noop)
+    lib = E.load_library()
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    launches0 = eng.stats()["kernel_launches"]
+    lat, rreq, rres, sizes, wall, placed = c5_replay(C.cast(lib.isl_place_batch, C.c_void_p).value, eng._h, n, arrivals, life, prof)
+    launches = eng.stats()["kernel_launches"] - launches0
+    clocks = sampler.stop()
+    occ_end = eng.read_occupancy()
+    eng.close()
+    # parity: everything that was submitted, call by call, through the oracle
+    import oracle
+    f = oracle.Fast(node_off, rows)
+    f.load(np.zeros(G, dtype=np.uint8))
+    ok, off = True, 0
+    for m in sizes.tolist():
+        ok = ok and np.array_equal(f.place(rreq[off:off + m]), rres[off:off + m])
+        off += m
+    ok = bool(ok and np.array_equal(occ_end, f.occupancy()))
+    # CPU baseline: the same trace through the same native driver with ref_fast as the placer, and with the reference as written
+    ol = oracle.lib()
+    f2 = oracle.Fast(node_off, rows)
+    f2.load(np.zeros(G, dtype=np.uint8))
+    lat_fast, *_ = c5_replay(C.cast(ol.orc_fast_place, C.c_void_p).value, f2._h, n, arrivals, life, prof)
+    n_f, arr_f, life_f = c5_trace(W, rate, min(seconds, 2.0))
+    ff = oracle.Faithful(node_off, rows)
+    lat_faith, _, _, sz_f, wall_f, _ = c5_replay(C.cast(ol.orc_f_place_batch, C.c_void_p).value, ff._h, n_f, arr_f, life_f, prof)
+    s = latency_summary(lat)
+    line = {"metric": "placement_latency_p50_us", "value": s["p50"], "unit": "us", "n_gpus": 1, "steps": 1, "warmup": a.warmup, "ms_per_step": wall * 1e3,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOADS["c5"], "seconds": seconds, "requests": n, "calls": int(len(sizes)), "mean_batch": float(sizes.mean()), "placed": int(placed),
+                       "driver": "native open-loop replay (instaslice_b200/host/replay_driver.cpp): every turn hands isl_place_batch the expired slices and the requests that arrived since the last call",
+                       "timing": "host steady_clock, arrival -> result available (a latency metric: the call is synchronous, there is nothing to bracket with CUDA events)",
+                       "l2": "n/a (latency of single small calls)"},
+            "latency_us": s, "parity": "bit-exact vs the CPU oracle (ref_fast): every call's results and the final occupancy" if ok else "MISMATCH vs the CPU oracle",
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": s["p50"], "unit": "us", "p99": s["p99"], "h2d_bytes_per_step": int(8 * sizes.mean()), "d2h_bytes_per_step": int(8 * sizes.mean()),
+                    "api": "isl_place_batch per driver turn (requests travel as kernel parameters, results through mapped pinned memory)"},
+            "roofline": {"bound": "hbm", "kernel": "k_few", "achieved": None, "peak": measured_peak()[0], "unit": "GB/s", "frac": None, "traffic": None,
+                         "note": "latency path: one launch of one CTA per call, ~16 B in and out; launch + synchronisation latency bounds it, not bandwidth"},
+            "cpu_baseline": {"value": latency_summary(lat_fast)["p50"], "unit": "us", "cores": 1, "kind": "port",
+                             "sample": "the same trace through the same native driver with oracle/ref_fast.cpp as the placer (p50 of arrival -> result)",
+                             "ref_fast_latency_us": latency_summary(lat_fast),
+                             "ref_faithful_latency_us": latency_summary(lat_faith),
+                             "ref_faithful_note": "the reference as written on the first %.0f s of the trace (%d requests, %d calls, wall %.2f s): it resolves ~10^4 pods/s on 4096 GPUs, "
+                                                  "so an open loop at 10^4 req/s keeps it saturated" % (min(seconds, 2.0), n_f, len(sz_f), wall_f),
+                             "parity_full_job_vs_ref_fast": ok}}
+    return line, ok
+
+
+# ---- config 4: the churn stream ---------------------------------------------------------------------------------------------
+def record_churn(E, W, min_age):
+    """Generate config 4 through the engine (untimed, one isl_place_batch per batch).  Returns (churn, prefilled occupancy,
+    churn batches, engine results per batch, [(pre-fill requests, results)])."""
+    ch = W.Churn(min_age=min_age)
     eng = E.Engine(max_gpus=ch.G, max_batch=65536)
     eng.load_profiles(ch.rows)
     eng.load_inventory(ch.node_off, np.zeros(ch.G, dtype=np.uint8))
@@ -128,283 +481,364 @@ def record_workload(E, W, torch):
     ch.generate(placer, after_prefill=lambda: snap.update(occ=eng.read_occupancy()))
     eng.close()
     nb = ch.n_prefill_batches
-    return ch, snap["occ"], ch.batches[nb:], results[nb:]
+    return ch, snap["occ"], ch.batches[nb:], results[nb:], list(zip(ch.batches[:nb], results[:nb]))
 
 
-def run_own(args):
-    import torch
-    import torch.distributed as dist
+def run_c4(ctx):
+    torch, dist = ctx.torch, ctx.dist
     from instaslice_b200 import engine as E
     from instaslice_b200 import workloads as W
+    a = ctx.args
+    A = max(1, a.min_age)
+    rank, world = ctx.rank, ctx.world
+    ch, occ0, batches, rec, prefill = record_churn(E, W, A)
+    nb, G = len(batches), ch.G
+    sizes = np.array([len(b) for b in batches], dtype=np.uint32)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n_ops = int(offs[-1])
+    n_alloc = int(sum(int((b["op"] == E.OP_ALLOC).sum()) for b in batches))
+    all_req = np.concatenate(batches).view(np.int64)
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    os.environ["NCCL_DEBUG"] = os.environ.get("ISL_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import __graft_entry__ as g
-    if rank == 0:
-        g.build()
-    if world > 1:
-        dist.barrier()
-
-    ch, occ0, batches, want = record_workload(E, W, torch)
-    n_ops = sum(len(b) for b in batches)
-    G = ch.G
-
-    # engine on torch's current stream so that torch.cuda.Event brackets its kernels
-    stream = torch.cuda.Stream()          # a real (non-default) stream: the legacy default stream has handle 0
-    torch.cuda.set_stream(stream)
     eng = E.Engine(max_gpus=G, max_batch=1 << 20)
-    eng.set_stream(stream.cuda_stream)
+    eng.set_stream(ctx.stream.cuda_stream)
     eng.load_profiles(ch.rows)
     eng.load_inventory(ch.node_off, occ0)
     d_occ0 = torch.from_numpy(occ0).cuda()
     occ_view = _device_view(torch, eng.device_occupancy(), G)
-    sizes = np.array([len(b) for b in batches], dtype=np.uint32)
-    all_req = np.concatenate(batches).view(np.int64)
     d_in_all = torch.from_numpy(all_req.copy()).cuda()            # the whole stream, batch after batch, resident in HBM
-    d_out_all = torch.empty_like(d_in_all)
-    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    d_in = [d_in_all[offs[i]:offs[i + 1]] for i in range(len(batches))]
-    d_out = [d_out_all[offs[i]:offs[i + 1]] for i in range(len(batches))]
+    d_res = _device_view(torch, eng.device_results(), n_ops, "<i8")      # the engine's own result array (rank 0: the ranks' records land here)
     h_in_all = torch.from_numpy(all_req.copy()).pin_memory()
-    h_out_all = torch.empty_like(h_in_all).pin_memory()
-    h_out = [h_out_all[offs[i]:offs[i + 1]] for i in range(len(batches))]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    h_out_all = torch.zeros_like(h_in_all).pin_memory()
 
-    if world > 1:
-        from instaslice_b200 import dist as D
-        lo, hi = D.partition_bounds(G, world, rank)
-        eng.set_partition(lo, hi)
-        D.connect_ring(eng, rank, world)          # next rank's token inbox mapped through CUDA IPC (peer store over NVLink)
-        stream_ids = iter(range(1, 1 << 30))
+    def split(x):
+        return [x[offs[i]:offs[i + 1]] for i in range(nb)]
 
-    def step_device():
-        occ_view.copy_(d_occ0)
-        if world == 1:      # ONE call for the stream of batches: the engine pipelines them over inventory segments
-            eng.place_stream_ptr(sizes, d_in_all.data_ptr(), d_out_all.data_ptr(), device=True)
-            return
-        # every rank runs the segment pipeline over its own GPU range; tokens cross ranks inside the running kernels
-        eng.place_stream_partitioned(sizes, d_in_all.data_ptr(), d_out_all.data_ptr(), next(stream_ids))
-        D.merge_results(d_out_all)                                        # NCCL all-reduce(MIN) of the 8-byte records
-        occ_view.copy_(D.gather_occupancy(occ_view[lo:hi], G, world, rank))   # NCCL all-gather of the occupancy shards
+    def results_of(t):
+        return split(t.cpu().numpy().view(E.RESULT_DTYPE) if t.is_cuda else t.numpy().view(E.RESULT_DTYPE).copy())
 
-    def step_e2e():         # pinned host buffers in, pinned host buffers out: H2D + kernels + D2H inside the timed region
-        occ_view.copy_(d_occ0)
-        if world == 1:
+    lines_extra, parity = {}, True
+    sampler = ClockSampler(ctx.local)
+
+    if world == 1:
+        # ---- the causal feed (headline)
+        def step_device():
+            occ_view.copy_(d_occ0)
+            eng.place_stream_ptr(sizes, d_in_all.data_ptr(), d_res.data_ptr(), device=True)
+
+        def open_stream_step(window):
+            def step():
+                occ_view.copy_(d_occ0)
+                eng.stream_open(nb)
+                t = []
+                for b in range(nb):
+                    if b >= window:
+                        eng.stream_wait(t[b - window])         # the results of batch b - window are in host memory: batch b may be composed
+                    t.append(eng.stream_submit_ptr(int(sizes[b]), h_in_all.data_ptr() + 8 * int(offs[b]), h_out_all.data_ptr() + 8 * int(offs[b])))
+                for b in range(max(0, nb - window), nb):
+                    eng.stream_wait(t[b])
+                eng.stream_close()
+            return step
+
+        sampler.start()
+        eng.set_causal_window(A)
+        launches0 = eng.stats()["kernel_launches"]
+        ms_dev, _ = ctx.timed(step_device, a.steps, a.warmup)
+        launches = eng.stats()["kernel_launches"] - launches0
+        got_dev, occ_dev = results_of(d_res), eng.read_occupancy()
+        eng.set_causal_window(0)
+        ms_e2e, wall_e2e = ctx.timed(open_stream_step(A), a.steps, a.warmup)
+        clocks = sampler.stop()
+        got_e2e, occ_e2e = results_of(h_out_all), eng.read_occupancy()
+        e2e_ms = max(ms_e2e, wall_e2e * 1e3)
+
+        # dominant kernel (k_pipeline), timed live with CUDA events on the engine's own stream in timing mode, same causal window
+        teng = E.Engine(max_gpus=G, max_batch=1 << 20, timing=True)
+        teng.load_profiles(ch.rows)
+        teng.set_causal_window(A)
+        for _ in range(3):
+            teng.load_inventory(ch.node_off, occ0)
+            teng.reset_stats()
+            teng.place_stream_ptr(sizes, d_in_all.data_ptr(), d_res.data_ptr(), device=True)
+            teng.synchronize()
+        st = teng.stats()
+        teng.close()
+        ms_pipe = st["ms_commit"]
+        alg_bytes = 16 * n_ops + 2 * G * nb                   # B_alg = 16 R + 2 G per batch, whole stream = one launch
+        peak, how = measured_peak()
+        achieved = alg_bytes / (ms_pipe / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_pipeline", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic(), "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms_pipe, "launches": 1,
+                    "note": "latency-bound exact commit chain pipelined over inventory segments (one CTA per SM); inventory, queues and candidates are "
+                            "shared-memory / L2 resident by construction, so DRAM traffic stays below the algorithmic bytes",
+                    "phase_ms_per_step": {"prepare": st["ms_free"], "partition": st["ms_partition"], "pipeline": st["ms_commit"], "total": st["ms_total"]}}
+
+        import oracle
+        faithful = faithful_from_prefill(oracle, ch.node_off, ch.rows, prefill)
+        cpu, ok = cpu_baseline_batches(ch.node_off, ch.rows, occ0, batches, got_dev, occ_dev, 0, faithful, a.faithful_ops,
+                                       "the first %d operations of the churn stream on the pre-filled 65536-GPU inventory (SURVEY 8d prefix)" % a.faithful_ops)
+        parity = ok and all(np.array_equal(x, y) for x, y in zip(got_e2e, got_dev)) and np.array_equal(occ_e2e, occ_dev)
+
+        # ---- the original stream: strict causal (one batch in flight) and the replay ceiling
+        if A != 1:
+            ch1, occ1, batches1, _, _ = record_churn(E, W, 1)
+        else:
+            ch1, occ1, batches1 = ch, occ0, batches
+        sizes1 = np.array([len(b) for b in batches1], dtype=np.uint32)
+        assert np.array_equal(sizes1, sizes)
+        req1 = np.concatenate(batches1).view(np.int64)
+        d_occ0.copy_(torch.from_numpy(occ1))
+        d_in_all.copy_(torch.from_numpy(req1.copy()))
+        h_in_all.copy_(torch.from_numpy(req1.copy()))
+        eng.load_inventory(ch1.node_off, occ1)
+        n_alloc1 = int(sum(int((b["op"] == E.OP_ALLOC).sum()) for b in batches1))
+        want1, want1_occ, t_fast1 = fast_replay(oracle, ch1.node_off, ch1.rows, occ1, batches1)
+        extra_ok = True
+
+        def check(got, occ):
+            return all(np.array_equal(x, y) for x, y in zip(got, want1)) and np.array_equal(occ, want1_occ)
+
+        eng.set_causal_window(1)
+        ms_s_dev, _ = ctx.timed(step_device, a.steps, 3)
+        extra_ok &= check(results_of(d_res), eng.read_occupancy())
+        eng.set_causal_window(0)
+        ms_s_e2e, wall_s = ctx.timed(open_stream_step(1), a.steps, 3)
+        extra_ok &= check(results_of(h_out_all), eng.read_occupancy())
+
+        def step_per_batch():       # the same through one synchronous isl_place_batch per batch
+            occ_view.copy_(d_occ0)
+            for i in range(nb):
+                eng.place_batch_ptr(int(sizes[i]), h_in_all.data_ptr() + 8 * int(offs[i]), h_out_all.data_ptr() + 8 * int(offs[i]))
+        ms_pb, wall_pb = ctx.timed(step_per_batch, a.steps, 3)
+        extra_ok &= check(results_of(h_out_all), eng.read_occupancy())
+        ms_r_dev, _ = ctx.timed(step_device, a.steps, 3)
+        extra_ok &= check(results_of(d_res), eng.read_occupancy())
+
+        def step_replay_e2e():
+            occ_view.copy_(d_occ0)
             eng.place_stream_ptr(sizes, h_in_all.data_ptr(), h_out_all.data_ptr(), device=False)
-            return
-        d_in_all.copy_(h_in_all, non_blocking=True)                       # every rank stages the request stream
-        eng.place_stream_partitioned(sizes, d_in_all.data_ptr(), d_out_all.data_ptr(), next(stream_ids))
-        D.merge_results(d_out_all)
+        ms_r_e2e, wall_r = ctx.timed(step_replay_e2e, a.steps, 3)
+        extra_ok &= check(results_of(h_out_all), eng.read_occupancy())
+        parity = parity and bool(extra_ok)
+        per = lambda ms: n_alloc1 * a.steps / (ms / 1e3)
+        lines_extra = {
+            "strict_causal": {"workload": "the original config-4 stream (a FREE may name any allocation live at batch start), ONE batch in flight",
+                              "value": per(ms_s_dev), "ms_per_step": ms_s_dev / a.steps,
+                              "e2e_value": per(max(ms_s_e2e, wall_s * 1e3)), "e2e_ms_per_step": max(ms_s_e2e, wall_s * 1e3) / a.steps,
+                              "e2e_api": "open stream, isl_stream_wait(b) before isl_stream_submit(b + 1)",
+                              "per_batch_calls_value": per(max(ms_pb, wall_pb * 1e3)), "per_batch_calls_note": "isl_place_batch once per batch, synchronous (SURVEY 8d's call)",
+                              "ref_fast_value": n_alloc1 / t_fast1, "unit": UNIT, "parity_vs_ref_fast": bool(extra_ok)},
+            "replay_value": per(ms_r_dev), "replay_ms_per_step": ms_r_dev / a.steps,
+            "replay_e2e_value": per(max(ms_r_e2e, wall_r * 1e3)),
+            "replay_note": "the original stream, all 16 batches handed over in one isl_place_stream* call: the pipelining ceiling; NOT causally available to a live caller",
+        }
+        value = n_alloc * a.steps / (ms_dev / 1e3)
+        line = base_line(ctx, "c4", value, ms_dev / a.steps,
+                         {"mode": "causal feed", "min_age_batches": A, "batches_in_flight": A,
+                          "workload_variant": "a FREE of batch b names an allocation placed by batch b - %d or earlier (min_age); A = 1 is the original stream (strict_causal)" % A,
+                          "ops_per_step": n_ops, "alloc_requests_per_step": n_alloc, "free_requests_per_step": n_ops - n_alloc,
+                          "ops_counted": "ALLOC decisions (placed or definitively no-capacity); FREEs are resolved inside the same step but not counted",
+                          "ops_per_sec_incl_frees": n_ops * a.steps / (ms_dev / 1e3),
+                          "batches_per_step": nb, "gpus_in_inventory": G, "policy": "first-fit", "parallelism": "segment pipeline, 1 GPU"},
+                         parity, launches, clocks)
+        line["e2e"] = {"value": n_alloc * a.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n_ops, "d2h_bytes_per_step": 8 * n_ops,
+                       "ms_per_step": e2e_ms / a.steps, "ops_per_sec_incl_frees": n_ops * a.steps / (e2e_ms / 1e3),
+                       "api": "isl_stream_open / isl_stream_submit / isl_stream_wait / isl_stream_close, pinned host buffers; batch b submitted after isl_stream_wait(b - %d); "
+                              "CUDA events around the step and the host clock, the larger is reported" % A}
+        line["roofline"] = roofline
+        line["cpu_baseline"] = cpu
+        line.update(lines_extra)
+        eng.close()
+        return line, parity
+
+    # ---- N > 1: partitioned inventory
+    from instaslice_b200 import dist as D
+    lo, hi = D.partition_bounds(G, world, rank)
+    eng.set_partition(lo, hi)
+    D.connect_ring(eng, rank, world)          # next rank's token inbox mapped through CUDA IPC (peer store over NVLink)
+    D.connect_owner(eng, rank, world)         # rank 0's result array mapped into every other rank; ring size for the causal window
+    eng.set_causal_window(A)
+    stream_ids = iter(range(1, 1 << 30))
+    side = torch.cuda.Stream()
+    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for k in ("dev",)}
+    phase_ms = {"pipeline": 0.0, "all_gather": 0.0, "steps": 0}
+
+    def step_device(record=False):
+        occ_view.copy_(d_occ0)
+        if record:
+            ev["dev"][0].record()
+        # every rank runs the segment pipeline over its own GPU range; tokens, PLACED records and the causal-window counter cross
+        # ranks inside the running kernels
+        eng.place_stream_partitioned(sizes, d_in_all.data_ptr(), d_res.data_ptr(), next(stream_ids))
+        if record:
+            ev["dev"][1].record()
+        occ_view.copy_(D.gather_occupancy(occ_view[lo:hi], G, world, rank))   # NCCL all-gather of the occupancy shards (also tells rank 0 every record has landed)
+        if record:
+            ev["dev"][2].record()
+
+    def step_device_timed():
+        step_device(True)
+        ev["dev"][2].synchronize()
+        phase_ms["pipeline"] += ev["dev"][0].elapsed_time(ev["dev"][1])
+        phase_ms["all_gather"] += ev["dev"][1].elapsed_time(ev["dev"][2])
+        phase_ms["steps"] += 1
+
+    def step_e2e():         # rank 0 is the controller: it owns the host buffers; the request stream reaches the other ranks over NVLink
+        occ_view.copy_(d_occ0)
+        if rank == 0:
+            d_in_all.copy_(h_in_all, non_blocking=True)
+        dist.broadcast(d_in_all, src=0)
+        eng.place_stream_partitioned(sizes, d_in_all.data_ptr(), d_res.data_ptr(), next(stream_ids))
         occ_view.copy_(D.gather_occupancy(occ_view[lo:hi], G, world, rank))
-        h_out_all.copy_(d_out_all, non_blocking=True)                     # merged results back to the host
+        if rank == 0:
+            h_out_all.copy_(d_res, non_blocking=True)
 
-    def timed(step_fn, steps, warmup, flush_l2=True):
-        for _ in range(warmup):
-            step_fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        total_ms = 0.0
-        for _ in range(steps):
-            if flush_l2:
-                flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step_fn()
-            e1.record()
-            e1.synchronize()
-            total_ms += e0.elapsed_time(e1)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms
-
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = eng.stats()["kernel_launches"]
-    ms_dev = timed(step_device, args.steps, args.warmup)
+    ms_dev, _ = ctx.timed(step_device, a.steps, a.warmup)
     launches = eng.stats()["kernel_launches"] - launches0
     clocks = sampler.stop() if rank == 0 else None
-    # parity gate on the last timed step: byte-identical to the recorded (single-GPU) results
-    got = [t.cpu().numpy().view(E.RESULT_DTYPE) for t in d_out]
-    parity = all(np.array_equal(a, b) for a, b in zip(got, want))
-
-    e2e = None
-    if world > 1:
-        ms_e2e = timed(step_e2e, args.steps, args.warmup)
-        parity = parity and all(np.array_equal(t.numpy().view(E.RESULT_DTYPE), b) for t, b in zip(h_out, want))
-        e2e = {"value": n_ops * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n_ops * world, "d2h_bytes_per_step": 8 * n_ops * world,
-               "ms_per_step": ms_e2e / args.steps, "api": "isl_place_stream_partitioned per rank + NCCL merge; every rank copies the stream in and the merged results out"}
-    if world == 1:
-        ms_e2e = timed(step_e2e, args.steps, args.warmup)
-        parity = parity and all(np.array_equal(t.numpy().view(E.RESULT_DTYPE), b) for t, b in zip(h_out, want))
-        # the same job submitted batch by batch (synchronous per-batch calls, no cross-batch pipelining), for reference
-        def step_per_batch():
-            occ_view.copy_(d_occ0)
-            for i, b in enumerate(batches):
-                eng.place_batch_ptr(len(b), h_in_all.data_ptr() + 8 * int(offs[i]), h_out_all.data_ptr() + 8 * int(offs[i]))
-        ms_pb = timed(step_per_batch, args.steps, 1)
-        e2e = {"value": n_ops * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n_ops, "d2h_bytes_per_step": 8 * n_ops,
-               "ms_per_step": ms_e2e / args.steps, "api": "isl_place_stream (16 batches per call; batches fed and results delivered while the pipeline runs)",
-               "per_batch_calls_value": n_ops * args.steps / (ms_pb / 1e3), "per_batch_calls_note": "isl_place_batch once per batch, synchronous"}
-
-    roofline = cpu = None
-    if rank == 0 and world == 1:
-        # dominant kernel (k_chain), timed live with CUDA events on the engine's own stream in timing mode
-        teng = E.Engine(max_gpus=G, max_batch=1 << 20, timing=True)
-        teng.load_profiles(ch.rows)
-        for rep in range(3):
-            teng.load_inventory(ch.node_off, occ0)
-            teng.reset_stats()
-            teng.place_stream_ptr(sizes, d_in_all.data_ptr(), d_out_all.data_ptr(), device=True)
-            teng.synchronize()
-        st = teng.stats()
-        ms_pipe = st["ms_commit"]                              # the single k_pipeline launch of the stream (CUDA events on the engine's stream)
-        alg_bytes = 16 * n_ops + 2 * G * len(batches)         # B_alg = 16 R + 2 G per batch, whole stream = one launch
+    got_dev = results_of(d_res) if rank == 0 else None
+    occ_dev = occ_view.cpu().numpy()
+    ms_e2e, wall_e2e = ctx.timed(step_e2e, a.steps, a.warmup)
+    got_e2e = results_of(h_out_all) if rank == 0 else None
+    for _ in range(3):
+        step_device_timed()
+    ph = torch.tensor([phase_ms["pipeline"] / 3, phase_ms["all_gather"] / 3], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    line = None
+    if rank == 0:
+        import oracle
+        cpu, ok = cpu_baseline_batches(ch.node_off, ch.rows, occ0, batches, got_dev, occ_dev, 0)
+        parity = ok and all(np.array_equal(x, y) for x, y in zip(got_e2e, got_dev))
+        ms_pipe = float(ph[0].item())
+        alg_bytes = 16 * n_ops + 2 * G * nb
         peak, how = measured_peak()
         achieved = alg_bytes / (ms_pipe / 1e3) / 1e9
-        # the sequential single-chain path on the same job, for the record (one k_chain launch per batch)
-        seng = E.Engine(max_gpus=G, max_batch=1 << 20, timing=True, flags=E.FLAG_NO_PIPELINE)
-        seng.load_profiles(ch.rows)
-        seng.load_inventory(ch.node_off, occ0)
-        seng.place_stream_ptr(sizes, d_in_all.data_ptr(), d_out_all.data_ptr(), device=True)
-        seng.synchronize()
-        sst = seng.stats()
-        seng.close()
-        roofline = {"bound": "hbm", "kernel": "k_pipeline", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ncu_traffic(), "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes,
-                    "avg_launch_ms": ms_pipe, "launches": 1,
-                    "note": "latency-bound exact commit chain pipelined over ~148 inventory segments (one CTA per SM); inventory, queues and candidates "
-                            "are shared-memory / L2 resident by construction, so DRAM traffic stays below the algorithmic bytes",
-                    "phase_ms_per_step": {"prepare": st["ms_free"], "partition": st["ms_partition"], "pipeline": st["ms_commit"], "total": st["ms_total"]},
-                    "single_chain_path_ms_per_step": {"prepare": sst["ms_free"], "partition": sst["ms_partition"], "sweep": sst["ms_sweep"],
-                                                      "chain+commit": sst["ms_commit"], "total": sst["ms_total"]}}
-        teng.close()
-        cpu = cpu_baseline(ch, occ0, batches, want)
-
-    if rank == 0:
-        line = {"metric": METRIC, "value": n_ops * args.steps / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
-                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "ops_per_step": n_ops, "alloc_requests_per_step": int(sum(int((b["op"] == E.OP_ALLOC).sum()) for b in batches)),
-                           "ops_counted": "every request resolved: ALLOC decisions (placed or no-capacity) and FREEs", "batches_per_step": len(batches), "gpus_in_inventory": G,
-                           "policy": "first-fit", "quirks": "REF_EXACT",
-                           "parallelism": "segment pipeline, 1 GPU" if world == 1 else "inventory partitioned over %d ranks: peer-memory token ring + NCCL all-reduce(MIN) of results + NCCL all-gather of occupancy" % world,
-                           "l2": "flushed between timed steps (256 MiB write)", "timing": "cuda events per step, max over ranks"},
-                "parity": "bit-exact vs recorded single-GPU results" if parity else "MISMATCH",
-                "gpu_launches": int(launches), "clocks": clocks}
-        if e2e:
-            line["e2e"] = e2e
-        if roofline:
-            line["roofline"] = roofline
-        if cpu:
-            line["cpu_baseline"] = cpu
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0 if parity else 1
+        value = n_alloc * a.steps / (ms_dev / 1e3)
+        line = base_line(ctx, "c4", value, ms_dev / a.steps,
+                         {"mode": "causal window (device-side, across ranks)", "min_age_batches": A, "batches_in_flight": A,
+                          "workload_variant": "a FREE of batch b names an allocation placed by batch b - %d or earlier (min_age)" % A,
+                          "ops_per_step": n_ops, "alloc_requests_per_step": n_alloc, "free_requests_per_step": n_ops - n_alloc,
+                          "ops_counted": "ALLOC decisions (placed or definitively no-capacity); FREEs are resolved inside the same step but not counted",
+                          "ops_per_sec_incl_frees": n_ops * a.steps / (ms_dev / 1e3),
+                          "batches_per_step": nb, "gpus_in_inventory": G, "policy": "first-fit",
+                          "parallelism": "inventory partitioned over %d ranks: peer-memory token ring + PLACED records peer-stored into rank 0's result array + "
+                                         "peer-atomic window counter + NCCL all-gather of the occupancy shards" % world},
+                         parity, launches, clocks)
+        e2e_ms = max(ms_e2e, 0.0)
+        line["e2e"] = {"value": n_alloc * a.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n_ops, "d2h_bytes_per_step": 8 * n_ops,
+                       "ms_per_step": e2e_ms / a.steps,
+                       "api": "rank 0: H2D of the stream + NCCL broadcast to the other ranks, isl_place_stream_partitioned per rank (causal window %d), NCCL all-gather of occupancy, "
+                              "D2H of rank 0's result array" % A}
+        line["roofline"] = {"bound": "hbm", "kernel": "k_pipeline", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                            "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms_pipe, "launches": world,
+                            "note": "per-rank k_pipeline incl. its waits for the predecessor's tokens (max over ranks); the chain is ONE sequential recurrence over the "
+                                    "whole inventory, more ranks add NVLink hops, not parallel work",
+                            "phase_ms_per_step_max_over_ranks": {"pre-pass + pipeline (enqueue to kernel end)": ms_pipe, "occupancy all-gather (NCCL) + copy back": float(ph[1].item()),
+                                                                  "result merge": 0.0}}
+        line["cpu_baseline"] = cpu
+    dist.barrier()
+    eng.close()
+    return line, parity
 
 
-def _device_view(torch, ptr: int, n: int):
-    """uint8 torch view of engine-owned device memory (no copy)."""
-    class _Holder:
-        pass
-    h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-    return torch.as_tensor(h, device="cuda")
-
-
-# ---- CPU legs (the only places that touch oracle/) ------------------------------------------------------------
-def _prefilled_faithful(oracle, ch, batches_prefill_results):
-    f = oracle.Faithful(ch.node_off, ch.rows)
-    pod = 0
-    for req, res in batches_prefill_results:
-        placed = (req["op"] == 0) & (res["status"] == 0)
-        for g, s, z in zip(res["gpu"][placed].tolist(), res["start"][placed].tolist(), res["size"][placed].tolist()):
-            f.add_allocation(g, s, z, pod)
-            pod += 1
-    return f
-
-
-def cpu_baseline(ch, occ0, batches, want, sample_ops=1500):
-    """ref_faithful (the reference as written, 1 reconcile worker) on the first `sample_ops` operations of churn
-    batch 0 against the pre-filled inventory; ref_fast on the whole job.  Also the parity check of that sample."""
-    import oracle
-    from instaslice_b200 import engine as E
-    f = oracle.Faithful(ch.node_off, ch.rows)
-    f.load_occupancy_as_dangling(occ0)       # the pre-fill as realised slices
-    req = batches[0][:sample_ops].copy()
-    req = req[req["op"] == E.OP_ALLOC]        # frees of the sample would name pod-keyed entries; the sample times allocations
-    t0 = time.perf_counter()
-    res = f.place(req)
-    dt = time.perf_counter() - t0
-    fast = oracle.Fast(ch.node_off, ch.rows)
-    fast.load(occ0)
-    t1 = time.perf_counter()
-    ok = True
-    for b, w in zip(batches, want):
-        ok = ok and np.array_equal(fast.place(b), w)
-    dt_fast = time.perf_counter() - t1
-    fast2 = oracle.Fast(ch.node_off, ch.rows)
-    fast2.load(occ0)
-    ok_sample = np.array_equal(fast2.place(req), res)
-    return {"value": len(req) / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "ref_faithful.cpp on the %d ALLOC requests among the first %d ops of churn batch 0, pre-filled 65536-GPU inventory, %.1f s" % (len(req), sample_ops, dt),
-            "ref_fast_value": sum(len(b) for b in batches) / dt_fast, "ref_fast_note": "bitmask restatement, whole job, 1 core (strong CPU baseline)",
-            "parity_full_job_vs_ref_fast": bool(ok), "parity_sample_faithful_vs_fast": bool(ok_sample)}
-
-
+# ---- the reference arm ----------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm (ref_faithful.cpp, the port — the Go binary cannot be built here)."""
+    """--impl reference: the reference's own CPU algorithm.  The Go binary cannot be built here (no go / gccgo, un-vendored deps),
+    so this is oracle/ref_faithful.cpp — the structure-for-structure port, one reconcile worker like the reference — on a bounded
+    sample of the same workload, counted in the same unit (ALLOC decisions/s)."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
     import oracle
-    from instaslice_b200 import engine as E
+    from instaslice_b200 import engine as E, tables
     from instaslice_b200 import workloads as W
     oracle.build()
-    # the recorded workload needs a placer; the reference arm may execute oracle/, so ref_fast records it
-    ch = W.Churn()
-    fast = oracle.Fast(ch.node_off, ch.rows)
-    fast.load(np.zeros(ch.G, dtype=np.uint8))
-    state = {"occ0": None}
-    ch.generate(fast.place, after_prefill=lambda: state.update(occ0=fast.occupancy()))
-    batches = ch.batches[ch.n_prefill_batches:]
-    sample_ops = args.sample
-    req = batches[0][:sample_ops].copy()
-    req = req[req["op"] == E.OP_ALLOC]
-    times = []
-    for i in range(args.warmup + args.steps):
-        f = oracle.Faithful(ch.node_off, ch.rows)
-        f.load_occupancy_as_dangling(state["occ0"])
+    cfgname = args.config
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if cfgname == "c5":
+        rate, seconds, G = 10000.0, min(float(args.seconds), 2.0), 4096
+        n, arrivals, life = c5_trace(W, rate, seconds)
+        rows = E.make_profiles(tables.A100_40GB)
+        node_off = W.node_offsets(G // 8, 8)
+        ff = oracle.Faithful(node_off, rows)
+        lat, _, _, sz, wall, _ = c5_replay(C.cast(oracle.lib().orc_f_place_batch, C.c_void_p).value, ff._h, n, arrivals, life, tables.profile_index(tables.A100_40GB, "3g.20gb"))
+        s = latency_summary(lat)
+        sample = "ref_faithful.cpp through the native open-loop driver, first %.0f s of the trace (%d requests)" % (seconds, n)
+        print(json.dumps({"impl": "reference", "metric": "placement_latency_p50_us", "value": s["p50"], "unit": "us", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                          "ms_per_step": wall * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": WORKLOADS["c5"], "sample": sample}, "latency_us": s,
+                          "cpu_baseline": {"value": s["p50"], "unit": "us", "cores": 1, "kind": "port", "sample": sample},
+                          "e2e": {"value": s["p50"], "unit": "us", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+    if cfgname == "c4":
+        # the own arm's workload (same min_age), recorded through ref_fast (this arm may execute oracle/)
+        ch = W.Churn(min_age=max(1, args.min_age))
+        fast = oracle.Fast(ch.node_off, ch.rows)
+        fast.load(np.zeros(ch.G, dtype=np.uint8))
+        results = []
+
+        def placer(req):
+            results.append(fast.place(req))
+            return results[-1]
+        ch.generate(placer)
+        nbp = ch.n_prefill_batches
+        prefill = list(zip(ch.batches[:nbp], results[:nbp]))
+        prefix = ch.batches[nbp][: args.faithful_ops]
+        node_off, rows = ch.node_off, ch.rows
+        make_state = lambda: faithful_from_prefill(oracle, node_off, rows, prefill)
+        what = "the first %d operations of churn batch 0 (SURVEY 8d prefix) on the pre-filled 65536-GPU inventory, split over the %d timed steps" % (len(prefix), steps)
+    else:
+        node_off, occ0, rows, req = {"c1": W.config1, "c2": W.config2, "c3": W.config3, "c3bf": W.config3}[cfgname]()
+        prefix = req if cfgname in ("c1", "c2") else req[:20000]
+
+        def make_state():
+            f = oracle.Faithful(node_off, rows)
+            f.load_occupancy_as_dangling(occ0)
+            return f
+        what = ("the whole job" if len(prefix) == len(req) else "the first %d requests of the job" % len(prefix)) + ", split over the %d timed steps" % steps
+    # warm-up on a state of its own (small), then ONE pass over the prefix cut into `steps` consecutive slices on one evolving state
+    if warmup:
+        w = make_state()
+        for _ in range(warmup):
+            w.place(prefix[: max(1, min(64, len(prefix)))])
+    f = make_state()
+    cuts = np.linspace(0, len(prefix), steps + 1).astype(int)
+    total, n_alloc = 0.0, 0
+    for i in range(steps):
+        piece = prefix[cuts[i]:cuts[i + 1]]
         t0 = time.perf_counter()
-        f.place(req)
-        dt = time.perf_counter() - t0
-        if i >= args.warmup:
-            times.append(dt)
-    total = sum(times)
-    value = len(req) * args.steps / total
-    sample = "ref_faithful.cpp, %d ALLOC requests among the first %d ops of churn batch 0 per step, pre-filled 65536-GPU inventory" % (len(req), sample_ops)
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                      "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-                      "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        f.place(piece)
+        total += time.perf_counter() - t0
+        n_alloc += int((piece["op"] == E.OP_ALLOC).sum())
+    value = n_alloc / total if total > 0 else 0.0
+    sample = "ref_faithful.cpp on %s: %d ops = %d ALLOC decisions in %.1f s" % (what, len(prefix), n_alloc, total)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                      "ms_per_step": total / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+                      "data": "synthetic", "config": {"workload": WORKLOADS[cfgname], "sample": sample, "min_age_batches": max(1, args.min_age) if cfgname == "c4" else None,
+                                                      "ops_counted": "ALLOC decisions (placed or definitively no-capacity)"},
                       "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                                        "note": "single reconcile worker like the reference (controller-runtime default); the Go binary cannot be built in this image; "
-                                               "counts ALLOC decisions only (a FREE is a map delete by the daemonset in the reference), the GPU arm's ops are ~50% FREEs"},
+                                               "API-server / etcd time is excluded on both arms"},
                       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
     return 0
+
+
+def run_own(args):
+    ctx = Ctx(args)
+    if args.config == "c4":
+        line, parity = run_c4(ctx)
+    elif args.config == "c5":
+        line, parity = run_c5(ctx) if ctx.rank == 0 else (None, True)
+    else:
+        line, parity = run_single_batch(ctx, args.config)
+    if ctx.rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+    if ctx.world > 1:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
+    return 0 if parity else 1
 
 
 def main():
@@ -413,7 +847,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--sample", type=int, default=1500, help="ops per step of the CPU reference arm")
+    ap.add_argument("--config", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--min-age", type=int, default=8, help="c4: a FREE names an allocation at least this many batches old = batches in flight of the causal feed")
+    ap.add_argument("--faithful-ops", type=int, default=10000, help="c4: operations of the churn prefix the reference-as-written port is timed on (SURVEY 8d)")
+    ap.add_argument("--seconds", type=float, default=10.0, help="c5: length of the replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
     sys.exit(run_reference(args) if args.impl == "reference" else run_own(args))

@@ -40,6 +40,7 @@
 #ifndef ISLPLACE_H
 #define ISLPLACE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -220,6 +221,32 @@ int  isl_place_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, 
 int  isl_place_stream_device(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const void* d_in, void* d_out);
 /* Same, requests and results already resident in device memory (CUdeviceptr as void*). */
 int  isl_place_batch_device(isl_engine* e, uint32_t n, const void* d_in, void* d_out);
+/* isl_place_batch restricted to the canonical GPU range [lo, hi) — findDeviceForASlice looks at ONE node's GPUs (:240-262), the node
+ * loop (:190) calls it node after node.  Restriction, placement and restore happen under one engine lock (two reconcile workers
+ * cannot interleave, nothing leaks when the call fails); the engine's own partition (isl_set_partition) is left untouched. */
+int  isl_place_batch_range(isl_engine* e, uint32_t lo, uint32_t hi, uint32_t n, const isl_request* in, isl_result* out);
+
+/* ---- open streams: the causal feed --------------------------------------- */
+/* A reconciler that composes batch b+1 from the results of batch b (a FREE names an allocation an earlier batch placed) cannot hand
+ * all batches over up front.  An open stream keeps ONE persistent pipeline kernel resident:
+ *   isl_stream_open(e, max_batches)            reserve tables for up to max_batches batches of <= 65 536 requests
+ *   isl_stream_submit(e, n, in, out, &ticket)  enqueue one batch: copy + pre-pass on the feed stream; returns at once.  `out` must be
+ *                                              mapped pinned host memory (isl_host_alloc / cudaHostAlloc / cudaHostRegister): the
+ *                                              running kernel writes the results there
+ *   isl_stream_wait(e, ticket)                 returns when that batch's results are in `out`
+ *   isl_stream_close(e)                        end of stream: the kernel drains, the occupancy is written back
+ * Results are exactly those of isl_place_batch per batch in submission order.  Batches submitted before earlier ones are waited for
+ * overlap on the device (segment pipeline).  While a stream is open every other call on the engine returns ISL_ESTATE. */
+int  isl_stream_open(isl_engine* e, uint32_t max_batches);
+int  isl_stream_submit(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out, uint32_t* ticket);
+int  isl_stream_wait(isl_engine* e, uint32_t ticket);
+int  isl_stream_close(isl_engine* e);
+/* Device-side causal window for isl_place_stream / isl_place_stream_device: batch b is not started before every inventory segment has
+ * committed batch b - window (0 = no constraint, the default).  Models a consumer that needs batch b - window's results to compose b. */
+int  isl_set_causal_window(isl_engine* e, uint32_t window);
+/* Mapped pinned host memory from the C side (cgo must not hand Go-heap pointers to a running kernel). NULL on failure. */
+void* isl_host_alloc(size_t bytes);
+void  isl_host_free(void* p);
 /* Releases spans (Allocations entries deleted by the daemonset). */
 int  isl_free_batch(isl_engine* e, uint32_t n, const isl_span* spans);
 /* getStartIndexFromPreparedState's search (:343-383) for n arbitrary occupancy
@@ -252,6 +279,22 @@ int  isl_place_stream_partitioned(isl_engine* e, uint32_t n_batches, const uint3
                                   uint32_t stream_id);
 /* Device address of the occupancy bytes owned by this engine (for the NCCL all-gather). */
 void* isl_device_occupancy(isl_engine* e);
+/* Results gathered on the owner rank (the controller's rank, rank 0) WITHOUT a collective: every other rank maps the owner's result
+ * array and its commit threads store each PLACED record there as well (peer store over NVLink inside the running kernel).  The owner's
+ * pre-pass has written the defaults of a batch before its token leaves rank 0, so a later rank's record always lands on top of them.
+ *   owner:  isl_ipc_results_handle(e, h) -> 64-byte handle; place with d_out = isl_device_results(e)
+ *   others: isl_ipc_connect_owner(e, h) (NULL disconnects); same-process engines: isl_connect_owner_local
+ * A collective or barrier that every rank enqueues behind its kernel (e.g. the occupancy all-gather) tells the owner that all records
+ * have arrived. */
+void* isl_device_results(isl_engine* e);
+int  isl_ipc_results_handle(isl_engine* e, void* handle64);
+int  isl_ipc_connect_owner(isl_engine* e, const void* owner_handle64);
+int  isl_connect_owner_local(isl_engine* e, isl_engine* owner);
+/* Number of ranks of the partitioned run.  With it set (and the owner's results mapped on every other rank) isl_set_causal_window also
+ * applies to isl_place_stream_partitioned: the rank that finishes a chunk adds 1 to a per-chunk counter behind the owner's result
+ * array (peer atomic), and the owner starts chunk c only when all `world` ranks are through with chunk c - window.  All ranks must be
+ * created with the same isl_config.max_batch. */
+int  isl_set_ring_world(isl_engine* e, uint32_t world);
 
 /* ---- diagnostics ------------------------------------------------------- */
 int         isl_get_stats(isl_engine* e, isl_stats* out);

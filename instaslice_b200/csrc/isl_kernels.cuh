@@ -904,7 +904,11 @@ __host__ __device__ inline uint32_t max_segment_for(uint32_t total_candidates) {
     return s >= kSegMax ? kSegMax : s / 64u * 64u;
 }
 
-struct ChunkDesc { uint32_t req_off, n, batch, first_of_batch; };
+struct ChunkDesc {
+    uint32_t req_off, n, batch, first_of_batch;
+    uint2* host_out;                // open streams: mapped pinned destination of this chunk's results (nullptr: PipeArgs.host_out + req_off)
+    uint64_t pad;
+};
 
 struct PipeArgs {
     uint32_t n_chunks, n_seg, seg, lo, hi, epoch;
@@ -929,6 +933,18 @@ struct PipeArgs {
     const uint32_t* ready;          // [batch] == epoch once the batch's requests are in HBM and its pre-pass is done (nullptr = all ready)
     uint32_t* done_cnt;             // [chunk] segments that have committed the chunk (zeroed per call; nullptr = no copier CTA)
     uint2* host_out;                // mapped pinned result array of the caller: CTA n_seg copies every complete chunk there
+    // open streams (isl_stream_open / _submit / _wait / _close): batches arrive while the kernel runs, one chunk per batch, n_chunks is
+    // the capacity; ready[b] == ~epoch closes the stream.  host_done[c] = epoch (mapped pinned) tells the host that chunk c is delivered.
+    uint32_t open, copier;          // copier: an extra CTA (index n_seg) delivers finished chunks to host memory
+    uint32_t* host_done;
+    // causal window: chunk c may start only after chunk c - window has been committed by every segment (0 = no constraint)
+    uint32_t window;
+    unsigned long long wait_ns;     // a starved wait traps after this long instead of hanging the GPU
+    // partitioned inventory, results gathered on the owner rank: peer-mapped result array of rank 0 (nullptr = keep results local)
+    uint2* owner_out;
+    // causal window across ranks: the CTA that completes a chunk on its rank adds 1 to ring_done[chunk] on the owner rank (peer atomic);
+    // the owner starts chunk c only when ring_done[c - window] == world
+    uint32_t* ring_done; uint32_t world;
     unsigned long long* trace;      // optional [chunk][segment][kTraceWords]: globaltimer ns of sweep done, token in, token out, commit done, chain start, chain end; decisions; jumps | visited << 32; ns of heads done, windows staged; 2 spare
 };
 
@@ -1023,23 +1039,48 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     __shared__ uint8_t s_tab[kSegMax];                                           // table of every local GPU
     __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_wbase[ISL_MAX_PROFILES], s_qbeg[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
     __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_minsize[ISL_MAX_PROFILES], s_usable[kMaxTables], s_plist[ISL_MAX_PROFILES], s_nplist;
-    __shared__ uint32_t s_warp[kPipeThreads / 32], s_ncand, s_nfree, s_nlog, s_idle;
+    __shared__ uint32_t s_warp[kPipeThreads / 32], s_ncand, s_nfree, s_nlog, s_idle, s_closed;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     if (seg == a.n_seg) {       // the extra CTA of a host-buffer stream: every chunk all segments have committed goes to the caller's
                                 // (mapped, pinned) result array right away, so the D2H of the results hides behind the rest of the stream
+        __shared__ uint32_t s_stop;
         for (uint32_t c = 0; c < a.n_chunks; ++c) {
-            const ChunkDesc cd = a.chunks[c];
-            if (tid == 0) while (ld_acquire_gpu(a.done_cnt + c) < a.n_seg) __nanosleep(256);
+            if (tid == 0) {
+                uint32_t stop = 0;
+                const unsigned long long t0 = globaltimer_ns();
+                while (ld_acquire_gpu(a.done_cnt + c) < a.n_seg) {
+                    // a closed (or aborted) stream never commits this chunk: ready[batch] holds ~epoch
+                    if (a.ready && ld_acquire_gpu(a.ready + (a.open ? c : a.chunks[c].batch)) == ~a.epoch) { stop = 1; break; }
+                    __nanosleep(256);
+                    if (globaltimer_ns() - t0 > a.wait_ns + 5000000000ull) __trap();
+                }
+                s_stop = stop;
+            }
             __syncthreads();
+            if (s_stop) break;
+            const ChunkDesc cd = a.chunks[c];
             const uint2* __restrict__ src = a.out + cd.req_off;
-            uint2* __restrict__ dst = a.host_out + cd.req_off;
-            const uint32_t head = min(cd.n, cd.req_off & 1u), pairs = (cd.n - head) >> 1;       // 16-byte body, 8-byte head / tail
-            if (tid == 0 && head) dst[0] = __ldcg(src);
-            const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src + head);
-            uint4* __restrict__ d4 = reinterpret_cast<uint4*>(dst + head);
+            uint2* __restrict__ dst = cd.host_out ? cd.host_out : a.host_out + cd.req_off;
+            // 16-byte body between an 8-byte head / tail when source and destination are 16-byte aligned at the same records;
+            // otherwise (a destination that is only 8-byte aligned relative to the staging buffer) plain 8-byte stores
+            const bool same = ((reinterpret_cast<uintptr_t>(src) ^ reinterpret_cast<uintptr_t>(dst)) & 8u) == 0;
+            if (same) {
+                const uint32_t head = min(cd.n, (uint32_t)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1u)), pairs = (cd.n - head) >> 1;
+                if (tid == 0 && head) dst[0] = __ldcg(src);
+                const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src + head);
+                uint4* __restrict__ d4 = reinterpret_cast<uint4*>(dst + head);
 #pragma unroll 4
-            for (uint32_t i = tid; i < pairs; i += kPipeThreads) d4[i] = __ldcg(s4 + i);
-            if (tid == 0 && ((cd.n - head) & 1u)) dst[cd.n - 1] = __ldcg(src + cd.n - 1);
+                for (uint32_t i = tid; i < pairs; i += kPipeThreads) d4[i] = __ldcg(s4 + i);
+                if (tid == 0 && ((cd.n - head) & 1u)) dst[cd.n - 1] = __ldcg(src + cd.n - 1);
+            } else {
+#pragma unroll 4
+                for (uint32_t i = tid; i < cd.n; i += kPipeThreads) dst[i] = __ldcg(src + i);
+            }
+            if (a.host_done) {          // the host may read the chunk's results as soon as it sees this word
+                __threadfence_system();
+                __syncthreads();
+                if (tid == 0) st_release_sys(a.host_done + c, a.epoch);
+            }
         }
         __threadfence_system();
         return;
@@ -1102,25 +1143,47 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa_q + off), "l"(src + off) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // fed streams: the requests of a batch may still be on their way (H2D + pre-pass on the feed stream) when the pipeline gets there
-    auto wait_ready = [&](uint32_t chunk) {
-        if (!a.ready) return;
+    // fed streams: the requests of a batch may still be on their way (H2D + pre-pass on the feed stream) when the pipeline gets there.
+    // Returns true when the stream ends in front of this chunk (an open stream was closed, or the host aborted a feed).
+    // Causal window: chunk c additionally waits until every segment has committed chunk c - window.
+    auto wait_ready = [&](uint32_t chunk) -> bool {
+        if (!a.ready && !a.window) return false;
+        const bool gate_ring = a.ring_done && !a.inbox;          // ranks behind the owner are gated by the token itself
         if (tid == 0) {
-            const uint32_t* f = a.ready + a.chunks[chunk].batch;
+            uint32_t closed = 0;
             const unsigned long long t0 = globaltimer_ns();
-            // the feed kernels are launched AFTER this one; a tool that serialises kernels would starve the wait (the host side switches
-            // feeding off when it detects one, ISL_NO_FEED=1 forces it) — fail loudly after 20 s instead of hanging the GPU
-            while (ld_acquire_gpu(f) != a.epoch) { __nanosleep(128); if (globaltimer_ns() - t0 > 20000000000ull) __trap(); }
+            if (a.ready) {
+                const uint32_t* f = a.ready + (a.open ? chunk : a.chunks[chunk].batch);
+                // the feed kernels are launched AFTER this one; a tool that serialises kernels would starve the wait (the host side switches
+                // feeding off when it detects one, ISL_NO_FEED=1 forces it) — fail loudly instead of hanging the GPU
+                while (true) {
+                    const uint32_t v = ld_acquire_gpu(f);
+                    if (v == a.epoch) break;
+                    if (v == ~a.epoch) { closed = 1; break; }
+                    __nanosleep(128);
+                    if (globaltimer_ns() - t0 > a.wait_ns) __trap();
+                }
+            }
+            if (!closed && a.window && chunk >= a.window) {
+                if (gate_ring) while (ld_acquire_sys(a.ring_done + chunk - a.window) < a.world) { __nanosleep(64); if (globaltimer_ns() - t0 > a.wait_ns) __trap(); }
+                else if (!a.ring_done) while (ld_acquire_gpu(a.done_cnt + chunk - a.window) < a.n_seg) { __nanosleep(64); if (globaltimer_ns() - t0 > a.wait_ns) __trap(); }
+            }
+            s_closed = closed;
         }
         __syncthreads();
+        return s_closed != 0;
     };
     auto chunk_done = [&](uint32_t chunk) {     // after the barrier that ends the chunk's commit
-        if (a.done_cnt && tid == 0) { __threadfence(); atomicAdd(a.done_cnt + chunk, 1u); }
+        if (a.done_cnt && tid == 0) {
+            if (a.ring_done) __threadfence_system(); else __threadfence();
+            const uint32_t before = atomicAdd(a.done_cnt + chunk, 1u);
+            if (a.ring_done && before + 1 == a.n_seg) atomicAdd_system(a.ring_done + chunk, 1u);     // this rank is through with the chunk
+        }
     };
-    wait_ready(0);
-    queue_load_async(0);
+    bool closed = wait_ready(0);
+    if (!closed) queue_load_async(0);
 
-    for (uint32_t c = 0; c < a.n_chunks; ++c) {
+    for (uint32_t c = 0; c < a.n_chunks && !closed; ++c) {
         const ChunkDesc cd = a.chunks[c];
         const Ctrl* cc = a.cctl + c;
         if (cd.first_of_batch) {            // 1. frees of this batch inside my range: one byte per GPU
@@ -1185,7 +1248,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     }
                 }
             } else if (a.inbox) {       // first segment of a rank that has a predecessor: the token comes over NVLink
-                if (tid == 0) { const uint32_t* flag = a.inbox + (size_t)c * kTokStride + ISL_MAX_PROFILES; while (ld_acquire_sys(flag) != a.xepoch) { } }
+                if (tid == 0) {     // a dead or stuck predecessor must not hang this GPU for good: trap like wait_ready does
+                    const uint32_t* flag = a.inbox + (size_t)c * kTokStride + ISL_MAX_PROFILES;
+                    const unsigned long long t0 = globaltimer_ns();
+                    while (ld_acquire_sys(flag) != a.xepoch) { if (globaltimer_ns() - t0 > a.wait_ns) __trap(); }
+                }
                 __syncwarp();
                 if (tid < ISL_MAX_PROFILES) h = ld_relaxed_sys(a.inbox + (size_t)c * kTokStride + tid);
             } else if (tid < ISL_MAX_PROFILES) h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
@@ -1228,7 +1295,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             }
             __syncthreads();
             chunk_done(c);
-            if (c + 1 < a.n_chunks) { wait_ready(c + 1); queue_load_async(c + 1); }
+            if (c + 1 < a.n_chunks) { closed = wait_ready(c + 1); if (!closed) queue_load_async(c + 1); }
             continue;
         }
         {   // windows of ready-made keys t << 15 | profile << 11, each closed by two INF sentinels — converted from the shared copy of
@@ -1376,23 +1443,26 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             }
         }
         __syncthreads();
-        if (c + 1 < a.n_chunks && !a.ready) queue_load_async(c + 1);    // the chain is done with the queues: fetch the next chunk's behind the commit
+        if (c + 1 < a.n_chunks && !a.ready && !a.window) queue_load_async(c + 1);    // the chain is done with the queues: fetch the next chunk's behind the commit
         {   // 6. commit
             const uint32_t nlog = s_nlog;
             for (uint32_t j = tid; j < nlog; j += kPipeThreads) {
                 const uint2 e = s_log[j];
                 const uint32_t l = s_cand[((e.y - sa_cand) >> 2) - 2] >> 16, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
-                a.out[cd.req_off + t] = pack_result(lo_s + l, __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
+                const uint2 rec = pack_result(lo_s + l, __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
+                a.out[cd.req_off + t] = rec;
+                if (a.owner_out) a.owner_out[cd.req_off + t] = rec;         // partitioned inventory: straight into the owner rank's result array (peer store over NVLink)
                 atomicOr(&s_occ32[l >> 2], mask << ((l & 3u) * 8u));
             }
         }
         __syncthreads();
         if (tr && tid == 0) tr[3] = globaltimer_ns();
         chunk_done(c);
-        if (c + 1 < a.n_chunks && a.ready) { wait_ready(c + 1); queue_load_async(c + 1); }   // fed stream: the next batch may not have arrived yet
+        if (c + 1 < a.n_chunks && (a.ready || a.window)) { closed = wait_ready(c + 1); if (!closed) queue_load_async(c + 1); }   // fed stream: the next batch may not have arrived yet
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     for (uint32_t i = tid; i < n_g; i += kPipeThreads) a.occ[lo_s + i] = reinterpret_cast<uint8_t*>(s_occ32)[i];
+    if (a.owner_out) __threadfence_system();        // the peer stores of this CTA are performed before the grid is seen as complete
     if (tid == 0 && st_steps + st_jumps) {
         atomicAdd(&a.stats->placed, st_steps);
         atomicAdd(&a.stats->steps, st_steps);

@@ -4,6 +4,7 @@
 // internal/controller/instaslice_controller.go:188-262,303-384 (see the header for the per-symbol map).
 // No Go pointer is retained after a call returns; every buffer the engine keeps is its own.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -80,6 +81,17 @@ struct isl_engine {
     uint8_t* d_occ_snap = nullptr; size_t snap_bytes = 0; uint32_t snap_G = 0;      // isl_snapshot_occupancy / isl_restore_occupancy
     bool delivered = false;          // the last run_stream call already put the results into the caller's host buffer
     size_t scratch_bytes = 0;
+    uint32_t window = 0;             // causal window of stream calls (isl_set_causal_window): chunk c starts after chunk c - window is committed
+    // open stream (isl_stream_open / _submit / _wait / _close): one persistent k_pipeline, batches arrive while it runs
+    struct Open {
+        bool active = false, launched = false;
+        uint32_t max_batches = 0, submitted = 0, epoch = 0, seg = 0, n_seg = 0, q_stride = 0, free_stride = 0, tiles_per_batch = 0;
+        uint32_t* h_done = nullptr; uint32_t* d_done_host = nullptr; uint32_t cap_done = 0;   // mapped pinned: [batch] = epoch once its results are in host memory
+        ChunkDesc* h_chunks = nullptr; TileDesc* h_tiles = nullptr; uint32_t cap_desc = 0;       // pinned staging of the per-batch descriptors
+    } open;
+    // partitioned inventory with the results gathered on the owner rank (rank 0): peer-mapped d_res of the owner
+    uint2* d_owner_out = nullptr; bool owner_local = false;
+    uint32_t ring_world = 0;         // ranks of the partitioned run (isl_set_ring_world); the causal window of a ring needs it
 
     // stats
     isl_stats st{};
@@ -124,12 +136,7 @@ int ensure_scratch(isl_engine* e, size_t bytes) {
 
 template <int K>
 int launch_chain(isl_engine* e, uint2* d_out_chunk, const uint32_t* d_heads_in, uint32_t* d_heads_out) {
-    const size_t smem = (size_t)kQCap * sizeof(uint16_t);
-    static bool attr_set[8] = {false};
-    if (!attr_set[e->device & 7]) {
-        ISL_CUDA(e, cudaFuncSetAttribute(k_chain<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[e->device & 7] = true;
-    }
+    const size_t smem = (size_t)kQCap * sizeof(uint16_t);      // opted in per device by isl_create
     k_chain<K><<<1, kChainThreads, smem, e->stream>>>(e->tab, e->d_ctrl, e->d_q, e->d_cand_o16, e->d_feas, e->d_log, d_heads_in, d_heads_out);
     if (int rc = check_launch(e, "k_chain")) return rc;
     k_commit<<<kChunk / 256, 256, 0, e->stream>>>(e->d_ctrl, e->d_log, e->d_cand, reinterpret_cast<uint32_t*>(e->d_occ), d_out_chunk);
@@ -195,11 +202,6 @@ int run_bestfit(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out) {
     const bool in_smem = Gr <= kBfSmemGpus;
     const size_t smem = in_smem ? (size_t)256 * stride * sizeof(uint32_t) : 0;
     if (!in_smem && !e->d_bf_bitmaps) ISL_CUDA(e, cudaMalloc(&e->d_bf_bitmaps, (size_t)256 * (kBfMaxGpus / 32 + kBfMaxGpus / 1024) * sizeof(uint32_t)));
-    static bool attr_set[8] = {false};
-    if (!attr_set[e->device & 7]) {
-        ISL_CUDA(e, cudaFuncSetAttribute(k_bestfit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(256 * (kBfSmemGpus / 32 + kBfSmemGpus / 1024) * sizeof(uint32_t))));
-        attr_set[e->device & 7] = true;
-    }
     const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
     if (timing) cudaEventRecord(e->ev[0], e->stream);
     k_prepare<<<ceil_div(n, kTile), kTileThreads, 0, e->stream>>>(n, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi,
@@ -288,13 +290,8 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
 
 template <int K, bool kP15>
 int launch_pipeline(isl_engine* e, PipeArgs& args) {
-    static bool attr_set[8] = {false};
-    if (!attr_set[e->device & 7]) {
-        ISL_CUDA(e, cudaFuncSetAttribute(k_pipeline<K, kP15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
-        attr_set[e->device & 7] = true;
-    }
     void* params[] = {&e->tab, &args};
-    const cudaError_t err = cudaLaunchCooperativeKernel((void*)k_pipeline<K, kP15>, dim3(args.n_seg + (args.host_out ? 1u : 0u)), dim3(kPipeThreads), params, kPipeSmem, e->stream);
+    const cudaError_t err = cudaLaunchCooperativeKernel((void*)k_pipeline<K, kP15>, dim3(args.n_seg + (args.copier ? 1u : 0u)), dim3(kPipeThreads), params, kPipeSmem, e->stream);
     if (err == cudaErrorCooperativeLaunchTooLarge || err == cudaErrorLaunchOutOfResources) {   // e.g. the GPU is shared: not all CTAs can be co-resident
         cudaGetLastError();
         return ISL_ESTATE;          // caller falls back to the chunk-by-chunk path
@@ -309,7 +306,6 @@ int query_coresident(isl_engine* e) {
     int per_sm = 0, sms = 0, coop = 0;
     ISL_CUDA(e, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
     ISL_CUDA(e, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
-    ISL_CUDA(e, cudaFuncSetAttribute(k_pipeline<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
     ISL_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline<4, true>, kPipeThreads, kPipeSmem));
     e->max_coresident = coop ? std::max(1, per_sm * sms) : -1;
     return ISL_OK;
@@ -325,6 +321,41 @@ int grow(isl_engine* e, T** buf, uint32_t* cap, size_t need, size_t elems_per_un
     *cap = (uint32_t)units;
     return ISL_OK;
 }
+
+// Segment geometry of the pipeline for a stream of n_chunks chunks of ~avg_chunk requests.  ISL_ERANGE: the inventory does not fit the
+// co-resident CTAs (or the tables need too many candidates per segment) — the caller takes the chunk-by-chunk path.
+int plan_pipeline(isl_engine* e, uint32_t n_chunks, double avg_chunk, bool want_feed, uint32_t* seg_out, uint32_t* n_seg_out) {
+    if (int rc = query_coresident(e)) return rc;
+    const uint32_t range = e->hi - e->lo;
+    uint32_t total_cand = 0;
+    for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) total_cand += e->tab.desc[k][l] >> 31;
+    const uint32_t seg_cap = max_segment_for(total_cand);      // queue windows of a segment must fit in shared memory
+    // Segments aimed for.  A batch's decisions form ONE sequential chain over the inventory, only different chunks overlap, so a
+    // stream of B chunks over S stages takes about (S + B - 1) x (D x t_dec / S + t_fix), D = decisions of a chunk (tools/chain_cost.py:
+    // t_dec 35-41 ns, t_fix 1.6-2.3 us per busy cell over the round: ratio ~0.018 / us).  Minimum at S = sqrt((B - 1) x D x t_dec / t_fix); D is estimated by the
+    // smaller of the chunk size and ~3.5 placements per GPU.  ISL_PIPE_SEGMENTS overrides (experiments).
+    uint32_t target = 148;
+    {
+        const double d_est = std::min(avg_chunk, 3.5 * (double)e->G);
+        const double s_opt = std::sqrt(std::max(1.0, (double)n_chunks - 1.0) * d_est * (0.041 / 2.3));
+        target = (uint32_t)std::min(148.0, std::max(1.0, std::floor(s_opt + 0.5)));
+    }
+    if (const char* v = getenv("ISL_PIPE_SEGMENTS")) target = std::max(1u, (uint32_t)strtoul(v, nullptr, 10));
+    target = std::min(target, (uint32_t)std::max(1, e->max_coresident));
+    // fed host streams run their per-batch pre-pass kernels WHILE the pipeline is resident: keep kFeedReserve SMs free of pipeline
+    // CTAs (one CTA fills an SM's shared memory, and kernels with another shared-memory carve-out cannot join it there)
+    if (want_feed && e->max_coresident > 2 * (int)kFeedReserve) target = std::min(target, (uint32_t)e->max_coresident - 1u - kFeedReserve);
+    // segment size from the WHOLE inventory: a partitioned rank keeps the global pipeline depth (~target stages over all ranks)
+    if (seg_cap < 64) return ISL_ERANGE;
+    const uint32_t seg = std::min(seg_cap, std::max(64u, (ceil_div(e->G, target) + 63u) / 64u * 64u));
+    const uint32_t n_seg = std::max(1u, ceil_div(range, seg));
+    if (e->max_coresident <= 0 || n_seg > (uint32_t)e->max_coresident) return ISL_ERANGE;
+    *seg_out = seg; *n_seg_out = n_seg;
+    return ISL_OK;
+}
+
+constexpr unsigned long long kWaitNs = 20000000000ull;          // a starved device-side wait traps after 20 s
+constexpr unsigned long long kOpenWaitNs = 600000000000ull;     // open streams may idle between batches: 10 min
 
 // Resolve a stream of batches (semantics: one batch after the other).  Enqueues only.
 // h_in / h_out (isl_place_stream): the caller's host buffers.  With the segment pipeline the batches are copied and pre-passed one
@@ -362,30 +393,9 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
                            !getenv("CUDA_INJECTION64_PATH") && !getenv("CUDA_LAUNCH_BLOCKING") && !getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
     uint32_t seg = 0, n_seg = 0;
     if (pipeline) {
-        if (int rc = query_coresident(e)) return rc;
-        uint32_t total_cand = 0;
-        for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) total_cand += e->tab.desc[k][l] >> 31;
-        const uint32_t seg_cap = max_segment_for(total_cand);      // queue windows of a segment must fit in shared memory
-        // Segments aimed for.  A batch's decisions form ONE sequential chain over the inventory, only different chunks overlap, so a
-        // stream of B chunks over S stages takes about (S + B - 1) x (D x t_dec / S + t_fix), D = decisions of a chunk (tools/chain_cost.py:
-        // t_dec 35-41 ns, t_fix 1.6-2.3 us per busy cell over the round: ratio ~0.018 / us).  Minimum at S = sqrt((B - 1) x D x t_dec / t_fix); D is estimated by the
-        // smaller of the chunk size and ~3.5 placements per GPU.  ISL_PIPE_SEGMENTS overrides (experiments).
-        uint32_t target = 148;
-        {
-            const double d_est = std::min((double)total / n_chunks, 3.5 * (double)e->G);
-            const double s_opt = std::sqrt(std::max(1.0, (double)(n_chunks - 1)) * d_est * (0.041 / 2.3));
-            target = (uint32_t)std::min(148.0, std::max(1.0, std::floor(s_opt + 0.5)));
-        }
-        if (const char* v = getenv("ISL_PIPE_SEGMENTS")) target = std::max(1u, (uint32_t)strtoul(v, nullptr, 10));
-        target = std::min(target, (uint32_t)std::max(1, e->max_coresident));
-        // fed host streams run their per-batch pre-pass kernels WHILE the pipeline is resident: keep kFeedReserve SMs free of pipeline
-        // CTAs (one CTA fills an SM's shared memory, and kernels with another shared-memory carve-out cannot join it there)
-        if (want_feed && e->max_coresident > 2 * (int)kFeedReserve) target = std::min(target, (uint32_t)e->max_coresident - 1u - kFeedReserve);
-        // segment size from the WHOLE inventory: a partitioned rank keeps the global pipeline depth (~target stages over all ranks)
-        seg = std::min(seg_cap, std::max(64u, (ceil_div(e->G, target) + 63u) / 64u * 64u));
-        if (seg_cap < 64) { if (ring) return ISL_ERANGE; pipeline = false; seg = 64; }
-        n_seg = std::max(1u, ceil_div(range, seg));
-        if (e->max_coresident <= 0 || n_seg > (uint32_t)e->max_coresident) { if (ring) return ISL_ERANGE; pipeline = false; }
+        const int prc = plan_pipeline(e, n_chunks, (double)total / n_chunks, want_feed, &seg, &n_seg);
+        if (prc == ISL_ECUDA) return prc;
+        if (prc != ISL_OK) { if (ring) return ISL_ERANGE; pipeline = false; }
     }
     if (!pipeline) {       // one batch after the other through the single-chain path
         if (int rc = copy_in_whole()) return rc;
@@ -444,15 +454,18 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
             ISL_CUDA(e, cudaEventCreateWithFlags(&e->ev_feed, cudaEventDisableTiming));
             ISL_CUDA(e, cudaEventCreateWithFlags(&e->ev_feed_done, cudaEventDisableTiming));
         }
-        if (int rc = grow(e, &e->d_ready, &e->cap_ready, n_batches, 1)) return rc;
-        if (int rc = grow(e, &e->d_done_cnt, &e->cap_done, n_chunks, 1)) return rc;
+        if (int rc = grow(e, &e->d_ready, &e->cap_ready, n_batches + 1, 1)) return rc;
     }
+    // causal window (device-side): chunk c waits for chunk c - window on every segment (of every rank: a ring counts ranks on the owner)
+    const uint32_t window = (ring && e->ring_world == 0) ? 0u : e->window;
+    const bool need_done = feed || window;
+    if (need_done) if (int rc = grow(e, &e->d_done_cnt, &e->cap_done, n_chunks, 1)) return rc;
     const cudaStream_t pre = feed ? e->feed_stream : e->stream;     // the stream the tables and the pre-pass go to
     if (feed) {     // the feed stream starts behind whatever the engine's stream still holds (earlier calls, load_inventory)
         ISL_CUDA(e, cudaEventRecord(e->ev_feed, e->stream));
         ISL_CUDA(e, cudaStreamWaitEvent(e->feed_stream, e->ev_feed, 0));
-        ISL_CUDA(e, cudaMemsetAsync(e->d_done_cnt, 0, (size_t)n_chunks * sizeof(uint32_t), pre));
     } else if (int rc = copy_in_whole()) return rc;
+    if (need_done) ISL_CUDA(e, cudaMemsetAsync(e->d_done_cnt, 0, (size_t)n_chunks * sizeof(uint32_t), pre));
     ISL_CUDA(e, cudaMemcpyAsync(e->d_chunks, e->h_chunks.data(), n_chunks * sizeof(ChunkDesc), cudaMemcpyHostToDevice, pre));
     ISL_CUDA(e, cudaMemcpyAsync(e->d_tiles, e->h_tiles.data(), n_tiles_total * sizeof(TileDesc), cudaMemcpyHostToDevice, pre));
     ISL_CUDA(e, cudaMemsetAsync(e->d_free_acc, 0, (size_t)n_batches * free_stride, pre));
@@ -493,7 +506,14 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     if (timing) cudaEventRecord(e->ev[2], e->stream);
     PipeArgs args{};
     args.n_chunks = n_chunks; args.n_seg = n_seg; args.seg = seg; args.lo = e->lo; args.hi = e->hi; args.epoch = epoch;
-    args.ready = feed ? e->d_ready : nullptr; args.done_cnt = h_out_dev ? e->d_done_cnt : nullptr; args.host_out = h_out_dev;
+    args.ready = feed ? e->d_ready : nullptr; args.done_cnt = (h_out_dev || window) ? e->d_done_cnt : nullptr; args.host_out = h_out_dev;
+    if (ring && window) {       // the owner's counters sit behind its result array; the other ranks reach them through the same peer mapping
+        uint2* base = e->has_prev ? e->d_owner_out : e->d_res;
+        if (!base) return ISL_ESTATE;
+        args.ring_done = reinterpret_cast<uint32_t*>(base + e->cfg.max_batch); args.world = e->ring_world;
+        if (!e->has_prev) ISL_CUDA(e, cudaMemsetAsync(args.ring_done, 0, (size_t)n_chunks * sizeof(uint32_t), e->stream));
+    }
+    args.copier = h_out_dev ? 1u : 0u; args.window = window; args.wait_ns = kWaitNs; args.owner_out = ring ? e->d_owner_out : nullptr;
     args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
     args.q_stride = q_stride; args.free_stride = free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab; args.out = d_out; args.feas = e->d_feas; args.stats = e->d_ctrl;
     args.heads_in = d_heads_in; args.heads_out = d_heads_out;
@@ -528,7 +548,14 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     }
     if (rc) return rc;
     if (feed) {     // the remaining batches, while the pipeline works on the first ones
-        for (uint32_t b = 1; b < n_batches; ++b) if (int rc2 = feed_batch(b)) return rc2;
+        for (uint32_t b = 1; b < n_batches; ++b)
+            if (int rc2 = feed_batch(b)) {
+                // the resident pipeline would spin on ready[b] until its trap: publish 'closed' for every batch not fed so that it drains
+                std::vector<uint32_t> closed(n_batches - b, ~epoch);
+                cudaMemcpy(e->d_ready + b, closed.data(), closed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+                cudaStreamSynchronize(e->stream);
+                return rc2;
+            }
         ISL_CUDA(e, cudaEventRecord(e->ev_feed_done, pre));
         ISL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_feed_done, 0));
         e->delivered = h_out_dev != nullptr;
@@ -549,6 +576,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
 
 int validate_ready(isl_engine* e, uint32_t n) {
     if (!e->have_profiles || !e->have_inventory) return ISL_ESTATE;
+    if (e->open.active) return ISL_ESTATE;         // an open stream owns the engine until isl_stream_close
     if (n > e->cfg.max_batch) return ISL_ERANGE;
     return ISL_OK;
 }
@@ -611,6 +639,14 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
                                  (const void*)k_pipeline<1, false>, (const void*)k_pipeline<1, true>, (const void*)k_pipeline<2, false>, (const void*)k_pipeline<2, true>,
                                  (const void*)k_pipeline<4, false>, (const void*)k_pipeline<4, true>};
         for (const void* k : kernels) ISL_TRY(cudaFuncGetAttributes(&fa, k));
+        // dynamic shared memory opt-in, once per engine on its own device (a process-wide cache keyed by a truncated ordinal would
+        // skip devices 8.. and race between threads)
+        const void* chains[] = {(const void*)k_chain<1>, (const void*)k_chain<2>, (const void*)k_chain<4>};
+        for (const void* k : chains) ISL_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kQCap * sizeof(uint16_t))));
+        ISL_TRY(cudaFuncSetAttribute((const void*)k_bestfit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(256 * (kBfSmemGpus / 32 + kBfSmemGpus / 1024) * sizeof(uint32_t))));
+        const void* pipes[] = {(const void*)k_pipeline<1, false>, (const void*)k_pipeline<1, true>, (const void*)k_pipeline<2, false>, (const void*)k_pipeline<2, true>,
+                               (const void*)k_pipeline<4, false>, (const void*)k_pipeline<4, true>};
+        for (const void* k : pipes) ISL_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
     }
     e->occ_bytes = ((size_t)cfg->max_gpus + kSweepBlock - 1) / kSweepBlock * kSweepBlock;
     const uint32_t max_tiles = ceil_div(cfg->max_batch, kTile) + 4096;   // + one partial tile per batch of a stream
@@ -625,7 +661,7 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
     ISL_TRY(cudaMemset(e->d_gtab, 0, e->occ_bytes));
     ISL_TRY(cudaMalloc(&e->d_cand_o16, e->occ_bytes * sizeof(uint16_t)));
     ISL_TRY(cudaMalloc(&e->d_req, (size_t)cfg->max_batch * sizeof(uint2)));
-    ISL_TRY(cudaMalloc(&e->d_res, (size_t)cfg->max_batch * sizeof(uint2)));
+    ISL_TRY(cudaMalloc(&e->d_res, (size_t)cfg->max_batch * sizeof(uint2) + kMaxStreamChunks * sizeof(uint32_t)));   // + per-chunk 'ranks done' counters of a partitioned run (peer-mapped with the results)
     ISL_TRY(cudaMalloc(&e->d_q, (size_t)kQCap * sizeof(uint16_t)));
     ISL_TRY(cudaMalloc(&e->d_tile_counts, (size_t)max_tiles * ISL_MAX_PROFILES * sizeof(uint32_t)));
     ISL_TRY(cudaMalloc(&e->d_cand, e->occ_bytes * sizeof(uint32_t)));
@@ -644,6 +680,7 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
 
 int isl_destroy(isl_engine* e) {
     if (!e) return ISL_EINVAL;
+    if (e->open.active) isl_stream_close(e);        // a persistent pipeline would never let the stream synchronise
     {
         DeviceGuard guard(e->device);
         if (e->stream) cudaStreamSynchronize(e->stream);
@@ -659,6 +696,10 @@ int isl_destroy(isl_engine* e) {
         if (e->ev_feed) cudaEventDestroy(e->ev_feed);
         if (e->ev_feed_done) cudaEventDestroy(e->ev_feed_done);
         if (e->h_small_out) cudaFreeHost(e->h_small_out);
+        if (e->open.h_done) cudaFreeHost(e->open.h_done);
+        if (e->open.h_chunks) cudaFreeHost(e->open.h_chunks);
+        if (e->open.h_tiles) cudaFreeHost(e->open.h_tiles);
+        if (e->d_owner_out && !e->owner_local) cudaIpcCloseMemHandle(e->d_owner_out);
         for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
         if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     }
@@ -777,6 +818,7 @@ int isl_load_inventory(isl_engine* e, uint32_t n_nodes, const uint32_t* node_off
     const uint32_t G = node_off[n_nodes];
     if (G == 0 || !occ) return ISL_EINVAL;
     if (G > e->cfg.max_gpus) return ISL_ERANGE;
+    if (e->open.active) return ISL_ESTATE;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
     e->node_off.assign(node_off, node_off + n_nodes + 1);
@@ -794,7 +836,7 @@ int isl_load_inventory(isl_engine* e, uint32_t n_nodes, const uint32_t* node_off
 
 int isl_read_occupancy(isl_engine* e, uint8_t* out) {
     if (!e || !out) return ISL_EINVAL;
-    if (!e->have_inventory) return ISL_ESTATE;
+    if (!e->have_inventory || e->open.active) return ISL_ESTATE;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
     ISL_CUDA(e, cudaMemcpyAsync(out, e->d_occ, e->G, cudaMemcpyDeviceToHost, e->stream));
@@ -804,7 +846,7 @@ int isl_read_occupancy(isl_engine* e, uint8_t* out) {
 
 int isl_write_occupancy(isl_engine* e, uint32_t first_gpu, uint32_t n, const uint8_t* occ) {
     if (!e || (n && !occ)) return ISL_EINVAL;
-    if (!e->have_inventory) return ISL_ESTATE;
+    if (!e->have_inventory || e->open.active) return ISL_ESTATE;
     if ((uint64_t)first_gpu + n > e->G) return ISL_ERANGE;
     if (n == 0) return ISL_OK;
     std::lock_guard<std::mutex> lk(e->mu);
@@ -847,12 +889,32 @@ uint32_t isl_gpu_to_node(const isl_engine* e, uint32_t gpu) {
     return (uint32_t)(it - e->node_off.begin()) - 1;
 }
 
+static int place_batch_locked(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out);
+
 int isl_place_batch(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out) {
     if (!e || (n && (!in || !out))) return ISL_EINVAL;
     if (int rc = validate_ready(e, n)) return rc;
     if (n == 0) return ISL_OK;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
+    return place_batch_locked(e, n, in, out);
+}
+
+int isl_place_batch_range(isl_engine* e, uint32_t lo, uint32_t hi, uint32_t n, const isl_request* in, isl_result* out) {
+    if (!e || (n && (!in || !out))) return ISL_EINVAL;
+    if (int rc = validate_ready(e, n)) return rc;
+    if (lo > hi || hi > e->G) return ISL_EINVAL;
+    if (n == 0) return ISL_OK;
+    std::lock_guard<std::mutex> lk(e->mu);          // restriction, placement and restore under ONE lock: two callers cannot interleave
+    DeviceGuard guard(e->device);
+    const uint32_t lo0 = e->lo, hi0 = e->hi;
+    e->lo = lo; e->hi = hi;
+    const int rc = place_batch_locked(e, n, in, out);
+    e->lo = lo0; e->hi = hi0;
+    return rc;
+}
+
+static int place_batch_locked(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out) {
     if (n <= kSmallInline && small_eligible(e, n)) {        // requests as kernel parameters, results into mapped pinned memory: 1 launch + 1 sync
         SmallReqs inl{};
         memcpy(inl.r, in, (size_t)n * sizeof(isl_request));
@@ -996,7 +1058,7 @@ void* isl_device_occupancy(isl_engine* e) { return e ? e->d_occ : nullptr; }
 
 int isl_free_batch(isl_engine* e, uint32_t n, const isl_span* spans) {
     if (!e || (n && !spans)) return ISL_EINVAL;
-    if (!e->have_inventory) return ISL_ESTATE;
+    if (!e->have_inventory || e->open.active) return ISL_ESTATE;
     if (n == 0) return ISL_OK;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
@@ -1062,6 +1124,230 @@ int isl_reset_stats(isl_engine* e) {
     ISL_CUDA(e, cudaMemsetAsync(&e->d_ctrl->placed, 0, 8 * sizeof(unsigned long long), e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     return ISL_OK;
+}
+
+// ---- causal window / pinned buffers / owner-gathered results --------------------------------------------------------------
+int isl_set_causal_window(isl_engine* e, uint32_t window) {
+    if (!e) return ISL_EINVAL;
+    if (e->open.active) return ISL_ESTATE;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->window = window;
+    return ISL_OK;
+}
+
+int isl_set_ring_world(isl_engine* e, uint32_t world) {
+    if (!e) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->ring_world = world;
+    return ISL_OK;
+}
+
+void* isl_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void isl_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void* isl_device_results(isl_engine* e) { return e ? e->d_res : nullptr; }
+
+int isl_ipc_results_handle(isl_engine* e, void* handle64) {
+    if (!e || !handle64) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    cudaIpcMemHandle_t h;
+    ISL_CUDA(e, cudaIpcGetMemHandle(&h, e->d_res));
+    memcpy(handle64, &h, sizeof h);
+    return ISL_OK;
+}
+
+int isl_ipc_connect_owner(isl_engine* e, const void* owner_handle64) {
+    if (!e) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    if (e->d_owner_out && !e->owner_local) cudaIpcCloseMemHandle(e->d_owner_out);
+    e->d_owner_out = nullptr; e->owner_local = false;
+    if (owner_handle64) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, owner_handle64, sizeof h);
+        void* p = nullptr;
+        ISL_CUDA(e, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        e->d_owner_out = static_cast<uint2*>(p);
+    }
+    return ISL_OK;
+}
+
+int isl_connect_owner_local(isl_engine* e, isl_engine* owner) {
+    if (!e) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (e->d_owner_out && !e->owner_local) cudaIpcCloseMemHandle(e->d_owner_out);
+    e->d_owner_out = owner ? owner->d_res : nullptr; e->owner_local = true;
+    return ISL_OK;
+}
+
+// ---- open streams: the causal feed ----------------------------------------------------------------------------------------
+// One persistent k_pipeline resolves batches that arrive WHILE it runs: isl_stream_submit copies a batch in and pre-passes it on the
+// feed stream, the kernel's extra CTA writes its results into the caller's pinned buffer and raises a host-visible word, and
+// isl_stream_wait returns as soon as that word is up — the caller composes batch b+1 (or b+k) from results it has already seen.
+int isl_stream_open(isl_engine* e, uint32_t max_batches) {
+    if (!e || max_batches == 0 || max_batches > kMaxStreamChunks) return ISL_EINVAL;
+    if (!e->have_profiles || !e->have_inventory || e->open.active) return ISL_ESTATE;
+    if (e->cfg.policy != ISL_POLICY_FIRST_FIT) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    auto& o = e->open;
+    const uint32_t pc = e->pipe_chunk;
+    if ((uint64_t)max_batches * pc > e->cfg.max_batch) return ISL_ERANGE;       // every batch owns a slot of the staging buffers
+    uint32_t seg = 0, n_seg = 0;
+    if (int rc = plan_pipeline(e, std::max(2u, max_batches), (double)pc, true, &seg, &n_seg)) return rc;
+    if (n_seg + 1 + kFeedReserve > (uint32_t)e->max_coresident) return ISL_ERANGE;  // the feed kernels need SMs next to the resident pipeline
+    o.seg = seg; o.n_seg = n_seg; o.max_batches = max_batches; o.submitted = 0; o.launched = false;
+    o.q_stride = pc + kQPad * ISL_MAX_PROFILES; o.free_stride = (uint32_t)e->occ_bytes; o.tiles_per_batch = pc / kTile;
+    if (int rc = grow(e, &e->d_chunks, &e->cap_chunks, max_batches, 1)) return rc;
+    if (int rc = grow(e, &e->d_cctl, &e->cap_cctl, max_batches, 1)) return rc;
+    if (int rc = grow(e, &e->d_qall, &e->cap_qall, (size_t)max_batches * o.q_stride, 1)) return rc;
+    if (int rc = grow(e, &e->d_tiles, &e->cap_tiles, (size_t)max_batches * o.tiles_per_batch, 1)) return rc;
+    if (int rc = grow(e, &e->d_free_acc, &e->cap_free, (size_t)max_batches * (o.free_stride / 4), 1)) return rc;
+    {
+        const uint32_t before = e->cap_tokens;
+        if (int rc = grow(e, &e->d_tokens, &e->cap_tokens, (size_t)max_batches * (n_seg + 1), kTokStride)) return rc;
+        if (e->cap_tokens != before) ISL_CUDA(e, cudaMemsetAsync(e->d_tokens, 0, (size_t)e->cap_tokens * kTokStride * sizeof(uint32_t), e->stream));
+    }
+    if (int rc = grow(e, &e->d_ready, &e->cap_ready, max_batches + 1, 1)) return rc;
+    if (int rc = grow(e, &e->d_done_cnt, &e->cap_done, max_batches, 1)) return rc;
+    if ((uint64_t)max_batches * o.tiles_per_batch > ceil_div(e->cfg.max_batch, kTile) + 4096) return ISL_ERANGE;
+    if (o.cap_done < max_batches) {
+        if (o.h_done) cudaFreeHost(o.h_done);
+        o.h_done = nullptr; o.cap_done = 0;
+        ISL_CUDA(e, cudaHostAlloc(&o.h_done, (size_t)max_batches * sizeof(uint32_t), cudaHostAllocMapped));
+        ISL_CUDA(e, cudaHostGetDevicePointer(&o.d_done_host, o.h_done, 0));
+        o.cap_done = max_batches;
+    }
+    if (o.cap_desc < max_batches) {
+        if (o.h_chunks) cudaFreeHost(o.h_chunks);
+        if (o.h_tiles) cudaFreeHost(o.h_tiles);
+        o.h_chunks = nullptr; o.h_tiles = nullptr; o.cap_desc = 0;
+        ISL_CUDA(e, cudaHostAlloc(&o.h_chunks, (size_t)max_batches * sizeof(ChunkDesc), cudaHostAllocDefault));
+        ISL_CUDA(e, cudaHostAlloc(&o.h_tiles, (size_t)max_batches * o.tiles_per_batch * sizeof(TileDesc), cudaHostAllocDefault));
+        o.cap_desc = max_batches;
+    }
+    memset(o.h_done, 0, (size_t)max_batches * sizeof(uint32_t));
+    if (!e->feed_stream) {
+        ISL_CUDA(e, cudaStreamCreateWithFlags(&e->feed_stream, cudaStreamNonBlocking));
+        ISL_CUDA(e, cudaEventCreateWithFlags(&e->ev_feed, cudaEventDisableTiming));
+        ISL_CUDA(e, cudaEventCreateWithFlags(&e->ev_feed_done, cudaEventDisableTiming));
+    }
+    uint32_t epoch = ++e->epoch;
+    if ((epoch & 0x7FFFu) == 0) epoch = ++e->epoch;
+    if ((epoch & 0x7FFFu) == 1 && epoch != 1 && e->d_tokens)
+        ISL_CUDA(e, cudaMemsetAsync(e->d_tokens, 0, (size_t)e->cap_tokens * kTokStride * sizeof(uint32_t), e->stream));
+    o.epoch = epoch;
+    // the feed stream starts behind whatever the engine's stream still holds
+    ISL_CUDA(e, cudaEventRecord(e->ev_feed, e->stream));
+    ISL_CUDA(e, cudaStreamWaitEvent(e->feed_stream, e->ev_feed, 0));
+    ISL_CUDA(e, cudaMemsetAsync(e->d_done_cnt, 0, (size_t)max_batches * sizeof(uint32_t), e->feed_stream));
+    ISL_CUDA(e, cudaMemsetAsync(e->d_ready, 0, (size_t)(max_batches + 1) * sizeof(uint32_t), e->feed_stream));
+    ISL_CUDA(e, cudaMemsetAsync(e->d_free_acc, 0, (size_t)max_batches * o.free_stride, e->feed_stream));
+    o.active = true;
+    return ISL_OK;
+}
+
+int isl_stream_submit(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out, uint32_t* ticket) {
+    if (!e || n == 0 || !in || !out) return ISL_EINVAL;
+    if (!e->open.active) return ISL_ESTATE;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    auto& o = e->open;
+    if (o.submitted >= o.max_batches || n > e->pipe_chunk) return ISL_ERANGE;
+    // the results are written by the running kernel: the destination must be mapped pinned host memory (isl_host_alloc, cudaHostAlloc,
+    // cudaHostRegister)
+    cudaPointerAttributes pa{};
+    if (cudaPointerGetAttributes(&pa, out) != cudaSuccess || pa.type != cudaMemoryTypeHost || !pa.devicePointer) { cudaGetLastError(); return ISL_EINVAL; }
+    const uint32_t b = o.submitted, pc = e->pipe_chunk, off = b * pc, tile0 = b * o.tiles_per_batch, n_tiles = ceil_div(n, kTile);
+    const cudaStream_t pre = e->feed_stream;
+    o.h_chunks[b] = ChunkDesc{off, n, b, 1u, static_cast<uint2*>(pa.devicePointer), 0};
+    for (uint32_t t = 0; t < n_tiles; ++t) o.h_tiles[tile0 + t] = TileDesc{off, n, b, tile0, b, tile0, n_tiles, off, n, 0, 0, 0};
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_chunks + b, o.h_chunks + b, sizeof(ChunkDesc), cudaMemcpyHostToDevice, pre));
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_tiles + tile0, o.h_tiles + tile0, (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, pre));
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_req + off, in, (size_t)n * sizeof(isl_request), cudaMemcpyHostToDevice, pre));
+    k_prepare<<<n_tiles, kTileThreads, 0, pre>>>(0, e->d_req, e->d_res, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi, e->prof,
+                                                 e->d_tile_counts, e->d_ctrl, e->d_tiles, e->d_free_acc, o.free_stride / 4, tile0);
+    if (int rc = check_launch(e, "k_prepare")) return rc;
+    k_partition<<<n_tiles, kTileThreads, 0, pre>>>(0, e->d_req, e->prof.n, e->d_tile_counts, 0, e->cand_profiles, e->d_qall, e->d_cctl,
+                                                   e->d_tiles, o.q_stride, tile0);
+    if (int rc = check_launch(e, "k_partition")) return rc;
+    k_set_flag<<<1, 1, 0, pre>>>(e->d_ready + b, o.epoch);
+    if (int rc = check_launch(e, "k_set_flag")) return rc;
+    if (!o.launched) {          // the persistent pipeline starts behind the first batch's tables
+        ISL_CUDA(e, cudaEventRecord(e->ev_feed, pre));
+        ISL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_feed, 0));
+        PipeArgs args{};
+        args.n_chunks = o.max_batches; args.n_seg = o.n_seg; args.seg = o.seg; args.lo = e->lo; args.hi = e->hi; args.epoch = o.epoch;
+        args.ready = e->d_ready; args.done_cnt = e->d_done_cnt; args.host_out = nullptr; args.copier = 1; args.open = 1;
+        args.host_done = o.d_done_host; args.window = 0; args.wait_ns = kOpenWaitNs;
+        args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
+        args.q_stride = o.q_stride; args.free_stride = o.free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab;
+        args.out = e->d_res; args.feas = e->d_feas; args.stats = e->d_ctrl;
+        int rc;
+        const bool p15 = e->prof.n == ISL_MAX_PROFILES;
+        switch (e->n_cand_slots) {
+            case 1: rc = p15 ? launch_pipeline<1, true>(e, args) : launch_pipeline<1, false>(e, args); break;
+            case 2: rc = p15 ? launch_pipeline<2, true>(e, args) : launch_pipeline<2, false>(e, args); break;
+            default: rc = p15 ? launch_pipeline<4, true>(e, args) : launch_pipeline<4, false>(e, args); break;
+        }
+        if (rc) return rc == ISL_ESTATE ? ISL_ERANGE : rc;
+        o.launched = true;
+    }
+    if (ticket) *ticket = b;
+    ++o.submitted;
+    ++e->st.batches; e->st.requests += n;
+    return ISL_OK;
+}
+
+int isl_stream_wait(isl_engine* e, uint32_t ticket) {
+    if (!e) return ISL_EINVAL;
+    auto& o = e->open;
+    if (!o.active || ticket >= o.submitted) return ISL_ESTATE;
+    // no lock: only reads a word the device raises; other threads may keep submitting
+    volatile uint32_t* flag = o.h_done + ticket;
+    const uint32_t epoch = o.epoch;
+    uint64_t spins = 0;
+    while (*flag != epoch) {
+        if ((++spins & 0xFFFFu) == 0) {                 // now and then: did the pipeline die (a trap, an earlier launch error)?
+            DeviceGuard guard(e->device);
+            const cudaError_t err = cudaStreamQuery(e->stream);
+            if (err != cudaSuccess && err != cudaErrorNotReady) { snprintf(e->cuda_err, sizeof(e->cuda_err), "isl_stream_wait: %s", cudaGetErrorString(err)); return ISL_ECUDA; }
+            if (err == cudaSuccess && *flag != epoch) { snprintf(e->cuda_err, sizeof(e->cuda_err), "isl_stream_wait: pipeline ended before batch %u", ticket); return ISL_ECUDA; }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return ISL_OK;
+}
+
+int isl_stream_close(isl_engine* e) {
+    if (!e) return ISL_EINVAL;
+    if (!e->open.active) return ISL_ESTATE;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    auto& o = e->open;
+    int rc = ISL_OK;
+    if (o.launched) {
+        if (o.submitted < o.max_batches) {
+            k_set_flag<<<1, 1, 0, e->feed_stream>>>(e->d_ready + o.submitted, ~o.epoch);     // 'closed': the kernel leaves its chunk loop
+            rc = check_launch(e, "k_set_flag");
+        }
+        cudaError_t err = cudaStreamSynchronize(e->feed_stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+        if (err != cudaSuccess) { snprintf(e->cuda_err, sizeof(e->cuda_err), "isl_stream_close: %s", cudaGetErrorString(err)); rc = ISL_ECUDA; }
+    } else {
+        cudaStreamSynchronize(e->feed_stream);
+    }
+    o.active = false; o.launched = false;
+    return rc;
 }
 
 }  // extern "C"

@@ -5,8 +5,10 @@ canonical GPU range ``partition_bounds(G, world, d)``; every rank holds the whol
 
 * the queue-head token of every chunk crosses rank boundaries INSIDE the running segment-pipeline kernels through
   CUDA-IPC peer memory (``connect_ring``) — no host round trip, no collective on the data path;
-* results: a request is placed by exactly one rank, every other rank keeps its NO_CAPACITY default, and a PLACED
-  record sorts below a NO_CAPACITY one as a little-endian 64-bit integer -> ``merge_results`` = all-reduce(MIN);
+* results are gathered on the OWNER rank (rank 0, where the controller runs) without a collective: ``connect_owner`` maps
+  the owner's result array into every other rank, and the commit threads of those ranks store each PLACED record there
+  as well (peer store inside the running kernel).  ``merge_results`` (all-reduce(MIN) over the 8-byte records: a PLACED
+  record sorts below a NO_CAPACITY one) remains for callers that want the full result array on EVERY rank;
 * occupancy: ``gather_occupancy`` all-gathers the per-rank shards (8 KiB per rank at config 4).
 
 Between two partitioned stream calls all ranks must pass a collective (``merge_results`` is one): the inbox slots of
@@ -43,6 +45,15 @@ def connect_ring(engine, rank: int, world: int, group=None):
     handles = [None] * world
     dist.all_gather_object(handles, engine.ipc_inbox_handle(), group=group)
     engine.ipc_connect(handles[rank + 1] if rank + 1 < world else None, has_prev=rank > 0)
+
+
+def connect_owner(engine, rank: int, world: int, group=None):
+    """Map the owner's (rank 0) result array into every other rank; tell every engine the size of the ring (causal window)."""
+    handles = [None] * world
+    dist.all_gather_object(handles, engine.ipc_results_handle() if rank == 0 else None, group=group)
+    if rank > 0:
+        engine.ipc_connect_owner(handles[0])
+    engine.set_ring_world(world)
 
 
 def merge_results(records_i64: torch.Tensor, group=None) -> torch.Tensor:

@@ -60,6 +60,8 @@ EXPORTED_SYMBOLS = [
     "isl_snapshot_occupancy", "isl_restore_occupancy", "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_place_stream", "isl_place_stream_device", "isl_free_batch",
     "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_ipc_inbox_handle", "isl_ipc_connect", "isl_connect_local", "isl_place_stream_partitioned", "isl_device_occupancy", "isl_get_stats", "isl_read_trace",
     "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
+    "isl_place_batch_range", "isl_stream_open", "isl_stream_submit", "isl_stream_wait", "isl_stream_close", "isl_set_causal_window",
+    "isl_host_alloc", "isl_host_free", "isl_device_results", "isl_ipc_results_handle", "isl_ipc_connect_owner", "isl_connect_owner_local", "isl_set_ring_world",
 ]
 
 _lib = None
@@ -108,6 +110,19 @@ def load_library(path: str = LIB_PATH):
         "isl_strerror": (C.c_char_p, [C.c_int]),
         "isl_last_cuda_error": (C.c_char_p, [p]),
         "isl_abi_version": (C.c_uint32, []),
+        "isl_place_batch_range": (C.c_int, [p, C.c_uint32, C.c_uint32, C.c_uint32, p, p]),
+        "isl_stream_open": (C.c_int, [p, C.c_uint32]),
+        "isl_stream_submit": (C.c_int, [p, C.c_uint32, p, p, C.POINTER(C.c_uint32)]),
+        "isl_stream_wait": (C.c_int, [p, C.c_uint32]),
+        "isl_stream_close": (C.c_int, [p]),
+        "isl_set_causal_window": (C.c_int, [p, C.c_uint32]),
+        "isl_host_alloc": (p, [C.c_size_t]),
+        "isl_host_free": (None, [p]),
+        "isl_device_results": (p, [p]),
+        "isl_ipc_results_handle": (C.c_int, [p, p]),
+        "isl_ipc_connect_owner": (C.c_int, [p, p]),
+        "isl_connect_owner_local": (C.c_int, [p, p]),
+        "isl_set_ring_world": (C.c_int, [p, C.c_uint32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -159,6 +174,32 @@ def make_profile_tables(table_list):
             seen.add(row[0])
             rows[t, names.index(row[0])] = make_profiles([row])[0]
     return names, rows
+
+
+class PinnedArray:
+    """A numpy view of mapped pinned host memory from the engine's own allocator (isl_host_alloc) — what the Go shim uses for the
+    buffers of an open stream."""
+
+    def __init__(self, n: int, dtype):
+        lib = load_library()
+        self.dtype = np.dtype(dtype)
+        self.nbytes = max(1, n) * self.dtype.itemsize
+        self.ptr = lib.isl_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("isl_host_alloc failed")
+        self.array = np.frombuffer((C.c_uint8 * self.nbytes).from_address(self.ptr), dtype=self.dtype, count=n)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            load_library().isl_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def _ptr(a: np.ndarray):
@@ -268,6 +309,32 @@ class Engine:
     def place_batch_device(self, n: int, d_in: int, d_out: int):
         self._check(self._lib.isl_place_batch_device(self._h, n, C.c_void_p(d_in), C.c_void_p(d_out)), "isl_place_batch_device")
 
+    def place_batch_range(self, lo: int, hi: int, requests: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """place_batch restricted to the canonical GPU range [lo, hi) (one node's GPUs) under one engine lock."""
+        requests = np.ascontiguousarray(requests, dtype=REQUEST_DTYPE)
+        if out is None:
+            out = np.empty(len(requests), dtype=RESULT_DTYPE)
+        self._check(self._lib.isl_place_batch_range(self._h, lo, hi, len(requests), _ptr(requests), _ptr(out)), "isl_place_batch_range")
+        return out
+
+    # -- open streams (the causal feed)
+    def stream_open(self, max_batches: int):
+        self._check(self._lib.isl_stream_open(self._h, max_batches), "isl_stream_open")
+
+    def stream_submit_ptr(self, n: int, in_ptr: int, out_ptr: int) -> int:
+        t = C.c_uint32()
+        self._check(self._lib.isl_stream_submit(self._h, n, C.c_void_p(in_ptr), C.c_void_p(out_ptr), C.byref(t)), "isl_stream_submit")
+        return t.value
+
+    def stream_wait(self, ticket: int):
+        self._check(self._lib.isl_stream_wait(self._h, ticket), "isl_stream_wait")
+
+    def stream_close(self):
+        self._check(self._lib.isl_stream_close(self._h), "isl_stream_close")
+
+    def set_causal_window(self, window: int):
+        self._check(self._lib.isl_set_causal_window(self._h, window), "isl_set_causal_window")
+
     def free_batch(self, spans: np.ndarray):
         spans = np.ascontiguousarray(spans, dtype=SPAN_DTYPE)
         self._check(self._lib.isl_free_batch(self._h, len(spans), _ptr(spans)), "isl_free_batch")
@@ -302,6 +369,23 @@ class Engine:
         sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
         self._check(self._lib.isl_place_stream_partitioned(self._h, len(sizes), _ptr(sizes), C.c_void_p(d_in), C.c_void_p(d_out), stream_id),
                     "isl_place_stream_partitioned")
+
+    def device_results(self) -> int:
+        return int(self._lib.isl_device_results(self._h) or 0)
+
+    def ipc_results_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.isl_ipc_results_handle(self._h, buf), "isl_ipc_results_handle")
+        return buf.raw
+
+    def ipc_connect_owner(self, handle: bytes | None):
+        self._check(self._lib.isl_ipc_connect_owner(self._h, handle), "isl_ipc_connect_owner")
+
+    def connect_owner_local(self, owner: "Engine | None"):
+        self._check(self._lib.isl_connect_owner_local(self._h, owner._h if owner is not None else None), "isl_connect_owner_local")
+
+    def set_ring_world(self, world: int):
+        self._check(self._lib.isl_set_ring_world(self._h, world), "isl_set_ring_world")
 
     def device_occupancy(self) -> int:
         return int(self._lib.isl_device_occupancy(self._h) or 0)

@@ -95,7 +95,13 @@ class Churn:
     """
 
     def __init__(self, n_nodes: int = 8192, gpus_per_node: int = 8, n_ops: int = 1_000_000, batch: int = 65_536,
-                 fill: float = 0.5, seed: int = 42, table=tables.H100_80GB, mix=MIX_80GB):
+                 fill: float = 0.5, seed: int = 42, table=tables.H100_80GB, mix=MIX_80GB, min_age: int = 1):
+        """``min_age`` = k: a FREE of churn batch b names an allocation placed by batch b - k or earlier (k = 1: any allocation live
+        when the batch starts — the original definition).  With k > 1 a caller may legitimately have k batches in flight: it can
+        compose batch b as soon as it has seen the results of batch b - k (the causal feed of ``isl_stream_submit``)."""
+        assert min_age >= 1
+        self.min_age = min_age
+        self._young = []          # [(batch index, gpu[], start[], size[])] placements not yet old enough to be freed
         self.node_off = node_offsets(n_nodes, gpus_per_node)
         self.G = n_nodes * gpus_per_node
         self.rows = make_profiles(table)
@@ -105,21 +111,33 @@ class Churn:
         self.batches: list[np.ndarray] = []
         self.n_prefill_batches = 0
         # live allocations as parallel arrays with swap-remove
-        cap = self.G * 7 + batch
+        cap = self.G * 7 + batch * (min_age + 1)
         self._gpu = np.zeros(cap, dtype=np.uint32)
         self._start = np.zeros(cap, dtype=np.uint8)
         self._size = np.zeros(cap, dtype=np.uint8)
         self._live = 0
         self._busy_slices = 0
 
-    def _absorb(self, req: np.ndarray, res: np.ndarray):
+    def _absorb(self, req: np.ndarray, res: np.ndarray, batch_index: int | None = None):
         placed = (req["op"] == OP_ALLOC) & (res["status"] == ST_PLACED)
-        k = int(placed.sum())
-        self._gpu[self._live:self._live + k] = res["gpu"][placed]
-        self._start[self._live:self._live + k] = res["start"][placed]
-        self._size[self._live:self._live + k] = res["size"][placed]
-        self._live += k
         self._busy_slices += int(res["size"][placed].astype(np.int64).sum())
+        if batch_index is None:       # pre-fill: old enough from the start
+            self._pool_add(res["gpu"][placed], res["start"][placed], res["size"][placed])
+        else:
+            self._young.append((batch_index, res["gpu"][placed].copy(), res["start"][placed].copy(), res["size"][placed].copy()))
+
+    def _pool_add(self, gpu, start, size):
+        k = len(gpu)
+        self._gpu[self._live:self._live + k] = gpu
+        self._start[self._live:self._live + k] = start
+        self._size[self._live:self._live + k] = size
+        self._live += k
+
+    def _age(self, batch_index: int):
+        """Placements of batches <= batch_index - min_age become eligible for FREEs (in placement order)."""
+        while self._young and self._young[0][0] <= batch_index - self.min_age:
+            _, gpu, start, size = self._young.pop(0)
+            self._pool_add(gpu, start, size)
 
     def generate(self, placer, after_prefill=None):
         """Run pre-fill and churn through ``placer``; returns the list of recorded batches.
@@ -137,7 +155,9 @@ class Churn:
         if after_prefill is not None:
             after_prefill()
         done = 0
+        bi = 0
         while done < self.n_ops:
+            self._age(bi)
             n = min(self.batch, self.n_ops - done)
             coin = (self.rng.next(n) >> np.uint64(63)).astype(bool)        # True -> FREE
             pick = self.rng.next(n)
@@ -158,9 +178,10 @@ class Churn:
                 gpu[j], start[j], size[j] = gpu[live], start[live], size[live]
             self._live = live
             res = placer(req)
-            self._absorb(req, res)
+            self._absorb(req, res, bi)
             self.batches.append(req)
             done += n
+            bi += 1
         return self.batches
 
 

@@ -47,6 +47,7 @@ int      orc_f_add_allocation(orc_faithful* h, uint32_t gpu, uint32_t start, uin
 /* Canonical batch: all FREEs, then ALLOCs in order (one Reconcile each).  all_nodes != 0 reproduces the
  * reference's missing `break` (Q5): the pod is allocated on every node with capacity; out[] reports the first. */
 int      orc_f_place(orc_faithful* h, uint32_t n, const isl_request* in, isl_result* out, int all_nodes);
+int      orc_f_place_batch(orc_faithful* h, uint32_t n, const isl_request* in, isl_result* out);   /* orc_f_place(..., all_nodes = 0) */
 void     orc_f_occupancy(orc_faithful* h, uint8_t* out);      /* :306-328 for every GPU */
 uint64_t orc_f_num_allocations(orc_faithful* h);
 

@@ -295,6 +295,9 @@ int orc_f_place(orc_faithful* h, uint32_t n, const isl_request* in, isl_result* 
     return ISL_OK;
 }
 
+// same shape as isl_place_batch / orc_fast_place (bench.py's C5 replay harness takes one placer signature)
+int orc_f_place_batch(orc_faithful* h, uint32_t n, const isl_request* in, isl_result* out) { return orc_f_place(h, n, in, out, 0); }
+
 void orc_f_occupancy(orc_faithful* h, uint8_t* out) {
     for (size_t g = 0; g < h->gpu_uuid.size(); ++g) {
         const Instaslice& is = h->items[h->gpu_node[g]];

@@ -48,3 +48,31 @@ def test_churn_small_is_consistent():
     # occupancy hovers around the pre-fill target
     busy = int(np.unpackbits(ref2.occupancy()).sum())
     assert 0.35 * 7 * ch.G < busy < 0.65 * 7 * ch.G
+
+
+def test_churn_min_age_is_causal():
+    """min_age = k: every FREE of churn batch b names an allocation placed by churn batch b - k or earlier (or by the pre-fill), i.e.
+    a caller that has seen the results of batch b - k can compose batch b (the causal feed of isl_stream_submit); k = 1 is the
+    original stream."""
+    for k in (1, 3):
+        ch = W.Churn(n_nodes=256, gpus_per_node=8, n_ops=8000, batch=1024, seed=5, min_age=k)
+        ref = oracle.Fast(ch.node_off, ch.rows)
+        ref.load(np.zeros(ch.G, dtype=np.uint8))
+        placed_by = {}                      # (gpu, start, size) -> churn batch that placed the live allocation (-1: pre-fill)
+        state = {"churn": False, "b": 0, "frees": 0}
+
+        def placer(req):
+            b = state["b"] if state["churn"] else -(1 << 20)      # the pre-fill happened long ago
+            fr = req[req["op"] == E.OP_FREE]
+            for g, s, z in zip(fr["handle"].tolist(), fr["start"].tolist(), fr["size"].tolist()):
+                assert placed_by.pop((g, s, z)) <= b - k, (k, b)
+                state["frees"] += 1
+            res = ref.place(req)
+            for r in res[(req["op"] == E.OP_ALLOC) & (res["status"] == E.ST_PLACED)]:
+                placed_by[(int(r["gpu"]), int(r["start"]), int(r["size"]))] = b
+            if state["churn"]:
+                state["b"] += 1
+            return res
+
+        ch.generate(placer, after_prefill=lambda: state.update(churn=True))
+        assert state["frees"] > 1000 and state["b"] == 8
