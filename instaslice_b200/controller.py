@@ -251,12 +251,13 @@ class InstasliceReconciler:
 
     def release(self, pod_uid: str):
         """The daemonset deleted ``Allocations[podUID]`` (instaslice_daemonset.go:261-263): free its span."""
-        for it in self.items:
+        for n, it in enumerate(self.items):
             a = it["spec"].get("allocations", {}).pop(pod_uid, None)
             if a is not None:
-                spans = np.zeros(1, dtype=E.SPAN_DTYPE)
-                spans[0] = (self.gpu_index[a["gpuUUID"]], a["start"], a["size"], 0)
-                self._engine.free_batch(spans)
+                # rebuild the node's bytes from the CR (OR over every remaining entry, :306-328) instead of clearing the span blindly:
+                # slices another entry still covers stay busy, exactly what the reference's next rebuild would say
+                lo, hi = int(self.node_off[n]), int(self.node_off[n + 1])
+                self._engine.write_occupancy(lo, np.array([occupancy_byte(it, u) for u in self.gpu_uuid[lo:hi]], dtype=np.uint8))
                 return True
         return False
 
@@ -266,11 +267,9 @@ class InstasliceReconciler:
         req["handle"] = np.arange(len(profile_names), dtype=np.uint32)
         req["profile"] = [self.profile_names.get(n, E.PROFILE_UNKNOWN) for n in profile_names]
         req["op"] = E.OP_ALLOC
-        self._engine.set_partition(lo, hi)
-        try:
-            return self._engine.place_batch(req)
-        finally:
-            self._engine.set_partition(0, len(self.gpu_uuid))
+        # ONE locked call restricts, places and restores (isl_place_batch_range): two reconcile workers cannot interleave and
+        # nothing leaks when the call fails
+        return self._engine.place_batch_range(lo, hi, req)
 
     def _release(self, res):
         spans = np.zeros(1, dtype=E.SPAN_DTYPE)

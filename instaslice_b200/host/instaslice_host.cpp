@@ -157,10 +157,8 @@ std::vector<isl_result> InstasliceReconciler::place(const std::vector<std::strin
         auto it = profiles_.find(names[i]);
         req[i] = isl_request{(uint32_t)i, it == profiles_.end() ? (uint8_t)ISL_PROFILE_UNKNOWN : it->second, (uint8_t)ISL_OP_ALLOC, 0, 0};
     }
-    check(isl_set_partition(h_, lo, hi), h_, "isl_set_partition");
-    const int rc = isl_place_batch(h_, (uint32_t)req.size(), req.data(), res.data());
-    isl_set_partition(h_, 0, (uint32_t)gpuUUID_.size());
-    check(rc, h_, "isl_place_batch");
+    // restriction, placement and restore under ONE engine lock: nothing leaks when the call throws, two callers cannot interleave
+    check(isl_place_batch_range(h_, lo, hi, (uint32_t)req.size(), req.data(), res.data()), h_, "isl_place_batch_range");
     return res;
 }
 
@@ -218,12 +216,14 @@ std::vector<Outcome> InstasliceReconciler::PlacePending(InstasliceList& list, Al
 }
 
 bool InstasliceReconciler::Release(InstasliceList& list, const std::string& podUID) {
-    for (Instaslice& is : list.Items) {
+    for (size_t n = 0; n < list.Items.size(); ++n) {
+        Instaslice& is = list.Items[n];
         auto it = is.Spec.Allocations.find(podUID);
         if (it == is.Spec.Allocations.end()) continue;
-        isl_span s{gpuIndex_.at(it->second.GPUUUID), (uint8_t)it->second.Start, (uint8_t)it->second.Size, 0};
-        check(isl_free_batch(h_, 1, &s), h_, "isl_free_batch");
         is.Spec.Allocations.erase(it);
+        // rebuild the node's bytes from the CR (OR over every remaining entry, :306-328) instead of clearing the span blindly:
+        // slices another entry still covers stay busy, exactly what the reference's next rebuild would say
+        UpdateNode(list, n);
         return true;
     }
     return false;

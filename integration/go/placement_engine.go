@@ -13,10 +13,7 @@ package controller
 #cgo CFLAGS: -I${SRCDIR}/../../include
 #cgo LDFLAGS: -lislplace -lcudart
 #include <stdlib.h>
-#include <cuda_runtime_api.h>
 #include "islplace.h"
-static void* isl_pinned(size_t n) { void* p = 0; return cudaHostAlloc(&p, n, cudaHostAllocDefault) == cudaSuccess ? p : 0; }
-static void  isl_unpin(void* p)   { cudaFreeHost(p); }
 */
 import "C"
 
@@ -38,6 +35,21 @@ type PlacementEngine struct {
 	profiles map[string]uint8  // profile name -> row index (FIRST Migplacement row with that name, :332-340)
 	orphans  bool              // a realised slice outlived its allocation: the :198-203 veto can fire
 	nodeOff  []C.uint32_t      // node index -> first canonical GPU index
+	nodeMig  [][]inferencev1alpha1.Mig // the Migplacement each node had at the last Sync (UpdateNode compares)
+}
+
+// hasOrphans: a Prepared entry that names a pod whose Allocations entry is gone — the only state in which the exact-match
+// veto (:198-203) can fire.  Recomputed by Sync AND by every UpdateNode.
+func hasOrphans(list *inferencev1alpha1.InstasliceList) bool {
+	for n := range list.Items {
+		is := &list.Items[n]
+		for _, p := range is.Spec.Prepared {
+			if _, live := is.Spec.Allocations[p.PodUUID]; p.PodUUID != "" && !live {
+				return true
+			}
+		}
+	}
+	return false
 }
 
 func NewPlacementEngine(maxGPUs, maxBatch uint32) (*PlacementEngine, error) {
@@ -112,6 +124,9 @@ func (e *PlacementEngine) Sync(list *inferencev1alpha1.InstasliceList) error {
 		nodeTable[n] = C.uint8_t(t)
 	}
 	P := len(e.profiles)
+	if P == 0 {
+		return fmt.Errorf("no node publishes a Migplacement row") // nothing could ever be placed; &rows[0] below would panic
+	}
 	rows := make([]C.isl_profile, len(tables)*P)
 	for t, mig := range tables {
 		seenName := map[string]bool{}
@@ -135,8 +150,10 @@ func (e *PlacementEngine) Sync(list *inferencev1alpha1.InstasliceList) error {
 	}
 	nodeOff := []C.uint32_t{0}
 	occ := []C.uint8_t{}
-	e.gpuUUID, e.gpuNode, e.orphans = nil, nil, false
+	e.gpuUUID, e.gpuNode, e.nodeMig = nil, nil, nil
+	e.orphans = hasOrphans(list)
 	for n := range list.Items {
+		e.nodeMig = append(e.nodeMig, list.Items[n].Spec.Migplacement)
 		is := &list.Items[n]
 		uuids := make([]string, 0, len(is.Spec.MigGPUUUID))
 		for u := range is.Spec.MigGPUUUID {
@@ -153,11 +170,9 @@ func (e *PlacementEngine) Sync(list *inferencev1alpha1.InstasliceList) error {
 			e.gpuNode = append(e.gpuNode, n)
 		}
 		nodeOff = append(nodeOff, C.uint32_t(len(e.gpuUUID)))
-		for _, p := range is.Spec.Prepared {
-			if _, live := is.Spec.Allocations[p.PodUUID]; p.PodUUID != "" && !live {
-				e.orphans = true
-			}
-		}
+	}
+	if len(occ) == 0 {
+		return fmt.Errorf("no GPU in any Instaslice object")
 	}
 	if rc := C.isl_load_profile_tables(e.h, C.uint32_t(len(tables)), C.uint32_t(P), &rows[0]); rc != C.ISL_OK {
 		return fmt.Errorf("isl_load_profile_tables: %s", C.GoString(C.isl_strerror(rc)))
@@ -175,10 +190,13 @@ func (e *PlacementEngine) Sync(list *inferencev1alpha1.InstasliceList) error {
 // UpdateNode is the incremental sync after ONE Instaslice object changed (an Allocations / Prepared entry appeared or was
 // deleted): only that node's occupancy bytes are rewritten (isl_write_occupancy) instead of re-listing the cluster (:85).
 func (e *PlacementEngine) UpdateNode(list *inferencev1alpha1.InstasliceList, n int) error {
+	if n >= len(e.nodeMig) || n+1 >= len(e.nodeOff) {
+		return e.Sync(list) // a node appeared
+	}
 	is := &list.Items[n]
 	lo, hi := int(e.nodeOff[n]), int(e.nodeOff[n+1])
-	if len(is.Spec.MigGPUUUID) != hi-lo {
-		return e.Sync(list)
+	if len(is.Spec.MigGPUUUID) != hi-lo || hi == lo || !reflect.DeepEqual(e.nodeMig[n], is.Spec.Migplacement) {
+		return e.Sync(list) // GPU set or profile table of the node changed
 	}
 	occ := make([]C.uint8_t, 0, hi-lo)
 	for g := lo; g < hi; g++ {
@@ -194,6 +212,7 @@ func (e *PlacementEngine) UpdateNode(list *inferencev1alpha1.InstasliceList, n i
 	if rc := C.isl_write_occupancy(e.h, C.uint32_t(lo), C.uint32_t(len(occ)), &occ[0]); rc != C.ISL_OK {
 		return fmt.Errorf("isl_write_occupancy: %s", C.GoString(C.isl_strerror(rc)))
 	}
+	e.orphans = hasOrphans(list)
 	return nil
 }
 
@@ -203,8 +222,76 @@ type PendingPod struct {
 	ProfileName string // r.extractProfileName(limits), :154
 }
 
+const errNoGpu = "failed to find allocatable gpu" // :261
+
+// FindDeviceForASlice is the literal replacement of the call at instaslice_controller.go:192
+//   allocDetails, err := r.findDeviceForASlice(&instaslice, profileName, policy, pod)
+// for the node list.Items[n]: the first GPU of THAT node with a legal start (:240-262), packed by the unchanged policy hook.
+// isl_place_batch_range restricts, places and restores under one engine lock.  Like the reference it does not record the
+// allocation (:257 is commented out there): the tentative commit is rolled back by rebuilding the node's bytes from the CR.
+func (r *InstasliceReconciler) FindDeviceForASlice(e *PlacementEngine, list *inferencev1alpha1.InstasliceList, n int, profileName string,
+	policy AllocationPolicy, pod *v1.Pod) (*inferencev1alpha1.AllocationDetails, error) {
+	row, ok := e.profiles[profileName]
+	if !ok {
+		return nil, fmt.Errorf(errNoGpu)
+	}
+	req := (*C.isl_request)(C.malloc(C.sizeof_isl_request))
+	res := (*C.isl_result)(C.malloc(C.sizeof_isl_result))
+	if req == nil || res == nil {
+		C.free(unsafe.Pointer(req))
+		C.free(unsafe.Pointer(res))
+		return nil, fmt.Errorf("out of memory")
+	}
+	defer C.free(unsafe.Pointer(req))
+	defer C.free(unsafe.Pointer(res))
+	*req = C.isl_request{handle: 0, profile: C.uint8_t(row), op: C.ISL_OP_ALLOC}
+	if rc := C.isl_place_batch_range(e.h, e.nodeOff[n], e.nodeOff[n+1], 1, req, res); rc != C.ISL_OK {
+		return nil, fmt.Errorf("isl_place_batch_range: %s (%s)", C.GoString(C.isl_strerror(rc)), C.GoString(C.isl_last_cuda_error(e.h)))
+	}
+	if res.status != C.ISL_ST_PLACED {
+		return nil, fmt.Errorf(errNoGpu)
+	}
+	is := &list.Items[n]
+	size, gi, ci, cieng := r.extractGpuProfile(is, profileName)
+	a := policy.SetAllocationDetails(profileName, uint32(res.start), uint32(size), string(pod.UID), is.Name, "creating",
+		gi, ci, cieng, pod.Namespace, pod.Name, e.gpuUUID[int(res.gpu)])
+	if err := e.UpdateNode(list, n); err != nil {
+		return nil, err
+	}
+	return a, nil
+}
+
+// commitOrVeto packs one PLACED result with the unchanged policy hook and applies the exact-match Prepared veto (:198-203).
+// A vetoed placement is rolled back by rebuilding the node's occupancy bytes from the CR (an OR over all entries, like
+// :306-328 — never a blind clear: an overlapping span must not be freed early).  Used by PlacePending AND PlaceBacklog.
+func (r *InstasliceReconciler) commitOrVeto(e *PlacementEngine, list *inferencev1alpha1.InstasliceList, policy AllocationPolicy,
+	p PendingPod, res C.isl_result) (*inferencev1alpha1.AllocationDetails, error) {
+	gpu := int(res.gpu)
+	n := e.gpuNode[gpu]
+	is := &list.Items[n]
+	size, gi, ci, cieng := r.extractGpuProfile(is, p.ProfileName) // :283-300, unchanged
+	a := policy.SetAllocationDetails(p.ProfileName, uint32(res.start), uint32(size), string(p.Pod.UID), is.Name, "creating",
+		gi, ci, cieng, p.Pod.Namespace, p.Pod.Name, e.gpuUUID[gpu]) // :254-256, unchanged
+	for _, item := range is.Spec.Prepared { // :198-203
+		if item.Parent == a.GPUUUID && item.Size == a.Size && item.Start == a.Start {
+			return nil, e.UpdateNode(list, n) // undo the tentative commit; the caller requeues after 1 s
+		}
+	}
+	return a, nil
+}
+
+func (e *PlacementEngine) fillRequests(req []C.isl_request, pods []PendingPod, base int) {
+	for i, p := range pods {
+		row, ok := e.profiles[p.ProfileName]
+		if !ok {
+			row = C.ISL_PROFILE_UNKNOWN
+		}
+		req[base+i] = C.isl_request{handle: C.uint32_t(base + i), profile: C.uint8_t(row), op: C.ISL_OP_ALLOC}
+	}
+}
+
 // PlacePending resolves the pods in order with ONE engine call and packs the answers with the unchanged policy
-// hook.  result[i] == nil means "failed to find allocatable gpu" on every node (:261, :229-232: requeue).
+// hook.  result[i] == nil means "failed to find allocatable gpu" on every node (:261, :229-232: requeue) or a veto.
 func (r *InstasliceReconciler) PlacePending(e *PlacementEngine, list *inferencev1alpha1.InstasliceList, policy AllocationPolicy,
 	pods []PendingPod) ([]*inferencev1alpha1.AllocationDetails, error) {
 	n := len(pods)
@@ -223,17 +310,17 @@ func (r *InstasliceReconciler) PlacePending(e *PlacementEngine, list *inferencev
 		return out, nil
 	}
 	// C-allocated request/result arrays: no Go pointer is retained by the engine after the call returns
-	req := (*[1 << 28]C.isl_request)(C.malloc(C.size_t(n) * C.sizeof_isl_request))[:n:n]
-	res := (*[1 << 28]C.isl_result)(C.malloc(C.size_t(n) * C.sizeof_isl_result))[:n:n]
-	defer C.free(unsafe.Pointer(&req[0]))
-	defer C.free(unsafe.Pointer(&res[0]))
-	for i, p := range pods {
-		row, ok := e.profiles[p.ProfileName]
-		if !ok {
-			row = C.ISL_PROFILE_UNKNOWN
-		}
-		req[i] = C.isl_request{handle: C.uint32_t(i), profile: C.uint8_t(row), op: C.ISL_OP_ALLOC}
+	reqP, resP := C.malloc(C.size_t(n)*C.sizeof_isl_request), C.malloc(C.size_t(n)*C.sizeof_isl_result)
+	if reqP == nil || resP == nil {
+		C.free(reqP)
+		C.free(resP)
+		return nil, fmt.Errorf("out of memory")
 	}
+	defer C.free(reqP)
+	defer C.free(resP)
+	req := (*[1 << 28]C.isl_request)(reqP)[:n:n]
+	res := (*[1 << 28]C.isl_result)(resP)[:n:n]
+	e.fillRequests(req, pods, 0)
 	if rc := C.isl_place_batch(e.h, C.uint32_t(n), &req[0], &res[0]); rc != C.ISL_OK {
 		return nil, fmt.Errorf("isl_place_batch: %s (%s)", C.GoString(C.isl_strerror(rc)), C.GoString(C.isl_last_cuda_error(e.h)))
 	}
@@ -241,43 +328,46 @@ func (r *InstasliceReconciler) PlacePending(e *PlacementEngine, list *inferencev
 		if res[i].status != C.ISL_ST_PLACED {
 			continue
 		}
-		gpu := int(res[i].gpu)
-		is := &list.Items[e.gpuNode[gpu]]
-		size, gi, ci, cieng := r.extractGpuProfile(is, p.ProfileName) // :283-300, unchanged
-		a := policy.SetAllocationDetails(p.ProfileName, uint32(res[i].start), uint32(size), string(p.Pod.UID), is.Name, "creating",
-			gi, ci, cieng, p.Pod.Namespace, p.Pod.Name, e.gpuUUID[gpu]) // :254-256, unchanged
-		vetoed := false
-		for _, item := range is.Spec.Prepared { // :198-203
-			if item.Parent == a.GPUUUID && item.Size == a.Size && item.Start == a.Start {
-				vetoed = true
-			}
-		}
-		if vetoed {
-			span := C.isl_span{gpu: res[i].gpu, start: res[i].start, size: res[i].size}
-			C.isl_free_batch(e.h, 1, &span) // undo the tentative commit; the caller requeues after 1 s
-			continue
+		a, err := r.commitOrVeto(e, list, policy, p, res[i])
+		if err != nil {
+			return nil, err
 		}
 		out[i] = a
 	}
 	return out, nil
 }
 
-// Release tells the engine that the daemonset removed Allocations[podUID] (instaslice_daemonset.go:261-263).
-func (e *PlacementEngine) Release(gpuIndex uint32, start, size uint8) {
-	span := C.isl_span{gpu: C.uint32_t(gpuIndex), start: C.uint8_t(start), size: C.uint8_t(size)}
-	C.isl_free_batch(e.h, 1, &span)
+// Release: the daemonset removed Allocations[podUID] from list.Items[n] (instaslice_daemonset.go:261-263).  The node's occupancy
+// bytes are REBUILT from the CR (OR over every remaining Prepared / Allocations entry, :306-328) rather than cleared blindly: if
+// another entry still covers part of the span, those slices stay busy — exactly what the reference's next rebuild would say.
+func (e *PlacementEngine) Release(list *inferencev1alpha1.InstasliceList, n int) error {
+	return e.UpdateNode(list, n)
+}
+
+// hostArrays returns mapped pinned request / result arrays from the engine's own allocator (isl_host_alloc) or, when that
+// fails, plain C.malloc'ed ones (pageable works for isl_place_stream, without the copy / delivery overlap).
+func hostArrays(total int) (req []C.isl_request, res []C.isl_result, pinned bool, free func(), err error) {
+	reqP, resP := C.isl_host_alloc(C.size_t(total)*C.sizeof_isl_request), C.isl_host_alloc(C.size_t(total)*C.sizeof_isl_result)
+	pinned = reqP != nil && resP != nil
+	if pinned {
+		free = func() { C.isl_host_free(reqP); C.isl_host_free(resP) }
+	} else {
+		C.isl_host_free(reqP)
+		C.isl_host_free(resP)
+		reqP, resP = C.malloc(C.size_t(total)*C.sizeof_isl_request), C.malloc(C.size_t(total)*C.sizeof_isl_result)
+		if reqP == nil || resP == nil {
+			C.free(reqP)
+			C.free(resP)
+			return nil, nil, false, nil, fmt.Errorf("out of memory")
+		}
+		free = func() { C.free(reqP); C.free(resP) }
+	}
+	return (*[1 << 28]C.isl_request)(reqP)[:total:total], (*[1 << 28]C.isl_result)(resP)[:total:total], pinned, free, nil
 }
 
 // PlaceBacklog resolves several ordered batches (e.g. per-namespace queues drained in turn) with ONE isl_place_stream
-// call: identical answers to PlacePending batch after batch, pipelined on the device.  The request / result arrays are
-// pinned (cudaHostAlloc through the tiny C helper below, or cudaHostRegister on C.malloc'ed arrays kept for the life of
-// the controller): the engine then copies batch b while it already places batch b-1 and writes finished chunks straight
-// into `res`.  Pageable arrays work as well, without that overlap.
-//
-//   // in the cgo preamble:
-//   //   #include <cuda_runtime_api.h>
-//   //   static void* isl_pinned(size_t n) { void* p = 0; return cudaHostAlloc(&p, n, cudaHostAllocDefault) == cudaSuccess ? p : 0; }
-//   //   static void  isl_unpin(void* p)   { cudaFreeHost(p); }
+// call: identical answers to PlacePending batch after batch, pipelined on the device.  With pinned arrays the engine copies
+// batch b while it already places batch b-1 and writes finished chunks straight into `res`.
 func (r *InstasliceReconciler) PlaceBacklog(e *PlacementEngine, list *inferencev1alpha1.InstasliceList, policy AllocationPolicy,
 	batches [][]PendingPod) ([][]*inferencev1alpha1.AllocationDetails, error) {
 	total := 0
@@ -297,20 +387,15 @@ func (r *InstasliceReconciler) PlaceBacklog(e *PlacementEngine, list *inferencev
 		}
 		return out, nil
 	}
-	req := (*[1 << 28]C.isl_request)(C.isl_pinned(C.size_t(total) * C.sizeof_isl_request))[:total:total]
-	res := (*[1 << 28]C.isl_result)(C.isl_pinned(C.size_t(total) * C.sizeof_isl_result))[:total:total]
-	defer C.isl_unpin(unsafe.Pointer(&req[0]))
-	defer C.isl_unpin(unsafe.Pointer(&res[0]))
+	req, res, _, free, err := hostArrays(total)
+	if err != nil {
+		return nil, err
+	}
+	defer free()
 	i := 0
 	for _, pods := range batches {
-		for _, p := range pods {
-			row, ok := e.profiles[p.ProfileName]
-			if !ok {
-				row = C.ISL_PROFILE_UNKNOWN
-			}
-			req[i] = C.isl_request{handle: C.uint32_t(i), profile: C.uint8_t(row), op: C.ISL_OP_ALLOC}
-			i++
-		}
+		e.fillRequests(req, pods, i)
+		i += len(pods)
 	}
 	if rc := C.isl_place_stream(e.h, C.uint32_t(len(batches)), &sizes[0], &req[0], &res[0]); rc != C.ISL_OK {
 		return nil, fmt.Errorf("isl_place_stream: %s (%s)", C.GoString(C.isl_strerror(rc)), C.GoString(C.isl_last_cuda_error(e.h)))
@@ -319,17 +404,90 @@ func (r *InstasliceReconciler) PlaceBacklog(e *PlacementEngine, list *inferencev
 	for b, pods := range batches {
 		out[b] = make([]*inferencev1alpha1.AllocationDetails, len(pods))
 		for k, p := range pods {
-			if res[i].status == C.ISL_ST_PLACED {
-				gpu := int(res[i].gpu)
-				is := &list.Items[e.gpuNode[gpu]]
-				size, gi, ci, cieng := r.extractGpuProfile(is, p.ProfileName) // :283-300, unchanged
-				out[b][k] = policy.SetAllocationDetails(p.ProfileName, uint32(res[i].start), uint32(size), string(p.Pod.UID), is.Name, "creating",
-					gi, ci, cieng, p.Pod.Namespace, p.Pod.Name, e.gpuUUID[gpu]) // :254-256, unchanged
+			if res[i].status == C.ISL_ST_PLACED { // same packing and the same :198-203 check as PlacePending
+				a, err := r.commitOrVeto(e, list, policy, p, res[i])
+				if err != nil {
+					return nil, err
+				}
+				out[b][k] = a
 			}
 			i++
 		}
 	}
 	return out, nil
+}
+
+// BacklogStream is the causal feed: batches are handed over WHILE earlier ones are still being placed, and the results of a
+// batch can be read as soon as Wait(ticket) returns — the reconciler composes the next batch (e.g. re-queues pods whose
+// allocation a deleted pod just released) from results it has already seen.  One persistent device kernel serves the whole
+// stream (isl_stream_open / _submit / _wait / _close); results equal PlacePending batch after batch.
+type BacklogStream struct {
+	e    *PlacementEngine
+	pods [][]PendingPod
+	res  [][]C.isl_result
+	free []func()
+}
+
+func (e *PlacementEngine) OpenBacklogStream(maxBatches int) (*BacklogStream, error) {
+	if e.orphans {
+		return nil, fmt.Errorf("realised slices without allocation present: resolve pods one by one (PlacePending)")
+	}
+	if rc := C.isl_stream_open(e.h, C.uint32_t(maxBatches)); rc != C.ISL_OK {
+		return nil, fmt.Errorf("isl_stream_open: %s", C.GoString(C.isl_strerror(rc)))
+	}
+	return &BacklogStream{e: e}, nil
+}
+
+// Submit enqueues one batch and returns its ticket at once.
+func (s *BacklogStream) Submit(pods []PendingPod) (int, error) {
+	req, res, pinned, free, err := hostArrays(len(pods))
+	if err != nil {
+		return -1, err
+	}
+	if !pinned { // the running kernel writes the results: they must live in mapped pinned memory
+		free()
+		return -1, fmt.Errorf("isl_host_alloc failed")
+	}
+	s.e.fillRequests(req, pods, 0)
+	var ticket C.uint32_t
+	if rc := C.isl_stream_submit(s.e.h, C.uint32_t(len(pods)), &req[0], &res[0], &ticket); rc != C.ISL_OK {
+		free()
+		return -1, fmt.Errorf("isl_stream_submit: %s (%s)", C.GoString(C.isl_strerror(rc)), C.GoString(C.isl_last_cuda_error(s.e.h)))
+	}
+	s.pods, s.res, s.free = append(s.pods, pods), append(s.res, res), append(s.free, free)
+	return int(ticket), nil
+}
+
+// Wait blocks until the batch's results are in host memory and packs them exactly like PlacePending.
+func (s *BacklogStream) Wait(r *InstasliceReconciler, list *inferencev1alpha1.InstasliceList, policy AllocationPolicy,
+	ticket int) ([]*inferencev1alpha1.AllocationDetails, error) {
+	if rc := C.isl_stream_wait(s.e.h, C.uint32_t(ticket)); rc != C.ISL_OK {
+		return nil, fmt.Errorf("isl_stream_wait: %s (%s)", C.GoString(C.isl_strerror(rc)), C.GoString(C.isl_last_cuda_error(s.e.h)))
+	}
+	out := make([]*inferencev1alpha1.AllocationDetails, len(s.pods[ticket]))
+	for k, p := range s.pods[ticket] {
+		if s.res[ticket][k].status != C.ISL_ST_PLACED {
+			continue
+		}
+		// the veto cannot fire here (no orphans at open; a veto rollback would need the engine, which the stream owns): pack only
+		gpu := int(s.res[ticket][k].gpu)
+		is := &list.Items[s.e.gpuNode[gpu]]
+		size, gi, ci, cieng := r.extractGpuProfile(is, p.ProfileName)
+		out[k] = policy.SetAllocationDetails(p.ProfileName, uint32(s.res[ticket][k].start), uint32(size), string(p.Pod.UID), is.Name, "creating",
+			gi, ci, cieng, p.Pod.Namespace, p.Pod.Name, s.e.gpuUUID[gpu])
+	}
+	return out, nil
+}
+
+func (s *BacklogStream) Close() error {
+	rc := C.isl_stream_close(s.e.h)
+	for _, f := range s.free {
+		f()
+	}
+	if rc != C.ISL_OK {
+		return fmt.Errorf("isl_stream_close: %s (%s)", C.GoString(C.isl_strerror(rc)), C.GoString(C.isl_last_cuda_error(s.e.h)))
+	}
+	return nil
 }
 
 // WhatIf runs `plan` against a device-side snapshot of the occupancy and puts the snapshot back: defragmentation planning

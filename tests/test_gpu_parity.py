@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import oracle
+from oracle import ref_py
 from instaslice_b200 import controller as ctl
 from instaslice_b200 import engine as E
 from instaslice_b200 import tables, workloads as W
@@ -407,6 +408,65 @@ def test_partitioned_ring_on_one_gpu(n_ranks):
         assert np.array_equal(occ, ref.occupancy())
 
 
+@pytest.mark.parametrize("n_ranks,window", [(2, 0), (3, 1), (2, 2)])
+def test_partitioned_ring_results_gathered_on_the_owner(n_ranks, window):
+    """The multi-GPU result path without a collective: every engine behind the owner (rank 0) maps the owner's result array
+    (isl_connect_owner_local here, CUDA IPC across processes) and its commit threads store each PLACED record there as well; the
+    causal window across ranks counts finished ranks per chunk on the owner (peer atomics).  The owner's array alone == the
+    global sequential first-fit."""
+    import torch
+    from instaslice_b200 import dist as D
+    rows = E.make_profiles(tables.H100_80GB)
+    rng = W.SplitMix64(777 + n_ranks + window)
+    G = 4096
+    node_off = W.node_offsets(G // 8, 8)
+    occ0 = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+    ref = oracle.Fast(node_off, rows)
+    ref.load(occ0)
+    batches, want, live = [], [], []
+    for b in range(7):
+        n = 2500 + 400 * b
+        req = W.alloc_requests(W.mix_profiles(rng, n))
+        for i in range(min(len(live), n // 3)):
+            g, s, z = live.pop(int(rng.next1() % len(live)))
+            req[int(rng.next1() % n)] = (g, 0, E.OP_FREE, s, z)
+        res = ref.place(req)
+        for r in res[(req["op"] == E.OP_ALLOC) & (res["status"] == E.ST_PLACED)]:
+            live.append((int(r["gpu"]), int(r["start"]), int(r["size"])))
+        batches.append(req)
+        want.append(res)
+    sizes = np.array([len(b) for b in batches], dtype=np.uint32)
+    total = int(sizes.sum())
+    d_in = torch.from_numpy(np.concatenate(batches).view(np.int64).copy()).cuda()
+    bounds = D.all_bounds(G, n_ranks, align=64)
+    engines = []
+    for r, (lo, hi) in enumerate(bounds):
+        eng = make_engine(node_off, occ0, rows)
+        eng.set_partition(lo, hi)
+        eng.ipc_inbox_handle()
+        engines.append(eng)
+    for r, eng in enumerate(engines):
+        eng.connect_local(engines[r + 1] if r + 1 < n_ranks else None, has_prev=r > 0)
+        eng.connect_owner_local(engines[0] if r > 0 else None)
+        eng.set_ring_world(n_ranks)
+        eng.set_causal_window(window)
+    torch.cuda.synchronize()
+    for stream_id in (11, 12):
+        for eng, (lo, hi) in zip(engines, bounds):
+            eng.load_inventory(node_off, occ0)
+            eng.set_partition(lo, hi)
+        for eng in engines:
+            eng.place_stream_partitioned(sizes, d_in.data_ptr(), eng.device_results(), stream_id)
+        for eng in engines:
+            eng.synchronize()
+        class _View:            # torch view of the owner's engine-owned result array (no copy)
+            __cuda_array_interface__ = {"shape": (total,), "typestr": "<i8", "data": (engines[0].device_results(), False), "version": 3}
+        owner = torch.as_tensor(_View(), device="cuda").cpu().numpy().view(E.RESULT_DTYPE)
+        assert np.array_equal(owner, np.concatenate(want)), (n_ranks, window, stream_id)
+        occ = np.concatenate([eng.read_occupancy()[lo:hi] for eng, (lo, hi) in zip(engines, bounds)])
+        assert np.array_equal(occ, ref.occupancy())
+
+
 # ---- best-fit (extension, SURVEY 8a-ext: no reference counterpart; parity against oracle/ref_fast.cpp best-fit) -----------
 def check_best_fit(node_off, occ, rows, batches, quirks=E.QUIRKS_REF_EXACT):
     eng = E.Engine(max_gpus=max(4096, len(occ)), max_batch=1 << 20, quirks=quirks, policy=E.POLICY_BEST_FIT)
@@ -484,31 +544,50 @@ def test_large_inventory_falls_back_to_single_chain():
     assert eng.gpu_to_node(G - 1) == G // 8 - 1
 
 
-def test_incremental_node_update_equals_full_sync():
-    """after one Instaslice object changes, rewriting only that node's occupancy bytes gives the same
-    placements as rebuilding the whole inventory from the custom resources."""
+def test_incremental_node_update_vs_python_restatement():
+    """after Instaslice objects change (the daemonset deletes allocations, dangling slices appear, a pod is
+    released), rewriting only the touched nodes' occupancy bytes must leave the engine in the state the reference would compute
+    from the mutated custom resources.  The checker is the independent restatement ``ref_py`` run on a deep copy of the SAME
+    mutated CRs (occupancy byte per GPU via :306-328, then pod by pod through the node loop :188-232) — not the engine itself."""
     gold = load("regress_crd.json")
-    case = gold["cases"][5]
-    items = copy.deepcopy(case["instaslices"])
-    r = ctl.InstasliceReconciler(items, quirks=case["quirks"])
-    pods = [{"uid": p["uid"], "name": p["uid"], "profile": p["profile"]} for p in case["pods"]]
-    first = r.place_pending_pods(pods[:6])
-    # the daemonset deletes two realised allocations on one node, a new dangling slice shows up on another
-    victim = next(a for v, a in first if a)
-    node = next(it for it in items if it["metadata"]["name"] == victim["nodename"])
-    node["spec"]["allocations"].pop(victim["podUUID"])
-    r.update_node(node)
-    other = items[-1]
-    uuid = sorted(other["spec"]["MigGPUUUID"])[0]
-    if ctl.occupancy_byte(other, uuid) & 0x40 == 0:
-        other["spec"].setdefault("prepared", {})["MIG-new"] = {"profile": "1g", "start": 6, "size": 1, "parent": uuid, "podUUID": "", "giinfo": 0, "ciinfo": 0}
-        r.update_node(other)
-    inc = r.engine.read_occupancy().copy()
-    full = ctl.InstasliceReconciler(copy.deepcopy(items), quirks=case["quirks"])
-    assert np.array_equal(inc, full.engine.read_occupancy())
-    a = r.place_pending_pods(copy.deepcopy(pods[6:]))
-    b = full.place_pending_pods(copy.deepcopy(pods[6:]))
-    assert [(v, x and (x["gpuUUID"], x["start"])) for v, x in a] == [(v, x and (x["gpuUUID"], x["start"])) for v, x in b]
+    for ci in (5, 2, 7):
+        case = gold["cases"][ci % len(gold["cases"])]
+        items = copy.deepcopy(case["instaslices"])
+        quirks = case["quirks"]
+        r = ctl.InstasliceReconciler(items, quirks=quirks)
+        pods = [{"uid": p["uid"], "name": p["uid"], "profile": p["profile"]} for p in case["pods"]]
+        shadow = copy.deepcopy(items)               # ref_py's world: mutated in lock-step, never touched by the engine mirror
+        first = r.place_pending_pods(pods[:6])
+        for pod in pods[:6]:
+            ref_py.reconcile_gated_pod(shadow, {"uid": pod["uid"], "name": pod["name"]}, pod["profile"], quirks)
+        # (1) the daemonset deletes a realised allocation on one node
+        victim = next((a for v, a in first if a), None)
+        if victim is not None:
+            for world in (items, shadow):
+                node = next(it for it in world if it["metadata"]["name"] == victim["nodename"])
+                node["spec"]["allocations"].pop(victim["podUUID"])
+            r.update_node(next(it for it in items if it["metadata"]["name"] == victim["nodename"]))
+        # (2) a new dangling slice shows up on another node
+        uuid = sorted(items[-1]["spec"]["MigGPUUUID"])[0]
+        if ctl.occupancy_byte(items[-1], uuid) & 0x40 == 0:
+            for world in (items, shadow):
+                world[-1]["spec"].setdefault("prepared", {})["MIG-new"] = {"profile": "1g", "start": 6, "size": 1, "parent": uuid, "podUUID": "", "giinfo": 0, "ciinfo": 0}
+            r.update_node(items[-1])
+        # (3) a pod is released through the mirror (OR-rebuild of its node)
+        second = next((a for v, a in first if a and a is not victim), None)
+        if second is not None:
+            assert r.release(second["podUUID"])
+            next(it for it in shadow if it["metadata"]["name"] == second["nodename"])["spec"]["allocations"].pop(second["podUUID"])
+        # engine occupancy == what the reference's rebuild (:306-328) gives on the mutated CRs
+        want_occ = [ctl.occupancy_byte(it, u) for it in shadow for u in sorted(it["spec"].get("MigGPUUUID", {}))]
+        assert r.engine.read_occupancy().tolist() == want_occ, ci
+        # and the remaining pods are placed exactly where ref_py places them on those CRs
+        got = r.place_pending_pods(copy.deepcopy(pods[6:]))
+        for pod, (verdict, alloc) in zip(pods[6:], got):
+            v, placed = ref_py.reconcile_gated_pod(shadow, {"uid": pod["uid"], "name": pod["name"]}, pod["profile"], quirks)
+            assert verdict == v, (ci, pod)
+            if v == "placed":
+                assert (alloc["gpuUUID"], alloc["start"], alloc["size"], alloc["nodename"]) == (placed[0]["gpuUUID"], placed[0]["start"], placed[0]["size"], placed[0]["nodename"])
 
 
 @pytest.mark.parametrize("quirks", [3, 0])
