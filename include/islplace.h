@@ -67,7 +67,14 @@ extern "C" {
 
 /* isl_config.policy */
 #define ISL_POLICY_FIRST_FIT 0u   /* the only policy the reference implements (:66-67, :436) */
-#define ISL_POLICY_BEST_FIT  1u   /* extension, no reference counterpart; parity unpinned */
+#define ISL_POLICY_BEST_FIT  1u   /* extension, no reference counterpart; parity unpinned: among the GPUs where the profile has a
+                                     legal start, the one with the fewest free slices; ties -> lowest canonical index */
+#define ISL_POLICY_RIGHT_TO_LEFT 2u /* first-fit over the GPUs in DESCENDING canonical order (last node first, last GPU of a node first) — what the
+                                     reference's RightToLeftPolicy stub (:464-469) names but never implemented; ISL_POLICY_FIRST_FIT is its
+                                     LeftToRightPolicy (:456-461).  The start inside a GPU still follows the row order (reverse the rows for
+                                     right-to-left starts as well) */
+#define ISL_POLICY_MIN_FRAG  3u   /* extension (SURVEY 8a-ext "richer score"): among the feasible GPUs, the one where the placement makes the fewest
+                                     (profile, start) pairs of the table infeasible; ties -> lowest canonical index */
 
 /* isl_config.quirks — bit set = reproduce the reference bug exactly */
 #define ISL_QUIRK_STRICT_BOUND 1u /* Q1: `value+size < 8` (:351,:360,:370) instead of <= 8 */
@@ -106,6 +113,9 @@ typedef struct isl_config {
 #define ISL_FLAG_NO_SMALL      16u  /* do not use the fused single-launch kernel for batches of <= 1024 requests (tests) */
 #define ISL_FLAG_TRACE          8u  /* record per (chunk, segment) timestamps of the segment pipeline (isl_read_trace) */
 #define ISL_FLAG_FORCE_PIPELINE 4u  /* use the segment pipeline even for a single chunk (tests) */
+#define ISL_FLAG_ALL_NODES     32u  /* isl_place_batch reproduces the reference's missing `break` (:190-227): a pod is allocated on EVERY
+                                       node that has capacity (state effect); the record reports the first node.  One restricted pass per node —
+                                       a compatibility mode for parity studies, not a fast path */
 
 /* One Migplacement row (api/v1alpha1/instaslice_types.go:23-29).  `size` is
  * Placements[0].Size (:334); `starts` is [p.Start for p in Placements] in CRD
@@ -202,6 +212,14 @@ int  isl_write_occupancy(isl_engine* e, uint32_t first_gpu, uint32_t n, const ui
  * snapshot back (a 1-byte-per-GPU device copy, no host round trip).  ISL_ESTATE if there is no inventory / no snapshot. */
 int  isl_snapshot_occupancy(isl_engine* e);
 int  isl_restore_occupancy(isl_engine* e);
+/* cap[p] (ISL_MAX_PROFILES entries) = how many more pods of profile p ALONE the inventory (the engine's partition) could still take:
+ * the sum over GPUs of the placements the start search (:343-383) would grant in a row.  A fragmentation measure per profile. */
+int  isl_capacity(isl_engine* e, uint64_t* cap);
+/* The what-if QUERY: resolve `plan` (FREEs and ALLOCs, batch semantics) against the live occupancy, report what fits (`out`) and the
+ * per-profile capacity before and after (either may be NULL), then put the live state back — all under one engine lock, so no other
+ * caller ever sees the hypothetical state.  "If these slices were released and these pods arrived: what fits, and what is left?"
+ * (A snapshot taken with isl_snapshot_occupancy is invalidated by this call.) */
+int  isl_what_if(isl_engine* e, uint32_t n, const isl_request* plan, isl_result* out, uint64_t* cap_before, uint64_t* cap_after);
 uint32_t isl_num_gpus(const isl_engine* e);
 /* node that owns canonical GPU index `gpu` (binary search over node_off), or ISL_GPU_NONE */
 uint32_t isl_gpu_to_node(const isl_engine* e, uint32_t gpu);

@@ -48,7 +48,13 @@ struct DevProfiles {            // kernel parameter (by value)
     uint32_t n;
     uint32_t quirks;
     isl_profile rows[ISL_MAX_PROFILES];
+    uint32_t flip;              // ISL_POLICY_RIGHT_TO_LEFT: G (the inventory is stored in REVERSE canonical order), else 0
 };
+
+// ISL_POLICY_RIGHT_TO_LEFT walks the GPUs in descending canonical order.  The engine stores such an inventory reversed (internal index
+// i = G - 1 - canonical) so that every scan stays an ascending sweep; only the two edges translate: the GPU a FREE names, and the GPU a
+// PLACED record reports.
+__host__ __device__ inline uint32_t flip_gpu(uint32_t g, uint32_t flip) { return flip ? flip - 1u - g : g; }
 
 // One (profile, start) candidate of the chain: bits  [3:0] profile | [6:4] order in the row |
 // [10:7] start | [14:11] size | [23:16] slot mask | [26:24] table | [31] valid
@@ -132,11 +138,12 @@ __global__ void k_eval_starts(const uint8_t* __restrict__ lut, uint32_t profile,
 }
 
 __global__ void k_free_spans(uint32_t n, const isl_span* __restrict__ spans, uint32_t* __restrict__ occ32,
-                             uint32_t G, uint32_t lo, uint32_t hi, Ctrl* ctrl) {
+                             uint32_t G, uint32_t lo, uint32_t hi, Ctrl* ctrl, uint32_t flip) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const isl_span s = spans[i];
+    isl_span s = spans[i];
     if (s.gpu >= G || s.size == 0 || (uint32_t)s.start + s.size > ISL_SLOTS) { atomicAdd(&ctrl->bad, 1ull); return; }
+    s.gpu = flip_gpu(s.gpu, flip);
     if (s.gpu < lo || s.gpu >= hi) return;
     const uint32_t m = (((1u << s.size) - 1u) << s.start) << ((s.gpu & 3u) * 8u);
     atomicAnd(&occ32[s.gpu >> 2], ~m);
@@ -196,10 +203,11 @@ __global__ void __launch_bounds__(kTileThreads) k_prepare(uint32_t n, const uint
             } else if (op == ISL_OP_FREE) {
                 if (handle >= G || size == 0 || start + size > ISL_SLOTS) out[i] = pack_result(handle, start, size, ISL_ST_BAD_SPAN);
                 else {
-                    if (handle >= lo && handle < hi) {
-                        const uint32_t span = (((1u << size) - 1u) << start) << ((handle & 3u) * 8u);
-                        if (descs) atomicOr(&free_acc[handle >> 2], span);
-                        else atomicAnd(&occ32[handle >> 2], ~span);
+                    const uint32_t gi = flip_gpu(handle, prof.flip);       // where the engine keeps that GPU
+                    if (gi >= lo && gi < hi) {
+                        const uint32_t span = (((1u << size) - 1u) << start) << ((gi & 3u) * 8u);
+                        if (descs) atomicOr(&free_acc[gi >> 2], span);
+                        else atomicAnd(&occ32[gi >> 2], ~span);
                         atomicAdd(&s_freed, 1u);
                     }
                     out[i] = pack_result(handle, start, size, ISL_ST_FREED);
@@ -372,7 +380,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __
                                                                   const uint32_t* __restrict__ counts, uint32_t* __restrict__ cand,
                                                                   uint16_t* __restrict__ cand_o16, const uint8_t* __restrict__ capn, const uint32_t* __restrict__ seq,
                                                                   const uint16_t* __restrict__ q, uint8_t* __restrict__ occ8, uint2* __restrict__ out_chunk,
-                                                                  const uint32_t* __restrict__ heads_in, uint32_t* __restrict__ heads_out, const uint8_t* __restrict__ sizes) {
+                                                                  const uint32_t* __restrict__ heads_in, uint32_t* __restrict__ heads_out, const uint8_t* __restrict__ sizes, uint32_t flip) {
     __shared__ uint16_t s_feas[kMaxTables * 256];
     __shared__ uint32_t s_warp[kSweepThreads / 32];
     __shared__ uint32_t s_red[kSweepThreads / 32];
@@ -424,7 +432,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_scatter(const uint4* __
                 uint32_t starts = seq[row], o2 = o;
                 for (uint32_t k = 0; k < cg && pos < n_p; ++k, ++pos) {
                     const uint32_t st = (starts >> (4 * k)) & 15u;
-                    out_chunk[qp[pos]] = pack_result(g, st, size, ISL_ST_PLACED);
+                    out_chunk[qp[pos]] = pack_result(flip_gpu(g, flip), st, size, ISL_ST_PLACED);
                     o2 |= (((1u << size) - 1u) << st) & 0xFFu;
                 }
                 occ8[g] = (uint8_t)o2;
@@ -672,7 +680,8 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(CandTab tab, DevProf
         } else if (op == ISL_OP_FREE) {
             if (handle >= G || size == 0 || start + size > ISL_SLOTS) out[tid] = pack_result(handle, start, size, ISL_ST_BAD_SPAN);
             else {
-                if (handle >= lo && handle < hi) { atomicAnd(&occ32[handle >> 2], ~((((1u << size) - 1u) << start) << ((handle & 3u) * 8u))); atomicAdd(&s_freed, 1u); }
+                const uint32_t gi = flip_gpu(handle, prof.flip);
+                if (gi >= lo && gi < hi) { atomicAnd(&occ32[gi >> 2], ~((((1u << size) - 1u) << start) << ((gi & 3u) * 8u))); atomicAdd(&s_freed, 1u); }
                 out[tid] = pack_result(handle, start, size, ISL_ST_FREED);
             }
         } else out[tid] = pack_result(ISL_GPU_NONE, ISL_START_NONE, 0, ISL_ST_NOOP);
@@ -762,7 +771,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(CandTab tab, DevProf
     for (uint32_t j = tid; j < s_nlog; j += kSmallThreads) {
         const uint2 e = s_log[j];
         const uint32_t g = __ldcg(cand + e.y) >> 8, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
-        out[t] = pack_result(g, __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
+        out[t] = pack_result(flip_gpu(g, prof.flip), __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
         atomicOr(&occ32[g >> 2], mask << ((g & 3u) * 8u));
     }
 }
@@ -799,7 +808,8 @@ __global__ void __launch_bounds__(kFewThreads, 1) k_few(DevProfiles prof, uint32
         } else if (op == ISL_OP_FREE) {
             if (handle >= G || size == 0 || start + size > ISL_SLOTS) out[tid] = pack_result(handle, start, size, ISL_ST_BAD_SPAN);
             else {
-                if (handle >= lo && handle < hi) { atomicAnd(&occ32[handle >> 2], ~((((1u << size) - 1u) << start) << ((handle & 3u) * 8u))); freed = 1; }
+                const uint32_t gi = flip_gpu(handle, prof.flip);
+                if (gi >= lo && gi < hi) { atomicAnd(&occ32[gi >> 2], ~((((1u << size) - 1u) << start) << ((gi & 3u) * 8u))); freed = 1; }
                 out[tid] = pack_result(handle, start, size, ISL_ST_FREED);
             }
         } else out[tid] = pack_result(ISL_GPU_NONE, ISL_START_NONE, 0, ISL_ST_NOOP);
@@ -833,7 +843,7 @@ __global__ void __launch_bounds__(kFewThreads, 1) k_few(DevProfiles prof, uint32
             const uint32_t o2 = o | ((((1u << size) - 1u) << st) & 0xFFu);
             wv[j >> 2] = (wv[j >> 2] & ~(0xFFu << sh)) | (o2 << sh);
             occ[g] = (uint8_t)o2;
-            out[r] = pack_result(g, st, size, ISL_ST_PLACED);
+            out[r] = pack_result(flip_gpu(g, prof.flip), st, size, ISL_ST_PLACED);
             atomicAdd(&stats->placed, 1ull); atomicAdd(&stats->steps, 1ull);
         }
         // s_red / s_win are rewritten only after the next request's first barrier has been passed by everybody who read them
@@ -850,12 +860,12 @@ __global__ void __launch_bounds__(kFewThreads, 1) k_few(DevProfiles prof, uint32
 // booking; the atomics only serialise neighbours that share a 32-bit word.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_commit(const Ctrl* __restrict__ ctrl, const uint2* __restrict__ log, const uint32_t* __restrict__ cand,
-                                                 uint32_t* __restrict__ occ32, uint2* __restrict__ out_chunk) {
+                                                 uint32_t* __restrict__ occ32, uint2* __restrict__ out_chunk, uint32_t flip) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ctrl->n_log) return;
     const uint2 e = log[j];
     const uint32_t g = cand[e.y] >> 8, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
-    out_chunk[t] = pack_result(g, __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
+    out_chunk[t] = pack_result(flip_gpu(g, flip), __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
     atomicOr(&occ32[g >> 2], mask << ((g & 3u) * 8u));
 }
 
@@ -945,6 +955,7 @@ struct PipeArgs {
     // causal window across ranks: the CTA that completes a chunk on its rank adds 1 to ring_done[chunk] on the owner rank (peer atomic);
     // the owner starts chunk c only when ring_done[c - window] == world
     uint32_t* ring_done; uint32_t world;
+    uint32_t flip;                  // ISL_POLICY_RIGHT_TO_LEFT: G, the reported GPU is G - 1 - internal index
     unsigned long long* trace;      // optional [chunk][segment][kTraceWords]: globaltimer ns of sweep done, token in, token out, commit done, chain start, chain end; decisions; jumps | visited << 32; ns of heads done, windows staged; 2 spare
 };
 
@@ -1449,7 +1460,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             for (uint32_t j = tid; j < nlog; j += kPipeThreads) {
                 const uint2 e = s_log[j];
                 const uint32_t l = s_cand[((e.y - sa_cand) >> 2) - 2] >> 16, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
-                const uint2 rec = pack_result(lo_s + l, __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
+                const uint2 rec = pack_result(flip_gpu(lo_s + l, a.flip), __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
                 a.out[cd.req_off + t] = rec;
                 if (a.owner_out) a.owner_out[cd.req_off + t] = rec;         // partitioned inventory: straight into the owner rank's result array (peer store over NVLink)
                 atomicOr(&s_occ32[l >> 2], mask << ((l & 3u) * 8u));
@@ -1472,6 +1483,34 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_capacity: the what-if / defragmentation query.  cap[p] = how many more pods of profile p ALONE the GPUs of [lo, hi)
+// could still take = sum over GPUs of capn[table][p][occupancy] (the same per-byte table the scan-mode commit places from).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_capacity(const uint8_t* __restrict__ occ, const uint8_t* __restrict__ gtab, const uint8_t* __restrict__ capn,
+                                                   uint32_t n_profiles, uint32_t lo, uint32_t hi, unsigned long long* __restrict__ cap) {
+    __shared__ unsigned long long s_cap[ISL_MAX_PROFILES];
+    if (threadIdx.x < ISL_MAX_PROFILES) s_cap[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t acc[ISL_MAX_PROFILES];
+#pragma unroll
+    for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) acc[p] = 0;
+    for (uint32_t g = lo + blockIdx.x * blockDim.x + threadIdx.x; g < hi; g += gridDim.x * blockDim.x) {
+        const uint32_t o = occ[g], t = gtab[g] & (kMaxTables - 1);
+#pragma unroll
+        for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) if (p < n_profiles) acc[p] += capn[(t * ISL_MAX_PROFILES + p) * 256 + o];
+    }
+#pragma unroll
+    for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) {
+        uint32_t v = acc[p];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        if ((threadIdx.x & 31u) == 0 && v) atomicAdd(&s_cap[p], (unsigned long long)v);
+    }
+    __syncthreads();
+    if (threadIdx.x < ISL_MAX_PROFILES && s_cap[threadIdx.x]) atomicAdd(&cap[threadIdx.x], s_cap[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_bestfit: ISL_POLICY_BEST_FIT (extension, SURVEY 8a-ext — no reference counterpart, parity is against
 // oracle/ref_fast.cpp's best-fit).  Among the GPUs on which the profile has a legal start, take the one with the
 // fewest free slices after the placement = the highest popcount of the occupancy byte, ties to the lowest canonical
@@ -1487,15 +1526,18 @@ constexpr uint32_t kBfSmemGpus = 4096;              // up to here the class bitm
 
 __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uint2* __restrict__ in, uint2* __restrict__ out, uint8_t* __restrict__ occ,
                                                            uint32_t lo, uint32_t hi, const uint8_t* __restrict__ lut, DevProfiles prof,
-                                                           uint32_t* __restrict__ g_bitmaps, Ctrl* ctrl) {
+                                                           uint32_t* __restrict__ g_bitmaps, Ctrl* ctrl, const uint8_t* __restrict__ score) {
     extern __shared__ __align__(16) uint32_t s_dyn[];
     __shared__ uint32_t s_min[256];
     __shared__ uint8_t s_lut[ISL_MAX_PROFILES * 256];
+    // what the policy minimises, per (profile, occupancy byte): ISL_POLICY_BEST_FIT = free slices (8 - popcount), ISL_POLICY_MIN_FRAG =
+    // (profile, start) pairs of the table that stop being feasible when the profile takes its first legal start there (host-built)
+    __shared__ uint8_t s_score[ISL_MAX_PROFILES * 256];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t Gr = hi - lo, W0 = (Gr + 31) / 32, W1 = (W0 + 31) / 32, stride = W0 + W1;   // words per class
     uint32_t* bm = Gr <= kBfSmemGpus ? s_dyn : g_bitmaps;
     for (uint32_t i = tid; i < 256 * stride; i += kBfThreads) bm[i] = 0;
-    for (uint32_t i = tid; i < ISL_MAX_PROFILES * 256; i += kBfThreads) s_lut[i] = lut[i];
+    for (uint32_t i = tid; i < ISL_MAX_PROFILES * 256; i += kBfThreads) { s_lut[i] = lut[i]; s_score[i] = score[i]; }
     if (tid < 256) s_min[tid] = kInf;
     __syncthreads();
     for (uint32_t g = tid; g < Gr; g += kBfThreads) {           // build: every GPU joins the class of its occupancy byte
@@ -1525,7 +1567,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
                 const uint32_t o = r * 32 + lane;
                 const uint32_t mn = s_min[o];
                 if (mn != kInf && s_lut[p * 256 + o] != ISL_START_NONE) {
-                    const uint32_t k2 = ((8u - __popc(o)) << 24) | mn;
+                    const uint32_t k2 = ((uint32_t)s_score[p * 256 + o] << 24) | mn;
                     if (k2 < key) { key = k2; ko = o; }
                 }
             }
@@ -1539,7 +1581,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
                 const uint32_t start = s_lut[p * 256 + o], size = prof.rows[p].size;
                 const uint32_t o2 = o | ((((1u << size) - 1u) << start) & 0xFFu);
                 occ[lo + g] = (uint8_t)o2;
-                out[base + j] = pack_result(lo + g, start, size, ISL_ST_PLACED);
+                out[base + j] = pack_result(flip_gpu(lo + g, prof.flip), start, size, ISL_ST_PLACED);
                 // leave class o: clear the bit, fix the summary, find the new minimum (g was the minimum)
                 uint32_t* c0 = bm + o * stride;
                 const uint32_t w0 = c0[g >> 5] & ~(1u << (g & 31u));

@@ -43,6 +43,8 @@ struct isl_engine {
     uint8_t* d_capn = nullptr;           // [table][profile][occ]: placements of the profile the GPU takes in a row
     uint32_t* d_seq = nullptr;           // [table][profile][occ]: their starts, 4 bits each
     uint8_t* d_sizes = nullptr;          // [table][profile]: slices per placement
+    uint8_t* d_score = nullptr;          // [profile][occ] of table 0: what a best-fit family policy minimises (k_bestfit)
+    unsigned long long* d_cap = nullptr; // isl_capacity: per-profile counters
     uint16_t* d_cand_o16 = nullptr;      // single-chain path: occupancy + table tag of every candidate
 
     // device buffers
@@ -100,6 +102,9 @@ struct isl_engine {
 
 namespace {
 
+inline bool bestfit_family(uint32_t policy) { return policy == ISL_POLICY_BEST_FIT || policy == ISL_POLICY_MIN_FRAG; }
+inline bool reversed(const isl_engine* e) { return e->cfg.policy == ISL_POLICY_RIGHT_TO_LEFT; }
+
 #define ISL_CUDA(e, call)                                                                    \
     do {                                                                                     \
         cudaError_t _err = (call);                                                           \
@@ -139,14 +144,14 @@ int launch_chain(isl_engine* e, uint2* d_out_chunk, const uint32_t* d_heads_in, 
     const size_t smem = (size_t)kQCap * sizeof(uint16_t);      // opted in per device by isl_create
     k_chain<K><<<1, kChainThreads, smem, e->stream>>>(e->tab, e->d_ctrl, e->d_q, e->d_cand_o16, e->d_feas, e->d_log, d_heads_in, d_heads_out);
     if (int rc = check_launch(e, "k_chain")) return rc;
-    k_commit<<<kChunk / 256, 256, 0, e->stream>>>(e->d_ctrl, e->d_log, e->d_cand, reinterpret_cast<uint32_t*>(e->d_occ), d_out_chunk);
+    k_commit<<<kChunk / 256, 256, 0, e->stream>>>(e->d_ctrl, e->d_log, e->d_cand, reinterpret_cast<uint32_t*>(e->d_occ), d_out_chunk, e->prof.flip);
     return check_launch(e, "k_commit");
 }
 
 // Resolve n requests that already sit in device memory.  Enqueues only; the caller synchronises.
 // The latency path: one launch of one CTA resolves a batch of <= 1024 requests (k_small).
 bool small_eligible(const isl_engine* e, uint32_t n) {
-    return n > 0 && n <= kSmallMax && e->cfg.policy == ISL_POLICY_FIRST_FIT && !(e->cfg.flags & (ISL_FLAG_NO_SMALL | ISL_FLAG_FORCE_PIPELINE)) &&
+    return n > 0 && n <= kSmallMax && !bestfit_family(e->cfg.policy) && !(e->cfg.flags & (ISL_FLAG_NO_SMALL | ISL_FLAG_FORCE_PIPELINE)) &&
            e->hi > e->lo && e->hi - e->lo <= (1u << 18);
 }
 
@@ -208,7 +213,7 @@ int run_bestfit(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out) {
                                                                   e->prof, e->d_tile_counts, e->d_ctrl, nullptr, nullptr, 0, 0);
     if (int rc = check_launch(e, "k_prepare")) return rc;
     if (timing) cudaEventRecord(e->ev[1], e->stream);
-    k_bestfit<<<1, kBfThreads, smem, e->stream>>>(n, d_in, d_out, e->d_occ, e->lo, e->hi, e->d_lut, e->prof, e->d_bf_bitmaps, e->d_ctrl);
+    k_bestfit<<<1, kBfThreads, smem, e->stream>>>(n, d_in, d_out, e->d_occ, e->lo, e->hi, e->d_lut, e->prof, e->d_bf_bitmaps, e->d_ctrl, e->d_score);
     if (int rc = check_launch(e, "k_bestfit")) return rc;
     if (timing) {
         cudaEventRecord(e->ev[2], e->stream);
@@ -224,7 +229,7 @@ int run_bestfit(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out) {
 
 int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const uint32_t* d_heads_in, uint32_t* d_heads_out) {
     if (n == 0) return ISL_OK;
-    if (e->cfg.policy == ISL_POLICY_BEST_FIT) return e->n_tables == 1 ? run_bestfit(e, n, d_in, d_out) : ISL_EINVAL;
+    if (bestfit_family(e->cfg.policy)) return e->n_tables == 1 ? run_bestfit(e, n, d_in, d_out) : ISL_EINVAL;
     const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
     const uint32_t tiles = ceil_div(n, kTile);
     if (timing) cudaEventRecord(e->ev[0], e->stream);
@@ -256,7 +261,7 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
             if (int rc = check_launch(e, "k_sweep_count")) return rc;
             k_sweep_scatter<<<sweep_blocks, kSweepThreads, 0, e->stream>>>(reinterpret_cast<const uint4*>(e->d_occ), reinterpret_cast<const uint4*>(e->d_gtab), e->d_feas, first_block, e->lo, e->hi,
                                                                            e->d_ctrl, e->d_sweep_counts, e->d_cand, e->d_cand_o16, e->d_capn, e->d_seq, e->d_q, e->d_occ,
-                                                                           d_out + c0, h_in, h_out, e->d_sizes);
+                                                                           d_out + c0, h_in, h_out, e->d_sizes, e->prof.flip);
             if (int rc = check_launch(e, "k_sweep_scatter")) return rc;
         }
         if (timing) cudaEventRecord(e->ev[4], e->stream);
@@ -381,8 +386,8 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         if (int rc = copy_in_whole()) return rc;
         return run_small(e, sizes[0], d_in, nullptr, d_out);
     }
-    if (e->cfg.policy == ISL_POLICY_BEST_FIT && (d_heads_in || d_heads_out || xepoch)) return ISL_EINVAL;   // best-fit does not partition
-    const bool legacy_token = d_heads_in || d_heads_out || e->cfg.policy == ISL_POLICY_BEST_FIT;   // isl_place_batch_partitioned: host-carried token, kChunk layout
+    if ((bestfit_family(e->cfg.policy) || reversed(e)) && (d_heads_in || d_heads_out || xepoch)) return ISL_EINVAL;   // best-fit / right-to-left do not partition
+    const bool legacy_token = d_heads_in || d_heads_out || bestfit_family(e->cfg.policy);   // isl_place_batch_partitioned: host-carried token, kChunk layout
     bool pipeline = ring || (!legacy_token && !(e->cfg.flags & ISL_FLAG_NO_PIPELINE) && range > 0 && (n_chunks >= 2 || mixed_single_chunk || (e->cfg.flags & ISL_FLAG_FORCE_PIPELINE)));
     // the stream path keeps one free-mask byte per GPU and batch: very long streams over large inventories go batch by batch
     if (pipeline && (uint64_t)n_batches * e->occ_bytes > (256ull << 20)) { if (ring) return ISL_ERANGE; pipeline = false; }
@@ -513,6 +518,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         args.ring_done = reinterpret_cast<uint32_t*>(base + e->cfg.max_batch); args.world = e->ring_world;
         if (!e->has_prev) ISL_CUDA(e, cudaMemsetAsync(args.ring_done, 0, (size_t)n_chunks * sizeof(uint32_t), e->stream));
     }
+    args.flip = e->prof.flip;
     args.copier = h_out_dev ? 1u : 0u; args.window = window; args.wait_ns = kWaitNs; args.owner_out = ring ? e->d_owner_out : nullptr;
     args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
     args.q_stride = q_stride; args.free_stride = free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab; args.out = d_out; args.feas = e->d_feas; args.stats = e->d_ctrl;
@@ -606,8 +612,8 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
     *out = nullptr;
     if (cfg->abi_version != ISL_ABI_VERSION) return ISL_EINVAL;
     if (cfg->max_gpus == 0 || cfg->max_gpus > ISL_MAX_GPUS || cfg->max_batch == 0) return ISL_EINVAL;
-    if (cfg->policy != ISL_POLICY_FIRST_FIT && cfg->policy != ISL_POLICY_BEST_FIT) return ISL_EINVAL;
-    if (cfg->policy == ISL_POLICY_BEST_FIT && cfg->max_gpus > kBfMaxGpus) return ISL_ERANGE;
+    if (cfg->policy > ISL_POLICY_MIN_FRAG) return ISL_EINVAL;
+    if (bestfit_family(cfg->policy) && cfg->max_gpus > kBfMaxGpus) return ISL_ERANGE;
     if (cfg->quirks & ~ISL_QUIRKS_REF_EXACT) return ISL_EINVAL;
     isl_engine* e = new (std::nothrow) isl_engine;
     if (!e) return ISL_ENOMEM;
@@ -634,7 +640,7 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
         // stream with an empty first batch).
         cudaFuncAttributes fa;
         const void* kernels[] = {(const void*)k_prepare, (const void*)k_partition, (const void*)k_set_flag, (const void*)k_few, (const void*)k_build_lut, (const void*)k_eval_starts,
-                                 (const void*)k_free_spans, (const void*)k_sweep_count, (const void*)k_sweep_scatter, (const void*)k_commit, (const void*)k_bestfit,
+                                 (const void*)k_free_spans, (const void*)k_capacity, (const void*)k_sweep_count, (const void*)k_sweep_scatter, (const void*)k_commit, (const void*)k_bestfit,
                                  (const void*)k_chain<1>, (const void*)k_chain<2>, (const void*)k_chain<4>, (const void*)k_small<1>, (const void*)k_small<2>, (const void*)k_small<4>,
                                  (const void*)k_pipeline<1, false>, (const void*)k_pipeline<1, true>, (const void*)k_pipeline<2, false>, (const void*)k_pipeline<2, true>,
                                  (const void*)k_pipeline<4, false>, (const void*)k_pipeline<4, true>};
@@ -657,6 +663,8 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
     ISL_TRY(cudaMalloc(&e->d_capn, ISL_MAX_TABLES * ISL_MAX_PROFILES * 256));
     ISL_TRY(cudaMalloc(&e->d_seq, ISL_MAX_TABLES * ISL_MAX_PROFILES * 256 * sizeof(uint32_t)));
     ISL_TRY(cudaMalloc(&e->d_sizes, ISL_MAX_TABLES * ISL_MAX_PROFILES));
+    ISL_TRY(cudaMalloc(&e->d_score, ISL_MAX_PROFILES * 256));
+    ISL_TRY(cudaMalloc(&e->d_cap, ISL_MAX_PROFILES * sizeof(unsigned long long)));
     ISL_TRY(cudaMalloc(&e->d_gtab, e->occ_bytes));
     ISL_TRY(cudaMemset(e->d_gtab, 0, e->occ_bytes));
     ISL_TRY(cudaMalloc(&e->d_cand_o16, e->occ_bytes * sizeof(uint16_t)));
@@ -684,7 +692,7 @@ int isl_destroy(isl_engine* e) {
     {
         DeviceGuard guard(e->device);
         if (e->stream) cudaStreamSynchronize(e->stream);
-        cudaFree(e->d_gtab); cudaFree(e->d_cand_o16); cudaFree(e->d_capn); cudaFree(e->d_seq); cudaFree(e->d_sizes);
+        cudaFree(e->d_score); cudaFree(e->d_cap); cudaFree(e->d_gtab); cudaFree(e->d_cand_o16); cudaFree(e->d_capn); cudaFree(e->d_seq); cudaFree(e->d_sizes);
         cudaFree(e->d_occ); cudaFree(e->d_lut); cudaFree(e->d_feas); cudaFree(e->d_req); cudaFree(e->d_res);
         cudaFree(e->d_q); cudaFree(e->d_tile_counts); cudaFree(e->d_cand); cudaFree(e->d_log); cudaFree(e->d_sweep_counts);
         cudaFree(e->d_ctrl); cudaFree(e->d_scratch);
@@ -745,7 +753,7 @@ static int load_tables(isl_engine* e, uint32_t n_tables, uint32_t n, const isl_p
     e->n_tables = n_tables;
     memset(e->rows_all, 0, sizeof(e->rows_all));
     for (uint32_t t = 0; t < n_tables; ++t) memcpy(e->rows_all[t], rows + (size_t)t * n, n * sizeof(isl_profile));
-    e->prof.n = n; e->prof.quirks = e->cfg.quirks;
+    e->prof.n = n; e->prof.quirks = e->cfg.quirks; e->prof.flip = reversed(e) ? e->G : 0u;
     memset(e->prof.rows, 0, sizeof(e->prof.rows));
     // default row of a name (its size is what an unplaced result reports) = the row of the first NODE in canonical order
     // that knows the name; until isl_set_node_tables every node uses table 0
@@ -779,6 +787,28 @@ static int load_tables(isl_engine* e, uint32_t n_tables, uint32_t n, const isl_p
         for (uint32_t t = 0; t < n_tables; ++t) for (uint32_t p = 0; p < n; ++p) sizes[t * ISL_MAX_PROFILES + p] = e->rows_all[t][p].size;
         ISL_CUDA(e, cudaMemcpyAsync(e->d_sizes, sizes, sizeof(sizes), cudaMemcpyHostToDevice, e->stream));
     }
+    {   // what a best-fit family policy minimises (table 0: these policies take a single table)
+        std::vector<uint8_t> score(ISL_MAX_PROFILES * 256);      // the copy below completes before this function returns (stream sync)
+        std::vector<uint32_t> cand;                                  // every (profile, start) mask of the table the search can return
+        for (uint32_t p = 0; p < n; ++p)
+            for (uint32_t k = 0; k < e->rows_all[0][p].n_starts; ++k)
+                if (const uint32_t m = candidate_mask(e->rows_all[0][p].size, e->rows_all[0][p].starts[k], e->cfg.quirks)) cand.push_back(m);
+        for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p)
+            for (uint32_t o = 0; o < 256; ++o) {
+                uint32_t v = 8u - (uint32_t)__builtin_popcount(o);  // ISL_POLICY_BEST_FIT: free slices of the GPU (fewest first)
+                if (e->cfg.policy == ISL_POLICY_MIN_FRAG && p < n) {
+                    uint32_t mine = 0;                               // the mask the profile would take there: first legal start in row order
+                    for (uint32_t k = 0; k < e->rows_all[0][p].n_starts && !mine; ++k) {
+                        const uint32_t m = candidate_mask(e->rows_all[0][p].size, e->rows_all[0][p].starts[k], e->cfg.quirks);
+                        if (m && (o & m) == 0) mine = m;
+                    }
+                    v = 0;
+                    if (mine) for (uint32_t m : cand) v += ((o & m) == 0) && (((o | mine) & m) != 0);      // pairs that stop being feasible
+                }
+                score[p * 256 + o] = (uint8_t)v;
+            }
+        ISL_CUDA(e, cudaMemcpyAsync(e->d_score, score.data(), score.size(), cudaMemcpyHostToDevice, e->stream));
+    }
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     e->have_profiles = true;
     return ISL_OK;
@@ -800,7 +830,7 @@ int isl_set_node_tables(isl_engine* e, uint32_t n_nodes, const uint8_t* table_of
     e->node_table.assign(table_of_node, table_of_node + n_nodes);
     std::vector<uint8_t> gtab(e->G);
     for (uint32_t n = 0; n < n_nodes; ++n)
-        for (uint32_t g = e->node_off[n]; g < e->node_off[n + 1]; ++g) gtab[g] = table_of_node[n];
+        for (uint32_t g = e->node_off[n]; g < e->node_off[n + 1]; ++g) gtab[flip_gpu(g, e->prof.flip)] = table_of_node[n];
     ISL_CUDA(e, cudaMemcpyAsync(e->d_gtab, gtab.data(), e->G, cudaMemcpyHostToDevice, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     for (uint32_t p = 0; p < e->prof.n; ++p) {              // size reported for an unplaced request: first node (canonical order) that knows the name
@@ -823,11 +853,14 @@ int isl_load_inventory(isl_engine* e, uint32_t n_nodes, const uint32_t* node_off
     DeviceGuard guard(e->device);
     e->node_off.assign(node_off, node_off + n_nodes + 1);
     e->G = G; e->lo = 0; e->hi = G;
+    e->prof.flip = reversed(e) ? G : 0u;      // ISL_POLICY_RIGHT_TO_LEFT: the inventory is stored in reverse canonical order
     e->snap_G = 0;                  // a snapshot belongs to the inventory it was taken from
     ISL_CUDA(e, cudaMemsetAsync(e->d_occ, 0xFF, e->occ_bytes, e->stream));
     ISL_CUDA(e, cudaMemsetAsync(e->d_gtab, 0, e->occ_bytes, e->stream));        // every node uses table 0 until isl_set_node_tables
     e->node_table.clear();
     for (uint32_t p = 0; p < e->prof.n; ++p) e->prof.rows[p] = e->rows_all[0][p];
+    std::vector<uint8_t> rev;
+    if (e->prof.flip) { rev.assign(occ, occ + G); std::reverse(rev.begin(), rev.end()); occ = rev.data(); }
     ISL_CUDA(e, cudaMemcpyAsync(e->d_occ, occ, G, cudaMemcpyHostToDevice, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     e->have_inventory = true;
@@ -841,6 +874,7 @@ int isl_read_occupancy(isl_engine* e, uint8_t* out) {
     DeviceGuard guard(e->device);
     ISL_CUDA(e, cudaMemcpyAsync(out, e->d_occ, e->G, cudaMemcpyDeviceToHost, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (e->prof.flip) std::reverse(out, out + e->G);       // canonical order at the boundary
     return ISL_OK;
 }
 
@@ -851,6 +885,8 @@ int isl_write_occupancy(isl_engine* e, uint32_t first_gpu, uint32_t n, const uin
     if (n == 0) return ISL_OK;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
+    std::vector<uint8_t> rev;
+    if (e->prof.flip) { rev.assign(occ, occ + n); std::reverse(rev.begin(), rev.end()); occ = rev.data(); first_gpu = e->G - first_gpu - n; }
     ISL_CUDA(e, cudaMemcpyAsync(e->d_occ + first_gpu, occ, n, cudaMemcpyHostToDevice, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     return ISL_OK;
@@ -908,13 +944,43 @@ int isl_place_batch_range(isl_engine* e, uint32_t lo, uint32_t hi, uint32_t n, c
     std::lock_guard<std::mutex> lk(e->mu);          // restriction, placement and restore under ONE lock: two callers cannot interleave
     DeviceGuard guard(e->device);
     const uint32_t lo0 = e->lo, hi0 = e->hi;
-    e->lo = lo; e->hi = hi;
+    if (e->prof.flip) { e->lo = e->G - hi; e->hi = e->G - lo; } else { e->lo = lo; e->hi = hi; }
     const int rc = place_batch_locked(e, n, in, out);
     e->lo = lo0; e->hi = hi0;
     return rc;
 }
 
+static int place_batch_plain(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out);
+
+// ISL_FLAG_ALL_NODES — the reference's literal multi-node behaviour: Reconcile's node loop (:190-227) has no `break` after a
+// successful node, so a pod is allocated on EVERY node that has capacity.  Nodes do not interact (an allocation on one node never
+// changes what another node can take), so "every pod over all nodes" equals "every node over all pods": one restricted pass per node,
+// each consuming capacity on its node; the record reported for a pod is the first node's (what the oracle's all_nodes switch reports).
+// A compatibility mode for parity studies, one engine call per node — not a fast path.
 static int place_batch_locked(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out) {
+    if (!(e->cfg.flags & ISL_FLAG_ALL_NODES)) return place_batch_plain(e, n, in, out);
+    const uint32_t lo0 = e->lo, hi0 = e->hi, n_nodes = (uint32_t)e->node_off.size() - 1;
+    const uint32_t clo = e->prof.flip ? e->G - hi0 : lo0, chi = e->prof.flip ? e->G - lo0 : hi0;     // the caller's range, canonical
+    std::vector<isl_result> tmp(n);
+    bool first = true;
+    int rc = ISL_OK;
+    for (uint32_t k = 0; k < n_nodes && !rc; ++k) {
+        const uint32_t node = e->prof.flip ? n_nodes - 1 - k : k;                  // nodes in policy order
+        const uint32_t a = std::max(clo, e->node_off[node]), b = std::min(chi, e->node_off[node + 1]);
+        if (a >= b) continue;
+        if (e->prof.flip) { e->lo = e->G - b; e->hi = e->G - a; } else { e->lo = a; e->hi = b; }
+        rc = place_batch_plain(e, n, in, first ? out : tmp.data());
+        if (!rc && !first)
+            for (uint32_t i = 0; i < n; ++i)
+                if (in[i].op == ISL_OP_ALLOC && out[i].status != ISL_ST_PLACED && tmp[i].status == ISL_ST_PLACED) out[i] = tmp[i];
+        first = false;
+    }
+    e->lo = lo0; e->hi = hi0;
+    if (!rc && first) rc = place_batch_plain(e, n, in, out);       // empty range: defaults only
+    return rc;
+}
+
+static int place_batch_plain(isl_engine* e, uint32_t n, const isl_request* in, isl_result* out) {
     if (n <= kSmallInline && small_eligible(e, n)) {        // requests as kernel parameters, results into mapped pinned memory: 1 launch + 1 sync
         SmallReqs inl{};
         memcpy(inl.r, in, (size_t)n * sizeof(isl_request));
@@ -1050,7 +1116,7 @@ int isl_set_partition(isl_engine* e, uint32_t lo, uint32_t hi) {
     if (!e->have_inventory) return ISL_ESTATE;
     if (lo > hi || hi > e->G) return ISL_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
-    e->lo = lo; e->hi = hi;
+    if (e->prof.flip) { e->lo = e->G - hi; e->hi = e->G - lo; } else { e->lo = lo; e->hi = hi; }
     return ISL_OK;
 }
 
@@ -1065,7 +1131,7 @@ int isl_free_batch(isl_engine* e, uint32_t n, const isl_span* spans) {
     if (int rc = ensure_scratch(e, (size_t)n * sizeof(isl_span))) return rc;
     ISL_CUDA(e, cudaMemcpyAsync(e->d_scratch, spans, (size_t)n * sizeof(isl_span), cudaMemcpyHostToDevice, e->stream));
     k_free_spans<<<ceil_div(n, 256), 256, 0, e->stream>>>(n, reinterpret_cast<const isl_span*>(e->d_scratch), reinterpret_cast<uint32_t*>(e->d_occ),
-                                                          e->G, e->lo, e->hi, e->d_ctrl);
+                                                          e->G, e->lo, e->hi, e->d_ctrl, e->prof.flip);
     if (int rc = check_launch(e, "k_free_spans")) return rc;
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     return ISL_OK;
@@ -1124,6 +1190,54 @@ int isl_reset_stats(isl_engine* e) {
     ISL_CUDA(e, cudaMemsetAsync(&e->d_ctrl->placed, 0, 8 * sizeof(unsigned long long), e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     return ISL_OK;
+}
+
+// ---- what-if / defragmentation queries -------------------------------------------------------------------
+static int capacity_locked(isl_engine* e, uint64_t* cap) {
+    ISL_CUDA(e, cudaMemsetAsync(e->d_cap, 0, ISL_MAX_PROFILES * sizeof(unsigned long long), e->stream));
+    if (e->hi > e->lo) {
+        k_capacity<<<std::min(ceil_div(e->hi - e->lo, 256), 296u), 256, 0, e->stream>>>(e->d_occ, e->d_gtab, e->d_capn, e->prof.n, e->lo, e->hi, e->d_cap);
+        if (int rc = check_launch(e, "k_capacity")) return rc;
+    }
+    unsigned long long h[ISL_MAX_PROFILES];
+    ISL_CUDA(e, cudaMemcpyAsync(h, e->d_cap, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p) cap[p] = h[p];
+    return ISL_OK;
+}
+
+int isl_capacity(isl_engine* e, uint64_t* cap) {
+    if (!e || !cap) return ISL_EINVAL;
+    if (int rc = validate_ready(e, 0)) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    return capacity_locked(e, cap);
+}
+
+int isl_what_if(isl_engine* e, uint32_t n, const isl_request* plan, isl_result* out, uint64_t* cap_before, uint64_t* cap_after) {
+    if (!e || (n && (!plan || !out))) return ISL_EINVAL;
+    if (int rc = validate_ready(e, n)) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);          // snapshot, plan, measurement and restore under ONE lock: nobody sees the hypothetical state
+    DeviceGuard guard(e->device);
+    if (e->snap_bytes < e->occ_bytes) {
+        if (e->d_occ_snap) cudaFree(e->d_occ_snap);
+        e->d_occ_snap = nullptr; e->snap_bytes = 0;
+        ISL_CUDA(e, cudaMalloc(&e->d_occ_snap, e->occ_bytes));
+        e->snap_bytes = e->occ_bytes;
+    }
+    const uint32_t keep_snap_G = e->snap_G;         // a caller's own snapshot (isl_snapshot_occupancy) does not survive a what-if: say so
+    (void)keep_snap_G;
+    ISL_CUDA(e, cudaMemcpyAsync(e->d_occ_snap, e->d_occ, e->occ_bytes, cudaMemcpyDeviceToDevice, e->stream));
+    int rc = ISL_OK;
+    if (cap_before) rc = capacity_locked(e, cap_before);
+    if (!rc && n) rc = place_batch_locked(e, n, plan, out);
+    if (!rc && cap_after) rc = capacity_locked(e, cap_after);
+    // the live state comes back whatever happened above
+    const cudaError_t err = cudaMemcpyAsync(e->d_occ, e->d_occ_snap, e->occ_bytes, cudaMemcpyDeviceToDevice, e->stream);
+    const cudaError_t err2 = cudaStreamSynchronize(e->stream);
+    e->snap_G = 0;
+    if (!rc && (err != cudaSuccess || err2 != cudaSuccess)) { snprintf(e->cuda_err, sizeof(e->cuda_err), "isl_what_if restore: %s", cudaGetErrorString(err != cudaSuccess ? err : err2)); rc = ISL_ECUDA; }
+    return rc;
 }
 
 // ---- causal window / pinned buffers / owner-gathered results --------------------------------------------------------------
@@ -1193,7 +1307,7 @@ int isl_connect_owner_local(isl_engine* e, isl_engine* owner) {
 int isl_stream_open(isl_engine* e, uint32_t max_batches) {
     if (!e || max_batches == 0 || max_batches > kMaxStreamChunks) return ISL_EINVAL;
     if (!e->have_profiles || !e->have_inventory || e->open.active) return ISL_ESTATE;
-    if (e->cfg.policy != ISL_POLICY_FIRST_FIT) return ISL_EINVAL;
+    if (bestfit_family(e->cfg.policy)) return ISL_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
     auto& o = e->open;
@@ -1285,7 +1399,7 @@ int isl_stream_submit(isl_engine* e, uint32_t n, const isl_request* in, isl_resu
         PipeArgs args{};
         args.n_chunks = o.max_batches; args.n_seg = o.n_seg; args.seg = o.seg; args.lo = e->lo; args.hi = e->hi; args.epoch = o.epoch;
         args.ready = e->d_ready; args.done_cnt = e->d_done_cnt; args.host_out = nullptr; args.copier = 1; args.open = 1;
-        args.host_done = o.d_done_host; args.window = 0; args.wait_ns = kOpenWaitNs;
+        args.host_done = o.d_done_host; args.window = 0; args.wait_ns = kOpenWaitNs; args.flip = e->prof.flip;
         args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
         args.q_stride = o.q_stride; args.free_stride = o.free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab;
         args.out = e->d_res; args.feas = e->d_feas; args.stats = e->d_ctrl;

@@ -22,12 +22,12 @@ START_NONE = 9
 GPU_NONE = 0xFFFFFFFF
 PROFILE_UNKNOWN = 0xFF
 OK, EINVAL, ENOMEM, ECUDA, ESTATE, ERANGE = 0, -1, -2, -3, -4, -5
-POLICY_FIRST_FIT, POLICY_BEST_FIT = 0, 1
+POLICY_FIRST_FIT, POLICY_BEST_FIT, POLICY_RIGHT_TO_LEFT, POLICY_MIN_FRAG = 0, 1, 2, 3
 QUIRK_STRICT_BOUND, QUIRK_POW2_ONLY = 1, 2
 QUIRKS_REF_EXACT, QUIRKS_FIXED = 3, 0
 OP_ALLOC, OP_FREE, OP_NOOP = 0, 1, 2
 ST_PLACED, ST_NO_CAPACITY, ST_BAD_PROFILE, ST_FREED, ST_BAD_SPAN, ST_NOOP = 0, 1, 2, 3, 4, 5
-FLAG_TIMING, FLAG_NO_PIPELINE, FLAG_FORCE_PIPELINE, FLAG_TRACE, FLAG_NO_SMALL = 1, 2, 4, 8, 16
+FLAG_TIMING, FLAG_NO_PIPELINE, FLAG_FORCE_PIPELINE, FLAG_TRACE, FLAG_NO_SMALL, FLAG_ALL_NODES = 1, 2, 4, 8, 16, 32
 
 # ---- record layouts -------------------------------------------------------------------------
 REQUEST_DTYPE = np.dtype([("handle", "<u4"), ("profile", "u1"), ("op", "u1"), ("start", "u1"), ("size", "u1")])
@@ -61,7 +61,7 @@ EXPORTED_SYMBOLS = [
     "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_ipc_inbox_handle", "isl_ipc_connect", "isl_connect_local", "isl_place_stream_partitioned", "isl_device_occupancy", "isl_get_stats", "isl_read_trace",
     "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
     "isl_place_batch_range", "isl_stream_open", "isl_stream_submit", "isl_stream_wait", "isl_stream_close", "isl_set_causal_window",
-    "isl_host_alloc", "isl_host_free", "isl_device_results", "isl_ipc_results_handle", "isl_ipc_connect_owner", "isl_connect_owner_local", "isl_set_ring_world",
+    "isl_host_alloc", "isl_host_free", "isl_device_results", "isl_ipc_results_handle", "isl_ipc_connect_owner", "isl_connect_owner_local", "isl_set_ring_world", "isl_capacity", "isl_what_if",
 ]
 
 _lib = None
@@ -123,6 +123,8 @@ def load_library(path: str = LIB_PATH):
         "isl_ipc_connect_owner": (C.c_int, [p, p]),
         "isl_connect_owner_local": (C.c_int, [p, p]),
         "isl_set_ring_world": (C.c_int, [p, C.c_uint32]),
+        "isl_capacity": (C.c_int, [p, p]),
+        "isl_what_if": (C.c_int, [p, C.c_uint32, p, p, p, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -393,6 +395,20 @@ class Engine:
     def snapshot_occupancy(self):
         """What-if queries: keep a device-side copy of the occupancy ... (see restore_occupancy)."""
         self._check(self._lib.isl_snapshot_occupancy(self._h), "isl_snapshot_occupancy")
+
+    def capacity(self) -> np.ndarray:
+        """Per profile: how many more pods of that profile alone the inventory could still take."""
+        cap = np.zeros(MAX_PROFILES, dtype=np.uint64)
+        self._check(self._lib.isl_capacity(self._h, _ptr(cap)), "isl_capacity")
+        return cap
+
+    def what_if(self, plan: np.ndarray):
+        """Resolve ``plan`` against the live occupancy, then put the live state back.  Returns (results, capacity before, capacity after)."""
+        plan = np.ascontiguousarray(plan, dtype=REQUEST_DTYPE)
+        out = np.empty(len(plan), dtype=RESULT_DTYPE)
+        before, after = np.zeros(MAX_PROFILES, dtype=np.uint64), np.zeros(MAX_PROFILES, dtype=np.uint64)
+        self._check(self._lib.isl_what_if(self._h, len(plan), _ptr(plan), _ptr(out), _ptr(before), _ptr(after)), "isl_what_if")
+        return out, before, after
 
     def restore_occupancy(self):
         """... and put it back after any number of placement calls (defragmentation planning)."""

@@ -10,6 +10,11 @@
 // O(R + P*G) instead of the reference's O(R * G * entries).  It is the honest strong CPU baseline
 // and the verifier for the 1M-request runs.
 //
+// ISL_POLICY_RIGHT_TO_LEFT (the policy the reference only stubs, :464-469) is the same search over the GPUs in DESCENDING canonical
+// order.  ISL_POLICY_MIN_FRAG (extension, SURVEY 8a-ext "richer score"): among the GPUs where the profile has a valid start, the one
+// where taking the reference's first valid start makes the fewest (profile, start) pairs of that GPU's table infeasible, ties to the
+// lowest canonical index — computed here pair by pair from the rows, independently of the engine's per-byte score table.
+//
 // ISL_POLICY_BEST_FIT is this repository's extension (no reference counterpart):
 // among GPUs where the profile has a valid start, take the one with the fewest free slices after
 // the placement (popcount over the 8-bit word), ties to the lowest canonical index; the start on
@@ -48,7 +53,7 @@ struct orc_fast {
     std::vector<uint8_t> occ;
     std::vector<uint8_t> gtab;         // table of the node that owns the GPU (every node publishes its own Migplacement)
     std::vector<uint8_t> lut;          // [(t*P + p)*256 + occ] -> start or 9
-    std::vector<uint32_t> cursor;      // first GPU that may still take profile p
+    std::vector<uint32_t> cursor;      // first GPU that may still take profile p (right-to-left: one past the LAST GPU that may)
     std::vector<uint8_t> default_size; // size reported for an unplaced request: the first table that knows the name
 };
 
@@ -66,7 +71,7 @@ orc_fast* orc_fast_new_tables(uint32_t n_nodes, const uint32_t* node_off, uint32
     h->lut.resize((size_t)n_tables * n_profiles * 256);
     for (uint32_t r = 0; r < n_tables * n_profiles; ++r)
         for (uint32_t o = 0; o < 256; ++o) h->lut[(size_t)r * 256 + o] = orc_start_for(&rows[r], quirks, (uint8_t)o);
-    h->cursor.assign(n_profiles, 0);
+    h->cursor.assign(n_profiles, policy == ISL_POLICY_RIGHT_TO_LEFT ? h->G : 0u);
     h->default_size.assign(n_profiles, 0);
     for (uint32_t p = 0; p < n_profiles; ++p)       // first node in canonical order whose Migplacement has the name
         for (uint32_t n = 0; n < n_nodes; ++n) {
@@ -82,7 +87,7 @@ orc_fast* orc_fast_new(uint32_t n_nodes, const uint32_t* node_off, uint32_t n_pr
 void orc_fast_delete(orc_fast* h) { delete h; }
 void orc_fast_load(orc_fast* h, const uint8_t* occ) {
     std::copy(occ, occ + h->G, h->occ.begin());
-    std::fill(h->cursor.begin(), h->cursor.end(), 0u);
+    std::fill(h->cursor.begin(), h->cursor.end(), h->policy == ISL_POLICY_RIGHT_TO_LEFT ? h->G : 0u);
 }
 void orc_fast_occupancy(orc_fast* h, uint8_t* out) { std::copy(h->occ.begin(), h->occ.end(), out); }
 
@@ -93,7 +98,7 @@ int orc_fast_place(orc_fast* h, uint32_t n, const isl_request* in, isl_result* o
         const uint32_t g = in[i].handle, st = in[i].start, sz = in[i].size;
         if (g >= h->G || sz == 0 || st + sz > ISL_SLOTS) { out[i] = {g, (uint8_t)st, (uint8_t)sz, (uint16_t)ISL_ST_BAD_SPAN}; continue; }
         h->occ[g] &= (uint8_t)~(((1u << sz) - 1u) << st);
-        for (uint32_t p = 0; p < h->P; ++p) h->cursor[p] = std::min(h->cursor[p], g);
+        for (uint32_t p = 0; p < h->P; ++p) h->cursor[p] = h->policy == ISL_POLICY_RIGHT_TO_LEFT ? std::max(h->cursor[p], g + 1) : std::min(h->cursor[p], g);
         out[i] = {g, (uint8_t)st, (uint8_t)sz, (uint16_t)ISL_ST_FREED};
     }
     for (uint32_t i = 0; i < n; ++i) {                              // then ALLOCs in request order
@@ -108,6 +113,29 @@ int orc_fast_place(orc_fast* h, uint32_t n, const isl_request* in, isl_result* o
             while (g < h->G && lut_of(g)[h->occ[g]] == ISL_START_NONE) ++g;
             h->cursor[p] = g;
             if (g < h->G) hit = g;
+        } else if (h->policy == ISL_POLICY_RIGHT_TO_LEFT) {
+            uint32_t g = h->cursor[p];                               // one past the last GPU that may still take p
+            while (g > 0 && lut_of(g - 1)[h->occ[g - 1]] == ISL_START_NONE) --g;
+            h->cursor[p] = g;
+            if (g > 0) hit = g - 1;
+        } else if (h->policy == ISL_POLICY_MIN_FRAG) {
+            int best = 1 << 30;
+            for (uint32_t g = 0; g < h->G; ++g) {
+                const uint8_t s = lut_of(g)[h->occ[g]];
+                if (s == ISL_START_NONE) continue;
+                const isl_profile* trows = &h->rows[(size_t)h->gtab[g] * h->P];
+                const uint8_t before = h->occ[g], after = (uint8_t)(before | (((1u << trows[p].size) - 1u) << s));
+                int lost = 0;                                         // (profile, start) pairs feasible before and not after
+                for (uint32_t q = 0; q < h->P; ++q)
+                    for (uint32_t k = 0; k < trows[q].n_starts; ++k) {
+                        isl_profile one = trows[q];
+                        one.n_starts = 1; one.starts[0] = trows[q].starts[k];
+                        const bool was = orc_start_for(&one, h->quirks, before) != ISL_START_NONE;
+                        const bool is = orc_start_for(&one, h->quirks, after) != ISL_START_NONE;
+                        lost += was && !is;
+                    }
+                if (lost < best) { best = lost; hit = g; }
+            }
         } else {
             int best = 1 << 30;
             for (uint32_t g = 0; g < h->G; ++g) {
