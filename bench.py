@@ -182,6 +182,7 @@ class Ctx:
         for _ in range(steps):
             if flush_l2:
                 self.flush.fill_(1)
+                torch.cuda.synchronize()        # the host clock below must not see the flush
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             e0.record()

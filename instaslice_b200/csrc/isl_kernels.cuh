@@ -891,7 +891,8 @@ __global__ void __launch_bounds__(256) k_commit(const Ctrl* __restrict__ ctrl, c
 // finished chunks into the caller's pinned result array (done counters).
 // Results are bit-identical to resolving the batches one after the other.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t kSegMax = 512;                   // GPUs per segment (2 per thread in the local sweep)
+constexpr uint32_t kSegMax = 512;                   // GPUs per (sub-)segment (2 per thread in the local sweep)
+constexpr uint32_t kSubMax = 8;                     // sub-segments one CTA walks per chunk: inventories beyond 148 x 512 GPUs stay on the pipeline
 #ifndef ISL_PIPE_THREADS
 #define ISL_PIPE_THREADS 256
 #endif
@@ -900,11 +901,11 @@ static_assert(kPipeThreads == kSegMax || 2 * kPipeThreads == kSegMax, "sweep lay
 constexpr uint32_t kLogCap = 8 * kSegMax;           // a GPU accepts at most 8 placements
 constexpr uint32_t kTokStride = 32;                 // uint32 per token: 16 tagged head words inside a GPU; raw heads[16] + flag at [16] across GPUs
 // shared memory: occupancy bytes | candidate records (+8 sentinels) | decision log (+1 pseudo-decision) | the chunk's queues (uint16) | queue-window keys
-constexpr uint32_t kPipeOffCand = kSegMax;
+constexpr uint32_t kPipeOffCand = kSegMax * kSubMax;      // occupancy bytes of the whole stage (all its sub-segments)
 constexpr uint32_t kPipeOffLog = kPipeOffCand + 4 * (kSegMax + 8);
 constexpr uint32_t kPipeOffQ = (kPipeOffLog + 8 * (kLogCap + 1) + 15u) & ~15u;
 constexpr uint32_t kPipeOffWin = kPipeOffQ + 2 * kQCap + 16;
-constexpr uint32_t kWinTotal = 14336;               // 32-bit queue-window keys a segment can stage for all profiles together
+constexpr uint32_t kWinTotal = 12288;               // 32-bit queue-window keys a segment can stage for all profiles together
 constexpr uint32_t kPipeSmem = kPipeOffWin + 4 * (kWinTotal + 4 * ISL_MAX_PROFILES);
 
 // largest segment whose worst-case queue windows (every candidate GPU accepting every legal start of every
@@ -921,7 +922,8 @@ struct ChunkDesc {
 };
 
 struct PipeArgs {
-    uint32_t n_chunks, n_seg, seg, lo, hi, epoch;
+    uint32_t n_chunks, n_seg, seg, lo, hi, epoch;     // seg: GPUs per pipeline stage (CTA) = sub x sub-segments
+    uint32_t sub;                                     // GPUs per sub-segment (<= kSegMax): what one sweep / chain / commit round covers
     const ChunkDesc* chunks;
     const Ctrl* cctl;               // per chunk: qoff / qcnt / active (written by k_partition)
     const uint16_t* q_all;          // per chunk queues, stride q_stride entries
@@ -1047,7 +1049,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + kPipeOffCand);         // records (local gpu << 16 | table tag | occ) + sentinels
     uint2* s_log = reinterpret_cast<uint2*>(smem + kPipeOffLog);                 // (key, candidate index) per decision
     __shared__ uint16_t s_feas[kMaxTables * 256];
-    __shared__ uint8_t s_tab[kSegMax];                                           // table of every local GPU
+    __shared__ uint8_t s_tab[kSegMax * kSubMax];                                 // table of every local GPU
     __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_wbase[ISL_MAX_PROFILES], s_qbeg[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
     __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_minsize[ISL_MAX_PROFILES], s_usable[kMaxTables], s_plist[ISL_MAX_PROFILES], s_nplist;
     __shared__ uint32_t s_warp[kPipeThreads / 32], s_ncand, s_nfree, s_nlog, s_idle, s_closed;
@@ -1102,9 +1104,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     uint32_t* s_wkey = reinterpret_cast<uint32_t*>(smem + kPipeOffWin);          // per-profile windows of ready-made keys t<<15 | p<<11
     const uint32_t sa_wkey = (uint32_t)__cvta_generic_to_shared(s_wkey);
 
-    for (uint32_t i = tid; i < kSegMax / 4; i += kPipeThreads) s_occ32[i] = 0xFFFFFFFFu;
+    for (uint32_t i = tid; i < kSegMax * kSubMax / 4; i += kPipeThreads) s_occ32[i] = 0xFFFFFFFFu;
     for (uint32_t i = tid; i < kMaxTables * 256; i += kPipeThreads) s_feas[i] = a.feas[i];
-    for (uint32_t i = tid; i < kSegMax; i += kPipeThreads) s_tab[i] = i < n_g ? a.gtab[lo_s + i] & (kMaxTables - 1) : 0;
+    for (uint32_t i = tid; i < kSegMax * kSubMax; i += kPipeThreads) s_tab[i] = i < n_g ? a.gtab[lo_s + i] & (kMaxTables - 1) : 0;
     if (tid < ISL_MAX_PROFILES) {
         uint32_t n = 0, sz = 8;
         for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) {
@@ -1206,6 +1208,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             __syncthreads();
         }
         const uint32_t active = cc->active;
+        // A stage is walked sub-segment by sub-segment (one for inventories up to 148 x 512 GPUs): sweep, heads, windows, chain, commit per
+        // sub-segment; the token is awaited in front of the first and published behind the last one (or as soon as nothing is pending).
+        const uint32_t n_sub = max(1u, (n_g + a.sub - 1) / a.sub);
+        bool prefetched = false;            // the next chunk's queues are on their way (they may only overwrite this chunk's after its last chain)
+        for (uint32_t sb = 0; sb < n_sub; ++sb) {
+        const uint32_t sb_base = sb * a.sub, n_sb = min(a.sub, n_g - min(n_g, sb_base));
+        const bool last_sub = sb + 1 == n_sub;
         {   // 2. local sweep: thread t owns kSegMax / kPipeThreads consecutive local GPUs; ordered compaction
             constexpr uint32_t kGpt = kSegMax / kPipeThreads;
             uint32_t og[kGpt], tg[kGpt];
@@ -1216,8 +1225,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
 #pragma unroll
             for (uint32_t x = 0; x < kGpt; ++x) {
                 const uint32_t g = kGpt * tid + x;
-                og[x] = reinterpret_cast<const uint8_t*>(s_occ32)[g]; tg[x] = s_tab[g];
-                fg[x] = g < n_g && (s_feas[tg[x] * 256 + og[x]] & active);
+                og[x] = reinterpret_cast<const uint8_t*>(s_occ32)[sb_base + g]; tg[x] = s_tab[sb_base + g];
+                fg[x] = g < n_sb && (s_feas[tg[x] * 256 + og[x]] & active);
                 if (fg[x]) cnt += 1u | ((uint32_t)__popc(~og[x] & s_usable[tg[x]]) << 16);
             }
             uint32_t incl = cnt;
@@ -1247,7 +1256,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             bool from_done = false;
             const uint32_t tag = a.epoch & 0x7FFFu;
             stamp_if(tr && tid == 0, tr + 0);
-            if (seg > 0) {
+            if (sb > 0) {               // behind the first sub-segment the heads are the ones its chain left
+                if (tid < ISL_MAX_PROFILES) h = s_heads[tid] + s_pop[tid];
+            } else if (seg > 0) {
                 const uint32_t* pt = a.tokens + (tok_chunk + seg - 1) * kTokStride + (tid & 15u);
                 const uint32_t* pd = a.tokens + (tok_chunk + a.n_seg) * kTokStride + (tid & 15u);
                 bool ok = tid >= ISL_MAX_PROFILES;
@@ -1268,7 +1279,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 if (tid < ISL_MAX_PROFILES) h = ld_relaxed_sys(a.inbox + (size_t)c * kTokStride + tid);
             } else if (tid < ISL_MAX_PROFILES) h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
             stamp_if(tr && tid == 0, tr + 1);
-            const bool all_done = __all_sync(0xFFFFFFFFu, from_done || tid >= ISL_MAX_PROFILES);
+            const bool all_done = sb == 0 && __all_sync(0xFFFFFFFFu, from_done || tid >= ISL_MAX_PROFILES);
             if (tid < ISL_MAX_PROFILES) {
                 const uint32_t qc = cc->qcnt[tid], qo = cc->qoff[tid];
                 left = ((active >> tid) & 1u) && qc > h ? qc - h : 0u;
@@ -1305,9 +1316,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 }
             }
             __syncthreads();
-            chunk_done(c);
-            if (c + 1 < a.n_chunks) { closed = wait_ready(c + 1); if (!closed) queue_load_async(c + 1); }
-            continue;
+            break;              // the remaining sub-segments have nothing to take either
         }
         {   // windows of ready-made keys t << 15 | profile << 11, each closed by two INF sentinels — converted from the shared copy of
             // the queues (a shared-memory round trip per round instead of an L2 one), only for profiles that own candidates
@@ -1436,11 +1445,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
 #pragma unroll
             for (int k = 0; k < K; ++k) if (reports[k]) s_pop[cprof[k]] = (wa[k] - wa0[k] - 12) >> 2;
             __syncwarp();
-            // 5. token for the next segment: heads first, then the flag (release)
+            // 5. token for the next segment: heads first, then the flag (release) — behind the stage's last sub-segment
             uint32_t* tok = a.tokens + (tok_chunk + seg) * kTokStride;
             const bool last = seg == a.n_seg - 1;
             uint32_t* peer = last && a.outbox ? a.outbox + (size_t)c * kTokStride : nullptr;
-            if (lane < ISL_MAX_PROFILES) {
+            if (last_sub && lane < ISL_MAX_PROFILES) {
                 const uint32_t h = s_heads[lane] + s_pop[lane];
                 st_relaxed_gpu(tok + lane, ((a.epoch & 0x7FFFu) << 17) | h);       // the next segment starts
                 if (last && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + lane] = h;
@@ -1448,18 +1457,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             }
             __syncwarp();
             if (lane == 0) {
-                if (peer) { __threadfence_system(); st_release_sys(peer + ISL_MAX_PROFILES, a.xepoch); }
+                if (last_sub && peer) { __threadfence_system(); st_release_sys(peer + ISL_MAX_PROFILES, a.xepoch); }
                 s_nlog = nlog;
                 if (tr) tr[2] = globaltimer_ns();
             }
         }
         __syncthreads();
-        if (c + 1 < a.n_chunks && !a.ready && !a.window) queue_load_async(c + 1);    // the chain is done with the queues: fetch the next chunk's behind the commit
+        if (last_sub && c + 1 < a.n_chunks && !a.ready && !a.window) { queue_load_async(c + 1); prefetched = true; }   // the chain is done with the queues: fetch the next chunk's behind the commit
         {   // 6. commit
             const uint32_t nlog = s_nlog;
             for (uint32_t j = tid; j < nlog; j += kPipeThreads) {
                 const uint2 e = s_log[j];
-                const uint32_t l = s_cand[((e.y - sa_cand) >> 2) - 2] >> 16, mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
+                const uint32_t l = sb_base + (s_cand[((e.y - sa_cand) >> 2) - 2] >> 16), mask = e.x & 0xFFu, t = (e.x >> 15) & 0xFFFFu;
                 const uint2 rec = pack_result(flip_gpu(lo_s + l, a.flip), __ffs(mask) - 1, __popc(mask), ISL_ST_PLACED);
                 a.out[cd.req_off + t] = rec;
                 if (a.owner_out) a.owner_out[cd.req_off + t] = rec;         // partitioned inventory: straight into the owner rank's result array (peer store over NVLink)
@@ -1468,8 +1477,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         }
         __syncthreads();
         if (tr && tid == 0) tr[3] = globaltimer_ns();
+        }   // sub-segments
         chunk_done(c);
-        if (c + 1 < a.n_chunks && (a.ready || a.window)) { closed = wait_ready(c + 1); if (!closed) queue_load_async(c + 1); }   // fed stream: the next batch may not have arrived yet
+        if (c + 1 < a.n_chunks && !prefetched) { closed = wait_ready(c + 1); if (!closed) queue_load_async(c + 1); }   // fed / windowed stream: the next batch may not be due yet
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     for (uint32_t i = tid; i < n_g; i += kPipeThreads) a.occ[lo_s + i] = reinterpret_cast<uint8_t*>(s_occ32)[i];

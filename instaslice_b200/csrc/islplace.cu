@@ -87,7 +87,7 @@ struct isl_engine {
     // open stream (isl_stream_open / _submit / _wait / _close): one persistent k_pipeline, batches arrive while it runs
     struct Open {
         bool active = false, launched = false;
-        uint32_t max_batches = 0, submitted = 0, epoch = 0, seg = 0, n_seg = 0, q_stride = 0, free_stride = 0, tiles_per_batch = 0;
+        uint32_t max_batches = 0, submitted = 0, epoch = 0, seg = 0, n_seg = 0, sub = 0, q_stride = 0, free_stride = 0, tiles_per_batch = 0;
         uint32_t* h_done = nullptr; uint32_t* d_done_host = nullptr; uint32_t cap_done = 0;   // mapped pinned: [batch] = epoch once its results are in host memory
         ChunkDesc* h_chunks = nullptr; TileDesc* h_tiles = nullptr; uint32_t cap_desc = 0;       // pinned staging of the per-batch descriptors
     } open;
@@ -329,7 +329,7 @@ int grow(isl_engine* e, T** buf, uint32_t* cap, size_t need, size_t elems_per_un
 
 // Segment geometry of the pipeline for a stream of n_chunks chunks of ~avg_chunk requests.  ISL_ERANGE: the inventory does not fit the
 // co-resident CTAs (or the tables need too many candidates per segment) — the caller takes the chunk-by-chunk path.
-int plan_pipeline(isl_engine* e, uint32_t n_chunks, double avg_chunk, bool want_feed, uint32_t* seg_out, uint32_t* n_seg_out) {
+int plan_pipeline(isl_engine* e, uint32_t n_chunks, double avg_chunk, bool want_feed, uint32_t* seg_out, uint32_t* n_seg_out, uint32_t* sub_out) {
     if (int rc = query_coresident(e)) return rc;
     const uint32_t range = e->hi - e->lo;
     uint32_t total_cand = 0;
@@ -351,11 +351,15 @@ int plan_pipeline(isl_engine* e, uint32_t n_chunks, double avg_chunk, bool want_
     // CTAs (one CTA fills an SM's shared memory, and kernels with another shared-memory carve-out cannot join it there)
     if (want_feed && e->max_coresident > 2 * (int)kFeedReserve) target = std::min(target, (uint32_t)e->max_coresident - 1u - kFeedReserve);
     // segment size from the WHOLE inventory: a partitioned rank keeps the global pipeline depth (~target stages over all ranks)
-    if (seg_cap < 64) return ISL_ERANGE;
-    const uint32_t seg = std::min(seg_cap, std::max(64u, (ceil_div(e->G, target) + 63u) / 64u * 64u));
+    if (seg_cap < 64 || e->max_coresident <= 0) return ISL_ERANGE;
+    // one sweep / chain / commit round covers `sub` GPUs; an inventory beyond target x sub gives every stage several sub-segments
+    const uint32_t sub = std::min(seg_cap, std::max(64u, (ceil_div(e->G, target) + 63u) / 64u * 64u));
+    const uint32_t n_sub = std::max(1u, ceil_div(ceil_div(e->G, sub), target));
+    if (n_sub > kSubMax) return ISL_ERANGE;
+    const uint32_t seg = sub * n_sub;
     const uint32_t n_seg = std::max(1u, ceil_div(range, seg));
-    if (e->max_coresident <= 0 || n_seg > (uint32_t)e->max_coresident) return ISL_ERANGE;
-    *seg_out = seg; *n_seg_out = n_seg;
+    if (n_seg > (uint32_t)e->max_coresident) return ISL_ERANGE;
+    *seg_out = seg; *n_seg_out = n_seg; *sub_out = sub;
     return ISL_OK;
 }
 
@@ -396,9 +400,9 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     // through CUDA_INJECTION64_PATH; ISL_NO_FEED=1 switches feeding off by hand)
     const bool want_feed = h_in && h_out && n_batches >= 2 && !(e->cfg.flags & (ISL_FLAG_TIMING | ISL_FLAG_TRACE)) && !ring && !getenv("ISL_NO_FEED") &&
                            !getenv("CUDA_INJECTION64_PATH") && !getenv("CUDA_LAUNCH_BLOCKING") && !getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
-    uint32_t seg = 0, n_seg = 0;
+    uint32_t seg = 0, n_seg = 0, sub = 0;
     if (pipeline) {
-        const int prc = plan_pipeline(e, n_chunks, (double)total / n_chunks, want_feed, &seg, &n_seg);
+        const int prc = plan_pipeline(e, n_chunks, (double)total / n_chunks, want_feed, &seg, &n_seg, &sub);
         if (prc == ISL_ECUDA) return prc;
         if (prc != ISL_OK) { if (ring) return ISL_ERANGE; pipeline = false; }
     }
@@ -510,7 +514,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     } else if (int rc = prepass(0, n_tiles_total)) return rc;
     if (timing) cudaEventRecord(e->ev[2], e->stream);
     PipeArgs args{};
-    args.n_chunks = n_chunks; args.n_seg = n_seg; args.seg = seg; args.lo = e->lo; args.hi = e->hi; args.epoch = epoch;
+    args.n_chunks = n_chunks; args.n_seg = n_seg; args.seg = seg; args.sub = sub; args.lo = e->lo; args.hi = e->hi; args.epoch = epoch;
     args.ready = feed ? e->d_ready : nullptr; args.done_cnt = (h_out_dev || window) ? e->d_done_cnt : nullptr; args.host_out = h_out_dev;
     if (ring && window) {       // the owner's counters sit behind its result array; the other ranks reach them through the same peer mapping
         uint2* base = e->has_prev ? e->d_owner_out : e->d_res;
@@ -1313,10 +1317,10 @@ int isl_stream_open(isl_engine* e, uint32_t max_batches) {
     auto& o = e->open;
     const uint32_t pc = e->pipe_chunk;
     if ((uint64_t)max_batches * pc > e->cfg.max_batch) return ISL_ERANGE;       // every batch owns a slot of the staging buffers
-    uint32_t seg = 0, n_seg = 0;
-    if (int rc = plan_pipeline(e, std::max(2u, max_batches), (double)pc, true, &seg, &n_seg)) return rc;
+    uint32_t seg = 0, n_seg = 0, sub = 0;
+    if (int rc = plan_pipeline(e, std::max(2u, max_batches), (double)pc, true, &seg, &n_seg, &sub)) return rc;
     if (n_seg + 1 + kFeedReserve > (uint32_t)e->max_coresident) return ISL_ERANGE;  // the feed kernels need SMs next to the resident pipeline
-    o.seg = seg; o.n_seg = n_seg; o.max_batches = max_batches; o.submitted = 0; o.launched = false;
+    o.seg = seg; o.n_seg = n_seg; o.sub = sub; o.max_batches = max_batches; o.submitted = 0; o.launched = false;
     o.q_stride = pc + kQPad * ISL_MAX_PROFILES; o.free_stride = (uint32_t)e->occ_bytes; o.tiles_per_batch = pc / kTile;
     if (int rc = grow(e, &e->d_chunks, &e->cap_chunks, max_batches, 1)) return rc;
     if (int rc = grow(e, &e->d_cctl, &e->cap_cctl, max_batches, 1)) return rc;
@@ -1397,7 +1401,7 @@ int isl_stream_submit(isl_engine* e, uint32_t n, const isl_request* in, isl_resu
         ISL_CUDA(e, cudaEventRecord(e->ev_feed, pre));
         ISL_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_feed, 0));
         PipeArgs args{};
-        args.n_chunks = o.max_batches; args.n_seg = o.n_seg; args.seg = o.seg; args.lo = e->lo; args.hi = e->hi; args.epoch = o.epoch;
+        args.n_chunks = o.max_batches; args.n_seg = o.n_seg; args.seg = o.seg; args.sub = o.sub; args.lo = e->lo; args.hi = e->hi; args.epoch = o.epoch;
         args.ready = e->d_ready; args.done_cnt = e->d_done_cnt; args.host_out = nullptr; args.copier = 1; args.open = 1;
         args.host_done = o.d_done_host; args.window = 0; args.wait_ns = kOpenWaitNs; args.flip = e->prof.flip;
         args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);

@@ -524,9 +524,10 @@ def test_best_fit_prefers_tightest_gpu():
     assert (int(res["gpu"][0]), int(res["start"][0])) == (2, 6) and (int(res["gpu"][1]), int(res["start"][1])) == (1, 4)
 
 
-def test_large_inventory_falls_back_to_single_chain():
-    """300k GPUs need more pipeline segments than can be co-resident: the engine must take the multi-CTA sweep +
-    single-chain path on its own (also for a stream call) and stay bit-exact."""
+def test_large_inventory_stays_on_the_pipeline():
+    """300k GPUs need more pipeline segments than CTAs can be co-resident: every stage then walks several sub-segments per chunk
+    (up to 8 x 512 GPUs, 148 stages = 606 208 GPUs per B200); beyond that the engine takes the multi-CTA sweep + single-chain path
+    on its own.  Bit-exact either way, also with frees between the batches."""
     rows = E.make_profiles(tables.H100_80GB)
     rng = W.SplitMix64(300)
     G = 300_000
@@ -542,6 +543,34 @@ def test_large_inventory_falls_back_to_single_chain():
         assert np.array_equal(g, w)
     assert np.array_equal(eng.read_occupancy(), ref.occupancy())
     assert eng.gpu_to_node(G - 1) == G // 8 - 1
+    # the pipeline served it: 2 pre-pass launches + 1 cooperative launch for the whole stream (the chunk-by-chunk path needs 6 per chunk)
+    assert eng.stats()["kernel_launches"] <= 6
+    # a churn stream with frees over the same large inventory, twice (the second run re-uses every buffer)
+    live = [(int(r["gpu"]), int(r["start"]), int(r["size"])) for g, b in zip(got, batches) for r in g[g["status"] == E.ST_PLACED]]
+    for rep in range(2):
+        stream = []
+        for n in (30_000, 66_000, 5_000):
+            req = W.alloc_requests(W.mix_profiles(rng, n))
+            for _ in range(min(len(live), n // 3)):
+                g_, s_, z_ = live.pop(int(rng.next1() % len(live)))
+                req[int(rng.next1() % n)] = (g_, 0, E.OP_FREE, s_, z_)
+            res = ref.place(req)
+            live.extend((int(r["gpu"]), int(r["start"]), int(r["size"])) for r in res[(req["op"] == E.OP_ALLOC) & (res["status"] == E.ST_PLACED)])
+            stream.append((req, res))
+        got2 = eng.place_stream([x[0] for x in stream])
+        assert all(np.array_equal(a, b[1]) for a, b in zip(got2, stream)), rep
+        assert np.array_equal(eng.read_occupancy(), ref.occupancy()), rep
+    # 700k GPUs are beyond 148 x 8 x 512: the single-chain path takes over
+    G2 = 700_000
+    node_off2 = W.node_offsets(G2 // 8, 8)
+    occ2 = ((rng.next(G2) | rng.next(G2)) & np.uint64(0x7F)).astype(np.uint8)
+    ref2 = oracle.Fast(node_off2, rows)
+    ref2.load(occ2)
+    b2 = [W.alloc_requests(W.mix_profiles(rng, 20_000)), W.alloc_requests(W.mix_profiles(rng, 9_000))]
+    want2 = [ref2.place(b) for b in b2]
+    eng2 = make_engine(node_off2, occ2, rows)
+    assert all(np.array_equal(a, b) for a, b in zip(eng2.place_stream(b2), want2))
+    assert np.array_equal(eng2.read_occupancy(), ref2.occupancy())
 
 
 def test_incremental_node_update_vs_python_restatement():
