@@ -1312,6 +1312,12 @@ int isl_stream_open(isl_engine* e, uint32_t max_batches) {
     if (!e || max_batches == 0 || max_batches > kMaxStreamChunks) return ISL_EINVAL;
     if (!e->have_profiles || !e->have_inventory || e->open.active) return ISL_ESTATE;
     if (bestfit_family(e->cfg.policy)) return ISL_EINVAL;
+    // a tool that serialises kernels (ncu, compute-sanitizer, CUDA_LAUNCH_BLOCKING) would starve a resident kernel that waits for kernels
+    // launched after it: refuse instead of hanging until the device-side trap (callers fall back to isl_place_batch per batch)
+    if (getenv("ISL_NO_FEED") || getenv("CUDA_INJECTION64_PATH") || getenv("CUDA_LAUNCH_BLOCKING") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) {
+        snprintf(e->cuda_err, sizeof(e->cuda_err), "isl_stream_open: kernel-serialising tool or ISL_NO_FEED set; open streams need concurrent kernels");
+        return ISL_ESTATE;
+    }
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard guard(e->device);
     auto& o = e->open;
