@@ -42,6 +42,22 @@ constexpr uint32_t kMaxTables = ISL_MAX_TABLES;   // per-node profile tables (he
 // The chain's occupancy word is 16 bits: the busy slices in the low byte and, in the high byte, every table bit set EXCEPT
 // the one of the table the GPU's node publishes.  A candidate of table t carries bit (8 + t) in its mask, so `(occ16 & mask) == 0`
 // holds only on GPUs of its own table — no extra instruction per decision.
+// A/B switches of the decision loop (tools/ab_build.sh builds the variants; the defaults are what measured fastest)
+#ifndef ISL_UNIFORM_WARP
+#define ISL_UNIFORM_WARP 1      // the chain warp is selected by a warp-UNIFORM predicate (redux of the warp index): ptxas then knows the warp
+#endif                          // is converged and drops the BRA.DIV / UMOV guard in front of every redux of the loop
+#ifndef ISL_DEFER_INF
+#define ISL_DEFER_INF 1         // the "nothing fits" test runs once per unrolled group instead of once per decision
+#endif
+// true for every lane of warp 0 and only there; with ISL_UNIFORM_WARP the predicate comes out of a redux (a uniform register)
+__device__ __forceinline__ bool is_chain_warp(uint32_t warp) {
+#if ISL_UNIFORM_WARP
+    return __reduce_or_sync(0xFFFFFFFFu, warp) == 0;
+#else
+    return warp == 0;
+#endif
+}
+
 __host__ __device__ inline uint32_t table_tag(uint32_t table) { return ((~(1u << table)) & 0xFFu) << 8; }
 
 struct DevProfiles {            // kernel parameter (by value)
@@ -624,7 +640,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain(CandTab tab, Ctrl* c
         for (uint32_t i = threadIdx.x; i < kMaxTables * 256; i += kChainThreads) s_feas[i] = feas[i];
     }
     __syncthreads();
-    if (threadIdx.x >= 32) return;
+    if (!is_chain_warp(threadIdx.x >> 5)) return;
     uint32_t visited, jumps;
     const uint32_t steps = chain_warp<K>(tab, ctrl->qoff, ctrl->qcnt, s_q, s_ring, s_feas, cand_o16, ctrl->n_cand, log, heads_in, heads_out, threadIdx.x,
                                          &visited, &jumps);
@@ -756,7 +772,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(CandTab tab, DevProf
     __threadfence();
     __syncthreads();
     // ---- C: the chain
-    if (warp == 0) {
+    if (is_chain_warp(warp)) {
         uint32_t visited = 0, jumps = 0;
         const uint32_t steps = active ? chain_warp<K>(tab, s_qoff, s_qcnt, s_q, s_ring, s_feas, cand_o16, s_base, s_log, nullptr, nullptr, lane, &visited, &jumps) : 0u;
         if (lane == 0) {
@@ -902,7 +918,9 @@ constexpr uint32_t kLogCap = 8 * kSegMax;           // a GPU accepts at most 8 p
 constexpr uint32_t kTokStride = 32;                 // uint32 per token: 16 tagged head words inside a GPU; raw heads[16] + flag at [16] across GPUs
 // shared memory: occupancy bytes | candidate records (+8 sentinels) | decision log (+1 pseudo-decision) | the chunk's queues (uint16) | queue-window keys
 constexpr uint32_t kPipeOffCand = kSegMax * kSubMax;      // occupancy bytes of the whole stage (all its sub-segments)
-constexpr uint32_t kPipeOffLog = kPipeOffCand + 4 * (kSegMax + 8);
+constexpr uint32_t kCandPad = 16;                   // INF records behind a segment's candidates: a group of pseudo-decisions may walk that far
+constexpr uint32_t kWinPad = 10;                    // INF keys behind every queue window: an exhausted lane is popped at most once per decision of a group
+constexpr uint32_t kPipeOffLog = kPipeOffCand + 4 * (kSegMax + kCandPad);
 constexpr uint32_t kPipeOffQ = (kPipeOffLog + 8 * (kLogCap + 1) + 15u) & ~15u;
 constexpr uint32_t kPipeOffWin = kPipeOffQ + 2 * kQCap + 16;
 constexpr uint32_t kWinTotal = 12288;               // 32-bit queue-window keys a segment can stage for all profiles together
@@ -911,7 +929,7 @@ constexpr uint32_t kPipeSmem = kPipeOffWin + 4 * (kWinTotal + 4 * ISL_MAX_PROFIL
 // largest segment whose worst-case queue windows (every candidate GPU accepting every legal start of every
 // profile) fit: n_cand * total_candidates + 2 sentinels per profile <= kWinTotal
 __host__ __device__ inline uint32_t max_segment_for(uint32_t total_candidates) {
-    const uint32_t s = (kWinTotal - 2 * ISL_MAX_PROFILES) / (total_candidates ? total_candidates : 1u);
+    const uint32_t s = (kWinTotal - kWinPad * ISL_MAX_PROFILES) / (total_candidates ? total_candidates : 1u);
     return s >= kSegMax ? kSegMax : s / 64u * 64u;
 }
 
@@ -1240,7 +1258,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             off &= 0xFFFFu;
 #pragma unroll
             for (uint32_t x = 0; x < kGpt; ++x) if (fg[x]) s_cand[off++] = ((kGpt * tid + x) << 16) | table_tag(tg[x]) | og[x];
-            if (tid == kPipeThreads - 1) { s_ncand = off; s_nfree = nfree; for (uint32_t x = 0; x < 8; ++x) s_cand[off + x] = kInf; }   // sentinels: nothing fits
+            if (tid == kPipeThreads - 1) { s_ncand = off; s_nfree = nfree; for (uint32_t x = 0; x < kCandPad; ++x) s_cand[off + x] = kInf; }   // sentinels: nothing fits
         }
         __syncthreads();                    // s_ncand / s_nfree of the sweep are visible to warp 0
         // 3. token of the previous segment
@@ -1291,10 +1309,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             const bool idle = __ballot_sync(0xFFFFFFFFu, left != 0) == 0;
             if (idle && !all_done && tid < ISL_MAX_PROFILES) st_relaxed_gpu(a.tokens + (tok_chunk + a.n_seg) * kTokStride + tid, (tag << 17) | h);
             if (tid == 0) s_idle = idle ? 1u : 0u;
-            uint32_t incl = wn + 2;                             // two INF sentinels close every window
+            uint32_t incl = wn + kWinPad;                       // INF sentinels close every window
 #pragma unroll
             for (int d = 1; d < 16; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
-            if (tid < ISL_MAX_PROFILES) s_wbase[tid] = incl - (wn + 2);
+            if (tid < ISL_MAX_PROFILES) s_wbase[tid] = incl - (wn + kWinPad);
         }
         __syncthreads();
         stamp_if(tr && tid == 0, tr + 8);
@@ -1326,14 +1344,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 const uint32_t p = s_plist[x], wn = s_wn[p], pk = p << 11, qb = s_qbeg[p];
                 uint32_t* __restrict__ dst = s_wkey + s_wbase[p];
                 // plain, unconditional (clamped) accesses: the loads of a round overlap instead of queueing behind each other
-                for (uint32_t i = tid; i < wn + 2; i += kPipeThreads) { const uint32_t v = sq[qb + min(i, wn)]; dst[i] = i < wn ? (v << 15) | pk : kInf; }
+                for (uint32_t i = tid; i < wn + kWinPad; i += kPipeThreads) { const uint32_t v = sq[qb + min(i, wn)]; dst[i] = i < wn ? (v << 15) | pk : kInf; }
             }
             stamp_if(tr && tid == 0, tr + 10);
             store_if(tr && tid == 0, tr + 11, s_wn[s_plist[0]] | ((unsigned long long)s_nfree << 32));
         }
         __syncthreads();
         stamp_if(tr && tid == 0, tr + 9);
-        if (warp == 0) {                    // 4. the decision chain (see k_chain), tuned for the shortest loop-carried path
+        if (is_chain_warp(warp)) {          // 4. the decision chain (see k_chain), tuned for the shortest loop-carried path
             const uint32_t n_cand = s_ncand;
             uint32_t tcur[K], tnext[K], tnn[K], wa[K], wa0[K];
 #pragma unroll
@@ -1378,11 +1396,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             first_key();
             const unsigned long long jumps0 = st_jumps;
             stamp_if(tr && lane == 0, tr + 4);
+            constexpr bool kDefer = ISL_DEFER_INF && !kP15;     // see the rare path below
             while (true) {
                 bool none = false;
+                uint32_t m = 0, mmax = 0;
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {     // unrolled: one taken branch per kUnroll decisions
-                    const uint32_t m = redux_min_u32(key);
+                    m = redux_min_u32(key);
 #pragma unroll
                     for (int k = 0; k < K; ++k) {       // in the shadow of the redux: the record fetched by the previous decision (the same one again if it did not advance)
                         z2[k] = a2 & cmask[k];
@@ -1392,8 +1412,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     uint32_t ks;
                     asm("shr.s32 %0, %1, 31;" : "=r"(ks) : "r"(m));                                            // all ones: landed on the next GPU
                     asm("mad.lo.s32 %0, %1, -4, %0;" : "+r"(ca) : "r"(ks));                                     // ca += sel * 4
-                    sts_v2_if(lane == 0, la, m, ca);                    // decision log: (key, address of the record two past the GPU it landed on)
-                    la += 8;
+                    if (kDefer) {       // a pseudo-decision (m == INF: nothing fits here or on the next GPU, move on by one) leaves no log record
+                        const bool real = m != kInf;
+                        sts_v2_if(lane == 0 && real, la, m, ca);
+                        la = add_if(real, la, 8u);
+                        mmax = max(mmax, m);
+                    } else {
+                        sts_v2_if(lane == 0, la, m, ca);                // decision log: (key, address of the record two past the GPU it landed on)
+                        la += 8;
+                    }
                     a2 = lds_u16(ca);
                     key = kInf;
 #pragma unroll
@@ -1414,7 +1441,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                         tnn[k] = lds_u32_if(adv, wa[k], tnn[k]);        // consumed at the earliest one pop later
                         wa[k] = add_if(adv, wa[k], 4u);
                     }
-                    if (!kP15) {
+                    if (!kP15 && !kDefer) {
                         none = m == kInf;
                         if (__builtin_expect(none, 0)) {
                             ca -= 4; la -= 8;                           // rewind the pseudo-decision
@@ -1425,11 +1452,23 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                         }
                     }
                 }
-                if (__builtin_expect(!none, 1)) continue;
+                uint32_t from = (ca - sa_cand) >> 2;        // record index of (current + 2)
+                if (kDefer) {
+                    // m == INF is a legitimate step of the recurrence ("neither this GPU nor the next takes anything: the next one becomes
+                    // current"; it pops only lanes whose window is exhausted, into their INF sentinels), so the loop body needs no exit
+                    // test per decision — one test per group: did ANY decision of the group find nothing?
+                    if (__builtin_expect(mmax != kInf, 1)) continue;
+                    // exhausted lanes were popped past the end of their windows: back onto the sentinels (at most kUnroll pops since the last time)
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        if (tcur[k] == kInf) { tnext[k] = kInf; tnn[k] = kInf; wa[k] = wa0[k] + 12 + 4 * s_wn[cprof[k]]; }
+                    if (m != kInf) continue;                // the group ended on a real decision: carry on
+                    from -= 1;                              // the pseudo-decision already moved on by one GPU: the new 'next' is still unexamined
+                } else if (__builtin_expect(!none, 1)) continue;
                 uint32_t alive = 0;
 #pragma unroll
                 for (int k = 0; k < K; ++k) alive |= tcur[k] != kInf ? 1u << cprof[k] : 0u;
-                const uint32_t j = pipeline_skip(sa_cand, s_feas, n_cand, ((ca - sa_cand) >> 2), alive, lane);
+                const uint32_t j = pipeline_skip(sa_cand, s_feas, n_cand, from, alive, lane);
                 ++st_jumps;
                 if (j == kInf) break;
                 ca = sa_cand + 4 * (j + 2);
@@ -1443,7 +1482,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             store_if(tr && lane == 0, tr + 7, (st_jumps - jumps0) | ((unsigned long long)(((ca - sa_cand) >> 2) - 2) << 32));
             st_steps += nlog; st_visited += ((ca - sa_cand) >> 2) - 2;
 #pragma unroll
-            for (int k = 0; k < K; ++k) if (reports[k]) s_pop[cprof[k]] = (wa[k] - wa0[k] - 12) >> 2;
+            for (int k = 0; k < K; ++k) if (reports[k]) s_pop[cprof[k]] = min((wa[k] - wa0[k] - 12) >> 2, s_wn[cprof[k]]);
             __syncwarp();
             // 5. token for the next segment: heads first, then the flag (release) — behind the stage's last sub-segment
             uint32_t* tok = a.tokens + (tok_chunk + seg) * kTokStride;
@@ -1557,7 +1596,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
         atomicMin(&s_min[o], g);
     }
     __syncthreads();
-    if (tid >= 32) return;
+    if (!is_chain_warp(tid >> 5)) return;
     uint32_t placed = 0;
     uint32_t dead = 0;              // profiles that found no GPU: occupancy only grows inside a batch's ALLOC phase, so they never will again
     for (uint32_t base = 0; base < n; base += 32) {

@@ -354,6 +354,9 @@ int plan_pipeline(isl_engine* e, uint32_t n_chunks, double avg_chunk, bool want_
     if (seg_cap < 64 || e->max_coresident <= 0) return ISL_ERANGE;
     // one sweep / chain / commit round covers `sub` GPUs; an inventory beyond target x sub gives every stage several sub-segments
     const uint32_t sub = std::min(seg_cap, std::max(64u, (ceil_div(e->G, target) + 63u) / 64u * 64u));
+    // a short stream wants few stages, a large inventory needs many (a stage holds at most kSubMax sub-segments): the inventory wins
+    const uint32_t stages_avail = (want_feed && e->max_coresident > 2 * (int)kFeedReserve) ? (uint32_t)e->max_coresident - 1u - kFeedReserve : (uint32_t)e->max_coresident;
+    target = std::max(target, std::min(stages_avail, ceil_div(ceil_div(e->G, sub), kSubMax)));
     const uint32_t n_sub = std::max(1u, ceil_div(ceil_div(e->G, sub), target));
     if (n_sub > kSubMax) return ISL_ERANGE;
     const uint32_t seg = sub * n_sub;
