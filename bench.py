@@ -151,9 +151,14 @@ class Ctx:
         import torch.distributed as dist
         self.torch, self.dist, self.args = torch, dist, args
         self.rank, self.world, self.local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-        # NCCL's own log shows the communicator (ranks, NVLS / P2P) — keep it, but on stderr: rank 0 prints ONE JSON line on stdout
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's own log shows the communicator (ranks, NVLS / P2P).  Whatever the caller's NCCL_DEBUG asks for is left alone (NCCL writes
+        # it to stdout: rank 0's JSON line is printed LAST, after the process group is gone); without one, INFO goes to a per-rank file
+        # that is copied to stderr at the end
+        self.nccl_log = None
+        if self.world > 1 and "NCCL_DEBUG" not in os.environ:
+            self.nccl_log = "/tmp/isl_nccl_%d_rank%d.log" % (os.getppid(), self.rank)
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ["NCCL_DEBUG_FILE"] = self.nccl_log
         if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
         torch.cuda.set_device(self.local)
@@ -670,29 +675,19 @@ def run_c4(ctx):
     D.connect_owner(eng, rank, world)         # rank 0's result array mapped into every other rank; ring size for the causal window
     eng.set_causal_window(A)
     stream_ids = iter(range(1, 1 << 30))
-    side = torch.cuda.Stream()
-    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for k in ("dev",)}
-    phase_ms = {"pipeline": 0.0, "all_gather": 0.0, "steps": 0}
+    triples = []          # (start, pipeline enqueued-to-end, all-gather done) events of every device step: the phase table comes from the TIMED steps
 
-    def step_device(record=False):
+    def step_device():
         occ_view.copy_(d_occ0)
-        if record:
-            ev["dev"][0].record()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
         # every rank runs the segment pipeline over its own GPU range; tokens, PLACED records and the causal-window counter cross
         # ranks inside the running kernels
         eng.place_stream_partitioned(sizes, d_in_all.data_ptr(), d_res.data_ptr(), next(stream_ids))
-        if record:
-            ev["dev"][1].record()
+        e[1].record()
         occ_view.copy_(D.gather_occupancy(occ_view[lo:hi], G, world, rank))   # NCCL all-gather of the occupancy shards (also tells rank 0 every record has landed)
-        if record:
-            ev["dev"][2].record()
-
-    def step_device_timed():
-        step_device(True)
-        ev["dev"][2].synchronize()
-        phase_ms["pipeline"] += ev["dev"][0].elapsed_time(ev["dev"][1])
-        phase_ms["all_gather"] += ev["dev"][1].elapsed_time(ev["dev"][2])
-        phase_ms["steps"] += 1
+        e[2].record()
+        triples.append(e)
 
     def step_e2e():         # rank 0 is the controller: it owns the host buffers; the request stream reaches the other ranks over NVLink
         occ_view.copy_(d_occ0)
@@ -714,9 +709,9 @@ def run_c4(ctx):
     occ_dev = occ_view.cpu().numpy()
     ms_e2e, wall_e2e = ctx.timed(step_e2e, a.steps, a.warmup)
     got_e2e = results_of(h_out_all) if rank == 0 else None
-    for _ in range(3):
-        step_device_timed()
-    ph = torch.tensor([phase_ms["pipeline"] / 3, phase_ms["all_gather"] / 3], dtype=torch.float64, device="cuda")
+    timed_triples = triples[a.warmup:a.warmup + a.steps]          # the K timed device steps (the e2e leg does not use step_device)
+    ph = torch.tensor([sum(e[0].elapsed_time(e[1]) for e in timed_triples) / a.steps, sum(e[1].elapsed_time(e[2]) for e in timed_triples) / a.steps],
+                      dtype=torch.float64, device="cuda")
     dist.all_reduce(ph, op=dist.ReduceOp.MAX)
     line = None
     if rank == 0:
@@ -845,11 +840,16 @@ def run_own(args):
         line, parity = run_c5(ctx) if ctx.rank == 0 else (None, True)
     else:
         line, parity = run_single_batch(ctx, args.config)
-    if ctx.rank == 0 and line is not None:
-        print(json.dumps(line), flush=True)
     if ctx.world > 1:
         ctx.dist.barrier()
         ctx.dist.destroy_process_group()
+        if ctx.nccl_log and os.path.exists(ctx.nccl_log):
+            with open(ctx.nccl_log, errors="replace") as f:
+                sys.stderr.write(f.read())
+            sys.stderr.flush()
+    if ctx.rank == 0 and line is not None:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)          # the LAST line of stdout
     return 0 if parity else 1
 
 
