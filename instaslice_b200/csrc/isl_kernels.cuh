@@ -1601,15 +1601,17 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
     uint32_t dead = 0;              // profiles that found no GPU: occupancy only grows inside a batch's ALLOC phase, so they never will again
     for (uint32_t base = 0; base < n; base += 32) {
         const uint2 mine = base + lane < n ? in[base + lane] : make_uint2(0, (uint32_t)ISL_OP_NOOP << 8);
-        const uint32_t cnt = min(32u, n - base);
-        {   // whole block without a live ALLOC (frees, unknown or dead profiles): nothing to decide
+        // only the live ALLOCs of the block are looked at (frees, unknown or dead profiles: defaults were written by k_prepare)
+        uint32_t live;
+        {
             const uint32_t wp = mine.y & 0xFFu, wop = (mine.y >> 8) & 0xFFu;
-            if (__ballot_sync(0xFFFFFFFFu, wop == ISL_OP_ALLOC && wp < prof.n && !((dead >> wp) & 1u)) == 0) continue;
+            live = __ballot_sync(0xFFFFFFFFu, wop == ISL_OP_ALLOC && wp < prof.n && !((dead >> wp) & 1u));
         }
-        for (uint32_t j = 0; j < cnt; ++j) {
-            const uint32_t w = __shfl_sync(0xFFFFFFFFu, mine.y, j);
-            const uint32_t p = w & 0xFFu, op = (w >> 8) & 0xFFu;
-            if (op != ISL_OP_ALLOC || p >= prof.n || ((dead >> p) & 1u)) continue;    // defaults / frees were written by k_prepare
+        while (live) {
+            const uint32_t j = __ffs(live) - 1;
+            live &= live - 1;
+            const uint32_t p = __shfl_sync(0xFFFFFFFFu, mine.y, j) & 0xFFu;
+            if ((dead >> p) & 1u) continue;                     // died inside this block
             uint32_t key = kInf, ko = 0;
 #pragma unroll
             for (uint32_t r = 0; r < 8; ++r) {                  // lane l looks at classes l, l+32, ...
@@ -1623,32 +1625,36 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
             const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, key);
             if (m == kInf) { dead |= 1u << p; continue; }      // stays NO_CAPACITY, and so does every later request of the profile
             const uint32_t g = m & 0xFFFFFFu;
-            const uint32_t o_win = __shfl_sync(0xFFFFFFFFu, ko, __ffs(__ballot_sync(0xFFFFFFFFu, key == m)) - 1);   // the class IS the occupancy byte
-            __syncwarp();                                       // all lanes have read the class minima before lane 0 rewrites them
-            if (lane == 0) {
-                const uint32_t o = o_win;
-                const uint32_t start = s_lut[p * 256 + o], size = prof.rows[p].size;
-                const uint32_t o2 = o | ((((1u << size) - 1u) << start) & 0xFFu);
+            const uint32_t o = __shfl_sync(0xFFFFFFFFu, ko, __ffs(__ballot_sync(0xFFFFFFFFu, key == m)) - 1);   // the class IS the occupancy byte
+            const uint32_t start = s_lut[p * 256 + o], size = prof.rows[p].size;
+            const uint32_t o2 = o | ((((1u << size) - 1u) << start) & 0xFFu);
+            uint32_t* c0 = bm + o * stride;
+            uint32_t* c1 = bm + o2 * stride;
+            __syncwarp();                                       // all lanes have read the class minima before they are rewritten
+            if (lane == 0) {                                    // the GPU leaves class o and joins class o2: independent words, loads first
+                const uint32_t w0 = c0[g >> 5] & ~(1u << (g & 31u)), w1 = c1[g >> 5] | (1u << (g & 31u));
+                const uint32_t s1 = c1[W0 + (g >> 10)] | (1u << ((g >> 5) & 31u));
+                c0[g >> 5] = w0; c1[g >> 5] = w1; c1[W0 + (g >> 10)] = s1;
+                if (w0 == 0) c0[W0 + (g >> 10)] &= ~(1u << ((g >> 5) & 31u));
                 occ[lo + g] = (uint8_t)o2;
                 out[base + j] = pack_result(flip_gpu(lo + g, prof.flip), start, size, ISL_ST_PLACED);
-                // leave class o: clear the bit, fix the summary, find the new minimum (g was the minimum)
-                uint32_t* c0 = bm + o * stride;
-                const uint32_t w0 = c0[g >> 5] & ~(1u << (g & 31u));
-                c0[g >> 5] = w0;
-                if (w0 == 0) c0[W0 + (g >> 10)] &= ~(1u << ((g >> 5) & 31u));
-                uint32_t mn = kInf;
-                for (uint32_t k = g >> 10; k < W1; ++k) {
-                    const uint32_t sw = c0[W0 + k];
-                    if (sw) { const uint32_t wi = k * 32 + __ffs(sw) - 1; mn = wi * 32 + __ffs(c0[wi]) - 1; break; }
-                }
-                s_min[o] = mn;
-                // join class o2
-                uint32_t* c1 = bm + o2 * stride;
-                c1[g >> 5] |= 1u << (g & 31u);
-                c1[W0 + (g >> 10)] |= 1u << ((g >> 5) & 31u);
                 if (g < s_min[o2]) s_min[o2] = g;
                 ++placed;
             }
+            __syncwarp();
+            // new minimum of class o (g was its minimum: nothing below it): the lanes look at 32 summary words at a time
+            uint32_t mn = kInf;
+            for (uint32_t k0 = (g >> 10) & ~31u; k0 < W1; k0 += 32) {
+                const uint32_t sw = k0 + lane < W1 ? c0[W0 + k0 + lane] : 0u;
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, sw != 0);
+                if (b) {
+                    const uint32_t src = __ffs(b) - 1;
+                    const uint32_t wi = (k0 + src) * 32 + __ffs(__shfl_sync(0xFFFFFFFFu, sw, src)) - 1;
+                    mn = wi * 32 + __ffs(c0[wi]) - 1;
+                    break;
+                }
+            }
+            if (lane == 0) s_min[o] = mn;
             __syncwarp();
         }
     }

@@ -83,6 +83,7 @@ struct isl_engine {
     uint8_t* d_occ_snap = nullptr; size_t snap_bytes = 0; uint32_t snap_G = 0;      // isl_snapshot_occupancy / isl_restore_occupancy
     bool delivered = false;          // the last run_stream call already put the results into the caller's host buffer
     size_t scratch_bytes = 0;
+    unsigned long long wait_ns = 20000000000ull;   // a starved device-side wait traps after this long (ISL_WAIT_SECONDS overrides the 20 s)
     uint32_t window = 0;             // causal window of stream calls (isl_set_causal_window): chunk c starts after chunk c - window is committed
     // open stream (isl_stream_open / _submit / _wait / _close): one persistent k_pipeline, batches arrive while it runs
     struct Open {
@@ -366,7 +367,6 @@ int plan_pipeline(isl_engine* e, uint32_t n_chunks, double avg_chunk, bool want_
     return ISL_OK;
 }
 
-constexpr unsigned long long kWaitNs = 20000000000ull;          // a starved device-side wait traps after 20 s
 constexpr unsigned long long kOpenWaitNs = 600000000000ull;     // open streams may idle between batches: 10 min
 
 // Resolve a stream of batches (semantics: one batch after the other).  Enqueues only.
@@ -526,7 +526,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
         if (!e->has_prev) ISL_CUDA(e, cudaMemsetAsync(args.ring_done, 0, (size_t)n_chunks * sizeof(uint32_t), e->stream));
     }
     args.flip = e->prof.flip;
-    args.copier = h_out_dev ? 1u : 0u; args.window = window; args.wait_ns = kWaitNs; args.owner_out = ring ? e->d_owner_out : nullptr;
+    args.copier = h_out_dev ? 1u : 0u; args.window = window; args.wait_ns = e->wait_ns; args.owner_out = ring ? e->d_owner_out : nullptr;
     args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
     args.q_stride = q_stride; args.free_stride = free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab; args.out = d_out; args.feas = e->d_feas; args.stats = e->d_ctrl;
     args.heads_in = d_heads_in; args.heads_out = d_heads_out;
@@ -631,6 +631,7 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
         pc = std::max(kTile, std::min(kChunk, pc / kTile * kTile));
         e->pipe_chunk = pc;
     }
+    if (const char* v = getenv("ISL_WAIT_SECONDS")) { const double sec = atof(v); if (sec > 0) e->wait_ns = (unsigned long long)(sec * 1e9); }
     int dev = cfg->device;
     if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) { delete e; return ISL_ECUDA; }
     int ndev = 0;
@@ -1412,7 +1413,7 @@ int isl_stream_submit(isl_engine* e, uint32_t n, const isl_request* in, isl_resu
         PipeArgs args{};
         args.n_chunks = o.max_batches; args.n_seg = o.n_seg; args.seg = o.seg; args.sub = o.sub; args.lo = e->lo; args.hi = e->hi; args.epoch = o.epoch;
         args.ready = e->d_ready; args.done_cnt = e->d_done_cnt; args.host_out = nullptr; args.copier = 1; args.open = 1;
-        args.host_done = o.d_done_host; args.window = 0; args.wait_ns = kOpenWaitNs; args.flip = e->prof.flip;
+        args.host_done = o.d_done_host; args.window = 0; args.wait_ns = std::max(kOpenWaitNs, e->wait_ns); args.flip = e->prof.flip;
         args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
         args.q_stride = o.q_stride; args.free_stride = o.free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab;
         args.out = e->d_res; args.feas = e->d_feas; args.stats = e->d_ctrl;

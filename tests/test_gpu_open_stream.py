@@ -184,3 +184,44 @@ def test_place_batch_range_is_one_node_scan_and_is_thread_safe():
     with pytest.raises(E.EngineError):
         eng.place_batch_range(40, 24, req)
     eng.close()
+
+
+def test_dead_predecessor_traps_instead_of_hanging():
+    """A rank of a partitioned run whose predecessor never delivers the token must not hang its GPU: the device-side wait traps after
+    the timeout (20 s; ISL_WAIT_SECONDS shortens it here) and the call reports a CUDA error.  Run in a child process: a trap poisons
+    the CUDA context."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, time
+import numpy as np
+from instaslice_b200 import engine as E, tables, workloads as W
+rows = E.make_profiles(tables.H100_80GB)
+G = 4096
+eng = E.Engine(max_gpus=G, max_batch=1 << 18)
+eng.load_profiles(rows)
+eng.load_inventory(W.node_offsets(G // 8, 8), np.zeros(G, dtype=np.uint8))
+eng.set_partition(2048, 4096)
+eng.ipc_inbox_handle()
+eng.connect_local(None, has_prev=True)            # a predecessor is expected, none will ever run
+import torch
+rng = W.SplitMix64(1)
+req = [W.alloc_requests(W.mix_profiles(rng, 3000)) for _ in range(2)]
+d_in = torch.from_numpy(np.concatenate(req).view(np.int64).copy()).cuda()
+d_out = torch.empty_like(d_in)
+t0 = time.time()
+eng.place_stream_partitioned(np.array([3000, 3000], dtype=np.uint32), d_in.data_ptr(), d_out.data_ptr(), 7)
+try:
+    eng.synchronize()
+    print("NO_ERROR")
+except E.EngineError as e:
+    print("TRAPPED after %.1f s: %s" % (time.time() - t0, e))
+sys.stdout.flush()
+import os
+os._exit(0)
+"""
+    env = dict(os.environ, ISL_WAIT_SECONDS="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=120)
+    assert "TRAPPED" in out.stdout, (out.stdout[-500:], out.stderr[-500:])
