@@ -195,7 +195,7 @@ int  isl_load_profiles(isl_engine* e, uint32_t n, const isl_profile* rows);
  * looks a profile up in the table of the node it is scanning (:332-340).  rows[t * n_profiles + p] is the row of profile
  * NAME p in table t; n_starts == 0 = that table has no row of the name (the reference then finds nothing on such a node).
  * Requests name a profile NAME index.  isl_set_node_tables (after isl_load_inventory) says which table each node uses
- * (default: table 0).  ISL_POLICY_BEST_FIT supports a single table only. */
+ * (default: table 0).  Every policy takes per-node tables (the best-fit family groups the GPUs by (table, occupancy byte)). */
 int  isl_load_profile_tables(isl_engine* e, uint32_t n_tables, uint32_t n_profiles, const isl_profile* rows);
 int  isl_set_node_tables(isl_engine* e, uint32_t n_nodes, const uint8_t* table_of_node);
 /* Replaces the occupancy rebuild (:306-328) for every GPU of every node.

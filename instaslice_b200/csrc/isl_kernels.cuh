@@ -1570,30 +1570,39 @@ __global__ void __launch_bounds__(256) k_capacity(const uint8_t* __restrict__ oc
 // redux.min picks the GPU; lane 0 moves it to its new class.  One CTA; all threads build the class structure.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kBfThreads = 1024;
-constexpr uint32_t kBfMaxGpus = 65536;              // 2048 words + 64 summary words per class
+constexpr uint32_t kBfMaxGpus = 1u << 20;           // class bitmaps: G / 32 words + G / 1024 summary words per (table, occupancy byte) class
 constexpr uint32_t kBfSmemGpus = 4096;              // up to here the class bitmaps live in shared memory (132 KiB)
 
 __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uint2* __restrict__ in, uint2* __restrict__ out, uint8_t* __restrict__ occ,
                                                            uint32_t lo, uint32_t hi, const uint8_t* __restrict__ lut, DevProfiles prof,
-                                                           uint32_t* __restrict__ g_bitmaps, Ctrl* ctrl, const uint8_t* __restrict__ score) {
+                                                           uint32_t* __restrict__ g_bitmaps, Ctrl* ctrl, const uint8_t* __restrict__ score,
+                                                           const uint8_t* __restrict__ gtab, const uint8_t* __restrict__ sizes, uint32_t n_tables) {
     extern __shared__ __align__(16) uint32_t s_dyn[];
-    __shared__ uint32_t s_min[256];
+    // a class = (table of the GPU's node, occupancy byte): every GPU of a class behaves the same for every profile
+    __shared__ uint32_t s_min[kMaxTables * 256];
     __shared__ uint8_t s_lut[ISL_MAX_PROFILES * 256];
-    // what the policy minimises, per (profile, occupancy byte): ISL_POLICY_BEST_FIT = free slices (8 - popcount), ISL_POLICY_MIN_FRAG =
+    // what the policy minimises, per (table, profile, occupancy byte): ISL_POLICY_BEST_FIT = free slices (8 - popcount), ISL_POLICY_MIN_FRAG =
     // (profile, start) pairs of the table that stop being feasible when the profile takes its first legal start there (host-built)
     __shared__ uint8_t s_score[ISL_MAX_PROFILES * 256];
+    __shared__ uint8_t s_sizes[kMaxTables * ISL_MAX_PROFILES];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t Gr = hi - lo, W0 = (Gr + 31) / 32, W1 = (W0 + 31) / 32, stride = W0 + W1;   // words per class
-    uint32_t* bm = Gr <= kBfSmemGpus ? s_dyn : g_bitmaps;
-    for (uint32_t i = tid; i < 256 * stride; i += kBfThreads) bm[i] = 0;
-    for (uint32_t i = tid; i < ISL_MAX_PROFILES * 256; i += kBfThreads) { s_lut[i] = lut[i]; s_score[i] = score[i]; }
-    if (tid < 256) s_min[tid] = kInf;
+    const uint32_t n_cls = n_tables * 256;
+    const bool small = n_tables == 1 && Gr <= kBfSmemGpus;      // bitmaps in shared memory; otherwise in global memory, zeroed by the host
+    uint32_t* bm = small ? s_dyn : g_bitmaps;
+    if (small) for (uint32_t i = tid; i < 256 * stride; i += kBfThreads) bm[i] = 0;
+    // one table: the per-byte tables sit in shared memory; several: they are read from global memory (L1-resident, 8 KiB per table)
+    if (n_tables == 1) for (uint32_t i = tid; i < ISL_MAX_PROFILES * 256; i += kBfThreads) { s_lut[i] = lut[i]; s_score[i] = score[i]; }
+    const uint8_t* lutp = n_tables == 1 ? s_lut : lut;
+    const uint8_t* scorep = n_tables == 1 ? s_score : score;
+    if (tid < kMaxTables * ISL_MAX_PROFILES) s_sizes[tid] = sizes[tid];
+    for (uint32_t i = tid; i < n_cls; i += kBfThreads) s_min[i] = kInf;
     __syncthreads();
-    for (uint32_t g = tid; g < Gr; g += kBfThreads) {           // build: every GPU joins the class of its occupancy byte
-        const uint32_t o = occ[lo + g];
-        atomicOr(&bm[o * stride + (g >> 5)], 1u << (g & 31u));
-        atomicOr(&bm[o * stride + W0 + (g >> 10)], 1u << ((g >> 5) & 31u));
-        atomicMin(&s_min[o], g);
+    for (uint32_t g = tid; g < Gr; g += kBfThreads) {           // build: every GPU joins its class
+        const uint32_t c = (n_tables > 1 ? (uint32_t)(gtab[lo + g] & (kMaxTables - 1)) * 256u : 0u) + occ[lo + g];
+        atomicOr(&bm[c * stride + (g >> 5)], 1u << (g & 31u));
+        atomicOr(&bm[c * stride + W0 + (g >> 10)], 1u << ((g >> 5) & 31u));
+        atomicMin(&s_min[c], g);
     }
     __syncthreads();
     if (!is_chain_warp(tid >> 5)) return;
@@ -1612,24 +1621,25 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
             live &= live - 1;
             const uint32_t p = __shfl_sync(0xFFFFFFFFu, mine.y, j) & 0xFFu;
             if ((dead >> p) & 1u) continue;                     // died inside this block
-            uint32_t key = kInf, ko = 0;
-#pragma unroll
-            for (uint32_t r = 0; r < 8; ++r) {                  // lane l looks at classes l, l+32, ...
-                const uint32_t o = r * 32 + lane;
-                const uint32_t mn = s_min[o];
-                if (mn != kInf && s_lut[p * 256 + o] != ISL_START_NONE) {
-                    const uint32_t k2 = ((uint32_t)s_score[p * 256 + o] << 24) | mn;
-                    if (k2 < key) { key = k2; ko = o; }
+            uint32_t key = kInf, kc = 0;
+#pragma unroll 8
+            for (uint32_t c = lane; c < n_cls; c += 32) {       // lane l looks at classes l, l+32, ...
+                const uint32_t mn = s_min[c];
+                const uint32_t idx = ((c >> 8) * ISL_MAX_PROFILES + p) * 256 + (c & 255u);
+                if (mn != kInf && lutp[idx] != ISL_START_NONE) {
+                    const uint32_t k2 = ((uint32_t)scorep[idx] << 24) | mn;
+                    if (k2 < key) { key = k2; kc = c; }
                 }
             }
             const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, key);
             if (m == kInf) { dead |= 1u << p; continue; }      // stays NO_CAPACITY, and so does every later request of the profile
             const uint32_t g = m & 0xFFFFFFu;
-            const uint32_t o = __shfl_sync(0xFFFFFFFFu, ko, __ffs(__ballot_sync(0xFFFFFFFFu, key == m)) - 1);   // the class IS the occupancy byte
-            const uint32_t start = s_lut[p * 256 + o], size = prof.rows[p].size;
-            const uint32_t o2 = o | ((((1u << size) - 1u) << start) & 0xFFu);
-            uint32_t* c0 = bm + o * stride;
-            uint32_t* c1 = bm + o2 * stride;
+            const uint32_t cw = __shfl_sync(0xFFFFFFFFu, kc, __ffs(__ballot_sync(0xFFFFFFFFu, key == m)) - 1);   // the class IS (table, occupancy byte)
+            const uint32_t t = cw >> 8, o = cw & 255u;
+            const uint32_t start = lutp[(t * ISL_MAX_PROFILES + p) * 256 + o], size = s_sizes[t * ISL_MAX_PROFILES + p];
+            const uint32_t o2 = o | ((((1u << size) - 1u) << start) & 0xFFu), cw2 = (t << 8) | o2;
+            uint32_t* c0 = bm + cw * stride;
+            uint32_t* c1 = bm + cw2 * stride;
             __syncwarp();                                       // all lanes have read the class minima before they are rewritten
             if (lane == 0) {                                    // the GPU leaves class o and joins class o2: independent words, loads first
                 const uint32_t w0 = c0[g >> 5] & ~(1u << (g & 31u)), w1 = c1[g >> 5] | (1u << (g & 31u));
@@ -1638,7 +1648,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
                 if (w0 == 0) c0[W0 + (g >> 10)] &= ~(1u << ((g >> 5) & 31u));
                 occ[lo + g] = (uint8_t)o2;
                 out[base + j] = pack_result(flip_gpu(lo + g, prof.flip), start, size, ISL_ST_PLACED);
-                if (g < s_min[o2]) s_min[o2] = g;
+                if (g < s_min[cw2]) s_min[cw2] = g;
                 ++placed;
             }
             __syncwarp();
@@ -1654,7 +1664,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
                     break;
                 }
             }
-            if (lane == 0) s_min[o] = mn;
+            if (lane == 0) s_min[cw] = mn;
             __syncwarp();
         }
     }

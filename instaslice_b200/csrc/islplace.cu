@@ -58,7 +58,7 @@ struct isl_engine {
     uint32_t* d_tile_counts = nullptr;
     uint32_t* d_cand = nullptr;
     uint2* d_log = nullptr;          // decision log of one chunk (chain -> commit)
-    uint32_t* d_bf_bitmaps = nullptr; // best-fit class bitmaps for inventories beyond the shared-memory size
+    uint32_t* d_bf_bitmaps = nullptr; size_t bf_words = 0;   // best-fit class bitmaps for inventories beyond the shared-memory size / several tables
     uint2* h_small_out = nullptr;     // mapped pinned results of tiny batches (k_small writes them over PCIe directly)
     uint2* d_small_out = nullptr;     // device alias of h_small_out
     uint32_t* d_sweep_counts = nullptr;
@@ -205,16 +205,25 @@ int run_bestfit(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out) {
     const uint32_t Gr = e->hi - e->lo;
     if (Gr == 0 || Gr > kBfMaxGpus) return ISL_ERANGE;
     const uint32_t W0 = (Gr + 31) / 32, W1 = (W0 + 31) / 32, stride = W0 + W1;
-    const bool in_smem = Gr <= kBfSmemGpus;
+    const bool in_smem = e->n_tables == 1 && Gr <= kBfSmemGpus;
     const size_t smem = in_smem ? (size_t)256 * stride * sizeof(uint32_t) : 0;
-    if (!in_smem && !e->d_bf_bitmaps) ISL_CUDA(e, cudaMalloc(&e->d_bf_bitmaps, (size_t)256 * (kBfMaxGpus / 32 + kBfMaxGpus / 1024) * sizeof(uint32_t)));
+    if (!in_smem) {         // class bitmaps in global memory: one set of 256 per table, zeroed here (HBM speed) instead of by the lone CTA
+        const size_t words = (size_t)256 * e->n_tables * stride;
+        if (words > e->bf_words) {
+            if (e->d_bf_bitmaps) cudaFree(e->d_bf_bitmaps);
+            e->d_bf_bitmaps = nullptr; e->bf_words = 0;
+            ISL_CUDA(e, cudaMalloc(&e->d_bf_bitmaps, words * sizeof(uint32_t)));
+            e->bf_words = words;
+        }
+        ISL_CUDA(e, cudaMemsetAsync(e->d_bf_bitmaps, 0, words * sizeof(uint32_t), e->stream));
+    }
     const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
     if (timing) cudaEventRecord(e->ev[0], e->stream);
     k_prepare<<<ceil_div(n, kTile), kTileThreads, 0, e->stream>>>(n, d_in, d_out, reinterpret_cast<uint32_t*>(e->d_occ), e->G, e->lo, e->hi,
                                                                   e->prof, e->d_tile_counts, e->d_ctrl, nullptr, nullptr, 0, 0);
     if (int rc = check_launch(e, "k_prepare")) return rc;
     if (timing) cudaEventRecord(e->ev[1], e->stream);
-    k_bestfit<<<1, kBfThreads, smem, e->stream>>>(n, d_in, d_out, e->d_occ, e->lo, e->hi, e->d_lut, e->prof, e->d_bf_bitmaps, e->d_ctrl, e->d_score);
+    k_bestfit<<<1, kBfThreads, smem, e->stream>>>(n, d_in, d_out, e->d_occ, e->lo, e->hi, e->d_lut, e->prof, e->d_bf_bitmaps, e->d_ctrl, e->d_score, e->d_gtab, e->d_sizes, e->n_tables);
     if (int rc = check_launch(e, "k_bestfit")) return rc;
     if (timing) {
         cudaEventRecord(e->ev[2], e->stream);
@@ -230,7 +239,7 @@ int run_bestfit(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out) {
 
 int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const uint32_t* d_heads_in, uint32_t* d_heads_out) {
     if (n == 0) return ISL_OK;
-    if (bestfit_family(e->cfg.policy)) return e->n_tables == 1 ? run_bestfit(e, n, d_in, d_out) : ISL_EINVAL;
+    if (bestfit_family(e->cfg.policy)) return run_bestfit(e, n, d_in, d_out);
     const bool timing = e->cfg.flags & ISL_FLAG_TIMING;
     const uint32_t tiles = ceil_div(n, kTile);
     if (timing) cudaEventRecord(e->ev[0], e->stream);
@@ -671,7 +680,7 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
     ISL_TRY(cudaMalloc(&e->d_capn, ISL_MAX_TABLES * ISL_MAX_PROFILES * 256));
     ISL_TRY(cudaMalloc(&e->d_seq, ISL_MAX_TABLES * ISL_MAX_PROFILES * 256 * sizeof(uint32_t)));
     ISL_TRY(cudaMalloc(&e->d_sizes, ISL_MAX_TABLES * ISL_MAX_PROFILES));
-    ISL_TRY(cudaMalloc(&e->d_score, ISL_MAX_PROFILES * 256));
+    ISL_TRY(cudaMalloc(&e->d_score, ISL_MAX_TABLES * ISL_MAX_PROFILES * 256));
     ISL_TRY(cudaMalloc(&e->d_cap, ISL_MAX_PROFILES * sizeof(unsigned long long)));
     ISL_TRY(cudaMalloc(&e->d_gtab, e->occ_bytes));
     ISL_TRY(cudaMemset(e->d_gtab, 0, e->occ_bytes));
@@ -795,26 +804,28 @@ static int load_tables(isl_engine* e, uint32_t n_tables, uint32_t n, const isl_p
         for (uint32_t t = 0; t < n_tables; ++t) for (uint32_t p = 0; p < n; ++p) sizes[t * ISL_MAX_PROFILES + p] = e->rows_all[t][p].size;
         ISL_CUDA(e, cudaMemcpyAsync(e->d_sizes, sizes, sizeof(sizes), cudaMemcpyHostToDevice, e->stream));
     }
-    {   // what a best-fit family policy minimises (table 0: these policies take a single table)
-        std::vector<uint8_t> score(ISL_MAX_PROFILES * 256);      // the copy below completes before this function returns (stream sync)
-        std::vector<uint32_t> cand;                                  // every (profile, start) mask of the table the search can return
-        for (uint32_t p = 0; p < n; ++p)
-            for (uint32_t k = 0; k < e->rows_all[0][p].n_starts; ++k)
-                if (const uint32_t m = candidate_mask(e->rows_all[0][p].size, e->rows_all[0][p].starts[k], e->cfg.quirks)) cand.push_back(m);
-        for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p)
-            for (uint32_t o = 0; o < 256; ++o) {
-                uint32_t v = 8u - (uint32_t)__builtin_popcount(o);  // ISL_POLICY_BEST_FIT: free slices of the GPU (fewest first)
-                if (e->cfg.policy == ISL_POLICY_MIN_FRAG && p < n) {
-                    uint32_t mine = 0;                               // the mask the profile would take there: first legal start in row order
-                    for (uint32_t k = 0; k < e->rows_all[0][p].n_starts && !mine; ++k) {
-                        const uint32_t m = candidate_mask(e->rows_all[0][p].size, e->rows_all[0][p].starts[k], e->cfg.quirks);
-                        if (m && (o & m) == 0) mine = m;
+    {   // what a best-fit family policy minimises, per table
+        std::vector<uint8_t> score((size_t)ISL_MAX_TABLES * ISL_MAX_PROFILES * 256);      // the copy below completes before this function returns (stream sync)
+        for (uint32_t t = 0; t < n_tables; ++t) {
+            std::vector<uint32_t> cand;                              // every (profile, start) mask of the table the search can return
+            for (uint32_t p = 0; p < n; ++p)
+                for (uint32_t k = 0; k < e->rows_all[t][p].n_starts; ++k)
+                    if (const uint32_t m = candidate_mask(e->rows_all[t][p].size, e->rows_all[t][p].starts[k], e->cfg.quirks)) cand.push_back(m);
+            for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p)
+                for (uint32_t o = 0; o < 256; ++o) {
+                    uint32_t v = 8u - (uint32_t)__builtin_popcount(o);  // ISL_POLICY_BEST_FIT: free slices of the GPU (fewest first)
+                    if (e->cfg.policy == ISL_POLICY_MIN_FRAG && p < n) {
+                        uint32_t mine = 0;                               // the mask the profile would take there: first legal start in row order
+                        for (uint32_t k = 0; k < e->rows_all[t][p].n_starts && !mine; ++k) {
+                            const uint32_t m = candidate_mask(e->rows_all[t][p].size, e->rows_all[t][p].starts[k], e->cfg.quirks);
+                            if (m && (o & m) == 0) mine = m;
+                        }
+                        v = 0;
+                        if (mine) for (uint32_t m : cand) v += ((o & m) == 0) && (((o | mine) & m) != 0);      // pairs that stop being feasible
                     }
-                    v = 0;
-                    if (mine) for (uint32_t m : cand) v += ((o & m) == 0) && (((o | mine) & m) != 0);      // pairs that stop being feasible
+                    score[((size_t)t * ISL_MAX_PROFILES + p) * 256 + o] = (uint8_t)v;
                 }
-                score[p * 256 + o] = (uint8_t)v;
-            }
+        }
         ISL_CUDA(e, cudaMemcpyAsync(e->d_score, score.data(), score.size(), cudaMemcpyHostToDevice, e->stream));
     }
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));

@@ -192,3 +192,46 @@ def test_all_nodes_flag_reproduces_the_missing_break(n_nodes, gpn, n):
     req = W.alloc_requests((rng.next(n) % np.uint64(len(rows))).astype(np.uint8))
     assert np.array_equal(eng2.place_batch(req), f2.place(req, all_nodes=False))
     eng.close(); eng2.close()
+
+
+@pytest.mark.parametrize("policy", [E.POLICY_BEST_FIT, E.POLICY_MIN_FRAG])
+def test_best_fit_family_with_per_node_tables_and_large_inventories(policy):
+    """The best-fit family groups the GPUs by (table of the node, occupancy byte): heterogeneous clusters and inventories far beyond
+    65 536 GPUs (class bitmaps in global memory) against the oracle's O(G)-per-request search."""
+    names, rows2d = E.make_profile_tables([tables.A100_40GB, tables.H100_80GB, tables.A30_24GB])
+    rng = W.SplitMix64(1234 + policy)
+    n_nodes = 700
+    node_off = W.node_offsets(n_nodes, 8)
+    G = n_nodes * 8
+    node_table = (rng.next(n_nodes) % np.uint64(3)).astype(np.uint8)
+    occ = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+    ref = oracle.Fast(node_off, rows2d, 3, policy=policy, node_table=node_table)
+    ref.load(occ)
+    batches = _churn(rng, ref, [9, 400, 1500], len(names))
+    eng = E.Engine(max_gpus=8192, max_batch=1 << 16, policy=policy)
+    eng.load_profile_tables(rows2d)
+    eng.load_inventory(node_off, occ)
+    eng.set_node_tables(node_table)
+    for i, (req, want) in enumerate(batches):
+        got = eng.place_batch(req)
+        bad = np.flatnonzero(got != want)
+        assert len(bad) == 0, (i, bad[:5], got[bad[:5]], want[bad[:5]])
+    assert np.array_equal(eng.read_occupancy(), ref.occupancy())
+    eng.close()
+    # one table, 200 000 GPUs
+    rows = E.make_profiles(tables.H100_80GB)
+    G = 200_000
+    node_off = W.node_offsets(G // 8, 8)
+    occ = ((rng.next(G) | rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+    ref = oracle.Fast(node_off, rows, 3, policy=policy)
+    ref.load(occ)
+    batches = _churn(rng, ref, [5, 250, 250], len(rows))
+    eng = E.Engine(max_gpus=G, max_batch=1 << 16, policy=policy)
+    eng.load_profiles(rows)
+    eng.load_inventory(node_off, occ)
+    for i, (req, want) in enumerate(batches):
+        got = eng.place_batch(req)
+        bad = np.flatnonzero(got != want)
+        assert len(bad) == 0, (i, bad[:5], got[bad[:5]], want[bad[:5]])
+    assert np.array_equal(eng.read_occupancy(), ref.occupancy())
+    eng.close()
