@@ -1573,6 +1573,7 @@ constexpr uint32_t kBfThreads = 1024;
 constexpr uint32_t kBfMaxGpus = 1u << 20;           // class bitmaps: G / 32 words + G / 1024 summary words per (table, occupancy byte) class
 constexpr uint32_t kBfSmemGpus = 4096;              // up to here the class bitmaps live in shared memory (132 KiB)
 
+template <bool kMulti>
 __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uint2* __restrict__ in, uint2* __restrict__ out, uint8_t* __restrict__ occ,
                                                            uint32_t lo, uint32_t hi, const uint8_t* __restrict__ lut, DevProfiles prof,
                                                            uint32_t* __restrict__ g_bitmaps, Ctrl* ctrl, const uint8_t* __restrict__ score,
@@ -1591,15 +1592,16 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
     const bool small = n_tables == 1 && Gr <= kBfSmemGpus;      // bitmaps in shared memory; otherwise in global memory, zeroed by the host
     uint32_t* bm = small ? s_dyn : g_bitmaps;
     if (small) for (uint32_t i = tid; i < 256 * stride; i += kBfThreads) bm[i] = 0;
-    // one table: the per-byte tables sit in shared memory; several: they are read from global memory (L1-resident, 8 KiB per table)
-    if (n_tables == 1) for (uint32_t i = tid; i < ISL_MAX_PROFILES * 256; i += kBfThreads) { s_lut[i] = lut[i]; s_score[i] = score[i]; }
-    const uint8_t* lutp = n_tables == 1 ? s_lut : lut;
-    const uint8_t* scorep = n_tables == 1 ? s_score : score;
+    // one table (kMulti == false): the per-byte tables sit in shared memory; several: they are read from global memory (L1-resident,
+    // 8 KiB per table)
+    if (!kMulti) for (uint32_t i = tid; i < ISL_MAX_PROFILES * 256; i += kBfThreads) { s_lut[i] = lut[i]; s_score[i] = score[i]; }
+    auto lut_at = [&](uint32_t idx) -> uint32_t { return kMulti ? (uint32_t)__ldg(lut + idx) : (uint32_t)s_lut[idx]; };
+    auto score_at = [&](uint32_t idx) -> uint32_t { return kMulti ? (uint32_t)__ldg(score + idx) : (uint32_t)s_score[idx]; };
     if (tid < kMaxTables * ISL_MAX_PROFILES) s_sizes[tid] = sizes[tid];
     for (uint32_t i = tid; i < n_cls; i += kBfThreads) s_min[i] = kInf;
     __syncthreads();
     for (uint32_t g = tid; g < Gr; g += kBfThreads) {           // build: every GPU joins its class
-        const uint32_t c = (n_tables > 1 ? (uint32_t)(gtab[lo + g] & (kMaxTables - 1)) * 256u : 0u) + occ[lo + g];
+        const uint32_t c = (kMulti ? (uint32_t)(gtab[lo + g] & (kMaxTables - 1)) * 256u : 0u) + occ[lo + g];
         atomicOr(&bm[c * stride + (g >> 5)], 1u << (g & 31u));
         atomicOr(&bm[c * stride + W0 + (g >> 10)], 1u << ((g >> 5) & 31u));
         atomicMin(&s_min[c], g);
@@ -1626,8 +1628,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
             for (uint32_t c = lane; c < n_cls; c += 32) {       // lane l looks at classes l, l+32, ...
                 const uint32_t mn = s_min[c];
                 const uint32_t idx = ((c >> 8) * ISL_MAX_PROFILES + p) * 256 + (c & 255u);
-                if (mn != kInf && lutp[idx] != ISL_START_NONE) {
-                    const uint32_t k2 = ((uint32_t)scorep[idx] << 24) | mn;
+                if (mn != kInf && lut_at(idx) != ISL_START_NONE) {
+                    const uint32_t k2 = (score_at(idx) << 24) | mn;
                     if (k2 < key) { key = k2; kc = c; }
                 }
             }
@@ -1636,7 +1638,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
             const uint32_t g = m & 0xFFFFFFu;
             const uint32_t cw = __shfl_sync(0xFFFFFFFFu, kc, __ffs(__ballot_sync(0xFFFFFFFFu, key == m)) - 1);   // the class IS (table, occupancy byte)
             const uint32_t t = cw >> 8, o = cw & 255u;
-            const uint32_t start = lutp[(t * ISL_MAX_PROFILES + p) * 256 + o], size = s_sizes[t * ISL_MAX_PROFILES + p];
+            const uint32_t start = lut_at((t * ISL_MAX_PROFILES + p) * 256 + o), size = s_sizes[t * ISL_MAX_PROFILES + p];
             const uint32_t o2 = o | ((((1u << size) - 1u) << start) & 0xFFu), cw2 = (t << 8) | o2;
             uint32_t* c0 = bm + cw * stride;
             uint32_t* c1 = bm + cw2 * stride;
@@ -1652,17 +1654,23 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
                 ++placed;
             }
             __syncwarp();
-            // new minimum of class o (g was its minimum: nothing below it): the lanes look at 32 summary words at a time
+            // new minimum of the class (g was its minimum: nothing below it).  Usually it sits under the summary word that held g: every
+            // lane reads that word (one broadcast); only when it is empty do the lanes look at the further summary words, 32 at a time
             uint32_t mn = kInf;
-            for (uint32_t k0 = (g >> 10) & ~31u; k0 < W1; k0 += 32) {
-                const uint32_t sw = k0 + lane < W1 ? c0[W0 + k0 + lane] : 0u;
-                const uint32_t b = __ballot_sync(0xFFFFFFFFu, sw != 0);
-                if (b) {
-                    const uint32_t src = __ffs(b) - 1;
-                    const uint32_t wi = (k0 + src) * 32 + __ffs(__shfl_sync(0xFFFFFFFFu, sw, src)) - 1;
-                    mn = wi * 32 + __ffs(c0[wi]) - 1;
-                    break;
-                }
+            {
+                const uint32_t k = g >> 10, sw = c0[W0 + k];
+                if (sw) { const uint32_t wi = k * 32 + __ffs(sw) - 1; mn = wi * 32 + __ffs(c0[wi]) - 1; }
+                else
+                    for (uint32_t k0 = k + 1; k0 < W1; k0 += 32) {
+                        const uint32_t s2 = k0 + lane < W1 ? c0[W0 + k0 + lane] : 0u;
+                        const uint32_t b = __ballot_sync(0xFFFFFFFFu, s2 != 0);
+                        if (b) {
+                            const uint32_t src = __ffs(b) - 1;
+                            const uint32_t wi = (k0 + src) * 32 + __ffs(__shfl_sync(0xFFFFFFFFu, s2, src)) - 1;
+                            mn = wi * 32 + __ffs(c0[wi]) - 1;
+                            break;
+                        }
+                    }
             }
             if (lane == 0) s_min[cw] = mn;
             __syncwarp();

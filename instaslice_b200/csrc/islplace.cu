@@ -223,7 +223,8 @@ int run_bestfit(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out) {
                                                                   e->prof, e->d_tile_counts, e->d_ctrl, nullptr, nullptr, 0, 0);
     if (int rc = check_launch(e, "k_prepare")) return rc;
     if (timing) cudaEventRecord(e->ev[1], e->stream);
-    k_bestfit<<<1, kBfThreads, smem, e->stream>>>(n, d_in, d_out, e->d_occ, e->lo, e->hi, e->d_lut, e->prof, e->d_bf_bitmaps, e->d_ctrl, e->d_score, e->d_gtab, e->d_sizes, e->n_tables);
+    if (e->n_tables == 1) k_bestfit<false><<<1, kBfThreads, smem, e->stream>>>(n, d_in, d_out, e->d_occ, e->lo, e->hi, e->d_lut, e->prof, e->d_bf_bitmaps, e->d_ctrl, e->d_score, e->d_gtab, e->d_sizes, 1);
+    else k_bestfit<true><<<1, kBfThreads, 0, e->stream>>>(n, d_in, d_out, e->d_occ, e->lo, e->hi, e->d_lut, e->prof, e->d_bf_bitmaps, e->d_ctrl, e->d_score, e->d_gtab, e->d_sizes, e->n_tables);
     if (int rc = check_launch(e, "k_bestfit")) return rc;
     if (timing) {
         cudaEventRecord(e->ev[2], e->stream);
@@ -657,7 +658,7 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
         // stream with an empty first batch).
         cudaFuncAttributes fa;
         const void* kernels[] = {(const void*)k_prepare, (const void*)k_partition, (const void*)k_set_flag, (const void*)k_few, (const void*)k_build_lut, (const void*)k_eval_starts,
-                                 (const void*)k_free_spans, (const void*)k_capacity, (const void*)k_sweep_count, (const void*)k_sweep_scatter, (const void*)k_commit, (const void*)k_bestfit,
+                                 (const void*)k_free_spans, (const void*)k_capacity, (const void*)k_sweep_count, (const void*)k_sweep_scatter, (const void*)k_commit, (const void*)k_bestfit<false>, (const void*)k_bestfit<true>,
                                  (const void*)k_chain<1>, (const void*)k_chain<2>, (const void*)k_chain<4>, (const void*)k_small<1>, (const void*)k_small<2>, (const void*)k_small<4>,
                                  (const void*)k_pipeline<1, false>, (const void*)k_pipeline<1, true>, (const void*)k_pipeline<2, false>, (const void*)k_pipeline<2, true>,
                                  (const void*)k_pipeline<4, false>, (const void*)k_pipeline<4, true>};
@@ -666,7 +667,7 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
         // skip devices 8.. and race between threads)
         const void* chains[] = {(const void*)k_chain<1>, (const void*)k_chain<2>, (const void*)k_chain<4>};
         for (const void* k : chains) ISL_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kQCap * sizeof(uint16_t))));
-        ISL_TRY(cudaFuncSetAttribute((const void*)k_bestfit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(256 * (kBfSmemGpus / 32 + kBfSmemGpus / 1024) * sizeof(uint32_t))));
+        ISL_TRY(cudaFuncSetAttribute((const void*)k_bestfit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(256 * (kBfSmemGpus / 32 + kBfSmemGpus / 1024) * sizeof(uint32_t))));
         const void* pipes[] = {(const void*)k_pipeline<1, false>, (const void*)k_pipeline<1, true>, (const void*)k_pipeline<2, false>, (const void*)k_pipeline<2, true>,
                                (const void*)k_pipeline<4, false>, (const void*)k_pipeline<4, true>};
         for (const void* k : pipes) ISL_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
@@ -813,13 +814,16 @@ static int load_tables(isl_engine* e, uint32_t n_tables, uint32_t n, const isl_p
                     if (const uint32_t m = candidate_mask(e->rows_all[t][p].size, e->rows_all[t][p].starts[k], e->cfg.quirks)) cand.push_back(m);
             for (uint32_t p = 0; p < ISL_MAX_PROFILES; ++p)
                 for (uint32_t o = 0; o < 256; ++o) {
-                    uint32_t v = 8u - (uint32_t)__builtin_popcount(o);  // ISL_POLICY_BEST_FIT: free slices of the GPU (fewest first)
-                    if (e->cfg.policy == ISL_POLICY_MIN_FRAG && p < n) {
-                        uint32_t mine = 0;                               // the mask the profile would take there: first legal start in row order
+                    uint32_t mine = 0;                                   // the mask the profile would take there: first legal start in row order
+                    if (p < n)
                         for (uint32_t k = 0; k < e->rows_all[t][p].n_starts && !mine; ++k) {
                             const uint32_t m = candidate_mask(e->rows_all[t][p].size, e->rows_all[t][p].starts[k], e->cfg.quirks);
                             if (m && (o & m) == 0) mine = m;
                         }
+                    // ISL_POLICY_BEST_FIT: free slices of the GPU AFTER the placement, fewest first (with several tables one name may
+                    // span different sizes, so "after" is not "before minus a constant")
+                    uint32_t v = 8u - (uint32_t)__builtin_popcount(o | mine);
+                    if (e->cfg.policy == ISL_POLICY_MIN_FRAG) {
                         v = 0;
                         if (mine) for (uint32_t m : cand) v += ((o & m) == 0) && (((o | mine) & m) != 0);      // pairs that stop being feasible
                     }
