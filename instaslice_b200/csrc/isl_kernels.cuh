@@ -956,7 +956,7 @@ struct PipeArgs {
     const uint32_t* heads_in;       // [chunk][16] token entering the first segment (nullptr = zeros)
     uint32_t* heads_out;            // [chunk][16] token leaving the last segment (may be nullptr)
     // partitioned inventory: the token crosses GPUs through peer-mapped memory (NVLink), system-scope release/acquire
-    const uint32_t* inbox;          // local [chunk][kTokStride], written by the previous rank's last segment (nullptr = first rank)
+    const uint32_t* inbox;          // local [chunk][kTokStride] of tagged head words, written by the previous rank's last segment (nullptr = first rank); cleared by the reader
     uint32_t* outbox;               // the next rank's inbox, peer-mapped (nullptr = last rank)
     uint32_t xepoch;                // stream id shared by all ranks
     // host-buffer streams (isl_place_stream): the batches are fed while the pipeline runs, the results leave chunk by chunk
@@ -1020,6 +1020,9 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
     uint32_t v;
@@ -1288,13 +1291,23 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     }
                 }
             } else if (a.inbox) {       // first segment of a rank that has a predecessor: the token comes over NVLink
-                if (tid == 0) {     // a dead or stuck predecessor must not hang this GPU for good: trap like wait_ready does
-                    const uint32_t* flag = a.inbox + (size_t)c * kTokStride + ISL_MAX_PROFILES;
-                    const unsigned long long t0 = globaltimer_ns();
-                    while (ld_acquire_sys(flag) != a.xepoch) { if (globaltimer_ns() - t0 > a.wait_ns) __trap(); }
+                // Self-validating words across GPUs as well: every head word carries the low 15 bits of the stream id above its 17 bits of
+                // payload, written with ONE relaxed system-scope store each (4-byte stores are single-copy atomic) — no fence and no flag on
+                // the sender's side, one NVLink write latency per hop instead of fence + flag.  The consumer clears its slot after reading,
+                // so a tag can never be mistaken for one of 32 768 streams ago.  A dead or stuck predecessor must not hang this GPU for
+                // good: the wait traps like wait_ready does.
+                uint32_t* slot = const_cast<uint32_t*>(a.inbox) + (size_t)c * kTokStride + (tid & 15u);
+                const uint32_t xtag = a.xepoch % 32767u + 1u;      // never 0: a cleared slot is never valid
+                bool ok = tid >= ISL_MAX_PROFILES;
+                const unsigned long long t0 = globaltimer_ns();
+                while (!__all_sync(0xFFFFFFFFu, ok)) {
+                    if (!ok) {
+                        const uint32_t v = ld_relaxed_sys(slot);
+                        if ((v >> 17) == xtag) { h = v & 0x1FFFFu; ok = true; }
+                        else if (globaltimer_ns() - t0 > a.wait_ns) __trap();
+                    }
                 }
-                __syncwarp();
-                if (tid < ISL_MAX_PROFILES) h = ld_relaxed_sys(a.inbox + (size_t)c * kTokStride + tid);
+                if (tid < ISL_MAX_PROFILES) st_relaxed_sys(slot, 0u);
             } else if (tid < ISL_MAX_PROFILES) h = a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + tid] : 0u;
             stamp_if(tr && tid == 0, tr + 1);
             const bool all_done = sb == 0 && __all_sync(0xFFFFFFFFu, from_done || tid >= ISL_MAX_PROFILES);
@@ -1325,11 +1338,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     const uint32_t h = s_heads[lane];
                     st_relaxed_gpu(tok + lane, ((a.epoch & 0x7FFFu) << 17) | h);
                     if (last && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + lane] = h;
-                    if (peer) peer[lane] = h;
+                    if (peer) st_relaxed_sys(peer + lane, ((a.xepoch % 32767u + 1u) << 17) | h);
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    if (peer) { __threadfence_system(); st_release_sys(peer + ISL_MAX_PROFILES, a.xepoch); }
                     if (tr) { tr[2] = globaltimer_ns(); tr[3] = tr[2]; }
                 }
             }
@@ -1492,11 +1504,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 const uint32_t h = s_heads[lane] + s_pop[lane];
                 st_relaxed_gpu(tok + lane, ((a.epoch & 0x7FFFu) << 17) | h);       // the next segment starts
                 if (last && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + lane] = h;
-                if (peer) peer[lane] = h;
+                if (peer) st_relaxed_sys(peer + lane, ((a.xepoch % 32767u + 1u) << 17) | h);
             }
             __syncwarp();
             if (lane == 0) {
-                if (last_sub && peer) { __threadfence_system(); st_release_sys(peer + ISL_MAX_PROFILES, a.xepoch); }
                 s_nlog = nlog;
                 if (tr) tr[2] = globaltimer_ns();
             }
@@ -1610,8 +1621,10 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_bestfit(uint32_t n, const uin
     if (!is_chain_warp(tid >> 5)) return;
     uint32_t placed = 0;
     uint32_t dead = 0;              // profiles that found no GPU: occupancy only grows inside a batch's ALLOC phase, so they never will again
+    uint2 ahead = lane < n ? in[lane] : make_uint2(0, (uint32_t)ISL_OP_NOOP << 8);
     for (uint32_t base = 0; base < n; base += 32) {
-        const uint2 mine = base + lane < n ? in[base + lane] : make_uint2(0, (uint32_t)ISL_OP_NOOP << 8);
+        const uint2 mine = ahead;                               // the next block's requests are fetched while this one is resolved
+        ahead = base + 32 + lane < n ? in[base + 32 + lane] : make_uint2(0, (uint32_t)ISL_OP_NOOP << 8);
         // only the live ALLOCs of the block are looked at (frees, unknown or dead profiles: defaults were written by k_prepare)
         uint32_t live;
         {
