@@ -1,0 +1,99 @@
+// guess.cpp — multiple shooting from an INFORMED guess: entry heads of every segment from an occupancy scan (what is conserved:
+// quads taken, slices filled) + a time-balanced split inside a trading group, then absolute chaining (entry(s+1) = end(s)).
+//   ./guess <c3|c4> <segment GPUs> [warm-up GPUs]
+#include "shoot_common.cpp"
+#include <cmath>
+static int psize(int p) { return profs[p].masks.empty() ? 0 : __builtin_popcount(profs[p].masks[0]); }
+// number of requests of profile p with time < tau
+static uint32_t cnt_before(int p, uint32_t tau) { return std::lower_bound(q[p].begin(), q[p].end(), tau) - q[p].begin(); }
+
+int main(int argc, char** argv) {
+    const std::string cfg = argc > 1 ? argv[1] : "c4";
+    const uint32_t seg = argc > 2 ? atoi(argv[2]) : 512;
+    const bool newton = argc > 3 ? atoi(argv[3]) : 0;
+    Loaded L = load_config(cfg);
+    const uint32_t G = L.occ.size(), S = (G + seg - 1) / seg;
+    size_t off = 0;
+    for (size_t b = 0; b < L.sizes.size() && b < 4; ++b) {
+        const uint32_t n = L.sizes[b];
+        open_batch(L, off, n);
+        const int np = (int)profs.size();
+        std::vector<Heads> truth(S + 1); Heads h0{}; truth[0] = h0;
+        std::vector<uint8_t> occ_new = L.occ; uint64_t dec = 0;
+        for (uint32_t s = 0; s < S; ++s) truth[s + 1] = simulate(L.occ, s * seg, std::min(G, (s + 1) * seg), truth[s], &dec, &occ_new);
+        // ---- the guess
+        std::vector<int> big, small;          // size >= 4 group / size 1,2 group
+        for (int p = 0; p < np; ++p) { int sz = psize(p); if (!sz || q[p].empty()) continue; if (sz >= 4) big.push_back(p); else small.push_back(p); }
+        uint64_t totbig = 0; for (int p : big) totbig += q[p].size();
+        uint64_t totsmall_mass = 0; for (int p : small) totsmall_mass += (uint64_t)q[p].size() * psize(p);
+        uint32_t usable1 = 0; for (int p : small) for (uint32_t m : profs[p].masks) usable1 |= m;
+        std::vector<Heads> H(S + 1, h0);
+        uint64_t Q = 0, R = 0;
+        for (uint32_t g = 0; g <= G; ++g) {
+            if (g % seg == 0 || g == G) {
+                const uint32_t s = g == G ? S : g / seg;
+                Heads h{};
+                // big group: first Q of the merged queue
+                { uint32_t lo = 0, hi = n; while (lo < hi) { uint32_t mid = (lo + hi) / 2; uint64_t c = 0; for (int p : big) c += cnt_before(p, mid); if (c >= Q) hi = mid; else lo = mid + 1; }
+                  for (int p : big) h[p] = cnt_before(p, lo); }
+                // small group: balanced time
+                { uint32_t lo = 0, hi = n; while (lo < hi) { uint32_t mid = (lo + hi) / 2; uint64_t c = 0; for (int p : small) c += (uint64_t)cnt_before(p, mid) * psize(p); if (c >= R) hi = mid; else lo = mid + 1; }
+                  for (int p : small) h[p] = cnt_before(p, lo); }
+                if (s <= S) H[s] = h;
+                if (g == G) break;
+            }
+            uint32_t o = L.occ[g];
+            if (Q < totbig) { for (int p : big) { bool took = false; for (uint32_t m : profs[p].masks) if (!(o & m)) { o |= m; ++Q; took = true; break; } if (took) break; } }
+            if (R < totsmall_mass) R += __builtin_popcount(~o & usable1);
+        }
+        H[0] = h0;
+        // ---- error of the guess
+        { double e1 = 0, e2 = 0; int busy = 0; long maxabs = 0;
+          for (uint32_t s = 1; s < S; ++s) { if (truth[s] == truth[s + 1] && s > 1) continue; ++busy;
+              long dq = 0, dr = 0; for (int p : big) dq += (long)H[s][p] - (long)truth[s][p]; for (int p : small) dr += ((long)H[s][p] - (long)truth[s][p]) * psize(p);
+              long d1 = 0; for (int p : small) if (psize(p) == 1) d1 += (long)H[s][p] - (long)truth[s][p];
+              e1 += std::abs(dq); e2 += std::abs(dr); maxabs = std::max(maxabs, std::labs(d1));
+              if (s % 8 == 1 && b == 0) printf("   seg %u: dQ %ld dR %ld d(1g) %ld\n", s, dq, dr, d1); }
+          printf("guess: busy %d, mean |dQ| %.2f, mean |dR| %.2f, max |d 1g| %ld\n", busy, e1 / busy, e2 / busy, maxabs); }
+        // ---- rounds, absolute chaining (with optional warm-up: segment s re-simulates from the entry of the segment 'warm' GPUs earlier)
+        std::vector<Heads> E(S + 1), Hn(S + 1);
+        auto cq = [&](const Heads& h) { long c = 0; for (int p : big) c += h[p]; return c; };
+        auto cr = [&](const Heads& h) { long c = 0; for (int p : small) c += (long)h[p] * psize(p); return c; };
+        std::vector<double> lq(S, 1.0), lr(S, 1.0); std::vector<long> peq(S), pxq(S), per(S), pxr(S); std::vector<bool> have(S, false);
+        const int secant = getenv("SECANT") ? atoi(getenv("SECANT")) : 0;
+        int rounds = 0; uint64_t crit = 0; uint32_t frontier = 0;
+        while (true) {
+            ++rounds; uint64_t maxw = 0;
+            for (uint32_t s = 0; s < S; ++s) { uint64_t d = 0; E[s + 1] = simulate(L.occ, s * seg, std::min(G, (s + 1) * seg), H[s], &d); maxw = std::max(maxw, d); }
+            crit += maxw;
+            Hn[0] = h0;
+            for (uint32_t s = 0; s < S; ++s) {
+                Hn[s + 1] = E[s + 1];
+                if (!newton) continue;
+                long dq = 0, dr = 0; for (int p : big) dq += (long)Hn[s][p] - (long)H[s][p]; for (int p : small) dr += ((long)Hn[s][p] - (long)H[s][p]) * psize(p);
+                if (secant) {
+                    const long eq = cq(H[s]), xq = cq(E[s + 1]), er = cr(H[s]), xr = cr(E[s + 1]);
+                    if (have[s]) { if (eq != peq[s]) lq[s] = std::min(1.0, std::max(0.0, double(xq - pxq[s]) / double(eq - peq[s])));
+                                   if (er != per[s]) lr[s] = std::min(1.0, std::max(0.0, double(xr - pxr[s]) / double(er - per[s]))); }
+                    have[s] = true; peq[s] = eq; pxq[s] = xq; per[s] = er; pxr[s] = xr;
+                    dq = std::lround(lq[s] * dq); dr = std::lround(lr[s] * dr);
+                }
+                Heads& h = Hn[s + 1];
+                // big group: advance / retreat |dq| requests in merged time order
+                while (dq > 0) { int bp = -1; uint32_t bt = 0xFFFFFFFFu; for (int p : big) if (h[p] < q[p].size() && q[p][h[p]] < bt) { bt = q[p][h[p]]; bp = p; } if (bp < 0) break; ++h[bp]; --dq; }
+                while (dq < 0) { int bp = -1; long bt = -1; for (int p : big) if (h[p] > 0 && (long)q[p][h[p] - 1] > bt) { bt = q[p][h[p] - 1]; bp = p; } if (bp < 0) break; --h[bp]; ++dq; }
+                // small group: same rule weighted by size (advance the class whose next request is earliest)
+                while (dr > 0) { int bp = -1; uint32_t bt = 0xFFFFFFFFu; for (int p : small) if (h[p] < q[p].size() && psize(p) <= dr && q[p][h[p]] < bt) { bt = q[p][h[p]]; bp = p; } if (bp < 0) break; ++h[bp]; dr -= psize(bp); }
+                while (dr < 0) { int bp = -1; long bt = -1; for (int p : small) if (h[p] > 0 && psize(p) <= -dr && (long)q[p][h[p] - 1] > bt) { bt = q[p][h[p] - 1]; bp = p; } if (bp < 0) break; --h[bp]; dr += psize(bp); }
+            }
+            bool any = false; uint32_t wrong = 0;
+            for (uint32_t s = 0; s <= S; ++s) { if (Hn[s] != H[s]) any = true; if (Hn[s] != truth[s]) ++wrong; H[s] = Hn[s]; }
+            if (getenv("VERB") && b == 0) { printf("      err:"); for (uint32_t s = 0; s < 48 && s <= S; ++s) { long d = 0; for (int p = 0; p < np; ++p) d += std::labs((long)H[s][p] - (long)truth[s][p]); printf(" %ld", d); } printf("\n"); }
+            frontier = 0; while (frontier <= S && H[frontier] == truth[frontier]) ++frontier;
+            printf("   round %d: boundaries still wrong %u, exact frontier %u / %u\n", rounds, wrong, frontier, S + 1);
+            if (!any || rounds > 200) break;
+        }
+        printf("%s batch %zu seg %u: sequential decisions %lu | rounds %d, critical path %lu decisions (%.3fx)\n", cfg.c_str(), b, seg, dec, rounds, crit, (double)crit / dec);
+        L.occ = occ_new; off += n;
+    }
+}
