@@ -176,6 +176,11 @@ typedef struct isl_stats {
     double   ms_commit;
     double   ms_total;             /* first kernel start -> last kernel end, per batch, summed */
     uint64_t scan_placed;          /* placements committed by the parallel capacity scan (single-profile chunks), no chain */
+    /* speculative rounds (isl_set_speculation): chunks resolved that way, rounds until their last inventory stage was certified
+     * (summed over the chunks), segment simulations run by all stages together */
+    uint64_t spec_chunks;
+    uint64_t spec_rounds;
+    uint64_t spec_sims;
 } isl_stats;
 
 /* ---- lifetime ---------------------------------------------------------- */
@@ -262,6 +267,18 @@ int  isl_stream_close(isl_engine* e);
 /* Device-side causal window for isl_place_stream / isl_place_stream_device: batch b is not started before every inventory segment has
  * committed batch b - window (0 = no constraint, the default).  Models a consumer that needs batch b - window's results to compose b. */
 int  isl_set_causal_window(isl_engine* e, uint32_t window);
+/* Speculative rounds inside the segment pipeline: a batch's decisions are ONE recurrence over the inventory (the reference's
+ * first-fit in arrival order, :240-262), so a batch that must be resolved before the next one may start keeps all inventory stages but
+ * one idle.  With speculation every stage simulates its segment at once from PREDICTED queue heads, the predictions are corrected
+ * round by round and a stage commits only when its entry is certified to be the true one — results are bit-identical, a batch's
+ * latency drops from (stages x segment time) to (rounds x segment time).  It pays when few batches may be in flight and costs
+ * throughput when many may overlap anyway:
+ *   ISL_SPEC_AUTO (default)  single batches and streams with a causal window of 1..3; open streams: when a window of 1..3 is set
+ *   ISL_SPEC_OFF / ISL_SPEC_ON  never / whenever the geometry allows it (one sub-segment per stage, no partitioned inventory) */
+#define ISL_SPEC_AUTO 0u
+#define ISL_SPEC_OFF  1u
+#define ISL_SPEC_ON   2u
+int  isl_set_speculation(isl_engine* e, uint32_t mode);
 /* Mapped pinned host memory from the C side (cgo must not hand Go-heap pointers to a running kernel). NULL on failure. */
 void* isl_host_alloc(size_t bytes);
 void  isl_host_free(void* p);

@@ -86,6 +86,7 @@ struct Ctrl {                   // device-resident control block, rewritten per 
     uint32_t heads_out[ISL_MAX_PROFILES];  // queue heads after the chain (token for the next rank)
     uint32_t n_log;                        // decisions logged by the chain of this chunk
     unsigned long long placed, freed, bad, steps, visited, allocs, jumps, scanned;
+    unsigned long long spec_sims, spec_rounds, spec_cells;   // speculative rounds: segment simulations run (all stages), rounds until the last stage was certified summed over chunks, chunks
 };
 
 // The one rule both the device table and the chain candidates come from: slot mask of placing a
@@ -977,7 +978,45 @@ struct PipeArgs {
     uint32_t* ring_done; uint32_t world;
     uint32_t flip;                  // ISL_POLICY_RIGHT_TO_LEFT: G, the reported GPU is G - 1 - internal index
     unsigned long long* trace;      // optional [chunk][segment][kTraceWords]: globaltimer ns of sweep done, token in, token out, commit done, chain start, chain end; decisions; jumps | visited << 32; ns of heads done, windows staged; 2 spare
+    // speculative rounds (below): every stage simulates its segment from PREDICTED queue heads at once, the predictions are corrected round
+    // by round and a stage commits once its entry heads are certified to be the true ones.  Record memory: spec_mem(), kSpecWordsPerChunk per chunk.
+    uint32_t spec;
+    unsigned long long* spec_mem;
 };
+
+// ---------------------------------------------------------------------------------------------
+// Speculative rounds over the stages of ONE chunk — exact, only faster.
+// A chunk's decisions are one recurrence over the inventory: stage s needs the queue heads stage s-1 leaves (the token).  Instead of
+// idling until the token has travelled, every stage simulates its segment at once from a PREDICTED token:
+//   round 0   every stage publishes what its occupancy can take (per contention group: placements of the size >= 4 profiles, slices left
+//             for the size 1/2 profiles); stage s predicts its entry heads from the sums over the stages in front of it
+//   round r   stage s simulates from its predicted entry H (the exact chain of 4.1, log kept in shared memory), publishes its exit heads
+//             X (to s+1) and the group masses it consumed D (to every later stage), reads X of s-1 and D of all j < s, and corrects:
+//             H' = X(s-1) shifted, per group, to the mass sum of D(j), j < s   (a Newton step: a shift of the entry by conserved
+//             quantities passes through a segment unchanged; the split inside a group heals by itself within a few hundred GPUs)
+//   stage s is CERTIFIED in round r when H(j) of round r-1 equalled X(j-1) of round r-1 for every j <= s: by induction from stage 0
+//             (whose entry is the true one) every such entry is the true token; it commits its log and publishes final records.
+// Every round certifies at least one more stage, so the worst case is the token travelling stage by stage as before; predictions that
+// hold certify whole runs of stages at once.  Words are self-validating (call epoch and round above the payload): no flags, no fences.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kSpecStride = 160;               // stage slots per row (>= 148 stages)
+constexpr uint32_t kSpecRounds = 160;               // rounds <= stages + 2
+constexpr uint32_t kSpecWordsPerChunk = kSpecStride * (32 + 16 + kSpecRounds + 1 + 2 + 1);
+struct SpecMem {
+    unsigned long long* x;          // [stage][round & 1][16]   tag(round) << 32 | exit head
+    unsigned long long* xf;         // [stage][16]              final: tagF << 32 | certified-in-round << 24 | exit head
+    unsigned long long* d;          // [round][stage]           tag(round) << 32 | c << 31 | dq << 13 | dr   (c: entry equalled the predecessor's exit one round earlier)
+    unsigned long long* df;         // [stage]                  final: tagF << 32 | certified-in-round << 24 | dq << 13 | dr
+    unsigned long long* m;          // [stage][2]               round 0: tag(0) << 32 | placements of the big group ; tag(0) << 32 | slices with << 16 | slices without them
+    unsigned long long* ack;        // [stage]                  epoch << 32 | last round whose X(stage - 1) this stage has read
+};
+__host__ __device__ inline SpecMem spec_mem(unsigned long long* base, uint32_t chunk) {
+    unsigned long long* p = base + (size_t)chunk * kSpecWordsPerChunk;
+    SpecMem s;
+    s.x = p; p += kSpecStride * 32; s.xf = p; p += kSpecStride * 16; s.d = p; p += (size_t)kSpecStride * kSpecRounds;
+    s.df = p; p += kSpecStride; s.m = p; p += kSpecStride * 2; s.ack = p;
+    return s;
+}
 
 constexpr uint32_t kTraceWords = 12;
 #ifndef ISL_UNROLL
@@ -1029,6 +1068,38 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
     asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Speculative rounds: move the heads of the profiles in `members` so that their mass (sum of weight x head) changes by d — shares
+// proportional to the queue lengths, the heaviest profiles first, the last (lightest) one takes the remainder so that the mass is met
+// exactly whenever the weights allow it.  One thread; h, qc, wsz in shared memory.
+__device__ inline void spec_spread(uint32_t* h, const uint32_t* qc, const uint32_t* wsz, uint32_t members, long long d, bool weighted) {
+    if (d == 0 || members == 0) return;
+    long long tot = 0;
+    for (uint32_t m = members; m; m &= m - 1) { const uint32_t p = __ffs(m) - 1; tot += (long long)qc[p] * (weighted ? wsz[p] : 1u); }
+    for (int pass = weighted ? 0 : 1; pass < 2; ++pass) {
+        for (uint32_t m = members; m; m &= m - 1) {
+            const uint32_t p = __ffs(m) - 1;
+            const long long w = weighted ? wsz[p] : 1u;
+            if (weighted && (pass == 0) != (w > 1)) continue;       // pass 0: spans of 2 and more, pass 1: single slices
+            uint32_t rest = members & ~((2u << p) - 1u);            // members behind p in this pass ...
+            if (weighted) { uint32_t r2 = 0; for (uint32_t x = rest; x; x &= x - 1) { const uint32_t q = __ffs(x) - 1; if ((wsz[q] > 1) == (w > 1)) r2 |= 1u << q; } rest = r2;
+                            if (pass == 0 && !rest) for (uint32_t x = members; x; x &= x - 1) { const uint32_t q = __ffs(x) - 1; if (wsz[q] <= 1) rest |= 1u << q; } }   // ... or in the next one
+            const long long num = d * (long long)qc[p];
+            long long dp = rest ? (tot > 0 ? (num + (num >= 0 ? tot / 2 : -(tot / 2))) / tot : 0) : d / w;
+            const long long v = (long long)h[p] + dp;
+            h[p] = (uint32_t)(v < 0 ? 0 : (v > (long long)qc[p] ? qc[p] : v));
+            d -= dp * w; tot -= (long long)qc[p] * w;
+        }
+    }
+}
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
@@ -1074,6 +1145,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     __shared__ uint32_t s_heads[ISL_MAX_PROFILES], s_wn[ISL_MAX_PROFILES], s_wbase[ISL_MAX_PROFILES], s_qbeg[ISL_MAX_PROFILES], s_pop[ISL_MAX_PROFILES];
     __shared__ uint32_t s_maxacc[ISL_MAX_PROFILES], s_minsize[ISL_MAX_PROFILES], s_usable[kMaxTables], s_plist[ISL_MAX_PROFILES], s_nplist;
     __shared__ uint32_t s_warp[kPipeThreads / 32], s_ncand, s_nfree, s_nlog, s_idle, s_closed;
+    // speculative rounds: predicted entry heads, own / predecessor's exit heads, queue lengths, gathered sums, contention groups
+    __shared__ uint32_t s_specH[ISL_MAX_PROFILES], s_specX[ISL_MAX_PROFILES], s_specXp[ISL_MAX_PROFILES], s_qc[ISL_MAX_PROFILES];
+    __shared__ uint32_t s_acc[4], s_grp_big, s_grp_small, s_specflag, s_bigd[32], s_nbigd, s_dqr[2];
+    __shared__ uint8_t s_smallm[kMaxTables][ISL_MAX_PROFILES];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     if (seg == a.n_seg) {       // the extra CTA of a host-buffer stream: every chunk all segments have committed goes to the caller's
                                 // (mapped, pinned) result array right away, so the D2H of the results hides behind the rest of the stream
@@ -1148,6 +1223,27 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         }
         s_usable[tid - 32] = u;
     }
+    if (a.spec && tid >= 64 && tid < 96) {      // speculative rounds: the (profile, start) candidates of >= 4 slices as a list; per (table, profile) the slices of its smaller spans
+        const uint32_t l = tid - 64;
+        uint32_t n = 0;
+        for (uint32_t k = 0; k < 4; ++k) {
+            const uint32_t d = tab.desc[k][l];
+            const bool big = (d >> 31) && __popc((d >> 16) & 0xFFu) >= 4;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, big);
+            if (big) { const uint32_t at = n + __popc(b & ((1u << l) - 1u)); if (at < 32) s_bigd[at] = d; }
+            n += __popc(b);
+        }
+        if (l == 0) s_nbigd = min(n, 32u);
+        for (uint32_t i = l; i < kMaxTables * ISL_MAX_PROFILES; i += 32) {
+            const uint32_t t = i / ISL_MAX_PROFILES, pp = i % ISL_MAX_PROFILES;
+            uint32_t u = 0;
+            for (uint32_t k = 0; k < 4; ++k) for (uint32_t x = 0; x < 32; ++x) {
+                const uint32_t d = tab.desc[k][x];
+                if ((d >> 31) && ((d >> 24) & 7u) == t && (d & 15u) == pp && __popc((d >> 16) & 0xFFu) < 4) u |= (d >> 16) & 0xFFu;
+            }
+            s_smallm[t][pp] = (uint8_t)u;
+        }
+    }
     __syncthreads();
     for (uint32_t i = tid; i < n_g; i += kPipeThreads) reinterpret_cast<uint8_t*>(s_occ32)[i] = a.occ[lo_s + i];
     __syncthreads();
@@ -1164,7 +1260,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         klow[k] = (((d >> 4) & 7u) << 8) | (cmask[k] & 0xFFu);            // order-in-row and slot mask; t and profile come from the window key
         reports[k] = valid[k] && ((d >> 4) & 7u) == 0;
     }
-    unsigned long long st_steps = 0, st_jumps = 0, st_visited = 0;
+    unsigned long long st_steps = 0, st_jumps = 0, st_visited = 0, st_sims = 0, st_rounds_sum = 0, st_cells = 0, spec_steps = 0, spec_visited = 0;
 
     // The queues of a chunk (k_partition wrote them before this kernel started) are copied into shared memory with cp.async
     // while the segment still waits for the chunk's token: they do not depend on the heads, so nothing is staged on the
@@ -1267,6 +1363,99 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         // 3. token of the previous segment
         unsigned long long* tr = a.trace ? a.trace + ((size_t)c * a.n_seg + seg) * kTraceWords : nullptr;
         const size_t tok_chunk = (size_t)c * (a.n_seg + 1);
+        const bool spec = a.spec != 0;      // host: only with one sub-segment per stage and no token ring
+        const SpecMem sm = spec_mem(a.spec_mem, spec ? c : 0);
+        const unsigned long long tagb = (unsigned long long)((a.epoch & 0xFFFFFFu) << 8) << 32, tagF = tagb | (0xFFull << 32);
+        if (spec) {     // round 0: what this stage's occupancy can take, per contention group -> predicted entry heads
+            uint16_t* s_mass = reinterpret_cast<uint16_t*>(s_wkey);             // scratch (the windows are staged later): [table][byte] = big << 8 | small-with << 4 | small-without
+            uint16_t* s_mj = s_mass + kMaxTables * 256;                         // [3][kSpecStride]: gathered masses of the stages in front
+            if (tid < ISL_MAX_PROFILES) {
+                const bool on = ((active >> tid) & 1u) && s_maxacc[tid] != 0 && cc->qcnt[tid] != 0;
+                s_qc[tid] = on ? cc->qcnt[tid] : 0u;
+                const uint32_t big = __ballot_sync(0xFFFFu, on && s_minsize[tid] >= 4), small = __ballot_sync(0xFFFFu, on && s_minsize[tid] < 4);
+                if (tid == 0) { s_grp_big = big; s_grp_small = small; s_acc[0] = 0; s_acc[1] = 0; s_acc[2] = 0; }
+            }
+            __syncthreads();
+            {
+                const uint32_t gb = s_grp_big, gs = s_grp_small, nb = s_nbigd;
+                for (uint32_t i = tid; i < kMaxTables * 256; i += kPipeThreads) {
+                    const uint32_t t = i >> 8, o0 = i & 0xFFu;
+                    uint32_t us = 0, o = o0, q = 0;
+                    for (uint32_t m = gs; m; m &= m - 1) us |= s_smallm[t][__ffs(m) - 1];
+                    for (uint32_t it = 0; it < 2; ++it) {       // greedy: the widest span that still fits, twice at most (two quads)
+                        uint32_t best = 0;
+                        for (uint32_t x = 0; x < nb; ++x) {
+                            const uint32_t d = s_bigd[x], mk = (d >> 16) & 0xFFu;
+                            if (((d >> 24) & 7u) == t && ((gb >> (d & 15u)) & 1u) && (o & mk) == 0 && __popc(mk) > __popc(best)) best = mk;
+                        }
+                        if (!best) break;
+                        o |= best; ++q;
+                    }
+                    s_mass[i] = (uint16_t)((q << 8) | (__popc(~o & us) << 4 & 0xF0u) | min(15, __popc(~o0 & us)));
+                }
+            }
+            __syncthreads();
+            {
+                constexpr uint32_t kGpt = kSegMax / kPipeThreads;
+                uint32_t mq = 0, mw = 0, mo = 0;
+#pragma unroll
+                for (uint32_t x = 0; x < kGpt; ++x) {
+                    const uint32_t g = kGpt * tid + x;
+                    if (g < n_sb) {
+                        const uint32_t v = s_mass[s_tab[sb_base + g] * 256u + reinterpret_cast<const uint8_t*>(s_occ32)[sb_base + g]];
+                        mq += v >> 8; mw += (v >> 4) & 15u; mo += v & 15u;
+                    }
+                }
+                mq = __reduce_add_sync(0xFFFFFFFFu, mq); mw = __reduce_add_sync(0xFFFFFFFFu, mw); mo = __reduce_add_sync(0xFFFFFFFFu, mo);
+                if (lane == 0) { atomicAdd(&s_acc[0], mq); atomicAdd(&s_acc[1], mw); atomicAdd(&s_acc[2], mo); }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                st_relaxed_gpu_u64(sm.m + seg * 2, tagb | s_acc[0]);
+                st_relaxed_gpu_u64(sm.m + seg * 2 + 1, tagb | (min(s_acc[1], 0xFFFFu) << 16) | min(s_acc[2], 0xFFFFu));
+            }
+            if (tid < seg) {        // masses of every stage in front of this one
+                const unsigned long long t0 = globaltimer_ns();
+                unsigned long long w0, w1;
+                uint32_t spins = 0;
+                while (true) {
+                    w0 = ld_relaxed_gpu_u64(sm.m + tid * 2); w1 = ld_relaxed_gpu_u64(sm.m + tid * 2 + 1);
+                    if ((w0 >> 32) == (tagb >> 32) && (w1 >> 32) == (tagb >> 32)) break;
+                    if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
+                }
+                s_mj[tid] = (uint16_t)w0; s_mj[kSpecStride + tid] = (uint16_t)(w1 >> 16); s_mj[2 * kSpecStride + tid] = (uint16_t)w1;
+            }
+            __syncthreads();
+            if (tid < 32) {         // the big group takes its placements until its queues run dry; the small group fills what is left
+                uint32_t totb = 0, tots = 0;
+                for (uint32_t m = s_grp_big; m; m &= m - 1) totb += s_qc[__ffs(m) - 1];
+                for (uint32_t m = s_grp_small; m; m &= m - 1) { const uint32_t pp = __ffs(m) - 1; tots += s_qc[pp] * s_minsize[pp]; }
+                constexpr uint32_t kPer = (kSpecStride + 31) / 32;
+                uint32_t ql = 0;
+                for (uint32_t x = 0; x < kPer; ++x) { const uint32_t j = lane * kPer + x; if (j < seg) ql += s_mj[j]; }
+                uint32_t incl = ql;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+                uint32_t run = incl - ql, r = 0;
+                for (uint32_t x = 0; x < kPer; ++x) {
+                    const uint32_t j = lane * kPer + x;
+                    if (j < seg) { r += run < totb ? s_mj[kSpecStride + j] : s_mj[2 * kSpecStride + j]; run += s_mj[j]; }
+                }
+                r = __reduce_add_sync(0xFFFFFFFFu, r);
+                const uint32_t Q = min(__shfl_sync(0xFFFFFFFFu, incl, 31), totb), R = min(r, tots);
+                if (lane < ISL_MAX_PROFILES) s_specH[lane] = seg == 0 && a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + lane] : 0u;
+                __syncwarp();
+                if (lane == 0 && seg > 0) {
+                    spec_spread(s_specH, s_qc, s_minsize, s_grp_big, Q, false);
+                    spec_spread(s_specH, s_qc, s_minsize, s_grp_small, R, true);
+                }
+            }
+            __syncthreads();
+        }
+        uint32_t rnd = 1;
+        bool c_prev = seg == 0, need_sim = true, idle_break = false;
+        while (true) {      // one pass unless the stage speculates
+        if (need_sim) {
         // Inside a GPU a token is self-validating: every head word carries the call's 15-bit epoch tag above its 17 bits of payload
         // (heads <= 65 536), so there is no separate flag, no fence on the producer side and no second round trip on this side —
         // lanes 0..15 of warp 0 each poll their own word of the previous segment's token or of the chunk's 'done' record (whichever
@@ -1277,7 +1466,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             bool from_done = false;
             const uint32_t tag = a.epoch & 0x7FFFu;
             stamp_if(tr && tid == 0, tr + 0);
-            if (sb > 0) {               // behind the first sub-segment the heads are the ones its chain left
+            if (spec) {                 // the predicted (or, at stage 0, the true) token
+                if (tid < ISL_MAX_PROFILES) h = s_specH[tid];
+            } else if (sb > 0) {        // behind the first sub-segment the heads are the ones its chain left
                 if (tid < ISL_MAX_PROFILES) h = s_heads[tid] + s_pop[tid];
             } else if (seg > 0) {
                 const uint32_t* pt = a.tokens + (tok_chunk + seg - 1) * kTokStride + (tid & 15u);
@@ -1320,7 +1511,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             }
             // nothing placeable is pending any more: tell every later segment at once instead of relaying hop by hop
             const bool idle = __ballot_sync(0xFFFFFFFFu, left != 0) == 0;
-            if (idle && !all_done && tid < ISL_MAX_PROFILES) st_relaxed_gpu(a.tokens + (tok_chunk + a.n_seg) * kTokStride + tid, (tag << 17) | h);
+            if (idle && !all_done && !spec && tid < ISL_MAX_PROFILES) st_relaxed_gpu(a.tokens + (tok_chunk + a.n_seg) * kTokStride + tid, (tag << 17) | h);
             if (tid == 0) s_idle = idle ? 1u : 0u;
             uint32_t incl = wn + kWinPad;                       // INF sentinels close every window
 #pragma unroll
@@ -1329,7 +1520,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         }
         __syncthreads();
         stamp_if(tr && tid == 0, tr + 8);
-        if (s_idle) {       // pass-through: the token (unchanged heads) still reaches the next rank / the caller from the last segment
+        if (s_idle && spec) { if (tid == 0) s_nlog = 0; }       // nothing pending at these heads: the exit equals the entry
+        else if (s_idle) {  // pass-through: the token (unchanged heads) still reaches the next rank / the caller from the last segment
             if (warp == 0) {
                 const bool last = seg == a.n_seg - 1;
                 uint32_t* tok = a.tokens + (tok_chunk + seg) * kTokStride;
@@ -1346,8 +1538,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 }
             }
             __syncthreads();
+            idle_break = true;
             break;              // the remaining sub-segments have nothing to take either
         }
+        if (!s_idle) {
         {   // windows of ready-made keys t << 15 | profile << 11, each closed by two INF sentinels — converted from the shared copy of
             // the queues (a shared-memory round trip per round instead of an L2 one), only for profiles that own candidates
             const uint32_t npl = s_nplist;
@@ -1492,7 +1686,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             stamp_if(tr && lane == 0, tr + 5);
             store_if(tr && lane == 0, tr + 6, nlog);
             store_if(tr && lane == 0, tr + 7, (st_jumps - jumps0) | ((unsigned long long)(((ca - sa_cand) >> 2) - 2) << 32));
-            st_steps += nlog; st_visited += ((ca - sa_cand) >> 2) - 2;
+            if (!spec) { st_steps += nlog; st_visited += ((ca - sa_cand) >> 2) - 2; }
+            else { spec_steps = nlog; spec_visited = ((ca - sa_cand) >> 2) - 2; ++st_sims; }
 #pragma unroll
             for (int k = 0; k < K; ++k) if (reports[k]) s_pop[cprof[k]] = min((wa[k] - wa0[k] - 12) >> 2, s_wn[cprof[k]]);
             __syncwarp();
@@ -1500,7 +1695,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             uint32_t* tok = a.tokens + (tok_chunk + seg) * kTokStride;
             const bool last = seg == a.n_seg - 1;
             uint32_t* peer = last && a.outbox ? a.outbox + (size_t)c * kTokStride : nullptr;
-            if (last_sub && lane < ISL_MAX_PROFILES) {
+            if (last_sub && lane < ISL_MAX_PROFILES && !spec) {
                 const uint32_t h = s_heads[lane] + s_pop[lane];
                 st_relaxed_gpu(tok + lane, ((a.epoch & 0x7FFFu) << 17) | h);       // the next segment starts
                 if (last && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + lane] = h;
@@ -1512,7 +1707,103 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 if (tr) tr[2] = globaltimer_ns();
             }
         }
+        }   // !s_idle
         __syncthreads();
+        }   // need_sim
+        if (!spec) break;
+        {   // ---- the round's exchange: publish exit heads and consumed masses, read the predecessor's exit and every earlier stage's masses
+            const unsigned long long tagr = tagb | ((unsigned long long)rnd << 32);
+            if (tid < 32) {
+                uint32_t X = 0, dq = 0, dr = 0;
+                if (tid < ISL_MAX_PROFILES) {
+                    const uint32_t pop = s_pop[tid];
+                    X = s_heads[tid] + pop; s_specX[tid] = X;
+                    if ((s_grp_big >> tid) & 1u) dq = pop;
+                    if ((s_grp_small >> tid) & 1u) dr = pop * s_minsize[tid];
+                }
+                dq = __reduce_add_sync(0xFFFFFFFFu, dq); dr = __reduce_add_sync(0xFFFFFFFFu, dr);
+                if (rnd >= 3 && seg + 1 < a.n_seg) {        // the slot of round rnd - 2 is overwritten: the successor must have read it
+                    const unsigned long long t0 = globaltimer_ns();
+                    uint32_t spins = 0;
+                    while (true) {
+                        const unsigned long long w = ld_relaxed_gpu_u64(sm.ack + seg + 1);
+                        if ((uint32_t)(w >> 32) == a.epoch && (uint32_t)w + 2u >= rnd) break;
+                        if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
+                    }
+                }
+                if (tid < ISL_MAX_PROFILES) st_relaxed_gpu_u64(sm.x + ((size_t)seg * 2 + (rnd & 1u)) * 16 + tid, tagr | X);
+                if (tid == 16) st_relaxed_gpu_u64(sm.d + (size_t)rnd * kSpecStride + seg, tagr | ((c_prev ? 1u : 0u) << 31) | (dq << 13) | dr);
+                if (tid == 0) { s_dqr[0] = dq; s_dqr[1] = dr; s_acc[0] = 0; s_acc[1] = 0; }
+            }
+            __syncthreads();
+            bool cbit = true;
+            if (tid < seg) {
+                const unsigned long long t0 = globaltimer_ns();
+                unsigned long long w;
+                uint32_t spins = 0;
+                while (true) {
+                    w = ld_relaxed_gpu_u64(sm.d + (size_t)rnd * kSpecStride + tid);
+                    if ((w >> 32) == (tagr >> 32)) { cbit = (w >> 31) & 1u; break; }
+                    w = ld_relaxed_gpu_u64(sm.df + tid);         // a certified stage no longer publishes rounds: its final record stands for all rounds from then on
+                    if ((w >> 32) == (tagF >> 32) && ((w >> 24) & 0xFFu) <= rnd) break;
+                    if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
+                }
+                atomicAdd(&s_acc[0], (uint32_t)(w >> 13) & 0x7FFu);
+                atomicAdd(&s_acc[1], (uint32_t)w & 0x1FFFu);
+            }
+            if (seg > 0 && tid >= 192 && tid < 192 + ISL_MAX_PROFILES) {
+                const uint32_t i = tid - 192;
+                const unsigned long long t0 = globaltimer_ns();
+                unsigned long long w;
+                uint32_t spins = 0;
+                while (true) {
+                    w = ld_relaxed_gpu_u64(sm.x + ((size_t)(seg - 1) * 2 + (rnd & 1u)) * 16 + i);
+                    if ((w >> 32) == (tagr >> 32)) break;
+                    w = ld_relaxed_gpu_u64(sm.xf + (size_t)(seg - 1) * 16 + i);
+                    if ((w >> 32) == (tagF >> 32) && ((w >> 24) & 0xFFu) <= rnd) break;
+                    if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
+                }
+                s_specXp[i] = (uint32_t)w & 0x1FFFFu;
+            }
+            const bool certified = __syncthreads_and(cbit) && c_prev;
+            if (seg > 0 && tid == 192) st_relaxed_gpu_u64(sm.ack + seg, ((unsigned long long)a.epoch << 32) | (certified ? 0xFFFFu : rnd));
+            if (certified) {    // every entry up to mine was the true token one round ago and has not moved since: the log in shared memory is THE log
+                if (tid < ISL_MAX_PROFILES) {
+                    st_relaxed_gpu_u64(sm.xf + (size_t)seg * 16 + tid, tagF | (rnd << 24) | s_specX[tid]);
+                    if (seg == a.n_seg - 1 && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + tid] = s_specX[tid];
+                }
+                if (tid == 16) st_relaxed_gpu_u64(sm.df + seg, tagF | (rnd << 24) | (s_dqr[0] << 13) | s_dqr[1]);
+                if (tid == 0) { st_steps += spec_steps; st_visited += spec_visited; if (seg == a.n_seg - 1) { st_rounds_sum += rnd; ++st_cells; } if (tr) { tr[2] = globaltimer_ns(); tr[6] = s_nlog; tr[11] = rnd; } }
+                break;
+            }
+            if (tid < 32) {     // c for the next round; the corrected prediction
+                const bool same = tid >= ISL_MAX_PROFILES || s_specH[tid] == s_specXp[tid];
+                const bool cnow = __all_sync(0xFFFFFFFFu, same);
+                uint32_t mq = 0, mr = 0, hold = 0;
+                if (tid < ISL_MAX_PROFILES) {
+                    hold = s_specH[tid];
+                    const uint32_t xp = s_specXp[tid];
+                    if ((s_grp_big >> tid) & 1u) mq = xp;
+                    if ((s_grp_small >> tid) & 1u) mr = xp * s_minsize[tid];
+                    s_specH[tid] = xp;
+                }
+                mq = __reduce_add_sync(0xFFFFFFFFu, mq); mr = __reduce_add_sync(0xFFFFFFFFu, mr);
+                __syncwarp();
+                if (tid == 0) {
+                    spec_spread(s_specH, s_qc, s_minsize, s_grp_big, (long long)s_acc[0] - (long long)mq, false);
+                    spec_spread(s_specH, s_qc, s_minsize, s_grp_small, (long long)s_acc[1] - (long long)mr, true);
+                }
+                __syncwarp();
+                const bool moved = tid < ISL_MAX_PROFILES && s_specH[tid] != hold;
+                const bool changed = __any_sync(0xFFFFFFFFu, moved);
+                if (tid == 0) s_specflag = (cnow ? 1u : 0u) | (changed ? 2u : 0u);
+            }
+            __syncthreads();
+            c_prev = s_specflag & 1u; need_sim = s_specflag & 2u;
+            if (++rnd >= kSpecRounds - 1) __trap();      // cannot happen: every round certifies at least one more stage
+        }
+        }   // rounds
+        if (idle_break) break;
         if (last_sub && c + 1 < a.n_chunks && !a.ready && !a.window) { queue_load_async(c + 1); prefetched = true; }   // the chain is done with the queues: fetch the next chunk's behind the commit
         {   // 6. commit
             const uint32_t nlog = s_nlog;
@@ -1539,6 +1830,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         atomicAdd(&a.stats->steps, st_steps);
         atomicAdd(&a.stats->visited, st_visited);
         atomicAdd(&a.stats->jumps, st_jumps);
+    }
+    if (tid == 0 && a.spec) {
+        atomicAdd(&a.stats->spec_sims, st_sims);
+        atomicAdd(&a.stats->spec_rounds, st_rounds_sum);
+        atomicAdd(&a.stats->spec_cells, (unsigned long long)st_cells);
     }
 }
 

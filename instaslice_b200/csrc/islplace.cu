@@ -85,10 +85,13 @@ struct isl_engine {
     size_t scratch_bytes = 0;
     unsigned long long wait_ns = 20000000000ull;   // a starved device-side wait traps after this long (ISL_WAIT_SECONDS overrides the 20 s)
     uint32_t window = 0;             // causal window of stream calls (isl_set_causal_window): chunk c starts after chunk c - window is committed
+    uint32_t spec_mode = ISL_SPEC_AUTO;     // speculative rounds (isl_set_speculation); ISL_SPEC=0|1 in the environment overrides
+    unsigned long long* d_spec = nullptr; uint32_t cap_spec = 0, spec_hi = 0;    // record memory of the rounds: kSpecWordsPerChunk words per chunk
     // open stream (isl_stream_open / _submit / _wait / _close): one persistent k_pipeline, batches arrive while it runs
     struct Open {
         bool active = false, launched = false;
         uint32_t max_batches = 0, submitted = 0, epoch = 0, seg = 0, n_seg = 0, sub = 0, q_stride = 0, free_stride = 0, tiles_per_batch = 0;
+        bool spec = false;
         uint32_t* h_done = nullptr; uint32_t* d_done_host = nullptr; uint32_t cap_done = 0;   // mapped pinned: [batch] = epoch once its results are in host memory
         ChunkDesc* h_chunks = nullptr; TileDesc* h_tiles = nullptr; uint32_t cap_desc = 0;       // pinned staging of the per-batch descriptors
     } open;
@@ -340,7 +343,7 @@ int grow(isl_engine* e, T** buf, uint32_t* cap, size_t need, size_t elems_per_un
 
 // Segment geometry of the pipeline for a stream of n_chunks chunks of ~avg_chunk requests.  ISL_ERANGE: the inventory does not fit the
 // co-resident CTAs (or the tables need too many candidates per segment) — the caller takes the chunk-by-chunk path.
-int plan_pipeline(isl_engine* e, uint32_t n_chunks, double avg_chunk, bool want_feed, uint32_t* seg_out, uint32_t* n_seg_out, uint32_t* sub_out) {
+int plan_pipeline(isl_engine* e, uint32_t n_chunks, double avg_chunk, bool want_feed, uint32_t* seg_out, uint32_t* n_seg_out, uint32_t* sub_out, bool spec = false) {
     if (int rc = query_coresident(e)) return rc;
     const uint32_t range = e->hi - e->lo;
     uint32_t total_cand = 0;
@@ -356,6 +359,7 @@ int plan_pipeline(isl_engine* e, uint32_t n_chunks, double avg_chunk, bool want_
         const double s_opt = std::sqrt(std::max(1.0, (double)n_chunks - 1.0) * d_est * (0.041 / 2.3));
         target = (uint32_t)std::min(148.0, std::max(1.0, std::floor(s_opt + 0.5)));
     }
+    if (spec) target = 148;      // speculative rounds: every stage works in every round — as many (short) segments as there are SMs
     if (const char* v = getenv("ISL_PIPE_SEGMENTS")) target = std::max(1u, (uint32_t)strtoul(v, nullptr, 10));
     target = std::min(target, (uint32_t)std::max(1, e->max_coresident));
     // fed host streams run their per-batch pre-pass kernels WHILE the pipeline is resident: keep kFeedReserve SMs free of pipeline
@@ -378,6 +382,25 @@ int plan_pipeline(isl_engine* e, uint32_t n_chunks, double avg_chunk, bool want_
 }
 
 constexpr unsigned long long kOpenWaitNs = 600000000000ull;     // open streams may idle between batches: 10 min
+
+// Speculative rounds (isl_kernels.cuh): wanted for this call?
+bool want_spec(isl_engine* e, uint32_t n_batches, uint32_t window, bool ring, bool legacy_token) {
+    if (ring || legacy_token || kPipeThreads < 208) return false;
+    uint32_t mode = e->spec_mode;
+    if (const char* v = getenv("ISL_SPEC")) mode = atoi(v) ? ISL_SPEC_ON : ISL_SPEC_OFF;
+    if (mode == ISL_SPEC_OFF) return false;
+    if (mode == ISL_SPEC_ON) return true;
+    return n_batches == 1 || (window >= 1 && window <= 3);
+}
+// record memory for n_chunks chunks; the words carry the call epoch (24 bits) — cleared when (re)allocated and when those bits wrap
+int prepare_spec(isl_engine* e, uint32_t n_chunks, uint32_t epoch, cudaStream_t st) {
+    const uint32_t before = e->cap_spec;
+    if (int rc = grow(e, &e->d_spec, &e->cap_spec, n_chunks, kSpecWordsPerChunk)) return rc;
+    const bool fresh = e->cap_spec != before, wrapped = (epoch >> 24) != e->spec_hi;
+    if (fresh || wrapped) ISL_CUDA(e, cudaMemsetAsync(e->d_spec, 0, (size_t)e->cap_spec * kSpecWordsPerChunk * sizeof(unsigned long long), st));
+    e->spec_hi = epoch >> 24;
+    return ISL_OK;
+}
 
 // Resolve a stream of batches (semantics: one batch after the other).  Enqueues only.
 // h_in / h_out (isl_place_stream): the caller's host buffers.  With the segment pipeline the batches are copied and pre-passed one
@@ -414,10 +437,19 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     const bool want_feed = h_in && h_out && n_batches >= 2 && !(e->cfg.flags & (ISL_FLAG_TIMING | ISL_FLAG_TRACE)) && !ring && !getenv("ISL_NO_FEED") &&
                            !getenv("CUDA_INJECTION64_PATH") && !getenv("CUDA_LAUNCH_BLOCKING") && !getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
     uint32_t seg = 0, n_seg = 0, sub = 0;
+    bool spec = false;
     if (pipeline) {
-        const int prc = plan_pipeline(e, n_chunks, (double)total / n_chunks, want_feed, &seg, &n_seg, &sub);
-        if (prc == ISL_ECUDA) return prc;
-        if (prc != ISL_OK) { if (ring) return ISL_ERANGE; pipeline = false; }
+        const uint32_t win = (ring && e->ring_world == 0) ? 0u : e->window;
+        if (want_spec(e, n_batches, win, ring, legacy_token)) {      // speculative rounds need one sub-segment per stage
+            const int src = plan_pipeline(e, n_chunks, (double)total / n_chunks, want_feed, &seg, &n_seg, &sub, true);
+            if (src == ISL_ECUDA) return src;
+            spec = src == ISL_OK && seg == sub && n_seg <= 148 && n_seg >= 2;
+        }
+        if (!spec) {
+            const int prc = plan_pipeline(e, n_chunks, (double)total / n_chunks, want_feed, &seg, &n_seg, &sub);
+            if (prc == ISL_ECUDA) return prc;
+            if (prc != ISL_OK) { if (ring) return ISL_ERANGE; pipeline = false; }
+        }
     }
     if (!pipeline) {       // one batch after the other through the single-chain path
         if (int rc = copy_in_whole()) return rc;
@@ -547,6 +579,10 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     }
     args.trace = (e->cfg.flags & ISL_FLAG_TRACE) ? e->d_trace : nullptr;
     args.inbox = ring && e->has_prev ? e->d_inbox : nullptr; args.outbox = ring ? e->d_outbox : nullptr; args.xepoch = xepoch;
+    if (spec) {
+        if (int rc2 = prepare_spec(e, n_chunks, epoch, e->stream)) return rc2;
+        args.spec = 1; args.spec_mem = e->d_spec;
+    }
     int rc;
     const bool p15 = e->prof.n == ISL_MAX_PROFILES;      // profile index 15 in use: the pop test needs the slower, INF-safe form
     switch (e->n_cand_slots) {
@@ -714,7 +750,7 @@ int isl_destroy(isl_engine* e) {
         cudaFree(e->d_occ); cudaFree(e->d_lut); cudaFree(e->d_feas); cudaFree(e->d_req); cudaFree(e->d_res);
         cudaFree(e->d_q); cudaFree(e->d_tile_counts); cudaFree(e->d_cand); cudaFree(e->d_log); cudaFree(e->d_sweep_counts);
         cudaFree(e->d_ctrl); cudaFree(e->d_scratch);
-        cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens);
+        cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens); cudaFree(e->d_spec);
         cudaFree(e->d_free_acc); cudaFree(e->d_tiles);
         if (e->d_outbox && !e->outbox_local) cudaIpcCloseMemHandle(e->d_outbox);
         cudaFree(e->d_inbox); cudaFree(e->d_trace); cudaFree(e->d_bf_bitmaps); cudaFree(e->d_ready); cudaFree(e->d_done_cnt); cudaFree(e->d_occ_snap);
@@ -1199,6 +1235,7 @@ int isl_get_stats(isl_engine* e, isl_stats* out) {
     ISL_CUDA(e, cudaMemcpyAsync(&c, e->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, e->stream));
     ISL_CUDA(e, cudaStreamSynchronize(e->stream));
     e->st.placed = c.placed; e->st.freed = c.freed; e->st.no_capacity = c.allocs - c.placed; e->st.chain_steps = c.steps; e->st.chain_gpus_visited = c.visited; e->st.chain_jumps = c.jumps; e->st.scan_placed = c.scanned;
+    e->st.spec_chunks = c.spec_cells; e->st.spec_rounds = c.spec_rounds; e->st.spec_sims = c.spec_sims;
     *out = e->st;
     return ISL_OK;
 }
@@ -1269,6 +1306,14 @@ int isl_set_causal_window(isl_engine* e, uint32_t window) {
     if (e->open.active) return ISL_ESTATE;
     std::lock_guard<std::mutex> lk(e->mu);
     e->window = window;
+    return ISL_OK;
+}
+
+int isl_set_speculation(isl_engine* e, uint32_t mode) {
+    if (!e || mode > ISL_SPEC_ON) return ISL_EINVAL;
+    if (e->open.active) return ISL_ESTATE;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->spec_mode = mode;
     return ISL_OK;
 }
 
@@ -1343,7 +1388,19 @@ int isl_stream_open(isl_engine* e, uint32_t max_batches) {
     const uint32_t pc = e->pipe_chunk;
     if ((uint64_t)max_batches * pc > e->cfg.max_batch) return ISL_ERANGE;       // every batch owns a slot of the staging buffers
     uint32_t seg = 0, n_seg = 0, sub = 0;
-    if (int rc = plan_pipeline(e, std::max(2u, max_batches), (double)pc, true, &seg, &n_seg, &sub)) return rc;
+    // speculative rounds: the caller says (isl_set_causal_window) that it keeps at most 1..3 batches in flight, or asks for them outright
+    o.spec = false;
+    {
+        uint32_t mode = e->spec_mode;
+        if (const char* v = getenv("ISL_SPEC")) mode = atoi(v) ? ISL_SPEC_ON : ISL_SPEC_OFF;
+        if (kPipeThreads >= 208 && (mode == ISL_SPEC_ON || (mode == ISL_SPEC_AUTO && e->window >= 1 && e->window <= 3)) &&
+            (uint64_t)max_batches * kSpecWordsPerChunk * 8ull <= (1ull << 30)) {
+            const int src = plan_pipeline(e, std::max(2u, max_batches), (double)pc, true, &seg, &n_seg, &sub, true);
+            if (src == ISL_ECUDA) return src;
+            o.spec = src == ISL_OK && seg == sub && n_seg <= 148 && n_seg >= 2 && n_seg + 1 + kFeedReserve <= (uint32_t)e->max_coresident;
+        }
+    }
+    if (!o.spec) if (int rc = plan_pipeline(e, std::max(2u, max_batches), (double)pc, true, &seg, &n_seg, &sub)) return rc;
     if (n_seg + 1 + kFeedReserve > (uint32_t)e->max_coresident) return ISL_ERANGE;  // the feed kernels need SMs next to the resident pipeline
     o.seg = seg; o.n_seg = n_seg; o.sub = sub; o.max_batches = max_batches; o.submitted = 0; o.launched = false;
     o.q_stride = pc + kQPad * ISL_MAX_PROFILES; o.free_stride = (uint32_t)e->occ_bytes; o.tiles_per_batch = pc / kTile;
@@ -1386,6 +1443,7 @@ int isl_stream_open(isl_engine* e, uint32_t max_batches) {
     if ((epoch & 0x7FFFu) == 1 && epoch != 1 && e->d_tokens)
         ISL_CUDA(e, cudaMemsetAsync(e->d_tokens, 0, (size_t)e->cap_tokens * kTokStride * sizeof(uint32_t), e->stream));
     o.epoch = epoch;
+    if (o.spec) if (int rc = prepare_spec(e, max_batches, epoch, e->stream)) return rc;
     // the feed stream starts behind whatever the engine's stream still holds
     ISL_CUDA(e, cudaEventRecord(e->ev_feed, e->stream));
     ISL_CUDA(e, cudaStreamWaitEvent(e->feed_stream, e->ev_feed, 0));
@@ -1432,6 +1490,7 @@ int isl_stream_submit(isl_engine* e, uint32_t n, const isl_request* in, isl_resu
         args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
         args.q_stride = o.q_stride; args.free_stride = o.free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab;
         args.out = e->d_res; args.feas = e->d_feas; args.stats = e->d_ctrl;
+        if (o.spec) { args.spec = 1; args.spec_mem = e->d_spec; }
         int rc;
         const bool p15 = e->prof.n == ISL_MAX_PROFILES;
         switch (e->n_cand_slots) {

@@ -28,6 +28,7 @@ QUIRKS_REF_EXACT, QUIRKS_FIXED = 3, 0
 OP_ALLOC, OP_FREE, OP_NOOP = 0, 1, 2
 ST_PLACED, ST_NO_CAPACITY, ST_BAD_PROFILE, ST_FREED, ST_BAD_SPAN, ST_NOOP = 0, 1, 2, 3, 4, 5
 FLAG_TIMING, FLAG_NO_PIPELINE, FLAG_FORCE_PIPELINE, FLAG_TRACE, FLAG_NO_SMALL, FLAG_ALL_NODES = 1, 2, 4, 8, 16, 32
+SPEC_AUTO, SPEC_OFF, SPEC_ON = 0, 1, 2
 
 # ---- record layouts -------------------------------------------------------------------------
 REQUEST_DTYPE = np.dtype([("handle", "<u4"), ("profile", "u1"), ("op", "u1"), ("start", "u1"), ("size", "u1")])
@@ -48,7 +49,8 @@ class Stats(C.Structure):
     _fields_ = [("batches", C.c_uint64), ("requests", C.c_uint64), ("placed", C.c_uint64), ("no_capacity", C.c_uint64),
                 ("freed", C.c_uint64), ("kernel_launches", C.c_uint64), ("chain_steps", C.c_uint64),
                 ("chain_gpus_visited", C.c_uint64), ("chain_jumps", C.c_uint64), ("ms_free", C.c_double), ("ms_partition", C.c_double),
-                ("ms_sweep", C.c_double), ("ms_commit", C.c_double), ("ms_total", C.c_double), ("scan_placed", C.c_uint64)]
+                ("ms_sweep", C.c_double), ("ms_commit", C.c_double), ("ms_total", C.c_double), ("scan_placed", C.c_uint64),
+                ("spec_chunks", C.c_uint64), ("spec_rounds", C.c_uint64), ("spec_sims", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -60,7 +62,7 @@ EXPORTED_SYMBOLS = [
     "isl_snapshot_occupancy", "isl_restore_occupancy", "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_place_stream", "isl_place_stream_device", "isl_free_batch",
     "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_ipc_inbox_handle", "isl_ipc_connect", "isl_connect_local", "isl_place_stream_partitioned", "isl_device_occupancy", "isl_get_stats", "isl_read_trace",
     "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
-    "isl_place_batch_range", "isl_stream_open", "isl_stream_submit", "isl_stream_wait", "isl_stream_close", "isl_set_causal_window",
+    "isl_place_batch_range", "isl_stream_open", "isl_stream_submit", "isl_stream_wait", "isl_stream_close", "isl_set_causal_window", "isl_set_speculation",
     "isl_host_alloc", "isl_host_free", "isl_device_results", "isl_ipc_results_handle", "isl_ipc_connect_owner", "isl_connect_owner_local", "isl_set_ring_world", "isl_capacity", "isl_what_if",
 ]
 
@@ -116,6 +118,7 @@ def load_library(path: str = LIB_PATH):
         "isl_stream_wait": (C.c_int, [p, C.c_uint32]),
         "isl_stream_close": (C.c_int, [p]),
         "isl_set_causal_window": (C.c_int, [p, C.c_uint32]),
+        "isl_set_speculation": (C.c_int, [p, C.c_uint32]),
         "isl_host_alloc": (p, [C.c_size_t]),
         "isl_host_free": (None, [p]),
         "isl_device_results": (p, [p]),
@@ -336,6 +339,10 @@ class Engine:
 
     def set_causal_window(self, window: int):
         self._check(self._lib.isl_set_causal_window(self._h, window), "isl_set_causal_window")
+
+    def set_speculation(self, mode: int):
+        """SPEC_AUTO / SPEC_OFF / SPEC_ON: speculative rounds inside the segment pipeline (include/islplace.h)."""
+        self._check(self._lib.isl_set_speculation(self._h, mode), "isl_set_speculation")
 
     def free_batch(self, spans: np.ndarray):
         spans = np.ascontiguousarray(spans, dtype=SPAN_DTYPE)

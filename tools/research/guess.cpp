@@ -39,6 +39,11 @@ int main(int argc, char** argv) {
                 // small group: balanced time
                 { uint32_t lo = 0, hi = n; while (lo < hi) { uint32_t mid = (lo + hi) / 2; uint64_t c = 0; for (int p : small) c += (uint64_t)cnt_before(p, mid) * psize(p); if (c >= R) hi = mid; else lo = mid + 1; }
                   for (int p : small) h[p] = cnt_before(p, lo); }
+                if (getenv("PROPG")) {
+                    uint64_t nb = 0, ns = 0; for (int p : big) nb += q[p].size(); for (int p : small) ns += (uint64_t)q[p].size() * psize(p);
+                    for (int p : big) h[p] = std::min<uint64_t>(q[p].size(), nb ? (Q * q[p].size() + nb / 2) / nb : 0);
+                    for (int p : small) h[p] = std::min<uint64_t>(q[p].size(), ns ? (R * q[p].size() + ns / 2) / ns : 0);
+                }
                 if (s <= S) H[s] = h;
                 if (g == G) break;
             }
@@ -79,6 +84,21 @@ int main(int argc, char** argv) {
                     dq = std::lround(lq[s] * dq); dr = std::lround(lr[s] * dr);
                 }
                 Heads& h = Hn[s + 1];
+                if (getenv("PROPA")) {
+                    long nb = 0, ns = 0; for (int p : big) nb += q[p].size(); for (int p : small) ns += (long)q[p].size() * psize(p);
+                    auto clampadd = [&](int p, long d) { long v = (long)h[p] + d; v = std::max(0l, std::min<long>(v, q[p].size())); h[p] = v; };
+                    // exact in mass: the heaviest profiles first, the lightest one takes the remainder
+                    auto spread = [&](std::vector<int> grp, long d, long tot) {
+                        std::sort(grp.begin(), grp.end(), [&](int x, int y) { return psize(x) > psize(y) || (psize(x) == psize(y) && x < y); });
+                        for (size_t i = 0; i < grp.size(); ++i) { int p = grp[i]; long w = psize(p);
+                            long dp = i + 1 == grp.size() ? d / w : (tot ? std::lround((double)d * q[p].size() / tot) : 0);
+                            clampadd(p, dp); d -= dp * w; tot -= (long)q[p].size() * w; }
+                    };
+                    { std::vector<int> b2 = big; long d = dq, tot = nb; std::sort(b2.begin(), b2.end());
+                      for (size_t i = 0; i < b2.size(); ++i) { int p = b2[i]; long dp = i + 1 == b2.size() ? d : (tot ? std::lround((double)d * q[p].size() / tot) : 0); clampadd(p, dp); d -= dp; tot -= q[p].size(); } }
+                    spread(small, dr, ns);
+                    continue;
+                }
                 // big group: advance / retreat |dq| requests in merged time order
                 while (dq > 0) { int bp = -1; uint32_t bt = 0xFFFFFFFFu; for (int p : big) if (h[p] < q[p].size() && q[p][h[p]] < bt) { bt = q[p][h[p]]; bp = p; } if (bp < 0) break; ++h[bp]; --dq; }
                 while (dq < 0) { int bp = -1; long bt = -1; for (int p : big) if (h[p] > 0 && (long)q[p][h[p] - 1] > bt) { bt = q[p][h[p] - 1]; bp = p; } if (bp < 0) break; --h[bp]; ++dq; }
