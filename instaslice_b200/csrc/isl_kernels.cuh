@@ -982,6 +982,8 @@ struct PipeArgs {
     // by round and a stage commits once its entry heads are certified to be the true ones.  Record memory: spec_mem(), kSpecWordsPerChunk per chunk.
     uint32_t spec;
     unsigned long long* spec_mem;
+    unsigned long long* spec_dbg;   // optional [kSpecRounds][8] globaltimer stamps of the rounds of ONE (chunk, stage) cell (ISL_SPEC_DBG=chunk,stage; tools/spec_trace.py)
+    uint32_t spec_dbg_cell;         // chunk << 16 | stage
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1080,44 +1082,27 @@ __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsign
 // Speculative rounds: move the heads of the profiles in `members` so that their mass (sum of weight x head) changes by d — shares
 // proportional to the queue lengths, the heaviest profiles first, the last (lightest) one takes the remainder so that the mass is met
 // exactly whenever the weights allow it.  One thread; h, qc, wsz in shared memory.
-__device__ inline void spec_spread(uint32_t* h, const uint32_t* qc, const uint32_t* wsz, uint32_t members, long long d, bool weighted) {
+__device__ inline void spec_spread(uint32_t* h, const uint32_t* qc, const uint32_t* wsz, uint32_t members, int d, bool weighted) {
     if (d == 0 || members == 0) return;
-    long long tot = 0;
-    for (uint32_t m = members; m; m &= m - 1) { const uint32_t p = __ffs(m) - 1; tot += (long long)qc[p] * (weighted ? wsz[p] : 1u); }
-    for (int pass = weighted ? 0 : 1; pass < 2; ++pass) {
-        for (uint32_t m = members; m; m &= m - 1) {
-            const uint32_t p = __ffs(m) - 1;
-            const long long w = weighted ? wsz[p] : 1u;
-            if (weighted && (pass == 0) != (w > 1)) continue;       // pass 0: spans of 2 and more, pass 1: single slices
-            uint32_t rest = members & ~((2u << p) - 1u);            // members behind p in this pass ...
-            if (weighted) { uint32_t r2 = 0; for (uint32_t x = rest; x; x &= x - 1) { const uint32_t q = __ffs(x) - 1; if ((wsz[q] > 1) == (w > 1)) r2 |= 1u << q; } rest = r2;
-                            if (pass == 0 && !rest) for (uint32_t x = members; x; x &= x - 1) { const uint32_t q = __ffs(x) - 1; if (wsz[q] <= 1) rest |= 1u << q; } }   // ... or in the next one
-            const long long num = d * (long long)qc[p];
-            long long dp = rest ? (tot > 0 ? (num + (num >= 0 ? tot / 2 : -(tot / 2))) / tot : 0) : d / w;
-            const long long v = (long long)h[p] + dp;
-            h[p] = (uint32_t)(v < 0 ? 0 : (v > (long long)qc[p] ? qc[p] : v));
-            d -= dp * w; tot -= (long long)qc[p] * w;
+    // two passes over the members: spans of 2 and more first, single slices last (unweighted groups: one pass); 32-bit / float arithmetic —
+    // |d| <= 2^13, queue lengths <= 2^17, and the shares are a prediction, not a result
+    uint32_t heavy = 0, light = members;
+    if (weighted) { light = 0; for (uint32_t m = members; m; m &= m - 1) { const uint32_t p = __ffs(m) - 1; if (wsz[p] > 1) heavy |= 1u << p; else light |= 1u << p; } }
+    float tot = 0.f;
+    for (uint32_t m = members; m; m &= m - 1) { const uint32_t p = __ffs(m) - 1; tot += (float)(qc[p] * (weighted ? wsz[p] : 1u)); }
+    for (int pass = 0; pass < 2; ++pass) {
+        uint32_t todo = pass == 0 ? heavy : light;
+        while (todo) {
+            const uint32_t p = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int w = weighted ? (int)wsz[p] : 1;
+            const bool last = todo == 0 && (pass == 1 || light == 0);
+            const int dp = last ? d / w : (tot > 0.f ? __float2int_rn((float)d * (float)qc[p] / tot) : 0);
+            const int v = (int)h[p] + dp;
+            h[p] = (uint32_t)(v < 0 ? 0 : (v > (int)qc[p] ? (int)qc[p] : v));
+            d -= dp * w; tot -= (float)(qc[p] * (uint32_t)w);
         }
     }
-}
-
-__device__ __forceinline__ uint32_t lds_u32(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
-__device__ __forceinline__ void sts_v2_if(bool pred, uint32_t sa, uint32_t x, uint32_t y) {
-    asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.v2.u32 [%1], {%2, %3}; }" ::"r"((uint32_t)pred), "r"(sa), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ uint32_t add_if(bool pred, uint32_t x, uint32_t inc) {         // one predicated add instead of select + move
-    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p add.u32 %0, %0, %2; }" : "+r"(x) : "r"((uint32_t)pred), "r"(inc));
-    return x;
-}
-__device__ __forceinline__ uint32_t redux_min_u32(uint32_t v) {
-    uint32_t r;
-    asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
-    return r;
-}
-__device__ __forceinline__ uint32_t lds_u32_if(bool pred, uint32_t sa, uint32_t keep) {   // predicated load: keeps `keep` when !pred
-    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p ld.shared.u32 %0, [%2]; }" : "+r"(keep) : "r"((uint32_t)pred), "r"(sa));
-    return keep;
 }
 
 // Rare path of the decision chain, kept out of line so that the hot loop stays free of divergence-capable constructs:
@@ -1147,7 +1132,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     __shared__ uint32_t s_warp[kPipeThreads / 32], s_ncand, s_nfree, s_nlog, s_idle, s_closed;
     // speculative rounds: predicted entry heads, own / predecessor's exit heads, queue lengths, gathered sums, contention groups
     __shared__ uint32_t s_specH[ISL_MAX_PROFILES], s_specX[ISL_MAX_PROFILES], s_specXp[ISL_MAX_PROFILES], s_qc[ISL_MAX_PROFILES];
-    __shared__ uint32_t s_acc[4], s_grp_big, s_grp_small, s_specflag, s_bigd[32], s_nbigd, s_dqr[2];
+    __shared__ uint32_t s_acc[4], s_grp_big, s_grp_small, s_specflag, s_bigd[32], s_nbigd, s_dqr[2], s_us[kMaxTables], s_qo[ISL_MAX_PROFILES];
     __shared__ uint8_t s_smallm[kMaxTables][ISL_MAX_PROFILES];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     if (seg == a.n_seg) {       // the extra CTA of a host-buffer stream: every chunk all segments have committed goes to the caller's
@@ -1367,43 +1352,35 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         const SpecMem sm = spec_mem(a.spec_mem, spec ? c : 0);
         const unsigned long long tagb = (unsigned long long)((a.epoch & 0xFFFFFFu) << 8) << 32, tagF = tagb | (0xFFull << 32);
         if (spec) {     // round 0: what this stage's occupancy can take, per contention group -> predicted entry heads
-            uint16_t* s_mass = reinterpret_cast<uint16_t*>(s_wkey);             // scratch (the windows are staged later): [table][byte] = big << 8 | small-with << 4 | small-without
-            uint16_t* s_mj = s_mass + kMaxTables * 256;                         // [3][kSpecStride]: gathered masses of the stages in front
+            uint16_t* s_mj = reinterpret_cast<uint16_t*>(s_wkey);               // scratch (the windows are staged later): [3][kSpecStride] gathered masses of the stages in front
             if (tid < ISL_MAX_PROFILES) {
                 const bool on = ((active >> tid) & 1u) && s_maxacc[tid] != 0 && cc->qcnt[tid] != 0;
-                s_qc[tid] = on ? cc->qcnt[tid] : 0u;
+                s_qc[tid] = on ? cc->qcnt[tid] : 0u; s_qo[tid] = cc->qoff[tid];
                 const uint32_t big = __ballot_sync(0xFFFFu, on && s_minsize[tid] >= 4), small = __ballot_sync(0xFFFFu, on && s_minsize[tid] < 4);
                 if (tid == 0) { s_grp_big = big; s_grp_small = small; s_acc[0] = 0; s_acc[1] = 0; s_acc[2] = 0; }
+                if (tid < kMaxTables) { uint32_t us = 0; for (uint32_t m = small; m; m &= m - 1) us |= s_smallm[tid][__ffs(m) - 1]; s_us[tid] = us; }   // slices the small group can use, per table
             }
             __syncthreads();
-            {
-                const uint32_t gb = s_grp_big, gs = s_grp_small, nb = s_nbigd;
-                for (uint32_t i = tid; i < kMaxTables * 256; i += kPipeThreads) {
-                    const uint32_t t = i >> 8, o0 = i & 0xFFu;
-                    uint32_t us = 0, o = o0, q = 0;
-                    for (uint32_t m = gs; m; m &= m - 1) us |= s_smallm[t][__ffs(m) - 1];
-                    for (uint32_t it = 0; it < 2; ++it) {       // greedy: the widest span that still fits, twice at most (two quads)
-                        uint32_t best = 0;
-                        for (uint32_t x = 0; x < nb; ++x) {
-                            const uint32_t d = s_bigd[x], mk = (d >> 16) & 0xFFu;
-                            if (((d >> 24) & 7u) == t && ((gb >> (d & 15u)) & 1u) && (o & mk) == 0 && __popc(mk) > __popc(best)) best = mk;
-                        }
-                        if (!best) break;
-                        o |= best; ++q;
-                    }
-                    s_mass[i] = (uint16_t)((q << 8) | (__popc(~o & us) << 4 & 0xF0u) | min(15, __popc(~o0 & us)));
-                }
-            }
-            __syncthreads();
-            {
+            {   // per GPU: the big group takes the widest span that still fits, twice at most (two quads); the small group fills the usable rest
                 constexpr uint32_t kGpt = kSegMax / kPipeThreads;
+                const uint32_t gb = s_grp_big, nb = s_nbigd;
                 uint32_t mq = 0, mw = 0, mo = 0;
 #pragma unroll
                 for (uint32_t x = 0; x < kGpt; ++x) {
                     const uint32_t g = kGpt * tid + x;
                     if (g < n_sb) {
-                        const uint32_t v = s_mass[s_tab[sb_base + g] * 256u + reinterpret_cast<const uint8_t*>(s_occ32)[sb_base + g]];
-                        mq += v >> 8; mw += (v >> 4) & 15u; mo += v & 15u;
+                        const uint32_t t = s_tab[sb_base + g], o0 = reinterpret_cast<const uint8_t*>(s_occ32)[sb_base + g], us = s_us[t];
+                        uint32_t o = o0;
+                        for (uint32_t it = 0; it < 2; ++it) {
+                            uint32_t best = 0;
+                            for (uint32_t y = 0; y < nb; ++y) {
+                                const uint32_t d = s_bigd[y], mk = (d >> 16) & 0xFFu;
+                                if (((d >> 24) & 7u) == t && ((gb >> (d & 15u)) & 1u) && (o & mk) == 0 && __popc(mk) > __popc(best)) best = mk;
+                            }
+                            if (!best) break;
+                            o |= best; ++mq;
+                        }
+                        mw += __popc(~o & us); mo += __popc(~o0 & us);
                     }
                 }
                 mq = __reduce_add_sync(0xFFFFFFFFu, mq); mw = __reduce_add_sync(0xFFFFFFFFu, mw); mo = __reduce_add_sync(0xFFFFFFFFu, mo);
@@ -1446,15 +1423,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 if (lane < ISL_MAX_PROFILES) s_specH[lane] = seg == 0 && a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + lane] : 0u;
                 __syncwarp();
                 if (lane == 0 && seg > 0) {
-                    spec_spread(s_specH, s_qc, s_minsize, s_grp_big, Q, false);
-                    spec_spread(s_specH, s_qc, s_minsize, s_grp_small, R, true);
+                    spec_spread(s_specH, s_qc, s_minsize, s_grp_big, (int)Q, false);
+                    spec_spread(s_specH, s_qc, s_minsize, s_grp_small, (int)R, true);
                 }
             }
             __syncthreads();
         }
         uint32_t rnd = 1;
         bool c_prev = seg == 0, need_sim = true, idle_break = false;
+        bool p_final = false; unsigned long long p_word = 0;      // pollers: a certified stage's final record is read once and kept
+        const unsigned long long t_cell = tr && spec ? globaltimer_ns() : 0ull, sims_cell = st_sims;   // spec trace: [0] sweep + prediction done, [2] certified, [7] simulations, [11] rounds
+        unsigned long long* dbg = a.spec_dbg && a.spec_dbg_cell == ((c << 16) | seg) ? a.spec_dbg : nullptr;
         while (true) {      // one pass unless the stage speculates
+        stamp_if(dbg && tid == 0, dbg + rnd * 8 + 0);
         if (need_sim) {
         // Inside a GPU a token is self-validating: every head word carries the call's 15-bit epoch tag above its 17 bits of payload
         // (heads <= 65 536), so there is no separate flag, no fence on the producer side and no second round trip on this side —
@@ -1503,7 +1484,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             stamp_if(tr && tid == 0, tr + 1);
             const bool all_done = sb == 0 && __all_sync(0xFFFFFFFFu, from_done || tid >= ISL_MAX_PROFILES);
             if (tid < ISL_MAX_PROFILES) {
-                const uint32_t qc = cc->qcnt[tid], qo = cc->qoff[tid];
+                const uint32_t qc = spec ? s_qc[tid] : cc->qcnt[tid], qo = spec ? s_qo[tid] : cc->qoff[tid];     // re-simulations: no trip to L2
                 left = ((active >> tid) & 1u) && qc > h ? qc - h : 0u;
                 wn = min(left, min(s_ncand * s_maxacc[tid], s_nfree / s_minsize[tid]));   // no more pops than that are possible here
                 s_heads[tid] = h; s_wn[tid] = wn; s_pop[tid] = 0;
@@ -1520,6 +1501,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         }
         __syncthreads();
         stamp_if(tr && tid == 0, tr + 8);
+        stamp_if(dbg && tid == 0, dbg + rnd * 8 + 1);
         if (s_idle && spec) { if (tid == 0) s_nlog = 0; }       // nothing pending at these heads: the exit equals the entry
         else if (s_idle) {  // pass-through: the token (unchanged heads) still reaches the next rank / the caller from the last segment
             if (warp == 0) {
@@ -1602,6 +1584,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             first_key();
             const unsigned long long jumps0 = st_jumps;
             stamp_if(tr && lane == 0, tr + 4);
+            stamp_if(dbg && lane == 0, dbg + rnd * 8 + 2);
             constexpr bool kDefer = ISL_DEFER_INF && !kP15;     // see the rare path below
             while (true) {
                 bool none = false;
@@ -1684,6 +1667,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             }
             const uint32_t nlog = (la - sa_log) >> 3;
             stamp_if(tr && lane == 0, tr + 5);
+            stamp_if(dbg && lane == 0, dbg + rnd * 8 + 3);
             store_if(tr && lane == 0, tr + 6, nlog);
             store_if(tr && lane == 0, tr + 7, (st_jumps - jumps0) | ((unsigned long long)(((ca - sa_cand) >> 2) - 2) << 32));
             if (!spec) { st_steps += nlog; st_visited += ((ca - sa_cand) >> 2) - 2; }
@@ -1707,6 +1691,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 if (tr) tr[2] = globaltimer_ns();
             }
         }
+        else if (spec && tid == kPipeThreads - 32 && rnd >= 3 && seg + 1 < a.n_seg) {
+            // in the shadow of the chain: the slot of round rnd - 2 is about to be overwritten — the successor must have read it (it has, as a rule)
+            const unsigned long long t0 = globaltimer_ns();
+            uint32_t spins = 0;
+            while (true) {
+                const unsigned long long w = ld_relaxed_gpu_u64(sm.ack + seg + 1);
+                if ((uint32_t)(w >> 32) == a.epoch && (uint32_t)w + 2u >= rnd) break;
+                if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
+            }
+        }
         }   // !s_idle
         __syncthreads();
         }   // need_sim
@@ -1722,7 +1716,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     if ((s_grp_small >> tid) & 1u) dr = pop * s_minsize[tid];
                 }
                 dq = __reduce_add_sync(0xFFFFFFFFu, dq); dr = __reduce_add_sync(0xFFFFFFFFu, dr);
-                if (rnd >= 3 && seg + 1 < a.n_seg) {        // the slot of round rnd - 2 is overwritten: the successor must have read it
+                if (rnd >= 3 && seg + 1 < a.n_seg && !(need_sim && !s_idle)) {      // the slot of round rnd - 2 is overwritten: the successor must have read it (checked behind the chain when one ran)
                     const unsigned long long t0 = globaltimer_ns();
                     uint32_t spins = 0;
                     while (true) {
@@ -1734,38 +1728,49 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 if (tid < ISL_MAX_PROFILES) st_relaxed_gpu_u64(sm.x + ((size_t)seg * 2 + (rnd & 1u)) * 16 + tid, tagr | X);
                 if (tid == 16) st_relaxed_gpu_u64(sm.d + (size_t)rnd * kSpecStride + seg, tagr | ((c_prev ? 1u : 0u) << 31) | (dq << 13) | dr);
                 if (tid == 0) { s_dqr[0] = dq; s_dqr[1] = dr; s_acc[0] = 0; s_acc[1] = 0; }
+                stamp_if(dbg && tid == 0, dbg + rnd * 8 + 4);
             }
             __syncthreads();
             bool cbit = true;
             if (tid < seg) {
-                const unsigned long long t0 = globaltimer_ns();
-                unsigned long long w;
-                uint32_t spins = 0;
-                while (true) {
-                    w = ld_relaxed_gpu_u64(sm.d + (size_t)rnd * kSpecStride + tid);
-                    if ((w >> 32) == (tagr >> 32)) { cbit = (w >> 31) & 1u; break; }
-                    w = ld_relaxed_gpu_u64(sm.df + tid);         // a certified stage no longer publishes rounds: its final record stands for all rounds from then on
-                    if ((w >> 32) == (tagF >> 32) && ((w >> 24) & 0xFFu) <= rnd) break;
-                    if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
+                unsigned long long w = p_word;
+                if (!p_final) {
+                    const unsigned long long t0 = globaltimer_ns();
+                    uint32_t spins = 0;
+                    while (true) {
+                        w = ld_relaxed_gpu_u64(sm.d + (size_t)rnd * kSpecStride + tid);
+                        if ((w >> 32) == (tagr >> 32)) { cbit = (w >> 31) & 1u; break; }
+                        if ((spins++ & 3u) == 0) {      // a certified stage no longer publishes rounds: its final record stands for every round from then on
+                            w = ld_relaxed_gpu_u64(sm.df + tid);
+                            if ((w >> 32) == (tagF >> 32) && ((w >> 24) & 0xFFu) <= rnd) { p_final = true; p_word = w; break; }
+                        }
+                        if ((spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
+                    }
                 }
                 atomicAdd(&s_acc[0], (uint32_t)(w >> 13) & 0x7FFu);
                 atomicAdd(&s_acc[1], (uint32_t)w & 0x1FFFu);
             }
             if (seg > 0 && tid >= 192 && tid < 192 + ISL_MAX_PROFILES) {
                 const uint32_t i = tid - 192;
-                const unsigned long long t0 = globaltimer_ns();
-                unsigned long long w;
-                uint32_t spins = 0;
-                while (true) {
-                    w = ld_relaxed_gpu_u64(sm.x + ((size_t)(seg - 1) * 2 + (rnd & 1u)) * 16 + i);
-                    if ((w >> 32) == (tagr >> 32)) break;
-                    w = ld_relaxed_gpu_u64(sm.xf + (size_t)(seg - 1) * 16 + i);
-                    if ((w >> 32) == (tagF >> 32) && ((w >> 24) & 0xFFu) <= rnd) break;
-                    if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
+                unsigned long long w = p_word;
+                if (!p_final) {
+                    const unsigned long long t0 = globaltimer_ns();
+                    uint32_t spins = 0;
+                    while (true) {
+                        w = ld_relaxed_gpu_u64(sm.x + ((size_t)(seg - 1) * 2 + (rnd & 1u)) * 16 + i);
+                        if ((w >> 32) == (tagr >> 32)) break;
+                        if ((spins++ & 3u) == 0) {
+                            w = ld_relaxed_gpu_u64(sm.xf + (size_t)(seg - 1) * 16 + i);
+                            if ((w >> 32) == (tagF >> 32) && ((w >> 24) & 0xFFu) <= rnd) { p_final = true; p_word = w; break; }
+                        }
+                        if ((spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
+                    }
                 }
                 s_specXp[i] = (uint32_t)w & 0x1FFFFu;
             }
             const bool certified = __syncthreads_and(cbit) && c_prev;
+            stamp_if(dbg && tid == 0, dbg + rnd * 8 + 5);
+            store_if(dbg && tid == 0, dbg + rnd * 8 + 7, s_nlog | ((unsigned long long)need_sim << 32));
             if (seg > 0 && tid == 192) st_relaxed_gpu_u64(sm.ack + seg, ((unsigned long long)a.epoch << 32) | (certified ? 0xFFFFu : rnd));
             if (certified) {    // every entry up to mine was the true token one round ago and has not moved since: the log in shared memory is THE log
                 if (tid < ISL_MAX_PROFILES) {
@@ -1773,7 +1778,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     if (seg == a.n_seg - 1 && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + tid] = s_specX[tid];
                 }
                 if (tid == 16) st_relaxed_gpu_u64(sm.df + seg, tagF | (rnd << 24) | (s_dqr[0] << 13) | s_dqr[1]);
-                if (tid == 0) { st_steps += spec_steps; st_visited += spec_visited; if (seg == a.n_seg - 1) { st_rounds_sum += rnd; ++st_cells; } if (tr) { tr[2] = globaltimer_ns(); tr[6] = s_nlog; tr[11] = rnd; } }
+                if (tid == 0) { st_steps += spec_steps; st_visited += spec_visited; if (seg == a.n_seg - 1) { st_rounds_sum += rnd; ++st_cells; } if (tr) { tr[0] = t_cell; tr[2] = globaltimer_ns(); tr[6] = s_nlog; tr[7] = st_sims - sims_cell; tr[11] = rnd; } }
                 break;
             }
             if (tid < 32) {     // c for the next round; the corrected prediction
@@ -1790,13 +1795,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 mq = __reduce_add_sync(0xFFFFFFFFu, mq); mr = __reduce_add_sync(0xFFFFFFFFu, mr);
                 __syncwarp();
                 if (tid == 0) {
-                    spec_spread(s_specH, s_qc, s_minsize, s_grp_big, (long long)s_acc[0] - (long long)mq, false);
-                    spec_spread(s_specH, s_qc, s_minsize, s_grp_small, (long long)s_acc[1] - (long long)mr, true);
+                    spec_spread(s_specH, s_qc, s_minsize, s_grp_big, (int)s_acc[0] - (int)mq, false);
+                    spec_spread(s_specH, s_qc, s_minsize, s_grp_small, (int)s_acc[1] - (int)mr, true);
                 }
                 __syncwarp();
                 const bool moved = tid < ISL_MAX_PROFILES && s_specH[tid] != hold;
                 const bool changed = __any_sync(0xFFFFFFFFu, moved);
                 if (tid == 0) s_specflag = (cnow ? 1u : 0u) | (changed ? 2u : 0u);
+                stamp_if(dbg && tid == 0, dbg + rnd * 8 + 6);
             }
             __syncthreads();
             c_prev = s_specflag & 1u; need_sim = s_specflag & 2u;

@@ -86,6 +86,7 @@ struct isl_engine {
     unsigned long long wait_ns = 20000000000ull;   // a starved device-side wait traps after this long (ISL_WAIT_SECONDS overrides the 20 s)
     uint32_t window = 0;             // causal window of stream calls (isl_set_causal_window): chunk c starts after chunk c - window is committed
     uint32_t spec_mode = ISL_SPEC_AUTO;     // speculative rounds (isl_set_speculation); ISL_SPEC=0|1 in the environment overrides
+    unsigned long long* d_specdbg = nullptr;
     unsigned long long* d_spec = nullptr; uint32_t cap_spec = 0, spec_hi = 0;    // record memory of the rounds: kSpecWordsPerChunk words per chunk
     // open stream (isl_stream_open / _submit / _wait / _close): one persistent k_pipeline, batches arrive while it runs
     struct Open {
@@ -582,6 +583,14 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     if (spec) {
         if (int rc2 = prepare_spec(e, n_chunks, epoch, e->stream)) return rc2;
         args.spec = 1; args.spec_mem = e->d_spec;
+        if (const char* v = getenv("ISL_SPEC_DBG")) {       // per-round stamps of one (chunk, stage) cell: tools/spec_trace.py
+            unsigned cchunk = 0, cstage = 0;
+            if (sscanf(v, "%u,%u", &cchunk, &cstage) == 2) {
+                if (!e->d_specdbg) ISL_CUDA(e, cudaMalloc(&e->d_specdbg, kSpecRounds * 8 * sizeof(unsigned long long)));
+                ISL_CUDA(e, cudaMemsetAsync(e->d_specdbg, 0, kSpecRounds * 8 * sizeof(unsigned long long), e->stream));
+                args.spec_dbg = e->d_specdbg; args.spec_dbg_cell = (cchunk << 16) | cstage;
+            }
+        }
     }
     int rc;
     const bool p15 = e->prof.n == ISL_MAX_PROFILES;      // profile index 15 in use: the pop test needs the slower, INF-safe form
@@ -750,7 +759,7 @@ int isl_destroy(isl_engine* e) {
         cudaFree(e->d_occ); cudaFree(e->d_lut); cudaFree(e->d_feas); cudaFree(e->d_req); cudaFree(e->d_res);
         cudaFree(e->d_q); cudaFree(e->d_tile_counts); cudaFree(e->d_cand); cudaFree(e->d_log); cudaFree(e->d_sweep_counts);
         cudaFree(e->d_ctrl); cudaFree(e->d_scratch);
-        cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens); cudaFree(e->d_spec);
+        cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens); cudaFree(e->d_spec); cudaFree(e->d_specdbg);
         cudaFree(e->d_free_acc); cudaFree(e->d_tiles);
         if (e->d_outbox && !e->outbox_local) cudaIpcCloseMemHandle(e->d_outbox);
         cudaFree(e->d_inbox); cudaFree(e->d_trace); cudaFree(e->d_bf_bitmaps); cudaFree(e->d_ready); cudaFree(e->d_done_cnt); cudaFree(e->d_occ_snap);
@@ -1306,6 +1315,16 @@ int isl_set_causal_window(isl_engine* e, uint32_t window) {
     if (e->open.active) return ISL_ESTATE;
     std::lock_guard<std::mutex> lk(e->mu);
     e->window = window;
+    return ISL_OK;
+}
+
+// debugging aid (not part of the boundary): the per-round stamps recorded under ISL_SPEC_DBG=chunk,stage; out: kSpecRounds x 8 uint64
+int isl_debug_spec_rounds(isl_engine* e, uint64_t* out, uint32_t max_words) {
+    if (!e || !out || !e->d_specdbg) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    ISL_CUDA(e, cudaStreamSynchronize(e->stream));
+    ISL_CUDA(e, cudaMemcpy(out, e->d_specdbg, std::min<size_t>(max_words, kSpecRounds * 8) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return ISL_OK;
 }
 

@@ -14,7 +14,7 @@ int main(int argc, char** argv) {
     Loaded L = load_config(cfg);
     const uint32_t G = L.occ.size(), S = (G + seg - 1) / seg;
     size_t off = 0;
-    for (size_t b = 0; b < L.sizes.size() && b < 4; ++b) {
+    for (size_t b = 0; b < L.sizes.size() && b < 16; ++b) {
         const uint32_t n = L.sizes[b];
         open_batch(L, off, n);
         const int np = (int)profs.size();
@@ -58,7 +58,7 @@ int main(int argc, char** argv) {
               long dq = 0, dr = 0; for (int p : big) dq += (long)H[s][p] - (long)truth[s][p]; for (int p : small) dr += ((long)H[s][p] - (long)truth[s][p]) * psize(p);
               long d1 = 0; for (int p : small) if (psize(p) == 1) d1 += (long)H[s][p] - (long)truth[s][p];
               e1 += std::abs(dq); e2 += std::abs(dr); maxabs = std::max(maxabs, std::labs(d1));
-              if (s % 8 == 1 && b == 0) printf("   seg %u: dQ %ld dR %ld d(1g) %ld\n", s, dq, dr, d1); }
+              if (s % 4 == 1 && getenv("VERB") && (int)b == atoi(getenv("VERB"))) { printf("   seg %u: dQ %ld dR %ld d(1g) %ld | truth", s, dq, dr, d1); for (int p = 0; p < np; ++p) printf(" %u/%zu", truth[s][p], q[p].size()); printf(" | guess"); for (int p = 0; p < np; ++p) printf(" %u", H[s][p]); printf("\n"); } }
           printf("guess: busy %d, mean |dQ| %.2f, mean |dR| %.2f, max |d 1g| %ld\n", busy, e1 / busy, e2 / busy, maxabs); }
         // ---- rounds, absolute chaining (with optional warm-up: segment s re-simulates from the entry of the segment 'warm' GPUs earlier)
         std::vector<Heads> E(S + 1), Hn(S + 1);
@@ -66,6 +66,7 @@ int main(int argc, char** argv) {
         auto cr = [&](const Heads& h) { long c = 0; for (int p : small) c += (long)h[p] * psize(p); return c; };
         std::vector<double> lq(S, 1.0), lr(S, 1.0); std::vector<long> peq(S), pxq(S), per(S), pxr(S); std::vector<bool> have(S, false);
         const int secant = getenv("SECANT") ? atoi(getenv("SECANT")) : 0;
+        std::vector<Heads> pH(S), pE(S); std::vector<bool> haveR(S, false); std::vector<double> lam(S, getenv("LAM0") ? atof(getenv("LAM0")) : 0.0);
         int rounds = 0; uint64_t crit = 0; uint32_t frontier = 0;
         while (true) {
             ++rounds; uint64_t maxw = 0;
@@ -74,8 +75,11 @@ int main(int argc, char** argv) {
             Hn[0] = h0;
             for (uint32_t s = 0; s < S; ++s) {
                 Hn[s + 1] = E[s + 1];
+                if (getenv("IDENT")) { for (int p = 0; p < np; ++p) { long v = (long)E[s + 1][p] + (long)Hn[s][p] - (long)H[s][p]; Hn[s + 1][p] = (uint32_t)std::max(0l, std::min<long>(v, q[p].size())); } continue; }
                 if (!newton) continue;
                 long dq = 0, dr = 0; for (int p : big) dq += (long)Hn[s][p] - (long)H[s][p]; for (int p : small) dr += ((long)Hn[s][p] - (long)H[s][p]) * psize(p);
+                if (getenv("LQ")) { dq = std::lround(atof(getenv("LQ")) * dq); }
+                if (getenv("LR")) { dr = std::lround(atof(getenv("LR")) * dr); }
                 if (secant) {
                     const long eq = cq(H[s]), xq = cq(E[s + 1]), er = cr(H[s]), xr = cr(E[s + 1]);
                     if (have[s]) { if (eq != peq[s]) lq[s] = std::min(1.0, std::max(0.0, double(xq - pxq[s]) / double(eq - peq[s])));
@@ -84,6 +88,7 @@ int main(int argc, char** argv) {
                     dq = std::lround(lq[s] * dq); dr = std::lround(lr[s] * dr);
                 }
                 Heads& h = Hn[s + 1];
+                const Heads base_exit = E[s + 1];
                 if (getenv("PROPA")) {
                     long nb = 0, ns = 0; for (int p : big) nb += q[p].size(); for (int p : small) ns += (long)q[p].size() * psize(p);
                     auto clampadd = [&](int p, long d) { long v = (long)h[p] + d; v = std::max(0l, std::min<long>(v, q[p].size())); h[p] = v; };
@@ -97,6 +102,32 @@ int main(int argc, char** argv) {
                     { std::vector<int> b2 = big; long d = dq, tot = nb; std::sort(b2.begin(), b2.end());
                       for (size_t i = 0; i < b2.size(); ++i) { int p = b2[i]; long dp = i + 1 == b2.size() ? d : (tot ? std::lround((double)d * q[p].size() / tot) : 0); clampadd(p, dp); d -= dp; tot -= q[p].size(); } }
                     spread(small, dr, ns);
+                    if (getenv("RESID")) {
+                        // what the mass step did: m = h - base_exit; the entry shift was sh = Hn[s] - H[s]; residual r = sh - m (zero mass per group); pass lambda_s * r on
+                        std::array<double, P> r{}; double nr = 0;
+                        for (int p = 0; p < np; ++p) { r[p] = ((double)Hn[s][p] - (double)H[s][p]) - ((double)h[p] - (double)base_exit[p]); nr += r[p] * r[p]; }
+                        // lambda estimate of stage s from its last two (entry, exit) pairs
+                        if (haveR[s]) {
+                            std::array<double, P> ri{}, ro{}; double a = 0, bb = 0;
+                            // residuals of the entry change and of the exit change between the last two simulations (mass part removed with the same spread)
+                            Heads z{}; 
+                            auto massres = [&](const Heads& a1, const Heads& a0, std::array<double, P>& out) {
+                                long mq = 0, mr = 0; for (int p : big) mq += (long)a1[p] - (long)a0[p]; for (int p : small) mr += ((long)a1[p] - (long)a0[p]) * psize(p);
+                                Heads t = a0; Heads& hh = t;
+                                auto clampadd2 = [&](int p, long d) { long v = (long)hh[p] + d; hh[p] = (uint32_t)std::max(0l, v); };
+                                { std::vector<int> b2 = big; long d = mq, tot = nb; std::sort(b2.begin(), b2.end());
+                                  for (size_t i = 0; i < b2.size(); ++i) { int p = b2[i]; long dp = i + 1 == b2.size() ? d : (tot ? std::lround((double)d * q[p].size() / tot) : 0); clampadd2(p, dp); d -= dp; tot -= q[p].size(); } }
+                                { std::vector<int> grp = small; long d = mr, tot = ns; std::sort(grp.begin(), grp.end(), [&](int x, int y) { return psize(x) > psize(y) || (psize(x) == psize(y) && x < y); });
+                                  for (size_t i = 0; i < grp.size(); ++i) { int p = grp[i]; long w = psize(p); long dp = i + 1 == grp.size() ? d / w : (tot ? std::lround((double)d * q[p].size() / tot) : 0); clampadd2(p, dp); d -= dp * w; tot -= (long)q[p].size() * w; } }
+                                for (int p = 0; p < np; ++p) out[p] = ((double)a1[p] - (double)a0[p]) - ((double)t[p] - (double)a0[p]);
+                            };
+                            massres(H[s], pH[s], ri); massres(E[s + 1], pE[s], ro);
+                            for (int p = 0; p < np; ++p) { a += ro[p] * ri[p]; bb += ri[p] * ri[p]; }
+                            if (bb > 0) lam[s] = std::min(1.0, std::max(0.0, a / bb));
+                        }
+                        if (H[s] != pH[s] || !haveR[s]) { pH[s] = H[s]; pE[s] = E[s + 1]; haveR[s] = true; }
+                        for (int p = 0; p < np; ++p) { long v = (long)h[p] + std::lround(lam[s] * r[p]); h[p] = (uint32_t)std::max(0l, std::min<long>(v, q[p].size())); }
+                    }
                     continue;
                 }
                 // big group: advance / retreat |dq| requests in merged time order
@@ -108,7 +139,9 @@ int main(int argc, char** argv) {
             }
             bool any = false; uint32_t wrong = 0;
             for (uint32_t s = 0; s <= S; ++s) { if (Hn[s] != H[s]) any = true; if (Hn[s] != truth[s]) ++wrong; H[s] = Hn[s]; }
-            if (getenv("VERB") && b == 0) { printf("      err:"); for (uint32_t s = 0; s < 48 && s <= S; ++s) { long d = 0; for (int p = 0; p < np; ++p) d += std::labs((long)H[s][p] - (long)truth[s][p]); printf(" %ld", d); } printf("\n"); }
+            if (getenv("VERB") && (int)b == atoi(getenv("VERB"))) { printf("      err:"); for (uint32_t s = 0; s < 48 && s <= S; ++s) { long d = 0; for (int p = 0; p < np; ++p) d += std::labs((long)H[s][p] - (long)truth[s][p]); printf(" %ld", d); } printf("\n"); }
+            if (getenv("VERBL") && (int)b == atoi(getenv("VERBL")) && rounds <= 16) { printf("      lam r%d:", rounds); for (uint32_t s = 0; s < 60; ++s) printf(" %.1f", lam[s]); printf("\n"); }
+            if (getenv("VERBP") && (int)b == atoi(getenv("VERBP")) && rounds >= 12 && rounds <= 14) { for (uint32_t s = 24; s < 40; ++s) { printf("      r%d b%u:", rounds, s); for (int p = 0; p < np; ++p) printf(" %ld", (long)H[s][p] - (long)truth[s][p]); printf("\n"); } }
             frontier = 0; while (frontier <= S && H[frontier] == truth[frontier]) ++frontier;
             printf("   round %d: boundaries still wrong %u, exact frontier %u / %u\n", rounds, wrong, frontier, S + 1);
             if (!any || rounds > 200) break;
