@@ -1105,6 +1105,25 @@ __device__ inline void spec_spread(uint32_t* h, const uint32_t* qc, const uint32
     }
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
+__device__ __forceinline__ void sts_v2_if(bool pred, uint32_t sa, uint32_t x, uint32_t y) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.v2.u32 [%1], {%2, %3}; }" ::"r"((uint32_t)pred), "r"(sa), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint32_t add_if(bool pred, uint32_t x, uint32_t inc) {         // one predicated add instead of select + move
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p add.u32 %0, %0, %2; }" : "+r"(x) : "r"((uint32_t)pred), "r"(inc));
+    return x;
+}
+__device__ __forceinline__ uint32_t redux_min_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u32_if(bool pred, uint32_t sa, uint32_t keep) {   // predicated load: keeps `keep` when !pred
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p ld.shared.u32 %0, [%2]; }" : "+r"(keep) : "r"((uint32_t)pred), "r"(sa));
+    return keep;
+}
+
 // Rare path of the decision chain, kept out of line so that the hot loop stays free of divergence-capable constructs:
 // first candidate index >= from + 2 on which a profile of `alive` fits, or kInf.
 __device__ __noinline__ uint32_t pipeline_skip(uint32_t sa_cand, const uint16_t* s_feas, uint32_t n_cand, uint32_t cur_plus2, uint32_t alive, uint32_t lane) {
