@@ -17,22 +17,24 @@ One "step" = one pass of the hot path over the whole workload of the config, sta
 occupancy bytes is a 64 KiB device copy inside the timed region).
 
 c4 in detail.  In the churn workload a FREE names an allocation an EARLIER batch placed, so a live caller cannot compose batch b
-before it has seen the results of earlier batches.  The headline therefore is the CAUSAL FEED: the workload variant in which a FREE
-of batch b names an allocation at least A batches old (--min-age A, default 2), submitted with at most A batches in flight.  (At
-config 4's own churn rate — ~32 700 FREEs per batch against ~110 000 live allocations — the whole live set turns over every ~3.4
-batches: A = 2 and 3 are sustainable, from A = 4 on the pool of old-enough allocations runs dry and the stream degenerates.)
-  value         ALLOC decisions/s, requests and results resident in HBM; the device-side causal window (isl_set_causal_window(A))
-                keeps batch b from starting before every inventory segment has committed batch b - A
-  e2e           the same through the open-stream API (isl_stream_open / _submit / _wait / _close) with pinned HOST buffers: batch b
-                is submitted only after isl_stream_wait returned the results of batch b - A to host memory
-  strict_causal the ORIGINAL config-4 stream (a FREE may name anything live), one batch in flight (A = 1) — what a reconciler that
-                needs every result before composing the next batch gets
+before it has seen the results of batch b - 1.  The headline therefore is STRICT CAUSAL (--min-age 1, the default): the original
+config-4 stream with ONE batch in flight — every batch is resolved before the next one starts, exactly what the reconciler's per-pod
+call sequence (instaslice_controller.go:192) implies.
+  value         ALLOC decisions/s, requests and results resident in HBM; one device-side stream call with isl_set_causal_window(1):
+                batch b does not start before every inventory stage has committed batch b - 1.  A batch's decisions are one exact
+                recurrence over the inventory; the stages resolve it by speculative rounds
+  e2e           one synchronous isl_place_batch per batch with HOST buffers (H2D and D2H inside every call) — the call SURVEY 8d
+                defines the metric on; e2e.open_stream_value: the same through isl_stream_open / _submit / _wait / _close
+  causal_feed   the variant whose FREEs name allocations at least 2 batches old (Churn(min_age=2)) with TWO batches in flight
+                (--min-age 2 makes it the headline).  At config 4's own churn rate the whole live set turns over every ~3.4 batches:
+                depths beyond 3 are not sustainable
   replay_*      the original stream handed over in one call (all 16 batches up front) — the pipelining ceiling, not causally available
 Every mode is checked byte for byte against the CPU oracle (ref_fast): results of every batch and the final occupancy.
-N > 1: the inventory is partitioned over the ranks (contiguous GPU ranges); the queue-head token of every chunk crosses ranks INSIDE
-the running kernels (peer store into the next rank's inbox over NVLink); the PLACED records go straight into rank 0's result array
-(peer stores from the commit threads — no result collective); the causal window is enforced across ranks by a per-chunk counter on
-rank 0 (peer atomics); the occupancy shards are all-gathered with NCCL.  Strong scaling (the job is fixed).
+N > 1: the inventory is partitioned over the ranks (contiguous GPU ranges); the stages of all ranks form one sequence and exchange the
+per-round records of the speculative rounds through peer memory (stores into the other ranks' record memory over NVLink, inside the
+running kernels); the PLACED records go straight into rank 0's result array (peer stores from the commit threads — no result
+collective); the causal window is enforced across ranks by a per-chunk counter on rank 0 (peer atomics); the occupancy shards are
+all-gathered with NCCL.  Strong scaling (the job is fixed).
 
 The CPU oracle is used only for the parity gate, the cpu_baseline leg and --impl reference.
 """
@@ -532,7 +534,15 @@ def run_c4(ctx):
     sampler = ClockSampler(ctx.local)
 
     if world == 1:
-        # ---- the causal feed (headline)
+        import oracle
+
+        def load_variant(chv, occv, batchesv):
+            reqv = np.concatenate(batchesv).view(np.int64)
+            d_occ0.copy_(torch.from_numpy(occv))
+            d_in_all.copy_(torch.from_numpy(reqv.copy()))
+            h_in_all.copy_(torch.from_numpy(reqv.copy()))
+            eng.load_inventory(chv.node_off, occv)
+
         def step_device():
             occ_view.copy_(d_occ0)
             eng.place_stream_ptr(sizes, d_in_all.data_ptr(), d_res.data_ptr(), device=True)
@@ -541,6 +551,7 @@ def run_c4(ctx):
             def step():
                 occ_view.copy_(d_occ0)
                 try:
+                    eng.set_causal_window(window)      # tells the engine how many batches this caller keeps in flight (1..3: speculative rounds)
                     eng.stream_open(nb)
                 except E.EngineError:       # under ncu / compute-sanitizer (kernels serialised) an open stream cannot run: per-batch calls
                     for i in range(nb):
@@ -554,19 +565,47 @@ def run_c4(ctx):
                 for b in range(max(0, nb - window), nb):
                     eng.stream_wait(t[b])
                 eng.stream_close()
+                eng.set_causal_window(0)
             return step
 
+        def step_per_batch():       # one synchronous isl_place_batch per batch, host buffers: the call SURVEY 8d defines the metric on
+            occ_view.copy_(d_occ0)
+            for i in range(nb):
+                eng.place_batch_ptr(int(sizes[i]), h_in_all.data_ptr() + 8 * int(offs[i]), h_out_all.data_ptr() + 8 * int(offs[i]))
+
+        def measure(chv, occv, batchesv, window, with_calls):
+            """device stream with the causal window, open stream with `window` batches in flight, optionally per-batch calls; all checked"""
+            load_variant(chv, occv, batchesv)
+            want, want_occ, t_fast = fast_replay(oracle, chv.node_off, chv.rows, occv, batchesv)
+            ok = lambda got, occ: all(np.array_equal(x, y) for x, y in zip(got, want)) and np.array_equal(occ, want_occ)
+            n_al = int(sum(int((b["op"] == E.OP_ALLOC).sum()) for b in batchesv))
+            out = {"n_alloc": n_al, "ref_fast_s": t_fast}
+            eng.set_causal_window(window)
+            eng.reset_stats()
+            l0 = eng.stats()["kernel_launches"]
+            ms, _ = ctx.timed(step_device, a.steps, a.warmup)
+            st = eng.stats()
+            out["launches"] = st["kernel_launches"] - l0
+            out["spec"] = {"chunks": st["spec_chunks"], "rounds_per_chunk": st["spec_rounds"] / max(1, st["spec_chunks"]), "simulations_per_chunk": st["spec_sims"] / max(1, st["spec_chunks"])}
+            out["got"], out["occ"] = results_of(d_res), eng.read_occupancy()
+            out["dev_ms"] = ms / a.steps
+            parity_ok = ok(out["got"], out["occ"])
+            eng.set_causal_window(0)
+            ms, wall = ctx.timed(open_stream_step(window), a.steps, a.warmup)
+            out["open_ms"] = max(ms, wall * 1e3) / a.steps
+            parity_ok &= ok(results_of(h_out_all), eng.read_occupancy())
+            if with_calls:
+                ms, wall = ctx.timed(step_per_batch, a.steps, a.warmup)
+                out["calls_ms"] = max(ms, wall * 1e3) / a.steps
+                parity_ok &= ok(results_of(h_out_all), eng.read_occupancy())
+            out["parity"] = bool(parity_ok)
+            return out
+
         sampler.start()
-        eng.set_causal_window(A)
-        launches0 = eng.stats()["kernel_launches"]
-        ms_dev, _ = ctx.timed(step_device, a.steps, a.warmup)
-        launches = eng.stats()["kernel_launches"] - launches0
-        got_dev, occ_dev = results_of(d_res), eng.read_occupancy()
-        eng.set_causal_window(0)
-        ms_e2e, wall_e2e = ctx.timed(open_stream_step(A), a.steps, a.warmup)
+        head = measure(ch, occ0, batches, A, A == 1)
         clocks = sampler.stop()
-        got_e2e, occ_e2e = results_of(h_out_all), eng.read_occupancy()
-        e2e_ms = max(ms_e2e, wall_e2e * 1e3)
+        per = lambda m, ms: m["n_alloc"] / (ms / 1e3)
+        parity = head["parity"]
 
         # dominant kernel (k_pipeline), timed live with CUDA events on the engine's own stream in timing mode, same causal window
         teng = E.Engine(max_gpus=G, max_batch=1 << 20, timing=True)
@@ -585,82 +624,77 @@ def run_c4(ctx):
         achieved = alg_bytes / (ms_pipe / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_pipeline", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic(), "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms_pipe, "launches": 1,
-                    "note": "latency-bound exact commit chain pipelined over inventory segments (one CTA per SM); inventory, queues and candidates are "
-                            "shared-memory / L2 resident by construction, so DRAM traffic stays below the algorithmic bytes",
+                    "note": "latency-bound: a batch's decisions are ONE exact recurrence over the inventory (first-fit in arrival order); with one batch in flight the "
+                            "inventory stages resolve it by speculative rounds (every stage simulates its segment from predicted queue heads, commits when certified). "
+                            "Inventory, queues and candidates are shared-memory / L2 resident by construction, so DRAM traffic stays below the algorithmic bytes",
+                    "speculative_rounds": head["spec"],
                     "phase_ms_per_step": {"prepare": st["ms_free"], "partition": st["ms_partition"], "pipeline": st["ms_commit"], "total": st["ms_total"]}}
 
-        import oracle
         faithful = faithful_from_prefill(oracle, ch.node_off, ch.rows, prefill)
-        cpu, ok = cpu_baseline_batches(ch.node_off, ch.rows, occ0, batches, got_dev, occ_dev, 0, faithful, a.faithful_ops,
-                                       "the first %d operations of the churn stream on the pre-filled 65536-GPU inventory (SURVEY 8d prefix)" % a.faithful_ops)
-        parity = ok and all(np.array_equal(x, y) for x, y in zip(got_e2e, got_dev)) and np.array_equal(occ_e2e, occ_dev)
+        cpu, ok_cpu = cpu_baseline_batches(ch.node_off, ch.rows, occ0, batches, head["got"], head["occ"], 0, faithful, a.faithful_ops,
+                                           "the first %d operations of the churn stream on the pre-filled 65536-GPU inventory (SURVEY 8d prefix)" % a.faithful_ops)
+        parity = parity and ok_cpu
 
-        # ---- the original stream: strict causal (one batch in flight) and the replay ceiling
-        if A != 1:
-            ch1, occ1, batches1, _, _ = record_churn(E, W, 1)
-        else:
+        # ---- beside the headline: the other causal depth, and the replay ceiling on the original stream
+        other_A = 2 if A == 1 else 1
+        cho, occo, batcheso, _, _ = record_churn(E, W, other_A)
+        assert np.array_equal(np.array([len(b) for b in batcheso], dtype=np.uint32), sizes)
+        other = measure(cho, occo, batcheso, other_A, other_A == 1)
+        parity = parity and other["parity"]
+        if A == 1:
             ch1, occ1, batches1 = ch, occ0, batches
-        sizes1 = np.array([len(b) for b in batches1], dtype=np.uint32)
-        assert np.array_equal(sizes1, sizes)
-        req1 = np.concatenate(batches1).view(np.int64)
-        d_occ0.copy_(torch.from_numpy(occ1))
-        d_in_all.copy_(torch.from_numpy(req1.copy()))
-        h_in_all.copy_(torch.from_numpy(req1.copy()))
-        eng.load_inventory(ch1.node_off, occ1)
+        else:
+            ch1, occ1, batches1 = cho, occo, batcheso
+        load_variant(ch1, occ1, batches1)
+        want1, want1_occ, _ = fast_replay(oracle, ch1.node_off, ch1.rows, occ1, batches1)
+        check1 = lambda got, occ: all(np.array_equal(x, y) for x, y in zip(got, want1)) and np.array_equal(occ, want1_occ)
         n_alloc1 = int(sum(int((b["op"] == E.OP_ALLOC).sum()) for b in batches1))
-        want1, want1_occ, t_fast1 = fast_replay(oracle, ch1.node_off, ch1.rows, occ1, batches1)
-        extra_ok = True
-
-        def check(got, occ):
-            return all(np.array_equal(x, y) for x, y in zip(got, want1)) and np.array_equal(occ, want1_occ)
-
-        eng.set_causal_window(1)
-        ms_s_dev, _ = ctx.timed(step_device, a.steps, 3)
-        extra_ok &= check(results_of(d_res), eng.read_occupancy())
         eng.set_causal_window(0)
-        ms_s_e2e, wall_s = ctx.timed(open_stream_step(1), a.steps, 3)
-        extra_ok &= check(results_of(h_out_all), eng.read_occupancy())
-
-        def step_per_batch():       # the same through one synchronous isl_place_batch per batch
-            occ_view.copy_(d_occ0)
-            for i in range(nb):
-                eng.place_batch_ptr(int(sizes[i]), h_in_all.data_ptr() + 8 * int(offs[i]), h_out_all.data_ptr() + 8 * int(offs[i]))
-        ms_pb, wall_pb = ctx.timed(step_per_batch, a.steps, 3)
-        extra_ok &= check(results_of(h_out_all), eng.read_occupancy())
         ms_r_dev, _ = ctx.timed(step_device, a.steps, 3)
-        extra_ok &= check(results_of(d_res), eng.read_occupancy())
+        extra_ok = check1(results_of(d_res), eng.read_occupancy())
 
         def step_replay_e2e():
             occ_view.copy_(d_occ0)
             eng.place_stream_ptr(sizes, h_in_all.data_ptr(), h_out_all.data_ptr(), device=False)
         ms_r_e2e, wall_r = ctx.timed(step_replay_e2e, a.steps, 3)
-        extra_ok &= check(results_of(h_out_all), eng.read_occupancy())
+        extra_ok &= check1(results_of(h_out_all), eng.read_occupancy())
         parity = parity and bool(extra_ok)
-        per = lambda ms: n_alloc1 * a.steps / (ms / 1e3)
+
+        def block(m, Ax):
+            d = {"batches_in_flight": Ax, "value": per(m, m["dev_ms"]), "ms_per_step": m["dev_ms"], "open_stream_e2e_value": per(m, m["open_ms"]), "open_stream_e2e_ms_per_step": m["open_ms"],
+                 "ref_fast_value": m["n_alloc"] / m["ref_fast_s"], "unit": UNIT, "parity_vs_ref_fast": m["parity"], "speculative_rounds": m["spec"]}
+            if "calls_ms" in m:
+                d["per_batch_calls_value"] = per(m, m["calls_ms"]); d["per_batch_calls_ms_per_step"] = m["calls_ms"]
+            return d
+        strict, feed = (head, other) if A == 1 else (other, head)
         lines_extra = {
-            "strict_causal": {"workload": "the original config-4 stream (a FREE may name any allocation live at batch start), ONE batch in flight",
-                              "value": per(ms_s_dev), "ms_per_step": ms_s_dev / a.steps,
-                              "e2e_value": per(max(ms_s_e2e, wall_s * 1e3)), "e2e_ms_per_step": max(ms_s_e2e, wall_s * 1e3) / a.steps,
-                              "e2e_api": "open stream, isl_stream_wait(b) before isl_stream_submit(b + 1)",
-                              "per_batch_calls_value": per(max(ms_pb, wall_pb * 1e3)), "per_batch_calls_note": "isl_place_batch once per batch, synchronous (SURVEY 8d's call)",
-                              "ref_fast_value": n_alloc1 / t_fast1, "unit": UNIT, "parity_vs_ref_fast": bool(extra_ok)},
-            "replay_value": per(ms_r_dev), "replay_ms_per_step": ms_r_dev / a.steps,
-            "replay_e2e_value": per(max(ms_r_e2e, wall_r * 1e3)),
+            "strict_causal": dict(block(strict, 1), workload="the original config-4 stream (a FREE may name any allocation live at batch start), ONE batch in flight: every batch "
+                                                                 "is resolved before the next one starts"),
+            "causal_feed": dict(block(feed, 2), workload="variant whose FREEs name allocations at least 2 batches old (Churn(min_age=2)), TWO batches in flight"),
+            "replay_value": n_alloc1 / (ms_r_dev / a.steps / 1e3), "replay_ms_per_step": ms_r_dev / a.steps,
+            "replay_e2e_value": n_alloc1 / (max(ms_r_e2e, wall_r * 1e3) / a.steps / 1e3),
             "replay_note": "the original stream, all 16 batches handed over in one isl_place_stream* call: the pipelining ceiling; NOT causally available to a live caller",
         }
-        value = n_alloc * a.steps / (ms_dev / 1e3)
-        line = base_line(ctx, "c4", value, ms_dev / a.steps,
-                         {"mode": "causal feed", "min_age_batches": A, "batches_in_flight": A,
-                          "workload_variant": "a FREE of batch b names an allocation placed by batch b - %d or earlier (min_age); A = 1 is the original stream (strict_causal)" % A,
+        value = per(head, head["dev_ms"])
+        variant = ("the original config-4 stream: a FREE may name any allocation live at batch start" if A == 1 else
+                   "a FREE of batch b names an allocation placed by batch b - %d or earlier (Churn(min_age))" % A)
+        line = base_line(ctx, "c4", value, head["dev_ms"],
+                         {"mode": "strict causal: one batch in flight" if A == 1 else "causal feed", "min_age_batches": A, "batches_in_flight": A,
+                          "workload_variant": variant,
                           "ops_per_step": n_ops, "alloc_requests_per_step": n_alloc, "free_requests_per_step": n_ops - n_alloc,
                           "ops_counted": "ALLOC decisions (placed or definitively no-capacity); FREEs are resolved inside the same step but not counted",
-                          "ops_per_sec_incl_frees": n_ops * a.steps / (ms_dev / 1e3),
-                          "batches_per_step": nb, "gpus_in_inventory": G, "policy": "first-fit", "parallelism": "segment pipeline, 1 GPU"},
-                         parity, launches, clocks)
-        line["e2e"] = {"value": n_alloc * a.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n_ops, "d2h_bytes_per_step": 8 * n_ops,
-                       "ms_per_step": e2e_ms / a.steps, "ops_per_sec_incl_frees": n_ops * a.steps / (e2e_ms / 1e3),
-                       "api": "isl_stream_open / isl_stream_submit / isl_stream_wait / isl_stream_close, pinned host buffers; batch b submitted after isl_stream_wait(b - %d); "
-                              "CUDA events around the step and the host clock, the larger is reported" % A}
+                          "ops_per_sec_incl_frees": n_ops / (head["dev_ms"] / 1e3),
+                          "batches_per_step": nb, "gpus_in_inventory": G, "policy": "first-fit", "parallelism": "segment pipeline with speculative rounds, 1 GPU"},
+                         parity, head["launches"], clocks)
+        if A == 1:
+            e2e_ms, api = head["calls_ms"], ("isl_place_batch once per batch, host buffers in and out, synchronous (the call SURVEY 8d defines the metric on; each call's H2D and D2H "
+                                             "inside); CUDA events around the step and the host clock, the larger is reported")
+        else:
+            e2e_ms, api = head["open_ms"], ("isl_stream_open / isl_stream_submit / isl_stream_wait / isl_stream_close, pinned host buffers; batch b submitted after "
+                                            "isl_stream_wait(b - %d); CUDA events around the step and the host clock, the larger is reported" % A)
+        line["e2e"] = {"value": per(head, e2e_ms), "unit": UNIT, "h2d_bytes_per_step": 8 * n_ops, "d2h_bytes_per_step": 8 * n_ops,
+                       "ms_per_step": e2e_ms, "ops_per_sec_incl_frees": n_ops / (e2e_ms / 1e3), "api": api,
+                       "open_stream_value": per(head, head["open_ms"]), "open_stream_ms_per_step": head["open_ms"]}
         line["roofline"] = roofline
         line["cpu_baseline"] = cpu
         line.update(lines_extra)
@@ -673,6 +707,7 @@ def run_c4(ctx):
     eng.set_partition(lo, hi)
     D.connect_ring(eng, rank, world)          # next rank's token inbox mapped through CUDA IPC (peer store over NVLink)
     D.connect_owner(eng, rank, world)         # rank 0's result array mapped into every other rank; ring size for the causal window
+    D.connect_spec(eng, rank, world, G)       # every rank's record memory of the speculative rounds mapped into every other rank
     eng.set_causal_window(A)
     stream_ids = iter(range(1, 1 << 30))
     triples = []          # (start, pipeline enqueued-to-end, all-gather done) events of every device step: the phase table comes from the TIMED steps
@@ -703,7 +738,11 @@ def run_c4(ctx):
         sampler.start()
     launches0 = eng.stats()["kernel_launches"]
     ms_dev, _ = ctx.timed(step_device, a.steps, a.warmup)
-    launches = eng.stats()["kernel_launches"] - launches0
+    st_n = eng.stats()
+    launches = st_n["kernel_launches"] - launches0
+    sp = torch.tensor([st_n["spec_chunks"], st_n["spec_rounds"], st_n["spec_sims"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(sp, op=dist.ReduceOp.SUM)       # the last stage (last rank) counts chunks and rounds, every rank its simulations
+    spec_stats = {"chunks": int(sp[0].item()), "rounds_per_chunk": float(sp[1].item()) / max(1.0, float(sp[0].item())), "simulations_per_chunk": float(sp[2].item()) / max(1.0, float(sp[0].item()))}
     clocks = sampler.stop() if rank == 0 else None
     got_dev = results_of(d_res) if rank == 0 else None
     occ_dev = occ_view.cpu().numpy()
@@ -724,14 +763,17 @@ def run_c4(ctx):
         achieved = alg_bytes / (ms_pipe / 1e3) / 1e9
         value = n_alloc * a.steps / (ms_dev / 1e3)
         line = base_line(ctx, "c4", value, ms_dev / a.steps,
-                         {"mode": "causal window (device-side, across ranks)", "min_age_batches": A, "batches_in_flight": A,
-                          "workload_variant": "a FREE of batch b names an allocation placed by batch b - %d or earlier (min_age)" % A,
+                         {"mode": ("strict causal: one batch in flight" if A == 1 else "causal feed") + " (device-side window across ranks)", "min_age_batches": A, "batches_in_flight": A,
+                          "workload_variant": ("the original config-4 stream: a FREE may name any allocation live at batch start" if A == 1 else
+                                               "a FREE of batch b names an allocation placed by batch b - %d or earlier (min_age)" % A),
                           "ops_per_step": n_ops, "alloc_requests_per_step": n_alloc, "free_requests_per_step": n_ops - n_alloc,
                           "ops_counted": "ALLOC decisions (placed or definitively no-capacity); FREEs are resolved inside the same step but not counted",
                           "ops_per_sec_incl_frees": n_ops * a.steps / (ms_dev / 1e3),
                           "batches_per_step": nb, "gpus_in_inventory": G, "policy": "first-fit",
-                          "parallelism": "inventory partitioned over %d ranks: peer-memory token ring + PLACED records peer-stored into rank 0's result array + "
-                                         "peer-atomic window counter + NCCL all-gather of the occupancy shards" % world},
+                          "parallelism": "inventory partitioned over %d ranks: ONE sequence of inventory stages over all ranks, speculative rounds with the per-round records "
+                                         "peer-stored into the other ranks' record memory + PLACED records peer-stored into rank 0's result array + "
+                                         "peer-atomic window counter + NCCL all-gather of the occupancy shards" % world,
+                          "speculative_rounds": spec_stats},
                          parity, launches, clocks)
         e2e_ms = max(ms_e2e, 0.0)
         line["e2e"] = {"value": n_alloc * a.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * n_ops, "d2h_bytes_per_step": 8 * n_ops,
@@ -740,8 +782,8 @@ def run_c4(ctx):
                               "D2H of rank 0's result array" % A}
         line["roofline"] = {"bound": "hbm", "kernel": "k_pipeline", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                             "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms_pipe, "launches": world,
-                            "note": "per-rank k_pipeline incl. its waits for the predecessor's tokens (max over ranks); the chain is ONE sequential recurrence over the "
-                                    "whole inventory, more ranks add NVLink hops, not parallel work",
+                            "note": "per-rank k_pipeline incl. its waits for the other ranks' records (max over ranks); a batch is ONE sequential recurrence over the "
+                                    "whole inventory, resolved by speculative rounds of all stages of all ranks — more ranks add NVLink latency to every round, not parallel work",
                             "phase_ms_per_step_max_over_ranks": {"pre-pass + pipeline (enqueue to kernel end)": ms_pipe, "occupancy all-gather (NCCL) + copy back": float(ph[1].item()),
                                                                   "result merge": 0.0}}
         line["cpu_baseline"] = cpu
@@ -860,7 +902,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--min-age", type=int, default=2, help="c4: a FREE names an allocation at least this many batches old = batches in flight of the causal feed")
+    ap.add_argument("--min-age", type=int, default=1, help="c4: a FREE names an allocation at least this many batches old = batches in flight of the causal feed")
     ap.add_argument("--faithful-ops", type=int, default=10000, help="c4: operations of the churn prefix the reference-as-written port is timed on (SURVEY 8d)")
     ap.add_argument("--seconds", type=float, default=10.0, help="c5: length of the replay")
     args = ap.parse_args()

@@ -325,6 +325,15 @@ void* isl_device_results(isl_engine* e);
 int  isl_ipc_results_handle(isl_engine* e, void* handle64);
 int  isl_ipc_connect_owner(isl_engine* e, const void* owner_handle64);
 int  isl_connect_owner_local(isl_engine* e, isl_engine* owner);
+/* Speculative rounds (isl_set_speculation) over a partitioned inventory: the stages of all ranks form one sequence and exchange their
+ * per-round records through peer memory, so every rank maps every other rank's record memory.
+ *   every rank:  isl_ipc_spec_handle(e, h)                  -> 64-byte handle of its record memory (allocates it)
+ *   every rank:  isl_ipc_connect_spec(e, world, rank, handles [world x 64 bytes], bounds [world + 1])
+ * bounds[r] .. bounds[r + 1] is the canonical GPU range of rank r (what isl_set_partition got).  Without it a partitioned stream keeps
+ * the token ring.  world = 0 disconnects.  isl_connect_spec_local: same-process engines. */
+int  isl_ipc_spec_handle(isl_engine* e, void* handle64);
+int  isl_ipc_connect_spec(isl_engine* e, uint32_t world, uint32_t rank, const void* handles, const uint32_t* bounds);
+int  isl_connect_spec_local(isl_engine* e, uint32_t world, uint32_t rank, isl_engine* const* engines, const uint32_t* bounds);
 /* Number of ranks of the partitioned run.  With it set (and the owner's results mapped on every other rank) isl_set_causal_window also
  * applies to isl_place_stream_partitioned: the rank that finishes a chunk adds 1 to a per-chunk counter behind the owner's result
  * array (peer atomic), and the owner starts chunk c only when all `world` ranks are through with chunk c - window.  All ranks must be

@@ -982,6 +982,10 @@ struct PipeArgs {
     // by round and a stage commits once its entry heads are certified to be the true ones.  Record memory: spec_mem(), kSpecWordsPerChunk per chunk.
     uint32_t spec;
     unsigned long long* spec_mem;
+    // partitioned inventory: the stages of all ranks form ONE sequence (global index spec_base + stage); every rank keeps the whole record
+    // memory and a stage stores what later ranks read straight into their copies (peer stores over NVLink, system scope)
+    uint32_t spec_world, spec_rank, spec_base, spec_total;
+    unsigned long long* spec_peer[8];
     unsigned long long* spec_dbg;   // optional [kSpecRounds][8] globaltimer stamps of the rounds of ONE (chunk, stage) cell (ISL_SPEC_DBG=chunk,stage; tools/spec_trace.py)
     uint32_t spec_dbg_cell;         // chunk << 16 | stage
 };
@@ -1077,6 +1081,14 @@ __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned 
 }
 __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Speculative rounds: move the heads of the profiles in `members` so that their mass (sum of weight x head) changes by d — shares
@@ -1369,7 +1381,23 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         const size_t tok_chunk = (size_t)c * (a.n_seg + 1);
         const bool spec = a.spec != 0;      // host: only with one sub-segment per stage and no token ring
         const SpecMem sm = spec_mem(a.spec_mem, spec ? c : 0);
-        const unsigned long long tagb = (unsigned long long)((a.epoch & 0xFFFFFFu) << 8) << 32, tagF = tagb | (0xFFull << 32);
+        // a partitioned inventory tags with the stream id all ranks share
+        const uint32_t tage = a.spec_world > 1 ? a.xepoch : a.epoch;
+        const unsigned long long tagb = (unsigned long long)((tage & 0xFFFFFFu) << 8) << 32, tagF = tagb | (0xFFull << 32);
+        const bool xr = a.spec_world > 1;                                  // records cross ranks
+        const uint32_t gseg = a.spec_base + seg, gtot = a.spec_total;      // my place in the sequence of all stages of all ranks
+        auto sld = [&](const unsigned long long* p) { return xr ? ld_relaxed_sys_u64(p) : ld_relaxed_gpu_u64(p); };
+        // a word every LATER stage reads: my copy and the copies of the ranks behind me
+        auto pub_down = [&](unsigned long long* p, unsigned long long v) {
+            st_relaxed_gpu_u64(p, v);
+            if (xr) for (uint32_t r = a.spec_rank + 1; r < a.spec_world; ++r) st_relaxed_sys_u64(a.spec_peer[r] + (p - a.spec_mem), v);
+        };
+        // a word only the next (prev = false) / the previous (prev = true) stage reads
+        auto pub_nb = [&](unsigned long long* p, unsigned long long v, bool prev) {
+            const bool remote = xr && (prev ? (seg == 0 && a.spec_rank > 0) : (seg + 1 == a.n_seg && a.spec_rank + 1 < a.spec_world));
+            if (remote) st_relaxed_sys_u64(a.spec_peer[prev ? a.spec_rank - 1 : a.spec_rank + 1] + (p - a.spec_mem), v);
+            else st_relaxed_gpu_u64(p, v);
+        };
         if (spec) {     // round 0: what this stage's occupancy can take, per contention group -> predicted entry heads
             uint16_t* s_mj = reinterpret_cast<uint16_t*>(s_wkey);               // scratch (the windows are staged later): [3][kSpecStride] gathered masses of the stages in front
             if (tid < ISL_MAX_PROFILES) {
@@ -1407,15 +1435,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             }
             __syncthreads();
             if (tid == 0) {
-                st_relaxed_gpu_u64(sm.m + seg * 2, tagb | s_acc[0]);
-                st_relaxed_gpu_u64(sm.m + seg * 2 + 1, tagb | (min(s_acc[1], 0xFFFFu) << 16) | min(s_acc[2], 0xFFFFu));
+                pub_down(sm.m + gseg * 2, tagb | s_acc[0]);
+                pub_down(sm.m + gseg * 2 + 1, tagb | (min(s_acc[1], 0xFFFFu) << 16) | min(s_acc[2], 0xFFFFu));
             }
-            if (tid < seg) {        // masses of every stage in front of this one
+            if (tid < gseg) {       // masses of every stage in front of this one
                 const unsigned long long t0 = globaltimer_ns();
                 unsigned long long w0, w1;
                 uint32_t spins = 0;
                 while (true) {
-                    w0 = ld_relaxed_gpu_u64(sm.m + tid * 2); w1 = ld_relaxed_gpu_u64(sm.m + tid * 2 + 1);
+                    w0 = sld(sm.m + tid * 2); w1 = sld(sm.m + tid * 2 + 1);
                     if ((w0 >> 32) == (tagb >> 32) && (w1 >> 32) == (tagb >> 32)) break;
                     if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
                 }
@@ -1428,20 +1456,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 for (uint32_t m = s_grp_small; m; m &= m - 1) { const uint32_t pp = __ffs(m) - 1; tots += s_qc[pp] * s_minsize[pp]; }
                 constexpr uint32_t kPer = (kSpecStride + 31) / 32;
                 uint32_t ql = 0;
-                for (uint32_t x = 0; x < kPer; ++x) { const uint32_t j = lane * kPer + x; if (j < seg) ql += s_mj[j]; }
+                for (uint32_t x = 0; x < kPer; ++x) { const uint32_t j = lane * kPer + x; if (j < gseg) ql += s_mj[j]; }
                 uint32_t incl = ql;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
                 uint32_t run = incl - ql, r = 0;
                 for (uint32_t x = 0; x < kPer; ++x) {
                     const uint32_t j = lane * kPer + x;
-                    if (j < seg) { r += run < totb ? s_mj[kSpecStride + j] : s_mj[2 * kSpecStride + j]; run += s_mj[j]; }
+                    if (j < gseg) { r += run < totb ? s_mj[kSpecStride + j] : s_mj[2 * kSpecStride + j]; run += s_mj[j]; }
                 }
                 r = __reduce_add_sync(0xFFFFFFFFu, r);
                 const uint32_t Q = min(__shfl_sync(0xFFFFFFFFu, incl, 31), totb), R = min(r, tots);
-                if (lane < ISL_MAX_PROFILES) s_specH[lane] = seg == 0 && a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + lane] : 0u;
+                if (lane < ISL_MAX_PROFILES) s_specH[lane] = gseg == 0 && a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + lane] : 0u;
                 __syncwarp();
-                if (lane == 0 && seg > 0) {
+                if (lane == 0 && gseg > 0) {
                     spec_spread(s_specH, s_qc, s_minsize, s_grp_big, (int)Q, false);
                     spec_spread(s_specH, s_qc, s_minsize, s_grp_small, (int)R, true);
                 }
@@ -1449,7 +1477,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             __syncthreads();
         }
         uint32_t rnd = 1;
-        bool c_prev = seg == 0, need_sim = true, idle_break = false;
+        bool c_prev = spec ? gseg == 0 : seg == 0, need_sim = true, idle_break = false;
         bool p_final = false; unsigned long long p_word = 0;      // pollers: a certified stage's final record is read once and kept
         const unsigned long long t_cell = tr && spec ? globaltimer_ns() : 0ull, sims_cell = st_sims;   // spec trace: [0] sweep + prediction done, [2] certified, [7] simulations, [11] rounds
         unsigned long long* dbg = a.spec_dbg && a.spec_dbg_cell == ((c << 16) | seg) ? a.spec_dbg : nullptr;
@@ -1710,13 +1738,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 if (tr) tr[2] = globaltimer_ns();
             }
         }
-        else if (spec && tid == kPipeThreads - 32 && rnd >= 3 && seg + 1 < a.n_seg) {
+        else if (spec && tid == kPipeThreads - 32 && rnd >= 3 && gseg + 1 < gtot) {
             // in the shadow of the chain: the slot of round rnd - 2 is about to be overwritten — the successor must have read it (it has, as a rule)
             const unsigned long long t0 = globaltimer_ns();
             uint32_t spins = 0;
             while (true) {
-                const unsigned long long w = ld_relaxed_gpu_u64(sm.ack + seg + 1);
-                if ((uint32_t)(w >> 32) == a.epoch && (uint32_t)w + 2u >= rnd) break;
+                const unsigned long long w = sld(sm.ack + gseg + 1);
+                if ((uint32_t)(w >> 32) == tage && (uint32_t)w + 2u >= rnd) break;
                 if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
             }
         }
@@ -1735,32 +1763,32 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     if ((s_grp_small >> tid) & 1u) dr = pop * s_minsize[tid];
                 }
                 dq = __reduce_add_sync(0xFFFFFFFFu, dq); dr = __reduce_add_sync(0xFFFFFFFFu, dr);
-                if (rnd >= 3 && seg + 1 < a.n_seg && !(need_sim && !s_idle)) {      // the slot of round rnd - 2 is overwritten: the successor must have read it (checked behind the chain when one ran)
+                if (rnd >= 3 && gseg + 1 < gtot && !(need_sim && !s_idle)) {      // the slot of round rnd - 2 is overwritten: the successor must have read it (checked behind the chain when one ran)
                     const unsigned long long t0 = globaltimer_ns();
                     uint32_t spins = 0;
                     while (true) {
-                        const unsigned long long w = ld_relaxed_gpu_u64(sm.ack + seg + 1);
-                        if ((uint32_t)(w >> 32) == a.epoch && (uint32_t)w + 2u >= rnd) break;
+                        const unsigned long long w = sld(sm.ack + gseg + 1);
+                        if ((uint32_t)(w >> 32) == tage && (uint32_t)w + 2u >= rnd) break;
                         if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
                     }
                 }
-                if (tid < ISL_MAX_PROFILES) st_relaxed_gpu_u64(sm.x + ((size_t)seg * 2 + (rnd & 1u)) * 16 + tid, tagr | X);
-                if (tid == 16) st_relaxed_gpu_u64(sm.d + (size_t)rnd * kSpecStride + seg, tagr | ((c_prev ? 1u : 0u) << 31) | (dq << 13) | dr);
+                if (tid < ISL_MAX_PROFILES) pub_nb(sm.x + ((size_t)gseg * 2 + (rnd & 1u)) * 16 + tid, tagr | X, false);
+                if (tid == 16) pub_down(sm.d + (size_t)rnd * kSpecStride + gseg, tagr | ((c_prev ? 1u : 0u) << 31) | (dq << 13) | dr);
                 if (tid == 0) { s_dqr[0] = dq; s_dqr[1] = dr; s_acc[0] = 0; s_acc[1] = 0; }
                 stamp_if(dbg && tid == 0, dbg + rnd * 8 + 4);
             }
             __syncthreads();
             bool cbit = true;
-            if (tid < seg) {
+            if (tid < gseg) {
                 unsigned long long w = p_word;
                 if (!p_final) {
                     const unsigned long long t0 = globaltimer_ns();
                     uint32_t spins = 0;
                     while (true) {
-                        w = ld_relaxed_gpu_u64(sm.d + (size_t)rnd * kSpecStride + tid);
+                        w = sld(sm.d + (size_t)rnd * kSpecStride + tid);
                         if ((w >> 32) == (tagr >> 32)) { cbit = (w >> 31) & 1u; break; }
                         if ((spins++ & 3u) == 0) {      // a certified stage no longer publishes rounds: its final record stands for every round from then on
-                            w = ld_relaxed_gpu_u64(sm.df + tid);
+                            w = sld(sm.df + tid);
                             if ((w >> 32) == (tagF >> 32) && ((w >> 24) & 0xFFu) <= rnd) { p_final = true; p_word = w; break; }
                         }
                         if ((spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
@@ -1769,17 +1797,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 atomicAdd(&s_acc[0], (uint32_t)(w >> 13) & 0x7FFu);
                 atomicAdd(&s_acc[1], (uint32_t)w & 0x1FFFu);
             }
-            if (seg > 0 && tid >= 192 && tid < 192 + ISL_MAX_PROFILES) {
+            if (gseg > 0 && tid >= 192 && tid < 192 + ISL_MAX_PROFILES) {
                 const uint32_t i = tid - 192;
                 unsigned long long w = p_word;
                 if (!p_final) {
                     const unsigned long long t0 = globaltimer_ns();
                     uint32_t spins = 0;
                     while (true) {
-                        w = ld_relaxed_gpu_u64(sm.x + ((size_t)(seg - 1) * 2 + (rnd & 1u)) * 16 + i);
+                        w = sld(sm.x + ((size_t)(gseg - 1) * 2 + (rnd & 1u)) * 16 + i);
                         if ((w >> 32) == (tagr >> 32)) break;
                         if ((spins++ & 3u) == 0) {
-                            w = ld_relaxed_gpu_u64(sm.xf + (size_t)(seg - 1) * 16 + i);
+                            w = sld(sm.xf + (size_t)(gseg - 1) * 16 + i);
                             if ((w >> 32) == (tagF >> 32) && ((w >> 24) & 0xFFu) <= rnd) { p_final = true; p_word = w; break; }
                         }
                         if ((spins & 255u) == 0 && globaltimer_ns() - t0 > a.wait_ns) __trap();
@@ -1790,14 +1818,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             const bool certified = __syncthreads_and(cbit) && c_prev;
             stamp_if(dbg && tid == 0, dbg + rnd * 8 + 5);
             store_if(dbg && tid == 0, dbg + rnd * 8 + 7, s_nlog | ((unsigned long long)need_sim << 32));
-            if (seg > 0 && tid == 192) st_relaxed_gpu_u64(sm.ack + seg, ((unsigned long long)a.epoch << 32) | (certified ? 0xFFFFu : rnd));
+            if (gseg > 0 && tid == 192) pub_nb(sm.ack + gseg, ((unsigned long long)tage << 32) | (certified ? 0xFFFFu : rnd), true);
             if (certified) {    // every entry up to mine was the true token one round ago and has not moved since: the log in shared memory is THE log
                 if (tid < ISL_MAX_PROFILES) {
-                    st_relaxed_gpu_u64(sm.xf + (size_t)seg * 16 + tid, tagF | (rnd << 24) | s_specX[tid]);
-                    if (seg == a.n_seg - 1 && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + tid] = s_specX[tid];
+                    pub_nb(sm.xf + (size_t)gseg * 16 + tid, tagF | (rnd << 24) | s_specX[tid], false);
+                    if (gseg == gtot - 1 && a.heads_out) a.heads_out[(size_t)c * ISL_MAX_PROFILES + tid] = s_specX[tid];
                 }
-                if (tid == 16) st_relaxed_gpu_u64(sm.df + seg, tagF | (rnd << 24) | (s_dqr[0] << 13) | s_dqr[1]);
-                if (tid == 0) { st_steps += spec_steps; st_visited += spec_visited; if (seg == a.n_seg - 1) { st_rounds_sum += rnd; ++st_cells; } if (tr) { tr[0] = t_cell; tr[2] = globaltimer_ns(); tr[6] = s_nlog; tr[7] = st_sims - sims_cell; tr[11] = rnd; } }
+                if (tid == 16) pub_down(sm.df + gseg, tagF | (rnd << 24) | (s_dqr[0] << 13) | s_dqr[1]);
+                if (tid == 0) { st_steps += spec_steps; st_visited += spec_visited; if (gseg == gtot - 1) { st_rounds_sum += rnd; ++st_cells; } if (tr) { tr[0] = t_cell; tr[2] = globaltimer_ns(); tr[6] = s_nlog; tr[7] = st_sims - sims_cell; tr[11] = rnd; } }
                 break;
             }
             if (tid < 32) {     // c for the next round; the corrected prediction

@@ -87,6 +87,9 @@ struct isl_engine {
     uint32_t window = 0;             // causal window of stream calls (isl_set_causal_window): chunk c starts after chunk c - window is committed
     uint32_t spec_mode = ISL_SPEC_AUTO;     // speculative rounds (isl_set_speculation); ISL_SPEC=0|1 in the environment overrides
     unsigned long long* d_specdbg = nullptr;
+    // partitioned inventory: every rank's record memory, peer-mapped (own entry = d_spec); bounds of all ranks; the shared memory never moves
+    unsigned long long* spec_peer[8] = {}; bool spec_peer_local = false, spec_shared = false;
+    uint32_t spec_world = 0, spec_rank = 0, spec_bounds[9] = {};
     unsigned long long* d_spec = nullptr; uint32_t cap_spec = 0, spec_hi = 0;    // record memory of the rounds: kSpecWordsPerChunk words per chunk
     // open stream (isl_stream_open / _submit / _wait / _close): one persistent k_pipeline, batches arrive while it runs
     struct Open {
@@ -386,7 +389,7 @@ constexpr unsigned long long kOpenWaitNs = 600000000000ull;     // open streams 
 
 // Speculative rounds (isl_kernels.cuh): wanted for this call?
 bool want_spec(isl_engine* e, uint32_t n_batches, uint32_t window, bool ring, bool legacy_token) {
-    if (ring || legacy_token || kPipeThreads < 208) return false;
+    if ((ring && e->spec_world < 2) || legacy_token || kPipeThreads < 208) return false;
     uint32_t mode = e->spec_mode;
     if (const char* v = getenv("ISL_SPEC")) mode = atoi(v) ? ISL_SPEC_ON : ISL_SPEC_OFF;
     if (mode == ISL_SPEC_OFF) return false;
@@ -395,6 +398,7 @@ bool want_spec(isl_engine* e, uint32_t n_batches, uint32_t window, bool ring, bo
 }
 // record memory for n_chunks chunks; the words carry the call epoch (24 bits) — cleared when (re)allocated and when those bits wrap
 int prepare_spec(isl_engine* e, uint32_t n_chunks, uint32_t epoch, cudaStream_t st) {
+    if (e->spec_shared) return n_chunks <= e->cap_spec ? ISL_OK : ISL_ERANGE;      // peers hold a mapping of it: fixed size, tags carry the stream id
     const uint32_t before = e->cap_spec;
     if (int rc = grow(e, &e->d_spec, &e->cap_spec, n_chunks, kSpecWordsPerChunk)) return rc;
     const bool fresh = e->cap_spec != before, wrapped = (epoch >> 24) != e->spec_hi;
@@ -442,9 +446,23 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     if (pipeline) {
         const uint32_t win = (ring && e->ring_world == 0) ? 0u : e->window;
         if (want_spec(e, n_batches, win, ring, legacy_token)) {      // speculative rounds need one sub-segment per stage
-            const int src = plan_pipeline(e, n_chunks, (double)total / n_chunks, want_feed, &seg, &n_seg, &sub, true);
-            if (src == ISL_ECUDA) return src;
-            spec = src == ISL_OK && seg == sub && n_seg <= 148 && n_seg >= 2;
+            if (ring) {
+                // one sequence of stages over all ranks: a power-of-two stage size that every rank boundary is a multiple of (all ranks evaluate
+                // the same predicate over the same bounds, so they agree)
+                uint32_t sz = 64;
+                while (ceil_div(e->G, sz) > 148u) sz *= 2;
+                bool ok = sz <= kSegMax && e->spec_world == e->ring_world && n_chunks <= e->cap_spec && e->spec_bounds[e->spec_world] == e->G &&
+                          e->spec_bounds[e->spec_rank] == e->lo && e->spec_bounds[e->spec_rank + 1] == e->hi && query_coresident(e) == ISL_OK;
+                for (uint32_t r = 0; ok && r <= e->spec_world; ++r) ok = e->spec_bounds[r] % sz == 0 || e->spec_bounds[r] == e->G;
+                for (uint32_t r = 0; ok && r < e->spec_world; ++r) ok = e->spec_bounds[r] < e->spec_bounds[r + 1] && ceil_div(e->spec_bounds[r + 1] - e->spec_bounds[r], sz) <= (uint32_t)std::max(1, e->max_coresident);
+                uint32_t tc = 0; for (uint32_t k = 0; k < 4; ++k) for (uint32_t l = 0; l < 32; ++l) tc += e->tab.desc[k][l] >> 31;
+                ok = ok && sz <= max_segment_for(tc);
+                if (ok) { seg = sub = sz; n_seg = ceil_div(range, sz); spec = true; }
+            } else {
+                const int src = plan_pipeline(e, n_chunks, (double)total / n_chunks, want_feed, &seg, &n_seg, &sub, true);
+                if (src == ISL_ECUDA) return src;
+                spec = src == ISL_OK && seg == sub && n_seg <= 148 && n_seg >= 2;
+            }
         }
         if (!spec) {
             const int prc = plan_pipeline(e, n_chunks, (double)total / n_chunks, want_feed, &seg, &n_seg, &sub);
@@ -582,7 +600,12 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     args.inbox = ring && e->has_prev ? e->d_inbox : nullptr; args.outbox = ring ? e->d_outbox : nullptr; args.xepoch = xepoch;
     if (spec) {
         if (int rc2 = prepare_spec(e, n_chunks, epoch, e->stream)) return rc2;
-        args.spec = 1; args.spec_mem = e->d_spec;
+        args.spec = 1; args.spec_mem = e->d_spec; args.spec_total = n_seg;
+        if (ring) {         // no token ring: the records themselves cross the ranks
+            args.inbox = nullptr; args.outbox = nullptr;
+            args.spec_world = e->spec_world; args.spec_rank = e->spec_rank; args.spec_base = e->lo / seg; args.spec_total = ceil_div(e->G, seg);
+            for (uint32_t r = 0; r < e->spec_world; ++r) args.spec_peer[r] = e->spec_peer[r];
+        }
         if (const char* v = getenv("ISL_SPEC_DBG")) {       // per-round stamps of one (chunk, stage) cell: tools/spec_trace.py
             unsigned cchunk = 0, cstage = 0;
             if (sscanf(v, "%u,%u", &cchunk, &cstage) == 2) {
@@ -647,6 +670,25 @@ int validate_ready(isl_engine* e, uint32_t n) {
     if (e->open.active) return ISL_ESTATE;         // an open stream owns the engine until isl_stream_close
     if (n > e->cfg.max_batch) return ISL_ERANGE;
     return ISL_OK;
+}
+
+constexpr uint32_t kSpecRingChunks = 64;         // chunks of one partitioned stream call that may speculate (17 MB of records per rank)
+
+int spec_shared_alloc(isl_engine* e) {
+    if (e->spec_shared) return ISL_OK;
+    if (e->d_spec) { cudaFree(e->d_spec); e->d_spec = nullptr; e->cap_spec = 0; }
+    ISL_CUDA(e, cudaMalloc(&e->d_spec, (size_t)kSpecRingChunks * kSpecWordsPerChunk * sizeof(unsigned long long)));
+    ISL_CUDA(e, cudaMemset(e->d_spec, 0, (size_t)kSpecRingChunks * kSpecWordsPerChunk * sizeof(unsigned long long)));
+    e->cap_spec = kSpecRingChunks; e->spec_shared = true;
+    return ISL_OK;
+}
+
+void spec_disconnect(isl_engine* e) {
+    for (uint32_t r = 0; r < 8; ++r) {
+        if (e->spec_peer[r] && e->spec_peer[r] != e->d_spec && !e->spec_peer_local) cudaIpcCloseMemHandle(e->spec_peer[r]);
+        e->spec_peer[r] = nullptr;
+    }
+    e->spec_world = 0;
 }
 
 }  // namespace
@@ -759,7 +801,7 @@ int isl_destroy(isl_engine* e) {
         cudaFree(e->d_occ); cudaFree(e->d_lut); cudaFree(e->d_feas); cudaFree(e->d_req); cudaFree(e->d_res);
         cudaFree(e->d_q); cudaFree(e->d_tile_counts); cudaFree(e->d_cand); cudaFree(e->d_log); cudaFree(e->d_sweep_counts);
         cudaFree(e->d_ctrl); cudaFree(e->d_scratch);
-        cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens); cudaFree(e->d_spec); cudaFree(e->d_specdbg);
+        cudaFree(e->d_chunks); cudaFree(e->d_cctl); cudaFree(e->d_qall); cudaFree(e->d_tokens); spec_disconnect(e); cudaFree(e->d_spec); cudaFree(e->d_specdbg);
         cudaFree(e->d_free_acc); cudaFree(e->d_tiles);
         if (e->d_outbox && !e->outbox_local) cudaIpcCloseMemHandle(e->d_outbox);
         cudaFree(e->d_inbox); cudaFree(e->d_trace); cudaFree(e->d_bf_bitmaps); cudaFree(e->d_ready); cudaFree(e->d_done_cnt); cudaFree(e->d_occ_snap);
@@ -1151,6 +1193,61 @@ int isl_connect_local(isl_engine* e, isl_engine* next, int has_prev) {
     return ISL_OK;
 }
 
+// ---- speculative rounds over a partitioned inventory: every rank's record memory mapped into every other rank ------------------------
+int isl_ipc_spec_handle(isl_engine* e, void* handle64) {
+    if (!e || !handle64) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    if (int rc = spec_shared_alloc(e)) return rc;
+    cudaIpcMemHandle_t h;
+    ISL_CUDA(e, cudaIpcGetMemHandle(&h, e->d_spec));
+    memcpy(handle64, &h, sizeof h);
+    return ISL_OK;
+}
+
+// handles: world x 64 bytes (isl_ipc_spec_handle of every rank, own entry ignored); bounds: world + 1 canonical GPU indices, rank r owns
+// [bounds[r], bounds[r + 1]).  world = 0 disconnects.
+int isl_ipc_connect_spec(isl_engine* e, uint32_t world, uint32_t rank, const void* handles, const uint32_t* bounds) {
+    if (!e) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    spec_disconnect(e);
+    if (world == 0) return ISL_OK;
+    if (world < 2 || world > 8 || rank >= world || !handles || !bounds) return ISL_EINVAL;
+    if (int rc = spec_shared_alloc(e)) return rc;
+    e->spec_peer_local = false;
+    for (uint32_t r = 0; r < world; ++r) {
+        if (r == rank) { e->spec_peer[r] = e->d_spec; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + 64 * r, sizeof h);
+        void* p = nullptr;
+        ISL_CUDA(e, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        e->spec_peer[r] = static_cast<unsigned long long*>(p);
+    }
+    for (uint32_t r = 0; r <= world; ++r) e->spec_bounds[r] = bounds[r];
+    e->spec_world = world; e->spec_rank = rank;
+    return ISL_OK;
+}
+
+// same-process engines (tests: several ranks on one GPU)
+int isl_connect_spec_local(isl_engine* e, uint32_t world, uint32_t rank, isl_engine* const* engines, const uint32_t* bounds) {
+    if (!e) return ISL_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard guard(e->device);
+    spec_disconnect(e);
+    if (world == 0) return ISL_OK;
+    if (world < 2 || world > 8 || rank >= world || !engines || !bounds) return ISL_EINVAL;
+    if (int rc = spec_shared_alloc(e)) return rc;
+    e->spec_peer_local = true;
+    for (uint32_t r = 0; r < world; ++r) {
+        if (r != rank && (!engines[r] || !engines[r]->spec_shared)) return ISL_ESTATE;     // every engine allocates first (isl_ipc_spec_handle)
+        e->spec_peer[r] = r == rank ? e->d_spec : engines[r]->d_spec;
+    }
+    for (uint32_t r = 0; r <= world; ++r) e->spec_bounds[r] = bounds[r];
+    e->spec_world = world; e->spec_rank = rank;
+    return ISL_OK;
+}
+
 int isl_place_stream_partitioned(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const void* d_in, void* d_out, uint32_t stream_id) {
     if (!e || !sizes || n_batches == 0 || n_batches > 4096 || !d_in || !d_out || stream_id == 0) return ISL_EINVAL;
     uint64_t total = 0;
@@ -1509,7 +1606,7 @@ int isl_stream_submit(isl_engine* e, uint32_t n, const isl_request* in, isl_resu
         args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
         args.q_stride = o.q_stride; args.free_stride = o.free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab;
         args.out = e->d_res; args.feas = e->d_feas; args.stats = e->d_ctrl;
-        if (o.spec) { args.spec = 1; args.spec_mem = e->d_spec; }
+        if (o.spec) { args.spec = 1; args.spec_mem = e->d_spec; args.spec_total = o.n_seg; }
         int rc;
         const bool p15 = e->prof.n == ISL_MAX_PROFILES;
         switch (e->n_cand_slots) {

@@ -56,6 +56,15 @@ def connect_owner(engine, rank: int, world: int, group=None):
     engine.set_ring_world(world)
 
 
+def connect_spec(engine, rank: int, world: int, G: int, group=None, align: int = SEGMENT):
+    """Speculative rounds across ranks: every rank maps every other rank's record memory (the per-round records of the stages cross
+    ranks as peer stores); ``partition_bounds`` must be what the engines' partitions are."""
+    handles = [None] * world
+    dist.all_gather_object(handles, engine.ipc_spec_handle(), group=group)
+    bounds = [lo for lo, _ in all_bounds(G, world, align)] + [G]
+    engine.ipc_connect_spec(world, rank, handles, bounds)
+
+
 def merge_results(records_i64: torch.Tensor, group=None) -> torch.Tensor:
     """Element-wise MIN over ranks of the 8-byte result records viewed as int64 (in place)."""
     dist.all_reduce(records_i64, op=dist.ReduceOp.MIN, group=group)

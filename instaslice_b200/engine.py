@@ -62,7 +62,7 @@ EXPORTED_SYMBOLS = [
     "isl_snapshot_occupancy", "isl_restore_occupancy", "isl_num_gpus", "isl_gpu_to_node", "isl_place_batch", "isl_place_batch_device", "isl_place_stream", "isl_place_stream_device", "isl_free_batch",
     "isl_eval_starts", "isl_set_partition", "isl_place_batch_partitioned", "isl_ipc_inbox_handle", "isl_ipc_connect", "isl_connect_local", "isl_place_stream_partitioned", "isl_device_occupancy", "isl_get_stats", "isl_read_trace",
     "isl_reset_stats", "isl_strerror", "isl_last_cuda_error", "isl_abi_version",
-    "isl_place_batch_range", "isl_stream_open", "isl_stream_submit", "isl_stream_wait", "isl_stream_close", "isl_set_causal_window", "isl_set_speculation",
+    "isl_place_batch_range", "isl_stream_open", "isl_stream_submit", "isl_stream_wait", "isl_stream_close", "isl_set_causal_window", "isl_set_speculation", "isl_ipc_spec_handle", "isl_ipc_connect_spec", "isl_connect_spec_local",
     "isl_host_alloc", "isl_host_free", "isl_device_results", "isl_ipc_results_handle", "isl_ipc_connect_owner", "isl_connect_owner_local", "isl_set_ring_world", "isl_capacity", "isl_what_if",
 ]
 
@@ -119,6 +119,9 @@ def load_library(path: str = LIB_PATH):
         "isl_stream_close": (C.c_int, [p]),
         "isl_set_causal_window": (C.c_int, [p, C.c_uint32]),
         "isl_set_speculation": (C.c_int, [p, C.c_uint32]),
+        "isl_ipc_spec_handle": (C.c_int, [p, C.c_void_p]),
+        "isl_ipc_connect_spec": (C.c_int, [p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+        "isl_connect_spec_local": (C.c_int, [p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
         "isl_host_alloc": (p, [C.c_size_t]),
         "isl_host_free": (None, [p]),
         "isl_device_results": (p, [p]),
@@ -339,6 +342,22 @@ class Engine:
 
     def set_causal_window(self, window: int):
         self._check(self._lib.isl_set_causal_window(self._h, window), "isl_set_causal_window")
+
+    def ipc_spec_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.isl_ipc_spec_handle(self._h, buf), "isl_ipc_spec_handle")
+        return buf.raw
+
+    def ipc_connect_spec(self, world: int, rank: int, handles: list, bounds):
+        """``handles``: the 64-byte ``ipc_spec_handle()`` of every rank; ``bounds``: world + 1 canonical GPU indices."""
+        blob = C.create_string_buffer(b"".join(h if h else b"\0" * 64 for h in handles), 64 * world)
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        self._check(self._lib.isl_ipc_connect_spec(self._h, world, rank, blob, _ptr(b)), "isl_ipc_connect_spec")
+
+    def connect_spec_local(self, world: int, rank: int, engines: list, bounds):
+        arr = (C.c_void_p * world)(*[e._h for e in engines])
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        self._check(self._lib.isl_connect_spec_local(self._h, world, rank, arr, _ptr(b)), "isl_connect_spec_local")
 
     def set_speculation(self, mode: int):
         """SPEC_AUTO / SPEC_OFF / SPEC_ON: speculative rounds inside the segment pipeline (include/islplace.h)."""

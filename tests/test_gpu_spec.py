@@ -161,3 +161,70 @@ def test_many_speculative_calls_reuse_the_record_memory():
         eng.load_inventory(node_off, occ)
         assert np.array_equal(eng.place_batch(req), ref.place(req)), it
     eng.close()
+
+
+@pytest.mark.parametrize("n_ranks,window", [(2, 1), (3, 2), (4, 1)])
+def test_speculative_rounds_across_ranks_on_one_gpu(n_ranks, window):
+    """A partitioned inventory: several engines in one process, each owning a GPU range, every engine's record memory wired into every
+    other one (isl_connect_spec_local; CUDA IPC across processes).  The stages of all engines form ONE sequence and exchange their
+    per-round records through each other's memory; PLACED records land in the owner's result array.  The owner's array alone == the
+    global sequential first-fit."""
+    import torch
+    from instaslice_b200 import dist as D
+    rows = E.make_profiles(tables.H100_80GB)
+    rng = W.SplitMix64(999 + n_ranks)
+    G = 4096
+    node_off = W.node_offsets(G // 8, 8)
+    occ0 = ((rng.next(G) & rng.next(G)) & np.uint64(0x7F)).astype(np.uint8)
+    ref = oracle.Fast(node_off, rows)
+    ref.load(occ0)
+    batches, want, live = [], [], []
+    for b in range(6):
+        n = 3000 + 700 * b
+        req = _mixed(rng, n, rows)
+        for i in range(min(len(live), n // 3)):
+            g, s, z = live.pop(int(rng.next1() % len(live)))
+            req[int(rng.next1() % n)] = (g, 0, E.OP_FREE, s, z)
+        res = ref.place(req)
+        for r in res[(req["op"] == E.OP_ALLOC) & (res["status"] == E.ST_PLACED)]:
+            live.append((int(r["gpu"]), int(r["start"]), int(r["size"])))
+        batches.append(req); want.append(res)
+    sizes = np.array([len(b) for b in batches], dtype=np.uint32)
+    n_ops = int(sizes.sum())
+    d_in = torch.from_numpy(np.concatenate(batches).view(np.int64).copy()).cuda()
+    bounds = D.all_bounds(G, n_ranks, align=64)
+    cuts = [lo for lo, _ in bounds] + [G]
+    engines = []
+    for r, (lo, hi) in enumerate(bounds):
+        eng = E.Engine(max_gpus=G, max_batch=1 << 16)
+        eng.load_profiles(rows)
+        eng.load_inventory(node_off, occ0)
+        eng.ipc_inbox_handle(); eng.ipc_spec_handle()          # allocate the shared buffers
+        engines.append(eng)
+    for r, eng in enumerate(engines):
+        eng.connect_local(engines[r + 1] if r + 1 < n_ranks else None, has_prev=r > 0)
+        eng.connect_owner_local(engines[0] if r > 0 else None)
+        eng.set_ring_world(n_ranks)
+        eng.connect_spec_local(n_ranks, r, engines, cuts)
+        eng.set_causal_window(window)
+        eng.set_speculation(E.SPEC_ON)
+    torch.cuda.synchronize()
+    for stream_id in (1, 2, 3):
+        for eng, (lo, hi) in zip(engines, bounds):
+            eng.load_inventory(node_off, occ0)
+            eng.set_partition(lo, hi)
+        for eng in engines:
+            eng.place_stream_partitioned(sizes, d_in.data_ptr(), eng.device_results(), stream_id)
+        for eng in engines:
+            eng.synchronize()
+
+        class _View:            # torch view of the owner's engine-owned result array (no copy)
+            __cuda_array_interface__ = {"shape": (n_ops,), "typestr": "<i8", "data": (engines[0].device_results(), False), "version": 3}
+        got = torch.as_tensor(_View(), device="cuda").cpu().numpy().view(E.RESULT_DTYPE)
+        assert np.array_equal(got, np.concatenate(want)), (n_ranks, window, stream_id)
+        occ = np.concatenate([eng.read_occupancy()[lo:hi] for eng, (lo, hi) in zip(engines, bounds)])
+        assert np.array_equal(occ, ref.occupancy())
+        st = engines[-1].stats()
+        assert st["spec_chunks"] >= len(batches), st
+    for eng in engines:
+        eng.close()
