@@ -102,6 +102,17 @@ int main(int argc, char** argv) {
                     { std::vector<int> b2 = big; long d = dq, tot = nb; std::sort(b2.begin(), b2.end());
                       for (size_t i = 0; i < b2.size(); ++i) { int p = b2[i]; long dp = i + 1 == b2.size() ? d : (tot ? std::lround((double)d * q[p].size() / tot) : 0); clampadd(p, dp); d -= dp; tot -= q[p].size(); } }
                     spread(small, dr, ns);
+                    if (getenv("LEAD")) {
+                        // hungry regime: the heavier small profile's pending request is much older than the lighter one's at both ends of the segment ->
+                        // it takes every span it can use, the split inside the group passes through the segment unchanged
+                        const long th = atol(getenv("LEAD"));
+                        int pl = -1, ph = -1; for (int p : small) { if (psize(p) == 1 && (pl < 0 || q[p].size() > q[pl].size())) pl = p; if (psize(p) > 1 && (ph < 0 || q[p].size() > q[ph].size())) ph = p; }
+                        if (pl >= 0 && ph >= 0) {
+                            auto lead = [&](const Heads& hh) { long t1 = hh[pl] < q[pl].size() ? (long)q[pl][hh[pl]] : (long)n, t2 = hh[ph] < q[ph].size() ? (long)q[ph][hh[ph]] : (long)n; return t1 - t2; };
+                            const bool hungry = lead(H[s]) > th && lead(E[s + 1]) > th;
+                            if (hungry) { for (int p : small) { long v = (long)base_exit[p] + (long)Hn[s][p] - (long)H[s][p]; h[p] = (uint32_t)std::max(0l, std::min<long>(v, q[p].size())); } }
+                        }
+                    }
                     if (getenv("RESID")) {
                         // what the mass step did: m = h - base_exit; the entry shift was sh = Hn[s] - H[s]; residual r = sh - m (zero mass per group); pass lambda_s * r on
                         std::array<double, P> r{}; double nr = 0;
