@@ -1165,6 +1165,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     __shared__ uint32_t s_specH[ISL_MAX_PROFILES], s_specX[ISL_MAX_PROFILES], s_specXp[ISL_MAX_PROFILES], s_qc[ISL_MAX_PROFILES];
     __shared__ uint32_t s_acc[4], s_grp_big, s_grp_small, s_specflag, s_bigd[32], s_nbigd, s_dqr[2], s_us[kMaxTables], s_qo[ISL_MAX_PROFILES];
     __shared__ uint8_t s_smallm[kMaxTables][ISL_MAX_PROFILES];
+    // speculative rounds, bounded simulations: entry / exit heads of the stage's last COMPLETE simulation; {decisions of the largest complete one,
+    // have one, the log in shared memory is a complete simulation of the current entry}; decisions this simulation may take; it was cut off
+    __shared__ uint32_t s_Hc[ISL_MAX_PROFILES], s_Xc[ISL_MAX_PROFILES], s_capst[3], s_cap, s_capped;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     if (seg == a.n_seg) {       // the extra CTA of a host-buffer stream: every chunk all segments have committed goes to the caller's
                                 // (mapped, pinned) result array right away, so the D2H of the results hides behind the rest of the stream
@@ -1478,6 +1481,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         }
         uint32_t rnd = 1;
         bool c_prev = spec ? gseg == 0 : seg == 0, need_sim = true, idle_break = false;
+        bool known_exact = gseg == 0;       // every stage in front had the true entry one round ago: so have I now
+        if (tid == 0) { s_capst[0] = 0; s_capst[1] = 0; s_capst[2] = 0; s_cap = kLogCap + 1; s_capped = 0; }
         bool p_final = false; unsigned long long p_word = 0;      // pollers: a certified stage's final record is read once and kept
         const unsigned long long t_cell = tr && spec ? globaltimer_ns() : 0ull, sims_cell = st_sims;   // spec trace: [0] sweep + prediction done, [2] certified, [7] simulations, [11] rounds
         unsigned long long* dbg = a.spec_dbg && a.spec_dbg_cell == ((c << 16) | seg) ? a.spec_dbg : nullptr;
@@ -1540,7 +1545,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             // nothing placeable is pending any more: tell every later segment at once instead of relaying hop by hop
             const bool idle = __ballot_sync(0xFFFFFFFFu, left != 0) == 0;
             if (idle && !all_done && !spec && tid < ISL_MAX_PROFILES) st_relaxed_gpu(a.tokens + (tok_chunk + a.n_seg) * kTokStride + tid, (tag << 17) | h);
-            if (tid == 0) s_idle = idle ? 1u : 0u;
+            if (tid == 0) {
+                s_idle = idle ? 1u : 0u;
+                // A speculative simulation from an entry that is far off can run several times longer than the segment's true work (everything the
+                // stages in front are wrongly believed to have left over lands here) and would hold up the whole round.  Unless the entry is known
+                // to be the true one, the simulation is cut off at 1.3 x the largest complete one so far; a cut-off round publishes the exit
+                // extrapolated from the last complete simulation instead (what the stages behind would assume anyway).
+                s_cap = spec && s_capst[1] && !known_exact ? min(kLogCap + 1, ((s_capst[0] * 21u) >> 4) + 64u) : kLogCap + 1;
+                s_capped = 0;
+            }
             uint32_t incl = wn + kWinPad;                       // INF sentinels close every window
 #pragma unroll
             for (int d = 1; d < 16; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
@@ -1633,7 +1646,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             stamp_if(tr && lane == 0, tr + 4);
             stamp_if(dbg && lane == 0, dbg + rnd * 8 + 2);
             constexpr bool kDefer = ISL_DEFER_INF && !kP15;     // see the rare path below
+            const uint32_t la_cap = sa_log + 8u * s_cap;
+            bool cut = false;
             while (true) {
+                if (!kDefer && la >= la_cap) { cut = true; break; }     // once per group of decisions, off the loop-carried path
                 bool none = false;
                 uint32_t m = 0, mmax = 0;
 #pragma unroll
@@ -1693,7 +1709,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     // m == INF is a legitimate step of the recurrence ("neither this GPU nor the next takes anything: the next one becomes
                     // current"; it pops only lanes whose window is exhausted, into their INF sentinels), so the loop body needs no exit
                     // test per decision — one test per group: did ANY decision of the group find nothing?
-                    if (__builtin_expect(mmax != kInf, 1)) continue;
+                    if (__builtin_expect(mmax != kInf && la < la_cap, 1)) continue;     // (the cut-off test rides on the group's one branch)
+                    if (la >= la_cap) { cut = true; break; }
                     // exhausted lanes were popped past the end of their windows: back onto the sentinels (at most kUnroll pops since the last time)
 #pragma unroll
                     for (int k = 0; k < K; ++k)
@@ -1735,6 +1752,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             __syncwarp();
             if (lane == 0) {
                 s_nlog = nlog;
+                s_capped = cut ? 1u : 0u;
                 if (tr) tr[2] = globaltimer_ns();
             }
         }
@@ -1755,13 +1773,31 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         {   // ---- the round's exchange: publish exit heads and consumed masses, read the predecessor's exit and every earlier stage's masses
             const unsigned long long tagr = tagb | ((unsigned long long)rnd << 32);
             if (tid < 32) {
-                uint32_t X = 0, dq = 0, dr = 0;
+                uint32_t X = 0, dq = 0, dr = 0, pop = 0;
+                const bool was_cut = s_capped != 0;
+                if (tid < ISL_MAX_PROFILES) { pop = s_pop[tid]; X = s_heads[tid] + pop; }
+                if (was_cut) {      // exit of the last complete simulation, moved by what the entry has moved since (per group, shares as always)
+                    int eq = 0, er = 0;
+                    if (tid < ISL_MAX_PROFILES) {
+                        const int d = (int)s_heads[tid] - (int)s_Hc[tid];
+                        if ((s_grp_big >> tid) & 1u) eq = d;
+                        if ((s_grp_small >> tid) & 1u) er = d * (int)s_minsize[tid];
+                        s_specX[tid] = s_Xc[tid];
+                    }
+                    eq = __reduce_add_sync(0xFFFFFFFFu, eq); er = __reduce_add_sync(0xFFFFFFFFu, er);
+                    __syncwarp();
+                    if (tid == 0) { spec_spread(s_specX, s_qc, s_minsize, s_grp_big, eq, false); spec_spread(s_specX, s_qc, s_minsize, s_grp_small, er, true); }
+                    __syncwarp();
+                    if (tid < ISL_MAX_PROFILES) { X = max(s_specX[tid], s_heads[tid]); pop = X - s_heads[tid]; }
+                    __syncwarp();
+                }
                 if (tid < ISL_MAX_PROFILES) {
-                    const uint32_t pop = s_pop[tid];
-                    X = s_heads[tid] + pop; s_specX[tid] = X;
+                    s_specX[tid] = X;
+                    if (!was_cut) { s_Hc[tid] = s_heads[tid]; s_Xc[tid] = X; }
                     if ((s_grp_big >> tid) & 1u) dq = pop;
                     if ((s_grp_small >> tid) & 1u) dr = pop * s_minsize[tid];
                 }
+                if (tid == 0) { if (was_cut) s_capst[2] = 0; else { s_capst[0] = max(s_capst[0], s_nlog); s_capst[1] = 1; s_capst[2] = 1; } }
                 dq = __reduce_add_sync(0xFFFFFFFFu, dq); dr = __reduce_add_sync(0xFFFFFFFFu, dr);
                 if (rnd >= 3 && gseg + 1 < gtot && !(need_sim && !s_idle)) {      // the slot of round rnd - 2 is overwritten: the successor must have read it (checked behind the chain when one ran)
                     const unsigned long long t0 = globaltimer_ns();
@@ -1815,7 +1851,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 }
                 s_specXp[i] = (uint32_t)w & 0x1FFFFu;
             }
-            const bool certified = __syncthreads_and(cbit) && c_prev;
+            const bool allc = __syncthreads_and(cbit);
+            const bool certified = allc && c_prev;
             stamp_if(dbg && tid == 0, dbg + rnd * 8 + 5);
             store_if(dbg && tid == 0, dbg + rnd * 8 + 7, s_nlog | ((unsigned long long)need_sim << 32));
             if (gseg > 0 && tid == 192) pub_nb(sm.ack + gseg, ((unsigned long long)tage << 32) | (certified ? 0xFFFFu : rnd), true);
@@ -1848,11 +1885,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 __syncwarp();
                 const bool moved = tid < ISL_MAX_PROFILES && s_specH[tid] != hold;
                 const bool changed = __any_sync(0xFFFFFFFFu, moved);
-                if (tid == 0) s_specflag = (cnow ? 1u : 0u) | (changed ? 2u : 0u);
+                // a cut-off simulation left no usable log: the entry is simulated again (in full once it is known to be the true one) and counts as
+                // inconsistent until then
+                if (tid == 0) s_specflag = (cnow && s_capst[2] ? 1u : 0u) | (changed || !s_capst[2] ? 2u : 0u);
                 stamp_if(dbg && tid == 0, dbg + rnd * 8 + 6);
             }
             __syncthreads();
-            c_prev = s_specflag & 1u; need_sim = s_specflag & 2u;
+            c_prev = s_specflag & 1u; need_sim = s_specflag & 2u; known_exact = allc;
             if (++rnd >= kSpecRounds - 1) __trap();      // cannot happen: every round certifies at least one more stage
         }
         }   // rounds

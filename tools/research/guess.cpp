@@ -67,10 +67,36 @@ int main(int argc, char** argv) {
         std::vector<double> lq(S, 1.0), lr(S, 1.0); std::vector<long> peq(S), pxq(S), per(S), pxr(S); std::vector<bool> have(S, false);
         const int secant = getenv("SECANT") ? atoi(getenv("SECANT")) : 0;
         std::vector<Heads> pH(S), pE(S); std::vector<bool> haveR(S, false); std::vector<double> lam(S, getenv("LAM0") ? atof(getenv("LAM0")) : 0.0);
-        int rounds = 0; uint64_t crit = 0; uint32_t frontier = 0;
+        int rounds = 0; uint64_t crit = 0; uint32_t frontier = 0, frontier1 = 0, frontier2 = 0; uint64_t ncapped = 0;
+        std::vector<Heads> Hsim(S), Xlast(S), Hc(S), Xc(S); std::vector<bool> logvalid(S, false), havec(S, false); std::vector<uint64_t> maxdec(S, 0);
         while (true) {
             ++rounds; uint64_t maxw = 0;
-            for (uint32_t s = 0; s < S; ++s) { uint64_t d = 0; E[s + 1] = simulate(L.occ, s * seg, std::min(G, (s + 1) * seg), H[s], &d); maxw = std::max(maxw, d); }
+            uint32_t maxs = 0; uint64_t sumw = 0, nb_ = 0, second = 0;
+            const bool docap = getenv("CAP") != nullptr; const double capf = docap ? atof(getenv("CAP")) : 0;
+            for (uint32_t s = 0; s < S; ++s) {
+                uint64_t d = 0;
+                const bool resim = rounds == 1 || H[s] != Hsim[s] || !logvalid[s];
+                if (!resim) { E[s + 1] = Xlast[s]; continue; }
+                Heads ex = simulate(L.occ, s * seg, std::min(G, (s + 1) * seg), H[s], &d);
+                const uint64_t cap = (uint64_t)(capf * maxdec[s]) + 64;
+                const bool exempt = !docap || !havec[s] || s <= frontier2;
+                if (!exempt && d > cap) {      // declined: extrapolate from the last complete simulation (what the successors would assume anyway)
+                    d = cap; logvalid[s] = false; Hsim[s] = H[s];
+                    long dq = 0, dr = 0; for (int p : big) dq += (long)H[s][p] - (long)Hc[s][p]; for (int p : small) dr += ((long)H[s][p] - (long)Hc[s][p]) * psize(p);
+                    Heads h = Xc[s];
+                    long nb = 0, ns = 0; for (int p : big) nb += q[p].size(); for (int p : small) ns += (long)q[p].size() * psize(p);
+                    auto clampadd = [&](int p, long dd) { long v = (long)h[p] + dd; v = std::max(0l, std::min<long>(v, q[p].size())); h[p] = v; };
+                    { std::vector<int> b2 = big; long dd = dq, tot = nb; std::sort(b2.begin(), b2.end());
+                      for (size_t i = 0; i < b2.size(); ++i) { int p = b2[i]; long dp = i + 1 == b2.size() ? dd : (tot ? std::lround((double)dd * q[p].size() / tot) : 0); clampadd(p, dp); dd -= dp; tot -= q[p].size(); } }
+                    { std::vector<int> grp = small; long dd = dr, tot = ns; std::sort(grp.begin(), grp.end(), [&](int x, int y) { return psize(x) > psize(y) || (psize(x) == psize(y) && x < y); });
+                      for (size_t i = 0; i < grp.size(); ++i) { int p = grp[i]; long w = psize(p); long dp = i + 1 == grp.size() ? dd / w : (tot ? std::lround((double)dd * q[p].size() / tot) : 0); clampadd(p, dp); dd -= dp * w; tot -= (long)q[p].size() * w; } }
+                    E[s + 1] = h; Xlast[s] = h; ++ncapped;
+                } else {
+                    E[s + 1] = ex; Xlast[s] = ex; Hsim[s] = H[s]; logvalid[s] = true; Hc[s] = H[s]; Xc[s] = ex; havec[s] = true; maxdec[s] = std::max<uint64_t>(maxdec[s], d);
+                }
+                if (d > maxw) { second = maxw; maxw = d; maxs = s; } else if (d > second) second = d; sumw += d; nb_ += d > 0;
+            }
+            if (getenv("VERBM") && (int)b == atoi(getenv("VERBM"))) printf("      round %d: max %lu at stage %u (second %lu), mean busy %.0f, frontier %u\n", rounds, maxw, maxs, second, nb_ ? (double)sumw / nb_ : 0.0, frontier);
             crit += maxw;
             Hn[0] = h0;
             for (uint32_t s = 0; s < S; ++s) {
@@ -153,11 +179,13 @@ int main(int argc, char** argv) {
             if (getenv("VERB") && (int)b == atoi(getenv("VERB"))) { printf("      err:"); for (uint32_t s = 0; s < 48 && s <= S; ++s) { long d = 0; for (int p = 0; p < np; ++p) d += std::labs((long)H[s][p] - (long)truth[s][p]); printf(" %ld", d); } printf("\n"); }
             if (getenv("VERBL") && (int)b == atoi(getenv("VERBL")) && rounds <= 16) { printf("      lam r%d:", rounds); for (uint32_t s = 0; s < 60; ++s) printf(" %.1f", lam[s]); printf("\n"); }
             if (getenv("VERBP") && (int)b == atoi(getenv("VERBP")) && rounds >= 12 && rounds <= 14) { for (uint32_t s = 24; s < 40; ++s) { printf("      r%d b%u:", rounds, s); for (int p = 0; p < np; ++p) printf(" %ld", (long)H[s][p] - (long)truth[s][p]); printf("\n"); } }
+            frontier2 = frontier1; frontier1 = frontier;
             frontier = 0; while (frontier <= S && H[frontier] == truth[frontier]) ++frontier;
             printf("   round %d: boundaries still wrong %u, exact frontier %u / %u\n", rounds, wrong, frontier, S + 1);
-            if (!any || rounds > 200) break;
+            bool allvalid = true; for (uint32_t s = 0; s < S; ++s) if (!logvalid[s]) allvalid = false;
+            if ((!any && allvalid) || rounds > 200) break;
         }
-        printf("%s batch %zu seg %u: sequential decisions %lu | rounds %d, critical path %lu decisions (%.3fx)\n", cfg.c_str(), b, seg, dec, rounds, crit, (double)crit / dec);
+        printf("%s batch %zu seg %u: sequential decisions %lu | rounds %d, critical path %lu decisions (%.3fx) capped %lu\n", cfg.c_str(), b, seg, dec, rounds, crit, (double)crit / dec, ncapped);
         L.occ = occ_new; off += n;
     }
 }
