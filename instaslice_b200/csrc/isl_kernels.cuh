@@ -1150,7 +1150,7 @@ __device__ __noinline__ uint32_t pipeline_skip(uint32_t sa_cand, const uint16_t*
     return kInf;
 }
 
-template <int K, bool kP15>
+template <int K, bool kP15, bool kSpec>
 __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t* s_occ32 = reinterpret_cast<uint32_t*>(smem);                       // kSegMax occupancy bytes
@@ -1242,7 +1242,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         }
         s_usable[tid - 32] = u;
     }
-    if (a.spec && tid >= 64 && tid < 96) {      // speculative rounds: the (profile, start) candidates of >= 4 slices as a list; per (table, profile) the slices of its smaller spans
+    if (kSpec && tid >= 64 && tid < 96) {      // speculative rounds: the (profile, start) candidates of >= 4 slices as a list; per (table, profile) the slices of its smaller spans
         const uint32_t l = tid - 64;
         uint32_t n = 0;
         for (uint32_t k = 0; k < 4; ++k) {
@@ -1382,7 +1382,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         // 3. token of the previous segment
         unsigned long long* tr = a.trace ? a.trace + ((size_t)c * a.n_seg + seg) * kTraceWords : nullptr;
         const size_t tok_chunk = (size_t)c * (a.n_seg + 1);
-        const bool spec = a.spec != 0;      // host: only with one sub-segment per stage and no token ring
+        constexpr bool spec = kSpec;        // host: only with one sub-segment per stage (a.spec); a separate instantiation, so that the plain pipeline's code is untouched by the rounds' machinery
         const SpecMem sm = spec_mem(a.spec_mem, spec ? c : 0);
         // a partitioned inventory tags with the stream id all ranks share
         const uint32_t tage = a.spec_world > 1 ? a.xepoch : a.epoch;
@@ -1923,7 +1923,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         atomicAdd(&a.stats->visited, st_visited);
         atomicAdd(&a.stats->jumps, st_jumps);
     }
-    if (tid == 0 && a.spec) {
+    if (kSpec && tid == 0) {
         atomicAdd(&a.stats->spec_sims, st_sims);
         atomicAdd(&a.stats->spec_rounds, st_rounds_sum);
         atomicAdd(&a.stats->spec_cells, (unsigned long long)st_cells);

@@ -314,7 +314,7 @@ int run_batch(isl_engine* e, uint32_t n, const uint2* d_in, uint2* d_out, const 
 template <int K, bool kP15>
 int launch_pipeline(isl_engine* e, PipeArgs& args) {
     void* params[] = {&e->tab, &args};
-    const cudaError_t err = cudaLaunchCooperativeKernel((void*)k_pipeline<K, kP15>, dim3(args.n_seg + (args.copier ? 1u : 0u)), dim3(kPipeThreads), params, kPipeSmem, e->stream);
+    const cudaError_t err = cudaLaunchCooperativeKernel(args.spec ? (void*)k_pipeline<K, kP15, true> : (void*)k_pipeline<K, kP15, false>, dim3(args.n_seg + (args.copier ? 1u : 0u)), dim3(kPipeThreads), params, kPipeSmem, e->stream);
     if (err == cudaErrorCooperativeLaunchTooLarge || err == cudaErrorLaunchOutOfResources) {   // e.g. the GPU is shared: not all CTAs can be co-resident
         cudaGetLastError();
         return ISL_ESTATE;          // caller falls back to the chunk-by-chunk path
@@ -329,7 +329,7 @@ int query_coresident(isl_engine* e) {
     int per_sm = 0, sms = 0, coop = 0;
     ISL_CUDA(e, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
     ISL_CUDA(e, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
-    ISL_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline<4, true>, kPipeThreads, kPipeSmem));
+    ISL_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline<4, true, true>, kPipeThreads, kPipeSmem));
     e->max_coresident = coop ? std::max(1, per_sm * sms) : -1;
     return ISL_OK;
 }
@@ -747,16 +747,20 @@ int isl_create(const isl_config* cfg, isl_engine** out) {
         const void* kernels[] = {(const void*)k_prepare, (const void*)k_partition, (const void*)k_set_flag, (const void*)k_few, (const void*)k_build_lut, (const void*)k_eval_starts,
                                  (const void*)k_free_spans, (const void*)k_capacity, (const void*)k_sweep_count, (const void*)k_sweep_scatter, (const void*)k_commit, (const void*)k_bestfit<false>, (const void*)k_bestfit<true>,
                                  (const void*)k_chain<1>, (const void*)k_chain<2>, (const void*)k_chain<4>, (const void*)k_small<1>, (const void*)k_small<2>, (const void*)k_small<4>,
-                                 (const void*)k_pipeline<1, false>, (const void*)k_pipeline<1, true>, (const void*)k_pipeline<2, false>, (const void*)k_pipeline<2, true>,
-                                 (const void*)k_pipeline<4, false>, (const void*)k_pipeline<4, true>};
+                                 (const void*)k_pipeline<1, false, false>, (const void*)k_pipeline<1, true, false>, (const void*)k_pipeline<2, false, false>, (const void*)k_pipeline<2, true, false>,
+                                 (const void*)k_pipeline<4, false, false>, (const void*)k_pipeline<4, true, false>,
+                                 (const void*)k_pipeline<1, false, true>, (const void*)k_pipeline<1, true, true>, (const void*)k_pipeline<2, false, true>, (const void*)k_pipeline<2, true, true>,
+                                 (const void*)k_pipeline<4, false, true>, (const void*)k_pipeline<4, true, true>};
         for (const void* k : kernels) ISL_TRY(cudaFuncGetAttributes(&fa, k));
         // dynamic shared memory opt-in, once per engine on its own device (a process-wide cache keyed by a truncated ordinal would
         // skip devices 8.. and race between threads)
         const void* chains[] = {(const void*)k_chain<1>, (const void*)k_chain<2>, (const void*)k_chain<4>};
         for (const void* k : chains) ISL_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kQCap * sizeof(uint16_t))));
         ISL_TRY(cudaFuncSetAttribute((const void*)k_bestfit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(256 * (kBfSmemGpus / 32 + kBfSmemGpus / 1024) * sizeof(uint32_t))));
-        const void* pipes[] = {(const void*)k_pipeline<1, false>, (const void*)k_pipeline<1, true>, (const void*)k_pipeline<2, false>, (const void*)k_pipeline<2, true>,
-                               (const void*)k_pipeline<4, false>, (const void*)k_pipeline<4, true>};
+        const void* pipes[] = {(const void*)k_pipeline<1, false, false>, (const void*)k_pipeline<1, true, false>, (const void*)k_pipeline<2, false, false>, (const void*)k_pipeline<2, true, false>,
+                               (const void*)k_pipeline<4, false, false>, (const void*)k_pipeline<4, true, false>,
+                               (const void*)k_pipeline<1, false, true>, (const void*)k_pipeline<1, true, true>, (const void*)k_pipeline<2, false, true>, (const void*)k_pipeline<2, true, true>,
+                               (const void*)k_pipeline<4, false, true>, (const void*)k_pipeline<4, true, true>};
         for (const void* k : pipes) ISL_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
     }
     e->occ_bytes = ((size_t)cfg->max_gpus + kSweepBlock - 1) / kSweepBlock * kSweepBlock;
