@@ -1485,7 +1485,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         if (tid == 0) { s_capst[0] = 0; s_capst[1] = 0; s_capst[2] = 0; s_cap = kLogCap + 1; s_capped = 0; }
         bool p_final = false; unsigned long long p_word = 0;      // pollers: a certified stage's final record is read once and kept
         const unsigned long long t_cell = tr && spec ? globaltimer_ns() : 0ull, sims_cell = st_sims;   // spec trace: [0] sweep + prediction done, [2] certified, [7] simulations, [11] rounds
+#ifdef ISL_SPEC_DBG_STAMPS      // per-round stamps of one cell (tools/spec_trace.py): a debugging build — the extra live pointer around the decision loop costs ~14 %
         unsigned long long* dbg = a.spec_dbg && a.spec_dbg_cell == ((c << 16) | seg) ? a.spec_dbg : nullptr;
+#else
+        constexpr unsigned long long* dbg = nullptr;
+#endif
         while (true) {      // one pass unless the stage speculates
         stamp_if(dbg && tid == 0, dbg + rnd * 8 + 0);
         if (need_sim) {
@@ -1643,7 +1647,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             };
             first_key();
             const unsigned long long jumps0 = st_jumps;
-            stamp_if(tr && lane == 0, tr + 4);
+            // (trace stamps next to the decision loop perturb its schedule in the instantiation with the rounds — measured 9 % of a round; that
+            // instantiation records its cell at certification instead)
+            if (!kSpec) stamp_if(tr && lane == 0, tr + 4);
             stamp_if(dbg && lane == 0, dbg + rnd * 8 + 2);
             constexpr bool kDefer = ISL_DEFER_INF && !kP15;     // see the rare path below
             const uint32_t la_cap = sa_log + 8u * s_cap;
@@ -1730,10 +1736,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 first_key();
             }
             const uint32_t nlog = (la - sa_log) >> 3;
+            if (!kSpec) {
             stamp_if(tr && lane == 0, tr + 5);
             stamp_if(dbg && lane == 0, dbg + rnd * 8 + 3);
             store_if(tr && lane == 0, tr + 6, nlog);
             store_if(tr && lane == 0, tr + 7, (st_jumps - jumps0) | ((unsigned long long)(((ca - sa_cand) >> 2) - 2) << 32));
+            }
             if (!spec) { st_steps += nlog; st_visited += ((ca - sa_cand) >> 2) - 2; }
             else { spec_steps = nlog; spec_visited = ((ca - sa_cand) >> 2) - 2; ++st_sims; }
 #pragma unroll

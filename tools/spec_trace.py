@@ -1,6 +1,9 @@
 """Timeline of the speculative rounds on config 4 (strict causal: one batch in flight) from the FLAG_TRACE stamps: per chunk the rounds,
 the simulations per stage, when each stage was certified (us after the chunk's first stage started) — the frontier of exactness over time.
-    python tools/spec_trace.py [chunk]"""
+    python tools/spec_trace.py [chunk]
+Per-round stamps of ONE (chunk, stage) cell (start / heads / chain / publish / gather / correction) need a debugging build — the stamps
+next to the decision loop cost ~14 % of a round and are compiled out by default:
+    tools/ab_build.sh dbg "-DISL_SPEC_DBG_STAMPS";  ISL_LIB=$PWD/tools/_ab/dbg.so ISL_SPEC_DBG=2,40 python tools/spec_trace.py 2"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
