@@ -153,14 +153,16 @@ class Ctx:
         import torch.distributed as dist
         self.torch, self.dist, self.args = torch, dist, args
         self.rank, self.world, self.local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-        # NCCL's own log shows the communicator (ranks, NVLS / P2P).  Whatever the caller's NCCL_DEBUG asks for is left alone (NCCL writes
-        # it to stdout: rank 0's JSON line is printed LAST, after the process group is gone); without one, INFO goes to a per-rank file
-        # that is copied to stderr at the end
-        self.nccl_log = None
-        if self.world > 1 and "NCCL_DEBUG" not in os.environ:
-            self.nccl_log = "/tmp/isl_nccl_%d_rank%d.log" % (os.getppid(), self.rank)
-            os.environ["NCCL_DEBUG"] = "INFO"
-            os.environ["NCCL_DEBUG_FILE"] = self.nccl_log
+        # NCCL's own log shows the communicator (ranks, NVLS / P2P): NCCL_DEBUG=INFO unless the caller asked for something else.  NCCL writes
+        # to the process's stdout, which must end with rank 0's JSON line: file descriptor 1 points at stderr while the process group lives
+        # (so the log lands on stderr, whole), the real stdout is restored for the one JSON line at the very end
+        self.real_stdout = None
+        if self.world > 1:
+            os.environ.setdefault("NCCL_DEBUG", "INFO")
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            sys.stdout.flush()
+            self.real_stdout = os.dup(1)
+            os.dup2(2, 1)
         if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
         torch.cuda.set_device(self.local)
@@ -885,10 +887,10 @@ def run_own(args):
     if ctx.world > 1:
         ctx.dist.barrier()
         ctx.dist.destroy_process_group()
-        if ctx.nccl_log and os.path.exists(ctx.nccl_log):
-            with open(ctx.nccl_log, errors="replace") as f:
-                sys.stderr.write(f.read())
-            sys.stderr.flush()
+        sys.stdout.flush()
+        if ctx.real_stdout is not None:
+            os.dup2(ctx.real_stdout, 1)
+            os.close(ctx.real_stdout)
     if ctx.rank == 0 and line is not None:
         sys.stdout.flush()
         print(json.dumps(line), flush=True)          # the LAST line of stdout

@@ -70,7 +70,7 @@ for n in (1, 2, 4, 8):
         rows.append((n, d["ms_per_step"], d["value"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["roofline"]["frac"], ph, d["parity"].startswith("bit-exact")))
 if rows:
     print()
-    print("| N GPUs (config 4 causal feed, strong scaling: the job is fixed) | ms per step (max over ranks) | ALLOC decisions/s | e2e | roofline frac | pre-pass + pipeline | occupancy all-gather | result merge | parity vs `ref_fast` |")
+    print("| N GPUs (config 4 strict causal, inventory partitioned over the ranks; strong scaling: the job is fixed) | ms per step (max over ranks) | ALLOC decisions/s | e2e | roofline frac | pre-pass + pipeline | occupancy all-gather | result merge | parity vs `ref_fast` |")
     print("|---|---|---|---|---|---|---|---|---|")
     for n, ms, v, e, ems, fr, ph, ok in rows:
         vals = list(ph.values())
