@@ -158,8 +158,10 @@ class Ctx:
         # (so the log lands on stderr, whole), the real stdout is restored for the one JSON line at the very end
         self.real_stdout = None
         if self.world > 1:
-            os.environ.setdefault("NCCL_DEBUG", "INFO")
-            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+                os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+            os.environ.pop("NCCL_DEBUG_FILE", None)
             sys.stdout.flush()
             self.real_stdout = os.dup(1)
             os.dup2(2, 1)

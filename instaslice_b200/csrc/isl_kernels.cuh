@@ -1091,30 +1091,23 @@ __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsign
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Speculative rounds: move the heads of the profiles in `members` so that their mass (sum of weight x head) changes by d — shares
-// proportional to the queue lengths, the heaviest profiles first, the last (lightest) one takes the remainder so that the mass is met
-// exactly whenever the weights allow it.  One thread; h, qc, wsz in shared memory.
-__device__ inline void spec_spread(uint32_t* h, const uint32_t* qc, const uint32_t* wsz, uint32_t members, int d, bool weighted) {
-    if (d == 0 || members == 0) return;
-    // two passes over the members: spans of 2 and more first, single slices last (unweighted groups: one pass); 32-bit / float arithmetic —
-    // |d| <= 2^13, queue lengths <= 2^17, and the shares are a prediction, not a result
-    uint32_t heavy = 0, light = members;
-    if (weighted) { light = 0; for (uint32_t m = members; m; m &= m - 1) { const uint32_t p = __ffs(m) - 1; if (wsz[p] > 1) heavy |= 1u << p; else light |= 1u << p; } }
-    float tot = 0.f;
-    for (uint32_t m = members; m; m &= m - 1) { const uint32_t p = __ffs(m) - 1; tot += (float)(qc[p] * (weighted ? wsz[p] : 1u)); }
-    for (int pass = 0; pass < 2; ++pass) {
-        uint32_t todo = pass == 0 ? heavy : light;
-        while (todo) {
-            const uint32_t p = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int w = weighted ? (int)wsz[p] : 1;
-            const bool last = todo == 0 && (pass == 1 || light == 0);
-            const int dp = last ? d / w : (tot > 0.f ? __float2int_rn((float)d * (float)qc[p] / tot) : 0);
-            const int v = (int)h[p] + dp;
-            h[p] = (uint32_t)(v < 0 ? 0 : (v > (int)qc[p] ? (int)qc[p] : v));
-            d -= dp * w; tot -= (float)(qc[p] * (uint32_t)w);
-        }
-    }
+// Speculative rounds: move the heads of the profiles in `members` so that their mass (sum of weight x head) changes by d.
+// By a whole warp: lane p < 16 holds head h of profile p and returns the moved head.  Shares proportional to the queue lengths; the single-slice profile with the highest index (a group without one:
+// its highest member) takes the remainder, so that the mass is met exactly whenever the weights allow it.  |d| <= 2^13: float shares.
+__device__ __forceinline__ uint32_t spec_spread_warp(uint32_t h, uint32_t qc, uint32_t w, uint32_t members, int d, bool weighted, uint32_t lane) {
+    const bool in = (members >> lane) & 1u;
+    if (!weighted) w = 1;
+    const uint32_t light = __ballot_sync(0xFFFFFFFFu, in && w <= 1), heavy = __ballot_sync(0xFFFFFFFFu, in && w > 1);
+    const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, in ? qc * w : 0u);
+    if (d == 0 || members == 0) return h;
+    const uint32_t last = 31u - __clz(light ? light : heavy);
+    int dp = in && lane != last && tot ? __float2int_rn((float)d * (float)qc / (float)tot) : 0;
+    const int used = __reduce_add_sync(0xFFFFFFFFu, dp * (int)w);
+    const int wl = (int)__shfl_sync(0xFFFFFFFFu, w, last);
+    if (lane == last) dp = (d - used) / wl;
+    if (!in) return h;
+    const int v = (int)h + dp;
+    return (uint32_t)(v < 0 ? 0 : (v > (int)qc ? (int)qc : v));
 }
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t sa) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
@@ -1470,11 +1463,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 }
                 r = __reduce_add_sync(0xFFFFFFFFu, r);
                 const uint32_t Q = min(__shfl_sync(0xFFFFFFFFu, incl, 31), totb), R = min(r, tots);
-                if (lane < ISL_MAX_PROFILES) s_specH[lane] = gseg == 0 && a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + lane] : 0u;
-                __syncwarp();
-                if (lane == 0 && gseg > 0) {
-                    spec_spread(s_specH, s_qc, s_minsize, s_grp_big, (int)Q, false);
-                    spec_spread(s_specH, s_qc, s_minsize, s_grp_small, (int)R, true);
+                {
+                    const uint32_t qcl = lane < ISL_MAX_PROFILES ? s_qc[lane] : 0u, wl = lane < ISL_MAX_PROFILES ? s_minsize[lane] : 1u;
+                    uint32_t hg = lane < ISL_MAX_PROFILES && gseg == 0 && a.heads_in ? a.heads_in[(size_t)c * ISL_MAX_PROFILES + lane] : 0u;
+                    if (gseg > 0) {
+                        hg = spec_spread_warp(hg, qcl, wl, s_grp_big, (int)Q, false, lane);
+                        hg = spec_spread_warp(hg, qcl, wl, s_grp_small, (int)R, true, lane);
+                    }
+                    if (lane < ISL_MAX_PROFILES) s_specH[lane] = hg;
                 }
             }
             __syncthreads();
@@ -1786,18 +1782,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 if (tid < ISL_MAX_PROFILES) { pop = s_pop[tid]; X = s_heads[tid] + pop; }
                 if (was_cut) {      // exit of the last complete simulation, moved by what the entry has moved since (per group, shares as always)
                     int eq = 0, er = 0;
+                    uint32_t xe = 0;
+                    const uint32_t qcl = tid < ISL_MAX_PROFILES ? s_qc[tid] : 0u, wl = tid < ISL_MAX_PROFILES ? s_minsize[tid] : 1u;
                     if (tid < ISL_MAX_PROFILES) {
                         const int d = (int)s_heads[tid] - (int)s_Hc[tid];
                         if ((s_grp_big >> tid) & 1u) eq = d;
                         if ((s_grp_small >> tid) & 1u) er = d * (int)s_minsize[tid];
-                        s_specX[tid] = s_Xc[tid];
+                        xe = s_Xc[tid];
                     }
                     eq = __reduce_add_sync(0xFFFFFFFFu, eq); er = __reduce_add_sync(0xFFFFFFFFu, er);
-                    __syncwarp();
-                    if (tid == 0) { spec_spread(s_specX, s_qc, s_minsize, s_grp_big, eq, false); spec_spread(s_specX, s_qc, s_minsize, s_grp_small, er, true); }
-                    __syncwarp();
-                    if (tid < ISL_MAX_PROFILES) { X = max(s_specX[tid], s_heads[tid]); pop = X - s_heads[tid]; }
-                    __syncwarp();
+                    xe = spec_spread_warp(xe, qcl, wl, s_grp_big, eq, false, lane);
+                    xe = spec_spread_warp(xe, qcl, wl, s_grp_small, er, true, lane);
+                    if (tid < ISL_MAX_PROFILES) { X = max(xe, s_heads[tid]); pop = X - s_heads[tid]; }
                 }
                 if (tid < ISL_MAX_PROFILES) {
                     s_specX[tid] = X;
@@ -1876,22 +1872,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             if (tid < 32) {     // c for the next round; the corrected prediction
                 const bool same = tid >= ISL_MAX_PROFILES || s_specH[tid] == s_specXp[tid];
                 const bool cnow = __all_sync(0xFFFFFFFFu, same);
-                uint32_t mq = 0, mr = 0, hold = 0;
+                uint32_t mq = 0, mr = 0, hold = 0, hn = 0;
+                const uint32_t qcl = tid < ISL_MAX_PROFILES ? s_qc[tid] : 0u, wl = tid < ISL_MAX_PROFILES ? s_minsize[tid] : 1u;
                 if (tid < ISL_MAX_PROFILES) {
                     hold = s_specH[tid];
-                    const uint32_t xp = s_specXp[tid];
-                    if ((s_grp_big >> tid) & 1u) mq = xp;
-                    if ((s_grp_small >> tid) & 1u) mr = xp * s_minsize[tid];
-                    s_specH[tid] = xp;
+                    hn = s_specXp[tid];
+                    if ((s_grp_big >> tid) & 1u) mq = hn;
+                    if ((s_grp_small >> tid) & 1u) mr = hn * s_minsize[tid];
                 }
                 mq = __reduce_add_sync(0xFFFFFFFFu, mq); mr = __reduce_add_sync(0xFFFFFFFFu, mr);
-                __syncwarp();
-                if (tid == 0) {
-                    spec_spread(s_specH, s_qc, s_minsize, s_grp_big, (int)s_acc[0] - (int)mq, false);
-                    spec_spread(s_specH, s_qc, s_minsize, s_grp_small, (int)s_acc[1] - (int)mr, true);
-                }
-                __syncwarp();
-                const bool moved = tid < ISL_MAX_PROFILES && s_specH[tid] != hold;
+                hn = spec_spread_warp(hn, qcl, wl, s_grp_big, (int)s_acc[0] - (int)mq, false, lane);
+                hn = spec_spread_warp(hn, qcl, wl, s_grp_small, (int)s_acc[1] - (int)mr, true, lane);
+                if (tid < ISL_MAX_PROFILES) s_specH[tid] = hn;
+                const bool moved = tid < ISL_MAX_PROFILES && hn != hold;
                 const bool changed = __any_sync(0xFFFFFFFFu, moved);
                 // a cut-off simulation left no usable log: the entry is simulated again (in full once it is known to be the true one) and counts as
                 // inconsistent until then
