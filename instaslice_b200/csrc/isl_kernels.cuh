@@ -929,8 +929,9 @@ constexpr uint32_t kPipeSmem = kPipeOffWin + 4 * (kWinTotal + 4 * ISL_MAX_PROFIL
 
 // largest segment whose worst-case queue windows (every candidate GPU accepting every legal start of every
 // profile) fit: n_cand * total_candidates + 2 sentinels per profile <= kWinTotal
+constexpr uint32_t kWinMargin = 32;                 // speculative rounds: queue entries staged on either side of a window, so that a corrected entry nearby re-uses it
 __host__ __device__ inline uint32_t max_segment_for(uint32_t total_candidates) {
-    const uint32_t s = (kWinTotal - kWinPad * ISL_MAX_PROFILES) / (total_candidates ? total_candidates : 1u);
+    const uint32_t s = (kWinTotal - (kWinPad + 2 * kWinMargin + 2) * ISL_MAX_PROFILES) / (total_candidates ? total_candidates : 1u);
     return s >= kSegMax ? kSegMax : s / 64u * 64u;
 }
 
@@ -1160,6 +1161,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     __shared__ uint8_t s_smallm[kMaxTables][ISL_MAX_PROFILES];
     // speculative rounds, bounded simulations: entry / exit heads of the stage's last COMPLETE simulation; {decisions of the largest complete one,
     // have one, the log in shared memory is a complete simulation of the current entry}; decisions this simulation may take; it was cut off
+    // speculative rounds: the staged key windows outlive a simulation — per profile the queue position of the first staged entry, the number
+    // of staged entries, where the current entry sits inside them; the windows are valid for this chunk; this simulation must stage anew
+    __shared__ uint32_t s_wlo[ISL_MAX_PROFILES], s_wlen[ISL_MAX_PROFILES], s_woff[ISL_MAX_PROFILES], s_wvalid, s_restage;
     __shared__ uint32_t s_Hc[ISL_MAX_PROFILES], s_Xc[ISL_MAX_PROFILES], s_capst[3], s_cap, s_capped;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     if (seg == a.n_seg) {       // the extra CTA of a host-buffer stream: every chunk all segments have committed goes to the caller's
@@ -1478,7 +1482,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         uint32_t rnd = 1;
         bool c_prev = spec ? gseg == 0 : seg == 0, need_sim = true, idle_break = false;
         bool known_exact = gseg == 0;       // every stage in front had the true entry one round ago: so have I now
-        if (tid == 0) { s_capst[0] = 0; s_capst[1] = 0; s_capst[2] = 0; s_cap = kLogCap + 1; s_capped = 0; }
+        if (tid == 0) { s_capst[0] = 0; s_capst[1] = 0; s_capst[2] = 0; s_cap = kLogCap + 1; s_capped = 0; s_wvalid = 0; }
         bool p_final = false; unsigned long long p_word = 0;      // pollers: a certified stage's final record is read once and kept
         const unsigned long long t_cell = tr && spec ? globaltimer_ns() : 0ull, sims_cell = st_sims;   // spec trace: [0] sweep + prediction done, [2] certified, [7] simulations, [11] rounds
 #ifdef ISL_SPEC_DBG_STAMPS      // per-round stamps of one cell (tools/spec_trace.py): a debugging build — the extra live pointer around the decision loop costs ~14 %
@@ -1539,8 +1543,34 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 const uint32_t qc = spec ? s_qc[tid] : cc->qcnt[tid], qo = spec ? s_qo[tid] : cc->qoff[tid];     // re-simulations: no trip to L2
                 left = ((active >> tid) & 1u) && qc > h ? qc - h : 0u;
                 wn = min(left, min(s_ncand * s_maxacc[tid], s_nfree / s_minsize[tid]));   // no more pops than that are possible here
-                s_heads[tid] = h; s_wn[tid] = wn; s_pop[tid] = 0;
-                s_qbeg[tid] = qo + h;                                           // first pending entry in the shared copy of the queues
+                s_heads[tid] = h; s_pop[tid] = 0;
+                if (!kSpec) {
+                    s_wn[tid] = wn;
+                    s_qbeg[tid] = qo + h;                                       // first pending entry in the shared copy of the queues
+                }
+            }
+            if (kSpec) {
+                // A corrected entry usually sits a few requests from the one simulated before: the windows are staged with kWinMargin entries on
+                // either side and stay for the next simulation when every profile's new window [h, h + wn + 2) lies inside what is staged (real
+                // keys behind the first wn entries are as good as the INF sentinels there: capacity, not the window, ends a profile's pops)
+                uint32_t lo = 0, len = 0, woff = 0;
+                bool ok = true;
+                const uint32_t qc = tid < ISL_MAX_PROFILES ? s_qc[tid] : 0u;
+                if (tid < ISL_MAX_PROFILES) {
+                    lo = s_wlo[tid]; len = s_wlen[tid];
+                    if (left == 0) woff = len;                                  // nothing pending: straight onto the sentinels
+                    else { ok = s_wvalid && h >= lo && (h + wn + 2 <= lo + len || lo + len >= qc); woff = h - lo; }
+                }
+                const bool keep = __all_sync(0xFFFFFFFFu, ok);
+                if (!keep && tid < ISL_MAX_PROFILES) {
+                    if (left == 0) { lo = h; len = 0; woff = 0; }
+                    else { lo = h - min(h, kWinMargin); len = min(qc - lo, (h - lo) + wn + kWinMargin + 2); woff = h - lo; }
+                    s_wlo[tid] = lo; s_wlen[tid] = len;
+                    s_qbeg[tid] = s_qo[tid] + lo;
+                }
+                if (tid < ISL_MAX_PROFILES) { s_woff[tid] = woff; s_wn[tid] = len - woff; }     // real entries from the entry to the staged end
+                if (tid == 0) { s_restage = keep ? 0u : 1u; s_wvalid = 1; }
+                wn = len;                                                       // the layout below counts the staged entries
             }
             // nothing placeable is pending any more: tell every later segment at once instead of relaying hop by hop
             const bool idle = __ballot_sync(0xFFFFFFFFu, left != 0) == 0;
@@ -1586,10 +1616,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         if (!s_idle) {
         {   // windows of ready-made keys t << 15 | profile << 11, each closed by two INF sentinels — converted from the shared copy of
             // the queues (a shared-memory round trip per round instead of an L2 one), only for profiles that own candidates
-            const uint32_t npl = s_nplist;
+            const uint32_t npl = kSpec && !s_restage ? 0u : s_nplist;
             const uint16_t* __restrict__ sq = reinterpret_cast<const uint16_t*>(smem + kPipeOffQ);
             for (uint32_t x = 0; x < npl; ++x) {
-                const uint32_t p = s_plist[x], wn = s_wn[p], pk = p << 11, qb = s_qbeg[p];
+                const uint32_t p = s_plist[x], wn = kSpec ? s_wlen[p] : s_wn[p], pk = p << 11, qb = s_qbeg[p];
                 uint32_t* __restrict__ dst = s_wkey + s_wbase[p];
                 // plain, unconditional (clamped) accesses: the loads of a round overlap instead of queueing behind each other
                 for (uint32_t i = tid; i < wn + kWinPad; i += kPipeThreads) { const uint32_t v = sq[qb + min(i, wn)]; dst[i] = i < wn ? (v << 15) | pk : kInf; }
@@ -1604,7 +1634,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             uint32_t tcur[K], tnext[K], tnn[K], wa[K], wa0[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                wa0[k] = sa_wkey + 4 * s_wbase[cprof[k]];
+                wa0[k] = sa_wkey + 4 * (s_wbase[cprof[k]] + (kSpec ? s_woff[cprof[k]] : 0u));
                 const bool has = valid[k];
                 tcur[k] = has ? lds_u32(wa0[k]) | klow[k] : kInf;               // INF | anything = INF
                 tnext[k] = has ? lds_u32(wa0[k] + 4) | klow[k] : kInf;
