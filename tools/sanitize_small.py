@@ -30,6 +30,13 @@ eng = E.Engine(max_gpus=4096, max_batch=1 << 16)
 eng.load_profiles(rows); eng.load_inventory(node_off, occ)
 got = eng.place_stream([b[0] for b in batches])
 assert all(np.array_equal(g, b[1]) for g, b in zip(got, batches))
+# speculative rounds: a stream with one batch in flight, and forced on for the unconstrained stream
+for window, mode in ((1, E.SPEC_AUTO), (0, E.SPEC_ON)):
+    sp = E.Engine(max_gpus=4096, max_batch=1 << 16)
+    sp.set_speculation(mode); sp.set_causal_window(window)
+    sp.load_profiles(rows); sp.load_inventory(node_off, occ)
+    got = sp.place_stream([b[0] for b in batches])
+    assert all(np.array_equal(g, b[1]) for g, b in zip(got, batches)) and sp.stats()["spec_chunks"] == len(batches)
 bf = E.Engine(max_gpus=4096, max_batch=1 << 16, policy=E.POLICY_BEST_FIT)
 bf.load_profiles(rows); bf.load_inventory(node_off, occ)
 rb = oracle.Fast(node_off, rows, 3, policy=1); rb.load(occ)
