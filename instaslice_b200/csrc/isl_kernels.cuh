@@ -1549,6 +1549,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     s_qbeg[tid] = qo + h;                                       // first pending entry in the shared copy of the queues
                 }
             }
+            bool win_keep = true;
             if (kSpec) {
                 // A corrected entry usually sits a few requests from the one simulated before: the windows are staged with kWinMargin entries on
                 // either side and stay for the next simulation when every profile's new window [h, h + wn + 2) lies inside what is staged (real
@@ -1561,7 +1562,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     if (left == 0) woff = len;                                  // nothing pending: straight onto the sentinels
                     else { ok = s_wvalid && h >= lo && (h + wn + 2 <= lo + len || lo + len >= qc); woff = h - lo; }
                 }
-                const bool keep = __all_sync(0xFFFFFFFFu, ok);
+                const bool keep = __all_sync(0xFFFFFFFFu, ok) && !(a.spec & 2u);      // (bit 1 of PipeArgs.spec: stage anew every time — a debugging switch, ISL_SPEC_NOREUSE)
                 if (!keep && tid < ISL_MAX_PROFILES) {
                     if (left == 0) { lo = h; len = 0; woff = 0; }
                     else { lo = h - min(h, kWinMargin); len = min(qc - lo, (h - lo) + wn + kWinMargin + 2); woff = h - lo; }
@@ -1569,7 +1570,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                     s_qbeg[tid] = s_qo[tid] + lo;
                 }
                 if (tid < ISL_MAX_PROFILES) { s_woff[tid] = woff; s_wn[tid] = len - woff; }     // real entries from the entry to the staged end
-                if (tid == 0) { s_restage = keep ? 0u : 1u; s_wvalid = 1; }
+                win_keep = keep;
                 wn = len;                                                       // the layout below counts the staged entries
             }
             // nothing placeable is pending any more: tell every later segment at once instead of relaying hop by hop
@@ -1577,6 +1578,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
             if (idle && !all_done && !spec && tid < ISL_MAX_PROFILES) st_relaxed_gpu(a.tokens + (tok_chunk + a.n_seg) * kTokStride + tid, (tag << 17) | h);
             if (tid == 0) {
                 s_idle = idle ? 1u : 0u;
+                if (kSpec) {        // an idle simulation stages nothing: a new layout that was never filled must not be kept by the next one
+                    s_restage = win_keep ? 0u : 1u;
+                    if (!win_keep) s_wvalid = idle ? 0u : 1u;
+                }
                 // A speculative simulation from an entry that is far off can run several times longer than the segment's true work (everything the
                 // stages in front are wrongly believed to have left over lands here) and would hold up the whole round.  Unless the entry is known
                 // to be the true one, the simulation is cut off at 1.3 x the largest complete one so far; a cut-off round publishes the exit

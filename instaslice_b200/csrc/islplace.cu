@@ -600,7 +600,7 @@ int run_stream(isl_engine* e, uint32_t n_batches, const uint32_t* sizes, const u
     args.inbox = ring && e->has_prev ? e->d_inbox : nullptr; args.outbox = ring ? e->d_outbox : nullptr; args.xepoch = xepoch;
     if (spec) {
         if (int rc2 = prepare_spec(e, n_chunks, epoch, e->stream)) return rc2;
-        args.spec = 1; args.spec_mem = e->d_spec; args.spec_total = n_seg;
+        args.spec = getenv("ISL_SPEC_NOREUSE") ? 3u : 1u; args.spec_mem = e->d_spec; args.spec_total = n_seg;
         if (ring) {         // no token ring: the records themselves cross the ranks
             args.inbox = nullptr; args.outbox = nullptr;
             args.spec_world = e->spec_world; args.spec_rank = e->spec_rank; args.spec_base = e->lo / seg; args.spec_total = ceil_div(e->G, seg);
@@ -1610,7 +1610,7 @@ int isl_stream_submit(isl_engine* e, uint32_t n, const isl_request* in, isl_resu
         args.chunks = e->d_chunks; args.cctl = e->d_cctl; args.q_all = e->d_qall; args.free_acc = reinterpret_cast<const uint8_t*>(e->d_free_acc);
         args.q_stride = o.q_stride; args.free_stride = o.free_stride; args.tokens = e->d_tokens; args.occ = e->d_occ; args.gtab = e->d_gtab;
         args.out = e->d_res; args.feas = e->d_feas; args.stats = e->d_ctrl;
-        if (o.spec) { args.spec = 1; args.spec_mem = e->d_spec; args.spec_total = o.n_seg; }
+        if (o.spec) { args.spec = getenv("ISL_SPEC_NOREUSE") ? 3u : 1u; args.spec_mem = e->d_spec; args.spec_total = o.n_seg; }
         int rc;
         const bool p15 = e->prof.n == ISL_MAX_PROFILES;
         switch (e->n_cand_slots) {

@@ -228,3 +228,40 @@ def test_speculative_rounds_across_ranks_on_one_gpu(n_ranks, window):
         assert st["spec_chunks"] >= len(batches), st
     for eng in engines:
         eng.close()
+
+
+@pytest.mark.parametrize("tname", ["a100-40gb", "h100-80gb", "a30-24gb", "b200-180gb"])
+@pytest.mark.parametrize("quirks", [3, 0])
+def test_randomised_inventories_and_frees_speculative(tname, quirks):
+    """Ragged nodes, occupancy with the unusable slot set, unknown profiles, frees of live allocations, batches of 1..6000 requests on a few
+    hundred to a few thousand GPUs — with the rounds forced on: entries that are idle in one round and not in the next, windows that are
+    re-used or staged anew, simulations that are cut off.  Everything byte-identical to the oracle."""
+    table = tables.TABLES[tname]
+    rows = E.make_profiles(table)
+    rng = W.SplitMix64(4711 + quirks + len(tname))
+    for trial in range(6):
+        n_nodes = 8 + int(rng.next1() % 900)
+        node_off = np.concatenate([[0], np.cumsum(1 + (rng.next(n_nodes) % np.uint64(9)).astype(np.int64))]).astype(np.uint32)
+        G = int(node_off[-1])
+        occ = ((rng.next(G) & rng.next(G)) & np.uint64(0xFF)).astype(np.uint8)
+        eng = E.Engine(max_gpus=max(4096, G), max_batch=1 << 16, quirks=quirks, flags=E.FLAG_FORCE_PIPELINE | E.FLAG_NO_SMALL)
+        eng.set_speculation(E.SPEC_ON)
+        eng.load_profiles(rows)
+        eng.load_inventory(node_off, occ)
+        ref = oracle.Fast(node_off, rows, quirks)
+        ref.load(occ)
+        live = []
+        for batch in range(5):
+            n = 1 + int(rng.next1() % 6000)
+            req = W.alloc_requests((rng.next(n) % np.uint64(len(table) + 1)).astype(np.uint8))
+            req["profile"][req["profile"] == len(table)] = E.PROFILE_UNKNOWN
+            for i in range(min(len(live), n // 3)):
+                g, s, z = live.pop(int(rng.next1() % len(live)))
+                req[int(rng.next1() % n)] = (g, 0, E.OP_FREE, s, z)
+            got, want = eng.place_batch(req), ref.place(req)
+            bad = np.flatnonzero(got != want)
+            assert len(bad) == 0, (tname, quirks, trial, batch, bad[:4], got[bad[:4]], want[bad[:4]])
+            assert np.array_equal(eng.read_occupancy(), ref.occupancy())
+            for r in got[(req["op"] == E.OP_ALLOC) & (got["status"] == E.ST_PLACED)]:
+                live.append((int(r["gpu"]), int(r["start"]), int(r["size"])))
+        eng.close()
