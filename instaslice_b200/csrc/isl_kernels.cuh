@@ -1597,7 +1597,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         __syncthreads();
         stamp_if(tr && tid == 0, tr + 8);
         stamp_if(dbg && tid == 0, dbg + rnd * 8 + 1);
-        if (s_idle && spec) { if (tid == 0) s_nlog = 0; }       // nothing pending at these heads: the exit equals the entry
+        if (s_idle && spec) { if (tid == 0) { s_nlog = 0; spec_steps = 0; spec_visited = 0; } }      // nothing pending at these heads: the exit equals the entry
         else if (s_idle) {  // pass-through: the token (unchanged heads) still reaches the next rank / the caller from the last segment
             if (warp == 0) {
                 const bool last = seg == a.n_seg - 1;

@@ -239,7 +239,8 @@ def test_randomised_inventories_and_frees_speculative(tname, quirks):
     table = tables.TABLES[tname]
     rows = E.make_profiles(table)
     rng = W.SplitMix64(4711 + quirks + len(tname))
-    for trial in range(6):
+    import os
+    for trial in range(6 * int(os.environ.get("ISL_STRESS", "1"))):
         n_nodes = 8 + int(rng.next1() % 900)
         node_off = np.concatenate([[0], np.cumsum(1 + (rng.next(n_nodes) % np.uint64(9)).astype(np.int64))]).astype(np.uint32)
         G = int(node_off[-1])
