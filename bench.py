@@ -160,7 +160,7 @@ class Ctx:
         if self.world > 1:
             if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
                 os.environ["NCCL_DEBUG"] = "INFO"
-            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
             os.environ.pop("NCCL_DEBUG_FILE", None)
             sys.stdout.flush()
             self.real_stdout = os.dup(1)
@@ -890,12 +890,12 @@ def run_own(args):
         ctx.dist.barrier()
         ctx.dist.destroy_process_group()
         sys.stdout.flush()
-        if ctx.real_stdout is not None:
-            os.dup2(ctx.real_stdout, 1)
-            os.close(ctx.real_stdout)
     if ctx.rank == 0 and line is not None:
         sys.stdout.flush()
-        print(json.dumps(line), flush=True)          # the LAST line of stdout
+        if ctx.real_stdout is not None:     # file descriptor 1 stays on stderr to the end (NCCL still logs while the process exits): the JSON line
+            os.write(ctx.real_stdout, (json.dumps(line) + "\n").encode())      # goes straight to the real stdout — its only line
+        else:
+            print(json.dumps(line), flush=True)
     return 0 if parity else 1
 
 
