@@ -428,9 +428,15 @@ type BacklogStream struct {
 	free []func()
 }
 
-func (e *PlacementEngine) OpenBacklogStream(maxBatches int) (*BacklogStream, error) {
+// inFlight: how many batches this caller keeps in flight (it Waits for batch b - inFlight before it Submits batch b).  1..3 tells the
+// engine to resolve every batch by speculative rounds (all inventory stages at once, DESIGN.md 4.5) instead of pipelining different
+// batches over the stages; 0 = no promise (deep backlogs).
+func (e *PlacementEngine) OpenBacklogStream(maxBatches int, inFlight int) (*BacklogStream, error) {
 	if e.orphans {
 		return nil, fmt.Errorf("realised slices without allocation present: resolve pods one by one (PlacePending)")
+	}
+	if rc := C.isl_set_causal_window(e.h, C.uint32_t(inFlight)); rc != C.ISL_OK {
+		return nil, fmt.Errorf("isl_set_causal_window: %s", C.GoString(C.isl_strerror(rc)))
 	}
 	if rc := C.isl_stream_open(e.h, C.uint32_t(maxBatches)); rc != C.ISL_OK {
 		return nil, fmt.Errorf("isl_stream_open: %s", C.GoString(C.isl_strerror(rc)))
