@@ -1164,6 +1164,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     // speculative rounds: the staged key windows outlive a simulation — per profile the queue position of the first staged entry, the number
     // of staged entries, where the current entry sits inside them; the windows are valid for this chunk; this simulation must stage anew
     __shared__ uint32_t s_wlo[ISL_MAX_PROFILES], s_wlen[ISL_MAX_PROFILES], s_woff[ISL_MAX_PROFILES], s_wvalid, s_restage;
+    __shared__ uint32_t s_predc;
     __shared__ uint32_t s_Hc[ISL_MAX_PROFILES], s_Xc[ISL_MAX_PROFILES], s_capst[3], s_cap, s_capped;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     if (seg == a.n_seg) {       // the extra CTA of a host-buffer stream: every chunk all segments have committed goes to the caller's
@@ -1481,7 +1482,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         }
         uint32_t rnd = 1;
         bool c_prev = spec ? gseg == 0 : seg == 0, need_sim = true, idle_break = false;
-        bool known_exact = gseg == 0;       // every stage in front had the true entry one round ago: so have I now
+        bool known_exact = gseg == 0;       // everything in front of the stage right in front of me was consistent one round ago: my next entry may be the true one
         if (tid == 0) { s_capst[0] = 0; s_capst[1] = 0; s_capst[2] = 0; s_cap = kLogCap + 1; s_capped = 0; s_wvalid = 0; }
         bool p_final = false; unsigned long long p_word = 0;      // pollers: a certified stage's final record is read once and kept
         const unsigned long long t_cell = tr && spec ? globaltimer_ns() : 0ull, sims_cell = st_sims;   // spec trace: [0] sweep + prediction done, [2] certified, [7] simulations, [11] rounds
@@ -1890,7 +1891,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 }
                 s_specXp[i] = (uint32_t)w & 0x1FFFFu;
             }
-            const bool allc = __syncthreads_and(cbit);
+            if (tid + 1 == gseg) s_predc = cbit ? 1u : 0u;         // the bit of the stage right in front of me
+            const int unset = __syncthreads_count(!cbit);
+            const bool allc = unset == 0;
+            // Knowledge lags a round: the stage whose entry becomes the true one NEXT round sits behind a consistent prefix whose last member's
+            // bit is not set yet (that member's own entry became the true one only this round).  So "everything in front but the stage right
+            // in front of me is consistent" already exempts the next simulation from the cut-off — otherwise the frontier itself could be cut
+            // off and every step of it would cost a second round (tests/spec_rounds_model.cpp).
+            const bool near = allc || (unset == 1 && !s_predc);
             const bool certified = allc && c_prev;
             stamp_if(dbg && tid == 0, dbg + rnd * 8 + 5);
             store_if(dbg && tid == 0, dbg + rnd * 8 + 7, s_nlog | ((unsigned long long)need_sim << 32));
@@ -1927,7 +1935,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 stamp_if(dbg && tid == 0, dbg + rnd * 8 + 6);
             }
             __syncthreads();
-            c_prev = s_specflag & 1u; need_sim = s_specflag & 2u; known_exact = allc;
+            c_prev = s_specflag & 1u; need_sim = s_specflag & 2u; known_exact = near;
             if (++rnd >= kSpecRounds - 1) __trap();      // cannot happen: every round certifies at least one more stage
         }
         }   // rounds
