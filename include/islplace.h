@@ -305,7 +305,7 @@ int  isl_place_batch_partitioned(isl_engine* e, uint32_t n, const void* d_in, vo
  *   1. every rank:  isl_ipc_inbox_handle(e, h)             -> 64-byte handle, exchanged by the caller (e.g. all_gather)
  *   2. every rank:  isl_ipc_connect(e, next rank's handle or NULL for the last rank, has_prev)
  *   3. every rank:  isl_place_stream_partitioned(..., stream_id) with the same batches and the same non-zero,
- *      never repeated stream_id; only enqueues.  Results: element-wise MIN over ranks as for the batch variant. */
+ *      never repeated stream_id (it tags what crosses the ranks; the speculative rounds use its low 24 bits); only enqueues.  Results: element-wise MIN over ranks as for the batch variant. */
 int  isl_ipc_inbox_handle(isl_engine* e, void* handle64);
 int  isl_ipc_connect(isl_engine* e, const void* next_handle64, int has_prev);
 /* Same wiring for two engines of ONE process (same device or peer-enabled devices): no IPC handle needed. */
