@@ -66,6 +66,7 @@ int main(int argc, char** argv) {
         auto cr = [&](const Heads& h) { long c = 0; for (int p : small) c += (long)h[p] * psize(p); return c; };
         std::vector<double> lq(S, 1.0), lr(S, 1.0); std::vector<long> peq(S), pxq(S), per(S), pxr(S); std::vector<bool> have(S, false);
         const int secant = getenv("SECANT") ? atoi(getenv("SECANT")) : 0;
+        std::vector<Heads> predA(S + 2), predB(S + 2); std::vector<bool> havePred(S + 2, false);
         std::vector<Heads> pH(S), pE(S); std::vector<bool> haveR(S, false); std::vector<double> lam(S, getenv("LAM0") ? atof(getenv("LAM0")) : 0.0);
         int rounds = 0; uint64_t crit = 0; uint32_t frontier = 0, frontier1 = 0, frontier2 = 0; uint64_t ncapped = 0;
         std::vector<Heads> Hsim(S), Xlast(S), Hc(S), Xc(S); std::vector<bool> logvalid(S, false), havec(S, false); std::vector<uint64_t> maxdec(S, 0);
@@ -101,6 +102,24 @@ int main(int argc, char** argv) {
             Hn[0] = h0;
             for (uint32_t s = 0; s < S; ++s) {
                 Hn[s + 1] = E[s + 1];
+                if (getenv("EXPERT") && rounds >= 2) {
+                    // candidates for stage s+1's next entry
+                    Heads A = E[s + 1];
+                    { long dq = 0, dr = 0; for (int p : big) dq += (long)Hn[s][p] - (long)H[s][p]; for (int p : small) dr += ((long)Hn[s][p] - (long)H[s][p]) * psize(p);
+                      long nb = 0, ns = 0; for (int p : big) nb += q[p].size(); for (int p : small) ns += (long)q[p].size() * psize(p);
+                      auto clampadd = [&](int p, long d) { long v = (long)A[p] + d; v = std::max(0l, std::min<long>(v, q[p].size())); A[p] = v; };
+                      { std::vector<int> b2 = big; long d = dq, tot = nb; std::sort(b2.begin(), b2.end()); for (size_t i = 0; i < b2.size(); ++i) { int p = b2[i]; long dp = i + 1 == b2.size() ? d : (tot ? std::lround((double)d * q[p].size() / tot) : 0); clampadd(p, dp); d -= dp; tot -= q[p].size(); } }
+                      { std::vector<int> grp = small; long d = dr, tot = ns; std::sort(grp.begin(), grp.end(), [&](int x, int y) { return psize(x) > psize(y) || (psize(x) == psize(y) && x < y); });
+                        for (size_t i = 0; i < grp.size(); ++i) { int p = grp[i]; long w = psize(p); long dp = i + 1 == grp.size() ? d / w : (tot ? std::lround((double)d * q[p].size() / tot) : 0); clampadd(p, dp); d -= dp * w; tot -= (long)q[p].size() * w; } } }
+                    Heads Bc = E[s + 1];
+                    // which rule would have predicted this round's entry better last round?  errA[s+1], errB[s+1] were recorded then
+                    auto dist = [&](const Heads& x, const Heads& y) { long d = 0; for (int p = 0; p < np; ++p) d += std::labs((long)x[p] - (long)y[p]); return d; };
+                    const long eA = !havePred[s + 1] ? 0 : dist(predA[s + 1], E[s + 1]), eB = !havePred[s + 1] ? 0 : dist(predB[s + 1], E[s + 1]);
+                    // (the better predictor of the predecessor's exit as it turned out now)
+                    predA[s + 1] = A; predB[s + 1] = Bc; havePred[s + 1] = true;
+                    Hn[s + 1] = eB < eA ? Bc : A;
+                    continue;
+                }
                 if (getenv("IDENT")) { for (int p = 0; p < np; ++p) { long v = (long)E[s + 1][p] + (long)Hn[s][p] - (long)H[s][p]; Hn[s + 1][p] = (uint32_t)std::max(0l, std::min<long>(v, q[p].size())); } continue; }
                 if (!newton) continue;
                 long dq = 0, dr = 0; for (int p : big) dq += (long)Hn[s][p] - (long)H[s][p]; for (int p : small) dr += ((long)Hn[s][p] - (long)H[s][p]) * psize(p);
