@@ -1164,7 +1164,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
     // speculative rounds: the staged key windows outlive a simulation — per profile the queue position of the first staged entry, the number
     // of staged entries, where the current entry sits inside them; the windows are valid for this chunk; this simulation must stage anew
     __shared__ uint32_t s_wlo[ISL_MAX_PROFILES], s_wlen[ISL_MAX_PROFILES], s_woff[ISL_MAX_PROFILES], s_wvalid, s_restage;
-    __shared__ uint32_t s_predc;
+    __shared__ uint32_t s_predc, s_predA[ISL_MAX_PROFILES], s_predB[ISL_MAX_PROFILES], s_havepred;
     __shared__ uint32_t s_Hc[ISL_MAX_PROFILES], s_Xc[ISL_MAX_PROFILES], s_capst[3], s_cap, s_capped;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, seg = blockIdx.x;
     if (seg == a.n_seg) {       // the extra CTA of a host-buffer stream: every chunk all segments have committed goes to the caller's
@@ -1483,7 +1483,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
         uint32_t rnd = 1;
         bool c_prev = spec ? gseg == 0 : seg == 0, need_sim = true, idle_break = false;
         bool known_exact = gseg == 0;       // everything in front of the stage right in front of me was consistent one round ago: my next entry may be the true one
-        if (tid == 0) { s_capst[0] = 0; s_capst[1] = 0; s_capst[2] = 0; s_cap = kLogCap + 1; s_capped = 0; s_wvalid = 0; }
+        if (tid == 0) { s_capst[0] = 0; s_capst[1] = 0; s_capst[2] = 0; s_cap = kLogCap + 1; s_capped = 0; s_wvalid = 0; s_havepred = 0; }
         bool p_final = false; unsigned long long p_word = 0;      // pollers: a certified stage's final record is read once and kept
         const unsigned long long t_cell = tr && spec ? globaltimer_ns() : 0ull, sims_cell = st_sims;   // spec trace: [0] sweep + prediction done, [2] certified, [7] simulations, [11] rounds
 #ifdef ISL_SPEC_DBG_STAMPS      // per-round stamps of one cell (tools/spec_trace.py): a debugging build — the extra live pointer around the decision loop costs ~14 %
@@ -1926,6 +1926,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_pipeline(CandTab tab, PipeA
                 mq = __reduce_add_sync(0xFFFFFFFFu, mq); mr = __reduce_add_sync(0xFFFFFFFFu, mr);
                 hn = spec_spread_warp(hn, qcl, wl, s_grp_big, (int)s_acc[0] - (int)mq, false, lane);
                 hn = spec_spread_warp(hn, qcl, wl, s_grp_small, (int)s_acc[1] - (int)mr, true, lane);
+                {   // Two candidates for the next entry: the Newton step (hn) and plain chaining (the exit of the stage in front as it is).  Where a
+                    // batch's contested front reaches far the Newton step over-corrects round after round; each stage uses the rule whose
+                    // candidate of the PREVIOUS round came closer to what the stage in front has published now (study, section 8).
+                    const uint32_t xp = tid < ISL_MAX_PROFILES ? s_specXp[tid] : 0u;
+                    uint32_t ea = 0, eb = 0;
+                    if (tid < ISL_MAX_PROFILES && s_havepred) { ea = (uint32_t)abs((int)s_predA[tid] - (int)xp); eb = (uint32_t)abs((int)s_predB[tid] - (int)xp); }
+                    ea = __reduce_add_sync(0xFFFFFFFFu, ea); eb = __reduce_add_sync(0xFFFFFFFFu, eb);
+                    __syncwarp();
+                    if (tid < ISL_MAX_PROFILES) { s_predA[tid] = hn; s_predB[tid] = xp; }
+                    if (tid == 0) s_havepred = 1;
+                    if (eb < ea) hn = xp;
+                }
                 if (tid < ISL_MAX_PROFILES) s_specH[tid] = hn;
                 const bool moved = tid < ISL_MAX_PROFILES && hn != hold;
                 const bool changed = __any_sync(0xFFFFFFFFu, moved);

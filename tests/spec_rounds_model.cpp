@@ -106,6 +106,7 @@ static int run_case(uint32_t G, uint32_t seg, uint32_t n_req, int table, bool bo
     { long qs = 0, rs = 0; for (uint32_t s = 0; s < S; ++s) { if (s) { spread(w, H[s], big, std::min(qs, totb), false); spread(w, H[s], small, std::min(rs, tots), true); } rs += qs < totb ? Rw[s] : Ro[s]; qs += Q[s]; } }
     std::vector<bool> certified(S, false), cprev(S, false), logvalid(S, false), have(S, false), known(S, false), need(S, true);
     std::vector<uint64_t> maxdec(S, 0);
+    std::vector<Heads> predA(S, Heads(np, 0)), predB(S, Heads(np, 0)); std::vector<bool> havepred(S, false);
     std::vector<long> Dq(S, 0), Dr(S, 0);
     cprev[0] = true; known[0] = true;
     uint32_t n_cert = 0;
@@ -144,6 +145,12 @@ static int run_case(uint32_t G, uint32_t seg, uint32_t n_req, int table, bool bo
                     if (s > 0) {
                         Heads h = X[s - 1];
                         spread(w, h, big, sq - massq(h), false); spread(w, h, small, sr - massr(h), true);
+                        {   // two candidates, the Newton step and plain chaining: the rule whose candidate of the previous round came closer to X(s-1) now
+                            long ea = 0, eb = 0;
+                            if (havepred[s]) for (int p = 0; p < np; ++p) { ea += std::labs((long)predA[s][p] - (long)X[s - 1][p]); eb += std::labs((long)predB[s][p] - (long)X[s - 1][p]); }
+                            predA[s] = h; predB[s] = X[s - 1]; havepred[s] = true;
+                            if (eb < ea) h = X[s - 1];
+                        }
                         if (allc && cnew[s] && h != H[s]) { printf("FAIL: the correction moved a consistent entry\n"); return 1; }
                         Hn[s] = h;
                     }
