@@ -180,6 +180,7 @@ static int run_case(uint32_t G, uint32_t seg, uint32_t n_req, int table, bool bo
     return 0;
 }
 
+#ifndef SPEC_MODEL_NO_MAIN
 int main(int argc, char** argv) {
     const int cases = argc > 1 ? atoi(argv[1]) : 60;
     int bad = 0;
@@ -197,3 +198,4 @@ int main(int argc, char** argv) {
     printf(bad ? "spec rounds model: FAILED\n" : "spec rounds model: ok (%d cases)\n", cases);
     return bad;
 }
+#endif
