@@ -274,7 +274,8 @@ int  isl_set_causal_window(isl_engine* e, uint32_t window);
  * latency drops from (stages x segment time) to (rounds x segment time).  It pays when few batches may be in flight and costs
  * throughput when many may overlap anyway:
  *   ISL_SPEC_AUTO (default)  single batches and streams with a causal window of 1..3; open streams: when a window of 1..3 is set
- *   ISL_SPEC_OFF / ISL_SPEC_ON  never / whenever the geometry allows it (one sub-segment per stage, no partitioned inventory) */
+ *   ISL_SPEC_OFF / ISL_SPEC_ON  never / whenever the geometry allows it: one sub-segment per inventory stage (<= 148 x 512 = 75 776 GPUs per
+ *                            engine; larger inventories keep the plain pipeline), a partitioned inventory only with isl_ipc_connect_spec */
 #define ISL_SPEC_AUTO 0u
 #define ISL_SPEC_OFF  1u
 #define ISL_SPEC_ON   2u
