@@ -5,6 +5,8 @@ canonical GPU range ``partition_bounds(G, world, d)``; every rank holds the whol
 
 * the queue-head token of every chunk crosses rank boundaries INSIDE the running segment-pipeline kernels through
   CUDA-IPC peer memory (``connect_ring``) — no host round trip, no collective on the data path;
+* with ``connect_spec`` the stages of all ranks form ONE sequence that resolves a batch by speculative rounds: every
+  rank maps every other rank's record memory and a stage stores the per-round records later ranks read straight into their copies;
 * results are gathered on the OWNER rank (rank 0, where the controller runs) without a collective: ``connect_owner`` maps
   the owner's result array into every other rank, and the commit threads of those ranks store each PLACED record there
   as well (peer store inside the running kernel).  ``merge_results`` (all-reduce(MIN) over the 8-byte records: a PLACED
